@@ -1,0 +1,103 @@
+"""ctypes binding of libgdr_b200.so — the C ABI declared in include/gdr.h.
+
+This is the whole "extension": no torch types cross the boundary, only raw device
+pointers (``tensor.data_ptr()``), sizes and the current CUDA stream handle.  There
+is deliberately NO fallback: if the shared library is missing or a call fails the
+caller gets an exception, never a CPU/eager result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgdr_b200.so")
+
+i64, i32, f32, vp, cp = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_char_p
+
+# name -> (restype, argtypes).  Pointers are passed as integers (void*).
+_SIGNATURES = {
+    "gdr_abi_version": (i32, []),
+    "gdr_last_error": (cp, []),
+    "gdr_device_info": (i32, [vp, vp, vp]),
+    "gdr_launch_count": (i64, []),
+    "gdr_sort_pairs_ws_bytes": (i64, [i64]),
+    "gdr_sort_pairs": (i32, [i64, i32, vp, vp, vp, i64, vp]),
+    "gdr_coo_to_csr_ws_bytes": (i64, [i64, i64, i64, i32]),
+    "gdr_coo_to_csr": (i32, [i64, i64, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_sym_normalize_ws_bytes": (i64, [i64, i64]),
+    "gdr_sym_normalize": (i32, [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_sym_normalize_dense_ws_bytes": (i64, [i64]),
+    "gdr_sym_normalize_dense": (i32, [i64, vp, i64, vp, i64, vp, i64, vp]),
+    "gdr_bipartite_normalize": (i32, [i64, i64, i64, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp]),
+    "gdr_csr_transpose_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_csr_transpose": (i32, [i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_csr_to_coo": (i32, [i64, vp, vp, vp, vp, vp]),
+    "gdr_spmm_prop": (i32, [i64, i64, vp, vp, vp, f32, vp, i64, vp, i64, vp, i64, f32, vp]),
+    "gdr_scale_rows": (i32, [i64, i64, f32, vp, i64, vp, i64, vp]),
+    "gdr_center_columns_ws_bytes": (i64, [i64, i64]),
+    "gdr_center_columns": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
+    "gdr_kmeans_assign_ws_bytes": (i64, [i64, i64, i64, i32]),
+    "gdr_kmeans_assign": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
+    "gdr_segment_sum_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_segment_sum": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
+    "gdr_label_histogram": (i32, [i64, i64, vp, vp, vp, vp]),
+    "gdr_kmeans_finalize": (i32, [i64, i64, vp, i64, vp, vp, i64, vp, i64, vp, i32, vp]),
+    "gdr_kmeans_relocate_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_kmeans_relocate": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
+    "gdr_inertia_ws_bytes": (i64, [i64, i64]),
+    "gdr_inertia": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp]),
+    "gdr_add_row_vector": (i32, [i64, i64, vp, i64, vp, f32, vp]),
+    "gdr_coarsen_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_coarsen": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_coarsen_scale": (i32, [i64, vp, vp, vp, vp, vp, vp, vp]),
+}
+
+ERROR_NAMES = {-1: "GDR_EINVAL", -2: "GDR_EWORKSPACE", -3: "GDR_ECUDA", -4: "GDR_ERANGE",
+               -5: "GDR_EUNSUPPORTED"}
+
+
+class GdrError(RuntimeError):
+    """A libgdr_b200 entry point returned a non-zero status."""
+
+    def __init__(self, fn: str, code: int, msg: str):
+        self.fn, self.code = fn, code
+        super().__init__(f"{fn} -> {ERROR_NAMES.get(code, code)}: {msg}")
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the distillation core."
+        )
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gdr_abi_version() != 1:
+        raise ImportError("libgdr_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise GdrError on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GdrError(name, rc, lib.gdr_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def query(name: str, *args) -> int:
+    """Invoke a *_ws_bytes / counter style entry point (returns its value)."""
+    return int(getattr(load(), name)(*args))

@@ -1,0 +1,761 @@
+// graph.cu — stage 1 (CSR construction, degrees, D^-1/2 A D^-1/2, bipartite
+// normalisation, transpose) and stage 4 (cluster-coarsened graph by segmented
+// edge counting).  All of it is integer / streaming work bound by HBM: packed
+// 64-bit keys, the stable radix sort of primitives.cu, head flags + scan, and
+// fixed-order run reductions — so integer outputs are bit-exact and float sums
+// are deterministic.
+//
+// Reference semantics followed (paths relative to /root/reference/ClustGDD):
+//   utils.py:66-67, distill_recsys.py:110-117   COO -> CSR, duplicates summed
+//   utils_graphsaint.py:20-22                   A + A^T ; A[A>1] = 1
+//   deep_robust_utils.py:180-207, 245-265       normalize_adj / normalize_adj_tensor
+//   distill_recsys.py:184-201                   build_condensed_bipartite
+//   clustgdd_agent_transduct.py:234-250         graph_compress
+//   distill_recsys.py:329-335                   bipartite degree normalisation
+#include "common.cuh"
+
+namespace gdr {
+
+static inline int bits_for(int64_t n) {  // bits needed to store values in [0, n)
+  int b = 1;
+  while ((1ll << b) < n) ++b;
+  return b;
+}
+
+// ----------------------------------------------------------------------------
+// reduce-by-key over SORTED (key, float payload) pairs
+// ----------------------------------------------------------------------------
+constexpr int RUN_SEQ_MAX = 64;  // runs up to this length are summed by one thread
+
+__global__ void k_head_flags(int64_t n, const uint64_t* __restrict__ keys, int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// pos = exclusive scan of head flags (pos[n] = #runs).  For every head i write
+// head_index[pos[i]] = i ; head_index[m] = n is written by the thread owning i = n-1.
+__global__ void k_head_index(int64_t n, const uint64_t* __restrict__ keys,
+                             const int32_t* __restrict__ pos, int32_t* __restrict__ head_index) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i == 0 || keys[i] != keys[i - 1]) head_index[pos[i]] = (int32_t)i;
+    if (i == n - 1) head_index[pos[n]] = (int32_t)n;
+  }
+}
+
+// One thread per run: unique key, run length, and (short runs) the sequential
+// fp32 sum in input order.  Long runs are queued for k_long_runs.
+__global__ void k_run_reduce(const int32_t* __restrict__ n_runs_dev, const uint64_t* __restrict__ keys,
+                             const uint32_t* __restrict__ payload,
+                             const int32_t* __restrict__ head_index, uint64_t* __restrict__ ukeys,
+                             int32_t* __restrict__ run_len, float* __restrict__ run_sum,
+                             int32_t* __restrict__ long_list, int32_t* __restrict__ long_count) {
+  int64_t m = *n_runs_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int b = head_index[p], e = head_index[p + 1];
+    ukeys[p] = keys[b];
+    run_len[p] = e - b;
+    if (run_sum) {
+      if (e - b <= RUN_SEQ_MAX) {
+        float s = 0.f;
+        for (int j = b; j < e; ++j) s = __fadd_rn(s, __uint_as_float(payload[j]));
+        run_sum[p] = s;
+      } else {
+        int slot = atomicAdd(long_count, 1);
+        long_list[slot] = (int32_t)p;
+      }
+    }
+  }
+}
+
+// One CTA per long run (grid-strided over the queue); fixed summation shape:
+// thread t adds elements t, t+256, ... in order, then a fixed tree.
+__global__ void __launch_bounds__(256) k_long_runs(const int32_t* __restrict__ long_list,
+                                                   const int32_t* __restrict__ long_count,
+                                                   const uint32_t* __restrict__ payload,
+                                                   const int32_t* __restrict__ head_index,
+                                                   float* __restrict__ run_sum) {
+  __shared__ float s_f[256];
+  int cnt = *long_count;
+  for (int q = blockIdx.x; q < cnt; q += gridDim.x) {
+    int p = long_list[q];
+    int b = head_index[p], e = head_index[p + 1];
+    float s = 0.f;
+    for (int j = b + threadIdx.x; j < e; j += 256) s = __fadd_rn(s, __uint_as_float(payload[j]));
+    s_f[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s_f[threadIdx.x] = __fadd_rn(s_f[threadIdx.x], s_f[threadIdx.x + o]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) run_sum[p] = s_f[0];
+    __syncthreads();
+  }
+}
+
+struct RunBuffers {
+  int32_t* pos;         // n+1  (flags, scanned in place); pos[n] = #runs
+  int32_t* head_index;  // n+1
+  uint64_t* ukeys;      // n
+  int32_t* run_len;     // n
+  float* run_sum;       // n (or null)
+  int32_t* long_list;   // n / RUN_SEQ_MAX + 1
+  int32_t* long_count;  // 1
+  void* scan_ws;
+  int64_t scan_ws_b;
+};
+
+static int64_t runs_ws_bytes(int64_t n, bool with_sum) {
+  return 2 * ws_need(n + 1, 4) + ws_need(n, 8) + ws_need(n, 4) + (with_sum ? ws_need(n, 4) : 0) +
+         ws_need(n / RUN_SEQ_MAX + 2, 4) + 256 + scan_ws_bytes(n) + 256;
+}
+
+static RunBuffers carve_runs(Workspace& W, int64_t n, bool with_sum) {
+  RunBuffers R;
+  R.pos = W.take<int32_t>(n + 1);
+  R.head_index = W.take<int32_t>(n + 1);
+  R.ukeys = W.take<uint64_t>(n);
+  R.run_len = W.take<int32_t>(n);
+  R.run_sum = with_sum ? W.take<float>(n) : nullptr;
+  R.long_list = W.take<int32_t>(n / RUN_SEQ_MAX + 2);
+  R.long_count = W.take<int32_t>(1);
+  R.scan_ws_b = scan_ws_bytes(n);
+  R.scan_ws = W.take<char>(R.scan_ws_b);
+  return R;
+}
+
+static unsigned grid_for(int64_t n, int threads = 256) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, threads), kSMs * 32));
+}
+
+// keys sorted ascending, payload (float bits) optional.
+static int reduce_runs(int64_t n, const uint64_t* keys, const uint32_t* payload, RunBuffers& R,
+                       cudaStream_t s) {
+  k_head_flags<<<grid_for(n), 256, 0, s>>>(n, keys, R.pos);
+  GDR_LAUNCHED();
+  int rc = exclusive_scan_i32(R.pos, R.pos, n, R.scan_ws, R.scan_ws_b, s);
+  if (rc) return rc;
+  k_head_index<<<grid_for(n), 256, 0, s>>>(n, keys, R.pos, R.head_index);
+  GDR_LAUNCHED();
+  GDR_CUDA(cudaMemsetAsync(R.long_count, 0, 4, s));
+  k_run_reduce<<<grid_for(n), 256, 0, s>>>(R.pos + n, keys, payload, R.head_index, R.ukeys, R.run_len,
+                                           payload ? R.run_sum : nullptr, R.long_list, R.long_count);
+  GDR_LAUNCHED();
+  if (payload) {
+    k_long_runs<<<kSMs * 2, 256, 0, s>>>(R.long_list, R.long_count, payload, R.head_index, R.run_sum);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
+}
+
+// rowptr[r] = first run whose (ukey >> shift) >= r, for r in [0, n_rows]
+__global__ void k_rowptr_from_ukeys(const int32_t* __restrict__ n_runs_dev, int64_t n_rows, int shift,
+                                    uint64_t valid_limit, const uint64_t* __restrict__ ukeys,
+                                    int32_t* __restrict__ rowptr, int64_t* __restrict__ nnz_out) {
+  int64_t m = *n_runs_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= m;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // keys >= valid_limit are sentinels (dropped entries): they sort last
+    int64_t lo = i == 0 ? -1 : (ukeys[i - 1] >= valid_limit ? n_rows : (int64_t)(ukeys[i - 1] >> shift));
+    int64_t hi = i == m ? n_rows : (ukeys[i] >= valid_limit ? n_rows : (int64_t)(ukeys[i] >> shift));
+    if (hi > n_rows) hi = n_rows;
+    for (int64_t r = lo + 1; r <= hi; ++r) rowptr[r] = (int32_t)i;
+    // all sentinel keys are equal, so they form at most one (the last) run
+    if (i == m) *nnz_out = (m > 0 && ukeys[m - 1] >= valid_limit) ? m - 1 : m;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// COO -> CSR
+// ----------------------------------------------------------------------------
+__global__ void k_pack_coo(int64_t nnz, int64_t n_rows, int64_t n_cols, const int64_t* __restrict__ row,
+                           const int64_t* __restrict__ col, const float* __restrict__ val,
+                           int symmetrize, int cbits, uint64_t* __restrict__ keys,
+                           uint32_t* __restrict__ payload, int32_t* __restrict__ status) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = row[e], c = col[e];
+    float v = val ? val[e] : 1.0f;
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) {
+      atomicOr(status, 1);
+      r = 0;
+      c = 0;
+      v = 0.f;
+    }
+    if (symmetrize) {
+      keys[2 * e] = ((uint64_t)r << cbits) | (uint64_t)c;
+      keys[2 * e + 1] = ((uint64_t)c << cbits) | (uint64_t)r;
+      payload[2 * e] = __float_as_uint(v);
+      payload[2 * e + 1] = __float_as_uint(v);
+    } else {
+      keys[e] = ((uint64_t)r << cbits) | (uint64_t)c;
+      payload[e] = __float_as_uint(v);
+    }
+  }
+}
+
+__global__ void k_emit_csr_entries(const int32_t* __restrict__ n_runs_dev,
+                                   const uint64_t* __restrict__ ukeys, const float* __restrict__ run_sum,
+                                   uint64_t cmask, int binarize, int32_t* __restrict__ colidx,
+                                   float* __restrict__ vals) {
+  int64_t m = *n_runs_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    colidx[p] = (int32_t)(ukeys[p] & cmask);
+    vals[p] = binarize ? 1.0f : run_sum[p];
+  }
+}
+
+// ----------------------------------------------------------------------------
+// CSR transpose
+// ----------------------------------------------------------------------------
+__global__ void k_pack_transpose(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ colidx, int rbits,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  // one warp per row
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = w; r < n_rows; r += nw) {
+    int b = rowptr[r], e = rowptr[r + 1];
+    for (int j = b + lane_id(); j < e; j += 32) {
+      keys[j] = ((uint64_t)(uint32_t)colidx[j] << rbits) | (uint64_t)r;
+      payload[j] = (uint32_t)j;
+    }
+  }
+}
+
+__global__ void k_unpack_transpose(int64_t nnz, int64_t n_cols, int rbits, const uint64_t* __restrict__ keys,
+                                   const uint32_t* __restrict__ payload, int32_t* __restrict__ t_rowptr,
+                                   int32_t* __restrict__ t_colidx, int32_t* __restrict__ t_perm) {
+  uint64_t rmask = (1ull << rbits) - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nnz) {
+      t_colidx[i] = (int32_t)(keys[i] & rmask);
+      t_perm[i] = (int32_t)payload[i];
+    }
+    int64_t lo = i == 0 ? -1 : (int64_t)(keys[i - 1] >> rbits);
+    int64_t hi = i == nnz ? n_cols : (int64_t)(keys[i] >> rbits);
+    for (int64_t c = lo + 1; c <= hi; ++c) t_rowptr[c] = (int32_t)i;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// symmetric normalisation
+// ----------------------------------------------------------------------------
+// flag[0] = 1 when the identity has to be added.
+__global__ void k_selfloop_flag(int64_t nnz, const int32_t* __restrict__ rowptr,
+                                const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                int mode, int32_t* __restrict__ flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (mode == 0) {
+    flag[0] = 0;
+  } else if (mode == 1) {
+    flag[0] = 1;
+  } else {
+    // reference quirk: `if mx[0, 0] == 0: mx = mx + I`  (deep_robust_utils.py:199-200)
+    float a00 = 0.f;
+    int b = rowptr[0], e = rowptr[1];
+    for (int j = b; j < e; ++j)
+      if (colidx[j] == 0) a00 += vals[j];
+    flag[0] = (a00 == 0.f) ? 1 : 0;
+  }
+}
+
+// one warp per row: degree (fp64 or fp32 chain, see k_norm_fill), diagonal presence, output length
+__global__ void __launch_bounds__(256) k_row_degree(int64_t n, const int32_t* __restrict__ rowptr,
+                                                    const int32_t* __restrict__ colidx,
+                                                    const float* __restrict__ vals,
+                                                    const int32_t* __restrict__ flag,
+                                                    double* __restrict__ deg, int32_t* __restrict__ out_len) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int add = flag[0];
+  int b = rowptr[r], e = rowptr[r + 1];
+  double s = 0.0;
+  float sf = 0.f;
+  int has_diag = 0;
+  for (int j = b + lane_id(); j < e; j += 32) {
+    float v = vals[j];
+    s += (double)v;
+    sf += v;
+    has_diag |= (colidx[j] == (int32_t)r);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sf += __shfl_xor_sync(0xffffffffu, sf, o);
+    has_diag |= __shfl_xor_sync(0xffffffffu, has_diag, o);
+  }
+  if (lane_id() == 0) {
+    // with +I the reference sums an fp64 matrix; without it the matrix (and the row sum) stay fp32
+    deg[r] = add ? s + 1.0 : (double)sf;
+    out_len[r] = (e - b) + ((add && !has_diag) ? 1 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_norm_fill(int64_t n, const int32_t* __restrict__ rowptr,
+                                                   const int32_t* __restrict__ colidx,
+                                                   const float* __restrict__ vals,
+                                                   const int32_t* __restrict__ flag,
+                                                   const double* __restrict__ deg,
+                                                   const int32_t* __restrict__ rowptr_out,
+                                                   int32_t* __restrict__ colidx_out,
+                                                   float* __restrict__ vals_out,
+                                                   int64_t* __restrict__ nnz_out) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int add = flag[0];
+  const int b = rowptr[r], e = rowptr[r + 1];
+  const int ob = rowptr_out[r];
+  const bool inserts = add && (rowptr_out[r + 1] - ob) > (e - b);
+  if (r == n - 1 && lane_id() == 0) *nnz_out = rowptr_out[n];
+  // r_i = deg^-1/2 ; inf -> 0   (deep_robust_utils.py:202-203)
+  const double di = deg[r];
+  if (add) {
+    const double ri = di == 0.0 ? 0.0 : 1.0 / sqrt(di);
+    // entries left of the diagonal keep their slot; the rest shift by one when I inserts
+    for (int j = b + lane_id(); j < e; j += 32) {
+      int c = colidx[j];
+      double a = (double)vals[j] + (c == (int32_t)r ? 1.0 : 0.0);
+      double dj = deg[c];
+      double rj = dj == 0.0 ? 0.0 : 1.0 / sqrt(dj);
+      int o = ob + (j - b) + ((inserts && c > (int32_t)r) ? 1 : 0);
+      colidx_out[o] = c;
+      vals_out[o] = (float)((ri * a) * rj);
+    }
+    if (inserts) {
+      // position of the new diagonal entry = #entries with col < r (one lane finds it)
+      int cnt = 0;
+      for (int j = b + lane_id(); j < e; j += 32) cnt += (colidx[j] < (int32_t)r);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane_id() == 0) {
+        colidx_out[ob + cnt] = (int32_t)r;
+        vals_out[ob + cnt] = (float)((ri * 1.0) * ri);
+      }
+    }
+  } else {
+    // fp32 path of the reference when no identity is added: r = fp32 deg ^ -1/2
+    const float dfi = (float)di;
+    const float ri = dfi == 0.f ? 0.f : (float)(1.0 / sqrt((double)dfi));
+    for (int j = b + lane_id(); j < e; j += 32) {
+      int c = colidx[j];
+      float dfj = (float)deg[c];
+      float rj = dfj == 0.f ? 0.f : (float)(1.0 / sqrt((double)dfj));
+      colidx_out[ob + (j - b)] = c;
+      vals_out[ob + (j - b)] = __fmul_rn(__fmul_rn(ri, vals[j]), rj);
+    }
+  }
+}
+
+// dense n x n:  mx = A + I ; r = rowsum^-1/2 ; out = r_i * mx_ij * r_j  (fp32)
+__global__ void __launch_bounds__(256) k_dense_rowsum(int64_t n, const float* __restrict__ A, int64_t lda,
+                                                      float* __restrict__ rinv) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  float s = 0.f;
+  for (int64_t c = lane_id(); c < n; c += 32) s += A[r * lda + c] + (c == r ? 1.f : 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) {
+    // torch CPU evaluates pow(x, -0.5) as 1 / sqrt(x) in fp32 (two roundings)
+    float ri = __fdiv_rn(1.f, __fsqrt_rn(s));
+    if (isinf(ri)) ri = 0.f;
+    rinv[r] = ri;
+  }
+}
+
+__global__ void k_dense_scale(int64_t n, const float* __restrict__ A, int64_t lda,
+                              const float* __restrict__ rinv, float* __restrict__ out, int64_t ldo) {
+  int64_t total = n * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / n, c = i - r * n;
+    float m = A[r * lda + c] + (c == r ? 1.f : 0.f);
+    out[r * ldo + c] = __fmul_rn(__fmul_rn(rinv[r], m), rinv[c]);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// bipartite normalisation
+// ----------------------------------------------------------------------------
+// sequential fp32 row sums (index_add_ order on the CPU reference), one thread per row
+__global__ void k_rowsum_seq(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                             const float* __restrict__ w, float* __restrict__ deg) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) s = __fadd_rn(s, w[perm ? perm[j] : j]);
+    deg[r] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bip_norm(int64_t n_u, const int32_t* __restrict__ rowptr,
+                                                  const int32_t* __restrict__ colidx,
+                                                  const float* __restrict__ w, const float* __restrict__ deg_u,
+                                                  const float* __restrict__ deg_i, float eps,
+                                                  float* __restrict__ norm_out) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_u) return;
+  float su = __fsqrt_rn(__fadd_rn(deg_u[r], eps));
+  for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+    float si = __fsqrt_rn(__fadd_rn(deg_i[colidx[j]], eps));
+    norm_out[j] = __fdiv_rn(w[j], __fmul_rn(su, si));
+  }
+}
+
+__global__ void k_gather_f32(int64_t n, const int32_t* __restrict__ perm, const float* __restrict__ in,
+                             float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[perm[i]];
+}
+
+// ----------------------------------------------------------------------------
+// coarsening
+// ----------------------------------------------------------------------------
+__global__ void k_pack_coarsen_coo(int64_t E, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                   const float* __restrict__ w, const int32_t* __restrict__ lab_s,
+                                   const int32_t* __restrict__ lab_d, int bbits, int drop_diag,
+                                   uint64_t sentinel, uint64_t* __restrict__ keys,
+                                   uint32_t* __restrict__ payload) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t a = (uint32_t)lab_s[src[e]], b = (uint32_t)lab_d[dst[e]];
+    keys[e] = (drop_diag && a == b) ? sentinel : (((uint64_t)a << bbits) | (uint64_t)b);
+    if (payload) payload[e] = __float_as_uint(w[e]);
+  }
+}
+
+__global__ void k_pack_coarsen_csr(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ colidx, const float* __restrict__ w,
+                                   const int32_t* __restrict__ lab_s, const int32_t* __restrict__ lab_d,
+                                   int bbits, int drop_diag, uint64_t sentinel,
+                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < n_rows; r += nw) {
+    uint32_t a = (uint32_t)lab_s[r];
+    for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+      uint32_t b = (uint32_t)lab_d[colidx[j]];
+      keys[j] = (drop_diag && a == b) ? sentinel : (((uint64_t)a << bbits) | (uint64_t)b);
+      if (payload) payload[j] = __float_as_uint(w[j]);
+    }
+  }
+}
+
+__global__ void k_emit_coarse(const int32_t* __restrict__ n_runs_dev, const uint64_t* __restrict__ ukeys,
+                              const int32_t* __restrict__ run_len, const float* __restrict__ run_sum,
+                              uint64_t bmask, uint64_t sentinel, int32_t* __restrict__ colidx,
+                              int32_t* __restrict__ counts, float* __restrict__ wsum) {
+  int64_t m = *n_runs_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    if (ukeys[p] >= sentinel) continue;
+    colidx[p] = (int32_t)(ukeys[p] & bmask);
+    counts[p] = run_len[p];
+    if (wsum) wsum[p] = run_sum[p];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_coarsen_scale(int64_t n_src, const int32_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx,
+                                                       const float* __restrict__ wsum,
+                                                       const int32_t* __restrict__ size_s,
+                                                       const int32_t* __restrict__ size_d,
+                                                       float* __restrict__ out) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_src) return;
+  float ia = __fdiv_rn(1.0f, (float)size_s[r]);
+  for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+    float ib = __fdiv_rn(1.0f, (float)size_d[colidx[j]]);
+    out[j] = __fmul_rn(__fmul_rn(wsum[j], ia), ib);
+  }
+}
+
+__global__ void k_csr_to_coo(int64_t n_rows, const int32_t* __restrict__ rowptr,
+                             const int32_t* __restrict__ colidx, int64_t* __restrict__ row_out,
+                             int64_t* __restrict__ col_out) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < n_rows; r += nw) {
+    for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+      row_out[j] = r;
+      if (col_out) col_out[j] = (int64_t)colidx[j];
+    }
+  }
+}
+
+}  // namespace gdr
+
+using namespace gdr;
+
+extern "C" {
+
+// ---------------- COO -> CSR ----------------
+int64_t gdr_coo_to_csr_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz_in, int symmetrize) {
+  (void)n_rows;
+  (void)n_cols;
+  int64_t n = nnz_in * (symmetrize ? 2 : 1);
+  if (n <= 0) return 256;
+  return ws_need(n, 8) + ws_need(n, 4) + sort_pairs_ws_bytes(n) + runs_ws_bytes(n, true) + 512;
+}
+
+int gdr_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz_in, const int64_t* row,
+                   const int64_t* col, const float* val, int symmetrize, int binarize,
+                   int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out_dev,
+                   int32_t* status_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && nnz_in >= 0, "coo_to_csr: negative size");
+  GDR_CHECK_ARG(rowptr && nnz_out_dev && status_dev, "coo_to_csr: null output");
+  GDR_CHECK_ARG(!symmetrize || n_rows == n_cols, "coo_to_csr: symmetrize needs a square matrix");
+  GDR_CHECK_ARG(n_rows < (1ll << 31) && n_cols < (1ll << 31), "coo_to_csr: dimension exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t n = nnz_in * (symmetrize ? 2 : 1);
+  if (n >= (1ll << 31)) {
+    set_error("coo_to_csr: %lld entries exceed the int32 CSR limit", (long long)n);
+    return GDR_ERANGE;
+  }
+  GDR_CUDA(cudaMemsetAsync(status_dev, 0, 4, s));
+  if (n == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_rows + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(row && col && colidx && vals, "coo_to_csr: null pointer");
+  if (ws_bytes < gdr_coo_to_csr_ws_bytes(n_rows, n_cols, nnz_in, symmetrize)) {
+    set_error("coo_to_csr: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(n);
+  uint32_t* payload = W.take<uint32_t>(n);
+  int64_t sws_b = sort_pairs_ws_bytes(n);
+  void* sws = W.take<char>(sws_b);
+  RunBuffers R = carve_runs(W, n, true);
+  int cbits = bits_for(n_cols), rbits = bits_for(n_rows);
+  k_pack_coo<<<grid_for(nnz_in), 256, 0, s>>>(nnz_in, n_rows, n_cols, row, col, val, symmetrize, cbits,
+                                              keys, payload, status_dev);
+  GDR_LAUNCHED();
+  int rc = sort_pairs(n, rbits + cbits, keys, payload, sws, sws_b, s);
+  if (rc) return rc;
+  rc = reduce_runs(n, keys, payload, R, s);
+  if (rc) return rc;
+  k_emit_csr_entries<<<grid_for(n), 256, 0, s>>>(R.pos + n, R.ukeys, R.run_sum, (1ull << cbits) - 1,
+                                                 binarize, colidx, vals);
+  GDR_LAUNCHED();
+  k_rowptr_from_ukeys<<<grid_for(n + 1), 256, 0, s>>>(R.pos + n, n_rows, cbits, ~0ull, R.ukeys, rowptr,
+                                                      nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- transpose ----------------
+int64_t gdr_csr_transpose_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz) {
+  (void)n_rows;
+  (void)n_cols;
+  if (nnz <= 0) return 256;
+  return ws_need(nnz, 8) + ws_need(nnz, 4) + sort_pairs_ws_bytes(nnz) + 256;
+}
+
+int gdr_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* rowptr,
+                      const int32_t* colidx, int32_t* t_rowptr, int32_t* t_colidx, int32_t* t_perm,
+                      void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && rowptr && t_rowptr, "csr_transpose: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nnz == 0) {
+    GDR_CUDA(cudaMemsetAsync(t_rowptr, 0, (n_cols + 1) * 4, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(colidx && t_colidx && t_perm, "csr_transpose: null pointer");
+  if (ws_bytes < gdr_csr_transpose_ws_bytes(n_rows, n_cols, nnz)) {
+    set_error("csr_transpose: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(nnz);
+  uint32_t* payload = W.take<uint32_t>(nnz);
+  int64_t sws_b = sort_pairs_ws_bytes(nnz);
+  void* sws = W.take<char>(sws_b);
+  int rbits = bits_for(n_rows), cbits = bits_for(n_cols);
+  k_pack_transpose<<<grid_for(n_rows * 32), 256, 0, s>>>(n_rows, rowptr, colidx, rbits, keys, payload);
+  GDR_LAUNCHED();
+  // rows are already ascending inside equal columns only after a sort on the column
+  // bits; the sort is stable and the input is row-major, so sorting the column bits suffices.
+  int rc = sort_pairs(nnz, rbits + cbits, keys, payload, sws, sws_b, s);
+  if (rc) return rc;
+  k_unpack_transpose<<<grid_for(nnz + 1), 256, 0, s>>>(nnz, n_cols, rbits, keys, payload, t_rowptr,
+                                                       t_colidx, t_perm);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- symmetric normalisation ----------------
+int64_t gdr_sym_normalize_ws_bytes(int64_t n, int64_t nnz) {
+  (void)nnz;
+  return ws_need(n + 1, 4) + ws_need(n, 8) + 256 + scan_ws_bytes(n) + 256;
+}
+
+int gdr_sym_normalize(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                      const float* vals, int self_loop_mode, int32_t* rowptr_out,
+                      int32_t* colidx_out, float* vals_out, double* deg_out, int64_t* nnz_out_dev,
+                      void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n > 0 && nnz >= 0, "sym_normalize: bad sizes");
+  GDR_CHECK_ARG(rowptr && rowptr_out && colidx_out && vals_out && nnz_out_dev, "sym_normalize: null pointer");
+  GDR_CHECK_ARG(nnz == 0 || (colidx && vals), "sym_normalize: null input");
+  GDR_CHECK_ARG(self_loop_mode >= 0 && self_loop_mode <= 2, "sym_normalize: self_loop_mode");
+  if (nnz + n >= (1ll << 31)) {
+    set_error("sym_normalize: nnz + n exceeds the int32 CSR limit");
+    return GDR_ERANGE;
+  }
+  if (ws_bytes < gdr_sym_normalize_ws_bytes(n, nnz)) {
+    set_error("sym_normalize: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  int32_t* out_len = W.take<int32_t>(n + 1);
+  double* deg_ws = W.take<double>(n);
+  int32_t* flag = W.take<int32_t>(1);
+  int64_t sws_b = scan_ws_bytes(n);
+  void* sws = W.take<char>(sws_b);
+  double* deg = deg_out ? deg_out : deg_ws;
+  k_selfloop_flag<<<1, 32, 0, s>>>(nnz, rowptr, colidx, vals, self_loop_mode, flag);
+  GDR_LAUNCHED();
+  unsigned grid = (unsigned)cdiv(n * 32, 256);
+  k_row_degree<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, out_len);
+  GDR_LAUNCHED();
+  int rc = exclusive_scan_i32(out_len, rowptr_out, n, sws, sws_b, s);
+  if (rc) return rc;
+  k_norm_fill<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, rowptr_out, colidx_out, vals_out,
+                                   nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_sym_normalize_dense_ws_bytes(int64_t n) { return ws_need(n, 4) + 256; }
+
+int gdr_sym_normalize_dense(int64_t n, const float* A, int64_t lda, float* out, int64_t ldo, void* ws,
+                            int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n > 0 && A && out && lda >= n && ldo >= n, "sym_normalize_dense: bad arguments");
+  if (ws_bytes < gdr_sym_normalize_dense_ws_bytes(n)) {
+    set_error("sym_normalize_dense: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* rinv = (float*)ws;
+  k_dense_rowsum<<<(unsigned)cdiv(n * 32, 256), 256, 0, s>>>(n, A, lda, rinv);
+  GDR_LAUNCHED();
+  k_dense_scale<<<grid_for(n * n), 256, 0, s>>>(n, A, lda, rinv, out, ldo);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- bipartite normalisation ----------------
+int gdr_bipartite_normalize(int64_t n_u, int64_t n_i, int64_t nnz, const int32_t* rowptr,
+                            const int32_t* colidx, const float* w, const int32_t* t_rowptr,
+                            const int32_t* t_perm, float eps, float* norm_out, float* t_norm_out,
+                            float* deg_u, float* deg_i, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_u > 0 && n_i > 0 && nnz >= 0 && rowptr && t_rowptr && deg_u && deg_i,
+                "bipartite_normalize: bad arguments");
+  GDR_CHECK_ARG(nnz == 0 || (colidx && w && t_perm && norm_out), "bipartite_normalize: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_rowsum_seq<<<grid_for(n_u), 256, 0, s>>>(n_u, rowptr, nullptr, w, deg_u);
+  GDR_LAUNCHED();
+  k_rowsum_seq<<<grid_for(n_i), 256, 0, s>>>(n_i, t_rowptr, t_perm, w, deg_i);
+  GDR_LAUNCHED();
+  if (nnz == 0) return GDR_OK;
+  k_bip_norm<<<(unsigned)cdiv(n_u * 32, 256), 256, 0, s>>>(n_u, rowptr, colidx, w, deg_u, deg_i, eps,
+                                                          norm_out);
+  GDR_LAUNCHED();
+  if (t_norm_out) {
+    k_gather_f32<<<grid_for(nnz), 256, 0, s>>>(nnz, t_perm, norm_out, t_norm_out);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
+}
+
+// ---------------- coarsening ----------------
+int64_t gdr_coarsen_ws_bytes(int64_t E, int64_t n_src, int64_t n_dst) {
+  (void)n_src;
+  (void)n_dst;
+  if (E <= 0) return 256;
+  return ws_need(E, 8) + ws_need(E, 4) + sort_pairs_ws_bytes(E) + runs_ws_bytes(E, true) + 512;
+}
+
+int gdr_coarsen(int64_t E, const int64_t* src, const int64_t* dst, int64_t n_rows,
+                const int32_t* csr_rowptr, const int32_t* csr_colidx, const float* w,
+                const int32_t* labels_src, const int32_t* labels_dst, int64_t n_src, int64_t n_dst,
+                int drop_diag, int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
+                int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(E >= 0 && n_src > 0 && n_dst > 0 && rowptr && nnz_out_dev, "coarsen: bad arguments");
+  GDR_CHECK_ARG(n_src < (1ll << 31) && n_dst < (1ll << 31) && E < (1ll << 31), "coarsen: size exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (E == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_src + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(labels_src && labels_dst && colidx && counts, "coarsen: null pointer");
+  GDR_CHECK_ARG((src && dst) || (csr_rowptr && csr_colidx && n_rows > 0), "coarsen: need COO or CSR edges");
+  GDR_CHECK_ARG(!wsum || w, "coarsen: wsum requested without weights");
+  if (ws_bytes < gdr_coarsen_ws_bytes(E, n_src, n_dst)) {
+    set_error("coarsen: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(E);
+  uint32_t* payload = W.take<uint32_t>(E);
+  int64_t sws_b = sort_pairs_ws_bytes(E);
+  void* sws = W.take<char>(sws_b);
+  RunBuffers R = carve_runs(W, E, true);
+  int abits = bits_for(n_src), bbits = bits_for(n_dst);
+  uint64_t sentinel = 1ull << (abits + bbits);
+  uint32_t* pl = wsum ? payload : nullptr;
+  if (src) {
+    k_pack_coarsen_coo<<<grid_for(E), 256, 0, s>>>(E, src, dst, w, labels_src, labels_dst, bbits,
+                                                   drop_diag, sentinel, keys, pl);
+  } else {
+    k_pack_coarsen_csr<<<grid_for(n_rows * 32), 256, 0, s>>>(n_rows, csr_rowptr, csr_colidx, w,
+                                                             labels_src, labels_dst, bbits, drop_diag,
+                                                             sentinel, keys, pl);
+  }
+  GDR_LAUNCHED();
+  int rc = sort_pairs(E, abits + bbits + (drop_diag ? 1 : 0), keys, pl, sws, sws_b, s);
+  if (rc) return rc;
+  rc = reduce_runs(E, keys, pl, R, s);
+  if (rc) return rc;
+  k_emit_coarse<<<grid_for(E), 256, 0, s>>>(R.pos + E, R.ukeys, R.run_len, R.run_sum,
+                                            (1ull << bbits) - 1, sentinel, colidx, counts, wsum);
+  GDR_LAUNCHED();
+  k_rowptr_from_ukeys<<<grid_for(E + 1), 256, 0, s>>>(R.pos + E, n_src, bbits, sentinel, R.ukeys, rowptr,
+                                                      nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int gdr_coarsen_scale(int64_t n_src, const int32_t* rowptr, const int32_t* colidx, const float* wsum,
+                      const int32_t* size_src, const int32_t* size_dst, float* vals_out,
+                      gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_src > 0 && rowptr && colidx && wsum && size_src && size_dst && vals_out,
+                "coarsen_scale: bad arguments");
+  k_coarsen_scale<<<(unsigned)cdiv(n_src * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      n_src, rowptr, colidx, wsum, size_src, size_dst, vals_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx, int64_t* row_out,
+                   int64_t* col_out, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0, "csr_to_coo: negative size");
+  if (n_rows == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && colidx && row_out, "csr_to_coo: null pointer");
+  k_csr_to_coo<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, row_out,
+                                                                       col_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+}  // extern "C"

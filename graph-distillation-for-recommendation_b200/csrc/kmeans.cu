@@ -1,0 +1,758 @@
+// kmeans.cu — stage 3: Lloyd k-means building blocks.
+//
+// Arithmetic follows scikit-learn's dense Lloyd iteration, the third-party code
+// the reference calls at clustgdd_agent_transduct.py:102-105,
+// clustgdd_agent_induct.py:131-136 and distill_recsys.py:172-180:
+//   sklearn/cluster/_kmeans.py:1487-1493   mean-centring
+//   sklearn/cluster/_k_means_lloyd.pyx:196-218  E-step + per-cluster sums
+//   sklearn/cluster/_k_means_common.pyx:167-311 relocate / average / shift
+//   sklearn/cluster/_k_means_common.pyx:94-124  inertia
+// This file holds the exact-fp32 SIMT E-step (precision_mode 0, also the
+// re-scoring kernel of the tensor-core path in kmeans_tc.cu), the deterministic
+// M-step and the small reductions around them.
+#include "common.cuh"
+#include <vector>
+
+namespace gdr {
+
+// implemented in kmeans_tc.cu
+int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D);
+int kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const float* C,
+                     int64_t ldc, int32_t* labels, const int32_t* labels_prev,
+                     int32_t* n_changed_dev, float* best_out, void* ws, int64_t ws_bytes,
+                     cudaStream_t s);
+
+// ----------------------------------------------------------------------------
+// column mean / variance (fp64) and centring
+// ----------------------------------------------------------------------------
+constexpr int CC_ROWS_PER_BLOCK = 512;
+
+__global__ void __launch_bounds__(256) k_colstats_partial(int64_t N, int D, const float* __restrict__ X,
+                                                          int64_t ldx, double* __restrict__ part) {
+  // block (32 x 8): x over columns, y over rows; each block covers CC_ROWS_PER_BLOCK rows.
+  __shared__ double s_sum[8][33], s_sq[8][33];
+  int64_t r0 = (int64_t)blockIdx.x * CC_ROWS_PER_BLOCK;
+  int64_t r1 = min(N, r0 + CC_ROWS_PER_BLOCK);
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    int c = c0 + threadIdx.x;
+    double su = 0.0, sq = 0.0;
+    if (c < D) {
+      for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+        double x = (double)X[r * ldx + c];
+        su += x;
+        sq += x * x;
+      }
+    }
+    s_sum[threadIdx.y][threadIdx.x] = su;
+    s_sq[threadIdx.y][threadIdx.x] = sq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        a += s_sum[y][threadIdx.x];
+        b += s_sq[y][threadIdx.x];
+      }
+      part[((int64_t)blockIdx.x * D + c) * 2 + 0] = a;
+      part[((int64_t)blockIdx.x * D + c) * 2 + 1] = b;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_colstats_final(int64_t N, int D, int nblocks,
+                                                        const double* __restrict__ part,
+                                                        float* __restrict__ mean_out,
+                                                        double* __restrict__ var_col) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += part[((int64_t)i * D + c) * 2 + 0];
+    b += part[((int64_t)i * D + c) * 2 + 1];
+  }
+  double m = a / (double)N;
+  double v = b / (double)N - m * m;
+  mean_out[c] = (float)m;
+  var_col[c] = v > 0.0 ? v : 0.0;
+}
+
+__global__ void k_var_mean(int D, const double* __restrict__ var_col, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int c = 0; c < D; ++c) s += var_col[c];
+    out[0] = s / (double)D;
+  }
+}
+
+__global__ void k_sub_rowvec(int64_t N, int D, int ldpad, const float* __restrict__ X, int64_t ldx,
+                             const float* __restrict__ mean, float* __restrict__ out, int64_t ldo) {
+  int64_t total = N * (int64_t)ldpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ldpad;
+    int c = (int)(i - r * ldpad);
+    out[r * ldo + c] = c < D ? __fsub_rn(X[r * ldx + c], mean[c]) : 0.f;
+  }
+}
+
+__global__ void k_add_rowvec(int64_t N, int D, float* __restrict__ X, int64_t ldx,
+                             const float* __restrict__ v, float sign) {
+  int64_t total = N * (int64_t)D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D;
+    int c = (int)(i - r * D);
+    X[r * ldx + c] = __fadd_rn(X[r * ldx + c], __fmul_rn(sign, v[c]));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// exact fp32 E-step (SIMT register-tiled GEMM with fused |c|^2 add + argmin)
+// ----------------------------------------------------------------------------
+constexpr int AS_BM = 128, AS_BN = 128, AS_BK = 16, AS_THREADS = 256;
+
+__global__ void __launch_bounds__(256) k_row_sqnorm(int64_t K, int D, const float* __restrict__ C,
+                                                    int64_t ldc, float* __restrict__ out) {
+  // one warp per row, fixed-order shuffle reduction
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= K) return;
+  float s = 0.f;
+  for (int c = lane_id(); c < D; c += 32) {
+    float x = C[row * ldc + c];
+    s = fmaf(x, x, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) out[row] = s;
+}
+
+__global__ void __launch_bounds__(AS_THREADS, 2)
+k_assign_simt(int64_t N, int K, int D, const float* __restrict__ X, int64_t ldx,
+              const float* __restrict__ C, int64_t ldc, const float* __restrict__ cnorm,
+              int32_t* __restrict__ labels, const int32_t* __restrict__ labels_prev,
+              int32_t* __restrict__ n_changed, float* __restrict__ best_out) {
+  __shared__ __align__(16) float As[AS_BK][AS_BM + 4];
+  __shared__ __align__(16) float Bs[AS_BK][AS_BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * AS_BM;
+
+  float best[8];
+  int bidx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    best[i] = INFINITY;
+    bidx[i] = 0;
+  }
+  // loader mapping: 128 rows x 16 k = 512 float4; thread -> (row = tid/4 + 64*h, k4 = tid%4)
+  const int lrow = tid >> 2, lk4 = tid & 3;
+
+  for (int j0 = 0; j0 < K; j0 += AS_BN) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < D; k0 += AS_BK) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int r = lrow + 64 * h;
+        int k = k0 + lk4 * 4;
+        float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), cb = xa;
+        int64_t gr = row0 + r;
+        if (gr < N && k < D) {
+          xa = *reinterpret_cast<const float4*>(X + gr * ldx + k);
+          if (k + 1 >= D) xa.y = 0.f;
+          if (k + 2 >= D) xa.z = 0.f;
+          if (k + 3 >= D) xa.w = 0.f;
+        }
+        int gc = j0 + r;
+        if (gc < K && k < D) {
+          cb = *reinterpret_cast<const float4*>(C + (int64_t)gc * ldc + k);
+          if (k + 1 >= D) cb.y = 0.f;
+          if (k + 2 >= D) cb.z = 0.f;
+          if (k + 3 >= D) cb.w = 0.f;
+        }
+        As[lk4 * 4 + 0][r] = xa.x;
+        As[lk4 * 4 + 1][r] = xa.y;
+        As[lk4 * 4 + 2][r] = xa.z;
+        As[lk4 * 4 + 3][r] = xa.w;
+        Bs[lk4 * 4 + 0][r] = cb.x;
+        Bs[lk4 * 4 + 1][r] = cb.y;
+        Bs[lk4 * 4 + 2][r] = cb.z;
+        Bs[lk4 * 4 + 3][r] = cb.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < AS_BK; ++kk) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    // epilogue: d = |c|^2 - 2 x.c ; strict '<' keeps the first minimum (ascending j)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int col = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (col < K) {
+        float cn = __ldg(cnorm + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = fmaf(-2.f, acc[i][j], cn);
+          if (d < best[i]) {
+            best[i] = d;
+            bidx[i] = col;
+          }
+        }
+      }
+    }
+  }
+  // combine the 16 threads (tx) that share a row: (min value, lowest index)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best[i], o);
+      int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+      if (ob < best[i] || (ob == best[i] && oi < bidx[i])) {
+        best[i] = ob;
+        bidx[i] = oi;
+      }
+    }
+  }
+  int changed = 0;
+  if (tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+      int64_t gr = row0 + r;
+      if (gr < N) {
+        labels[gr] = bidx[i];
+        if (best_out) best_out[gr] = best[i];
+        if (labels_prev && labels_prev[gr] != bidx[i]) ++changed;
+      }
+    }
+  }
+  if (n_changed) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+    if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// M-step: membership lists (stable sort by label) + gather-sum through the SpMM
+// ----------------------------------------------------------------------------
+__global__ void k_label_keys(int64_t N, const int32_t* __restrict__ labels, uint64_t* __restrict__ keys,
+                             uint32_t* __restrict__ ids) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = (uint64_t)(uint32_t)labels[i];
+    ids[i] = (uint32_t)i;
+  }
+}
+
+// rowptr[k] = first sorted position whose key >= k  (keys ascending), k in [0, K]
+__global__ void k_bounds_from_sorted(int64_t N, int64_t K, const uint64_t* __restrict__ keys,
+                                     int32_t* __restrict__ rowptr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = i == 0 ? -1 : (int64_t)keys[i - 1];
+    int64_t hi = i == N ? K : (int64_t)keys[i];
+    if (hi > K) hi = K;
+    for (int64_t k = lo + 1; k <= hi; ++k) rowptr[k] = (int32_t)i;
+  }
+}
+
+__global__ void k_counts_from_rowptr(int64_t K, const int32_t* __restrict__ rowptr,
+                                     int32_t* __restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K;
+       i += (int64_t)gridDim.x * blockDim.x)
+    counts[i] = rowptr[i + 1] - rowptr[i];
+}
+
+__global__ void k_label_hist(int64_t N, int64_t K, const int32_t* __restrict__ labels,
+                             int32_t* __restrict__ counts, int32_t* __restrict__ status) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int l = labels[i];
+    if (l < 0 || l >= K) {
+      if (status) atomicOr(status, 1);
+    } else {
+      atomicAdd(&counts[l], 1);  // integer: order-independent
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// finalize: average, shift, empties
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_average(int64_t K, int D, const float* __restrict__ sums,
+                                                 int64_t lds, const int32_t* __restrict__ counts,
+                                                 const float* __restrict__ C_old, int64_t ldo,
+                                                 float* __restrict__ C_new, int64_t ldn,
+                                                 double* __restrict__ shift_arr, int mean_mode) {
+  int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= K) return;
+  int cnt = counts[k];
+  double sh = 0.0;
+  if (cnt > 0) {
+    float alpha = 1.0f / (float)cnt;  // sklearn multiplies by the fp32 reciprocal
+    for (int c = lane_id(); c < D; c += 32) {
+      float v = mean_mode ? __fdiv_rn(sums[k * lds + c], (float)cnt) : __fmul_rn(sums[k * lds + c], alpha);
+      C_new[k * ldn + c] = v;
+      if (C_old) {
+        double d = (double)v - (double)C_old[k * ldo + c];
+        sh += d * d;
+      }
+    }
+  } else if (mean_mode) {
+    for (int c = lane_id(); c < D; c += 32) C_new[k * ldn + c] = __int_as_float(0x7fc00000);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
+  if (lane_id() == 0) shift_arr[k] = sh;
+}
+
+// single block: total shift (fixed order), #empty, first argmax of counts; then the
+// empty clusters take the centre of the largest cluster and their shift is added.
+__global__ void __launch_bounds__(1024) k_finalize_tail(int64_t K, int D,
+                                                        const int32_t* __restrict__ counts,
+                                                        const float* __restrict__ C_old, int64_t ldo,
+                                                        float* __restrict__ C_new, int64_t ldn,
+                                                        double* __restrict__ shift_arr,
+                                                        double* __restrict__ stats, int mean_mode) {
+  __shared__ double s_d[1024];
+  __shared__ int s_cnt[1024], s_idx[1024], s_emp[1024];
+  int t = threadIdx.x;
+  int bc = -1, bi = 0, ne = 0;
+  for (int64_t k = t; k < K; k += 1024) {
+    int c = counts[k];
+    if (c > bc) {
+      bc = c;
+      bi = (int)k;
+    }
+    if (c == 0) ++ne;
+  }
+  s_cnt[t] = bc;
+  s_idx[t] = bi;
+  s_emp[t] = ne;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) {
+      if (s_cnt[t + o] > s_cnt[t] || (s_cnt[t + o] == s_cnt[t] && s_idx[t + o] < s_idx[t])) {
+        s_cnt[t] = s_cnt[t + o];
+        s_idx[t] = s_idx[t + o];
+      }
+      s_emp[t] += s_emp[t + o];
+    }
+    __syncthreads();
+  }
+  const int amax = s_idx[0];
+  const int n_empty = s_emp[0];
+  if (!mean_mode && n_empty > 0) {
+    // one warp per empty cluster (strided), copies row amax and recomputes its shift
+    int w = t >> 5, l = t & 31;
+    for (int64_t k = w; k < K; k += 32) {
+      if (counts[k] != 0) continue;
+      double sh = 0.0;
+      for (int c = l; c < D; c += 32) {
+        float v = C_new[(int64_t)amax * ldn + c];
+        C_new[k * ldn + c] = v;
+        if (C_old) {
+          double d = (double)v - (double)C_old[k * ldo + c];
+          sh += d * d;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sh += __shfl_xor_sync(0xffffffffu, sh, o);
+      if (l == 0) shift_arr[k] = sh;
+    }
+    __syncthreads();
+  }
+  double s = 0.0;
+  for (int64_t k = t; k < K; k += 1024) s += shift_arr[k];
+  s_d[t] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) s_d[t] += s_d[t + o];
+    __syncthreads();
+  }
+  if (t == 0) {
+    stats[0] = s_d[0];
+    stats[1] = (double)n_empty;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// inertia / per-row distance to own centre
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_dist(int64_t N, int D, const float* __restrict__ X,
+                                                  int64_t ldx, const float* __restrict__ C, int64_t ldc,
+                                                  const int32_t* __restrict__ labels,
+                                                  float* __restrict__ dist_out,
+                                                  double* __restrict__ block_part) {
+  // one warp per row; fp32 squared differences, fixed-order shuffle tree
+  __shared__ double s_w[8];
+  int w = threadIdx.x >> 5;
+  int64_t row = (int64_t)blockIdx.x * 8 + w;
+  float s = 0.f;
+  if (row < N) {
+    int j = labels[row];
+    for (int c = lane_id(); c < D; c += 32) {
+      float d = __fsub_rn(X[row * ldx + c], C[(int64_t)j * ldc + c]);
+      s = fmaf(d, d, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) {
+    if (row < N && dist_out) dist_out[row] = s;
+    s_w[w] = row < N ? (double)s : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && block_part) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += s_w[i];
+    block_part[blockIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_sum_f64(int64_t n, const double* __restrict__ in,
+                                                  double* __restrict__ out) {
+  __shared__ double s_d[1024];
+  int t = threadIdx.x;
+  double s = 0.0;
+  for (int64_t i = t; i < n; i += 1024) s += in[i];
+  s_d[t] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) s_d[t] += s_d[t + o];
+    __syncthreads();
+  }
+  if (t == 0) out[0] = s_d[0];
+}
+
+// argmax of a float array (first index wins); two-stage, deterministic
+__global__ void __launch_bounds__(256) k_argmax_part(int64_t n, const float* __restrict__ d,
+                                                     float* __restrict__ pv, int32_t* __restrict__ pi) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float v = d[i];
+    if (v > bv || (v == bv && (int)i < bi)) {
+      bv = v;
+      bi = (int)i;
+    }
+  }
+  sv[threadIdx.x] = bv;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      float ov = sv[threadIdx.x + o];
+      int oi = si[threadIdx.x + o];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov;
+        si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    pv[blockIdx.x] = sv[0];
+    pi[blockIdx.x] = si[0];
+  }
+}
+
+// moves sample far (argmax over the partials) from its cluster to `new_cluster`
+__global__ void __launch_bounds__(256) k_relocate_one(int nparts, const float* __restrict__ pv,
+                                                      const int32_t* __restrict__ pi, int D,
+                                                      const float* __restrict__ X, int64_t ldx,
+                                                      const int32_t* __restrict__ labels,
+                                                      float* __restrict__ sums, int64_t lds,
+                                                      int32_t* __restrict__ counts, int new_cluster,
+                                                      float* __restrict__ dist) {
+  __shared__ int s_far;
+  if (threadIdx.x == 0) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = 0; i < nparts; ++i) {
+      if (pv[i] > bv || (pv[i] == bv && pi[i] < bi)) {
+        bv = pv[i];
+        bi = pi[i];
+      }
+    }
+    s_far = bi;
+  }
+  __syncthreads();
+  int far = s_far;
+  int old = labels[far];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float x = X[(int64_t)far * ldx + c];
+    sums[(int64_t)old * lds + c] = __fsub_rn(sums[(int64_t)old * lds + c], x);
+    sums[(int64_t)new_cluster * lds + c] = x;
+  }
+  if (threadIdx.x == 0) {
+    counts[new_cluster] = 1;
+    counts[old] -= 1;
+    dist[far] = -1.f;  // never picked again
+  }
+}
+
+}  // namespace gdr
+
+using namespace gdr;
+
+extern "C" {
+
+int64_t gdr_center_columns_ws_bytes(int64_t N, int64_t D) {
+  int64_t nb = cdiv(N > 0 ? N : 1, CC_ROWS_PER_BLOCK);
+  return ws_need(nb * D * 2, 8) + ws_need(D, 8) + 256;
+}
+
+int gdr_center_columns(int64_t N, int64_t D, const float* X, int64_t ldx, float* mean_out,
+                       double* var_mean_out, float* Xc, int64_t ldxc, void* ws, int64_t ws_bytes,
+                       gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && D > 0 && X && mean_out && ldx >= D, "center_columns: bad arguments");
+  GDR_CHECK_ARG(!Xc || ldxc >= D, "center_columns: ldxc < D");
+  if (ws_bytes < gdr_center_columns_ws_bytes(N, D)) {
+    set_error("center_columns: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int nb = (int)cdiv(N, CC_ROWS_PER_BLOCK);
+  Workspace W(ws, ws_bytes);
+  double* part = W.take<double>((int64_t)nb * D * 2);
+  double* var_col = W.take<double>(D);
+  k_colstats_partial<<<nb, dim3(32, 8), 0, s>>>(N, (int)D, X, ldx, part);
+  GDR_LAUNCHED();
+  k_colstats_final<<<(unsigned)cdiv(D, 256), 256, 0, s>>>(N, (int)D, nb, part, mean_out, var_col);
+  GDR_LAUNCHED();
+  if (var_mean_out) {
+    k_var_mean<<<1, 32, 0, s>>>((int)D, var_col, var_mean_out);
+    GDR_LAUNCHED();
+  }
+  if (Xc) {
+    int ldpad = (int)std::min<int64_t>(ldxc, align_up(D, 4));
+    int64_t total = N * ldpad;
+    unsigned grid = (unsigned)std::min<int64_t>(cdiv(total, 256), kSMs * 16);
+    k_sub_rowvec<<<grid, 256, 0, s>>>(N, (int)D, ldpad, X, ldx, mean_out, Xc, ldxc);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
+}
+
+int gdr_add_row_vector(int64_t rows, int64_t D, float* X, int64_t ldx, const float* v, float sign,
+                       gdr_stream_t stream) {
+  GDR_CHECK_ARG(rows >= 0 && D >= 0, "add_row_vector: negative size");
+  if (rows == 0 || D == 0) return GDR_OK;
+  GDR_CHECK_ARG(X && v && ldx >= D, "add_row_vector: bad arguments");
+  unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows * D, 256), kSMs * 16);
+  k_add_rowvec<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, (int)D, X, ldx, v, sign);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_kmeans_assign_ws_bytes(int64_t N, int64_t K, int64_t D, int precision_mode) {
+  int64_t b = ws_need(K, 4) + 256;
+  if (precision_mode == 1) b += kmeans_assign_tc_ws_bytes(N, K, D);
+  return b;
+}
+
+int gdr_kmeans_assign(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const float* C,
+                      int64_t ldc, int32_t* labels, const int32_t* labels_prev,
+                      int32_t* n_changed_dev, float* best_out, int precision_mode, void* ws,
+                      int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && K > 0 && D > 0, "kmeans_assign: bad sizes");
+  if (N == 0) return GDR_OK;
+  GDR_CHECK_ARG(X && C && labels, "kmeans_assign: null pointer");
+  GDR_CHECK_ARG(ldx % 4 == 0 && ldc % 4 == 0 && ldx >= D && ldc >= D &&
+                    ((uintptr_t)X & 15) == 0 && ((uintptr_t)C & 15) == 0,
+                "kmeans_assign: X/C need 16B alignment and ld %% 4 == 0");
+  GDR_CHECK_ARG(K < (1ll << 31) && D < (1 << 20), "kmeans_assign: K or D too large");
+  GDR_CHECK_ARG(precision_mode == 0 || precision_mode == 1, "kmeans_assign: precision_mode");
+  if (ws_bytes < gdr_kmeans_assign_ws_bytes(N, K, D, precision_mode)) {
+    set_error("kmeans_assign: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (precision_mode == 1) {
+    return kmeans_assign_tc(N, K, D, X, ldx, C, ldc, labels, labels_prev, n_changed_dev, best_out,
+                            ws, ws_bytes, s);
+  }
+  Workspace W(ws, ws_bytes);
+  float* cnorm = W.take<float>(K);
+  k_row_sqnorm<<<(unsigned)cdiv(K, 8), 256, 0, s>>>(K, (int)D, C, ldc, cnorm);
+  GDR_LAUNCHED();
+  k_assign_simt<<<(unsigned)cdiv(N, AS_BM), AS_THREADS, 0, s>>>(N, (int)K, (int)D, X, ldx, C, ldc, cnorm,
+                                                               labels, labels_prev, n_changed_dev,
+                                                               best_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_segment_sum_ws_bytes(int64_t N, int64_t K, int64_t D) {
+  (void)D;
+  return ws_need(N, 8) + ws_need(N, 4) + ws_need(K + 1, 4) + sort_pairs_ws_bytes(N) + 256;
+}
+
+int gdr_segment_sum(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx,
+                    const int32_t* labels, float* sums, int64_t lds, int32_t* counts, void* ws,
+                    int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && K > 0 && D > 0, "segment_sum: bad sizes");
+  GDR_CHECK_ARG(X && labels && sums, "segment_sum: null pointer");
+  GDR_CHECK_ARG(ldx % 4 == 0 && lds % 4 == 0 && ldx >= align_up(D, 4) && lds >= align_up(D, 4) &&
+                    ((uintptr_t)X & 15) == 0 && ((uintptr_t)sums & 15) == 0,
+                "segment_sum: X/sums need 16B alignment and ld %% 4 == 0, ld >= D rounded to 4");
+  GDR_CHECK_ARG(N < (1ll << 31), "segment_sum: N too large");
+  if (ws_bytes < gdr_segment_sum_ws_bytes(N, K, D)) {
+    set_error("segment_sum: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(N);
+  uint32_t* ids = W.take<uint32_t>(N);
+  int32_t* mptr = W.take<int32_t>(K + 1);
+  int64_t sws_bytes = sort_pairs_ws_bytes(N);
+  void* sws = W.take<char>(sws_bytes);
+  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(N, 256), kSMs * 16));
+  if (N > 0) {
+    k_label_keys<<<grid, 256, 0, s>>>(N, labels, keys, ids);
+    GDR_LAUNCHED();
+    int bits = 1;
+    while ((1ll << bits) < K) ++bits;
+    int rc = sort_pairs(N, bits, keys, ids, sws, sws_bytes, s);
+    if (rc) return rc;
+  }
+  k_bounds_from_sorted<<<grid, 256, 0, s>>>(N, K, keys, mptr);
+  GDR_LAUNCHED();
+  if (counts) {
+    k_counts_from_rowptr<<<(unsigned)cdiv(K, 256), 256, 0, s>>>(K, mptr, counts);
+    GDR_LAUNCHED();
+  }
+  return spmm_launch(K, D, mptr, (const int32_t*)ids, nullptr, 1.0f, X, ldx, sums, lds, nullptr, 0,
+                     0.f, s);
+}
+
+int gdr_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t lds, const int32_t* counts,
+                        const float* C_old, int64_t ldc_old, float* C_new, int64_t ldc_new,
+                        double* stats_dev, int mean_mode, gdr_stream_t stream) {
+  GDR_CHECK_ARG(K > 0 && D > 0 && sums && counts && C_new && stats_dev, "kmeans_finalize: bad arguments");
+  GDR_CHECK_ARG(K <= (1 << 22), "kmeans_finalize: K too large for the shift scratch");
+  cudaStream_t s = (cudaStream_t)stream;
+  // shift scratch lives behind stats (caller provides f64[2 + K])
+  double* shift_arr = stats_dev + 2;
+  k_average<<<(unsigned)cdiv(K, 8), 256, 0, s>>>(K, (int)D, sums, lds, counts, C_old, ldc_old, C_new,
+                                                ldc_new, shift_arr, mean_mode);
+  GDR_LAUNCHED();
+  k_finalize_tail<<<1, 1024, 0, s>>>(K, (int)D, counts, C_old, ldc_old, C_new, ldc_new, shift_arr,
+                                     stats_dev, mean_mode);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_inertia_ws_bytes(int64_t N, int64_t D) {
+  (void)D;
+  return ws_need(cdiv(N > 0 ? N : 1, 8), 8) + 256;
+}
+
+int gdr_inertia(int64_t N, int64_t D, const float* X, int64_t ldx, const float* C, int64_t ldc,
+                const int32_t* labels, double* out_dev, void* ws, int64_t ws_bytes,
+                gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && D > 0 && X && C && labels && out_dev, "inertia: bad arguments");
+  if (ws_bytes < gdr_inertia_ws_bytes(N, D)) {
+    set_error("inertia: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t nb = cdiv(N, 8);
+  double* part = (double*)ws;
+  k_row_dist<<<(unsigned)nb, 256, 0, s>>>(N, (int)D, X, ldx, C, ldc, labels, nullptr, part);
+  GDR_LAUNCHED();
+  k_sum_f64<<<1, 1024, 0, s>>>(nb, part, out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_kmeans_relocate_ws_bytes(int64_t N, int64_t K, int64_t D) {
+  (void)D;
+  (void)K;
+  return ws_need(N, 4) + 2 * ws_need(1024, 4) + 256;
+}
+
+int gdr_kmeans_relocate(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx,
+                        const float* C_old, int64_t ldc, const int32_t* labels, float* sums,
+                        int64_t lds, int32_t* counts, void* ws, int64_t ws_bytes,
+                        gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && K > 0 && D > 0 && X && C_old && labels && sums && counts,
+                "kmeans_relocate: bad arguments");
+  if (ws_bytes < gdr_kmeans_relocate_ws_bytes(N, K, D)) {
+    set_error("kmeans_relocate: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<int32_t> h_counts(K);
+  GDR_CUDA(cudaMemcpyAsync(h_counts.data(), counts, K * 4, cudaMemcpyDeviceToHost, s));
+  GDR_CUDA(cudaStreamSynchronize(s));
+  std::vector<int> empties;
+  for (int64_t k = 0; k < K; ++k)
+    if (h_counts[k] == 0) empties.push_back((int)k);
+  if (empties.empty()) return GDR_OK;
+  Workspace W(ws, ws_bytes);
+  float* dist = W.take<float>(N);
+  float* pv = W.take<float>(1024);
+  int32_t* pi = W.take<int32_t>(1024);
+  k_row_dist<<<(unsigned)cdiv(N, 8), 256, 0, s>>>(N, (int)D, X, ldx, C_old, ldc, labels, dist, nullptr);
+  GDR_LAUNCHED();
+  int nparts = (int)std::min<int64_t>(1024, cdiv(N, 256));
+  // sklearn skips relocation when max(distances) == 0
+  k_argmax_part<<<nparts, 256, 0, s>>>(N, dist, pv, pi);
+  GDR_LAUNCHED();
+  std::vector<float> h_pv(nparts);
+  GDR_CUDA(cudaMemcpyAsync(h_pv.data(), pv, nparts * 4, cudaMemcpyDeviceToHost, s));
+  GDR_CUDA(cudaStreamSynchronize(s));
+  float mx = 0.f;
+  for (float v : h_pv) mx = v > mx ? v : mx;
+  if (mx == 0.f) return GDR_OK;
+  for (size_t e = 0; e < empties.size(); ++e) {
+    if (e > 0) {
+      k_argmax_part<<<nparts, 256, 0, s>>>(N, dist, pv, pi);
+      GDR_LAUNCHED();
+    }
+    k_relocate_one<<<1, 256, 0, s>>>(nparts, pv, pi, (int)D, X, ldx, labels, sums, lds, counts,
+                                     empties[e], dist);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
+}
+
+int gdr_label_histogram(int64_t N, int64_t K, const int32_t* labels, int32_t* counts,
+                        int32_t* status_dev, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && K > 0 && counts, "label_histogram: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  GDR_CUDA(cudaMemsetAsync(counts, 0, K * 4, s));
+  if (status_dev) GDR_CUDA(cudaMemsetAsync(status_dev, 0, 4, s));
+  if (N == 0) return GDR_OK;
+  GDR_CHECK_ARG(labels, "label_histogram: null labels");
+  unsigned grid = (unsigned)std::min<int64_t>(cdiv(N, 256), kSMs * 16);
+  k_label_hist<<<grid, 256, 0, s>>>(N, K, labels, counts, status_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// primitives.cu — device-wide exclusive scan (int32) and a stable LSD radix
+// sort of (u64 key, u32 payload) pairs.  Both are HBM-streaming integer work:
+// coalesced tile loads, shared-memory staging, warp ballots — no tensor cores.
+//
+// They carry stage 1 (COO -> CSR with duplicate summation: what scipy's
+// coo_tocsr + csr_sum_duplicates do on the host for utils.py:66-67 and
+// distill_recsys.py:116-117), the k-means M-step (cluster membership lists) and
+// stage 4 (segmented edge counting, distill_recsys.py:196-201).
+#include "common.cuh"
+
+namespace gdr {
+
+// ----------------------------------------------------------------------------
+// exclusive scan
+// ----------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one int per thread; returns exclusive prefix and
+// the block total through *total.
+__device__ __forceinline__ int block_excl_scan(int v, int* smem_warp /*[32]*/, int* total) {
+  int incl = warp_incl_scan(v);
+  int w = threadIdx.x >> 5;
+  if (lane_id() == 31) smem_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    int x = lane_id() < nw ? smem_warp[lane_id()] : 0;
+    int xi = warp_incl_scan(x);
+    smem_warp[lane_id()] = xi - x;  // exclusive warp offsets
+    if (lane_id() == 31) smem_warp[32] = xi;
+  }
+  __syncthreads();
+  int r = smem_warp[w] + incl - v;
+  *total = smem_warp[32];
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int32_t* __restrict__ in,
+                                                              int32_t* __restrict__ block_sums,
+                                                              int64_t n) {
+  __shared__ int sw[33];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    if (idx < n) s += in[idx];
+  }
+  int total;
+  block_excl_scan(s, sw, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int32_t* __restrict__ in,
+                                                             const int32_t* __restrict__ block_offs,
+                                                             int32_t* __restrict__ out, int64_t n,
+                                                             int write_total) {
+  __shared__ int sw[33];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? in[idx] : 0;
+    s += v[i];
+  }
+  int total;
+  int excl = block_excl_scan(s, sw, &total);
+  int run = excl + (block_offs ? block_offs[blockIdx.x] : 0);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = run;
+    run += v[i];
+    if (write_total && idx == n - 1) out[n] = run;
+  }
+}
+
+__global__ void k_zero_one(int32_t* out) { out[0] = 0; }
+
+int64_t scan_ws_bytes(int64_t n) {
+  int64_t total = 0;
+  while (n > SCAN_TILE) {
+    int64_t nb = cdiv(n, SCAN_TILE);
+    total += ws_need(nb + 1, 4);
+    n = nb;
+  }
+  return total + 256;
+}
+
+// out may alias in.  out has n+1 entries when write_total != 0.
+static int scan_rec(const int32_t* in, int32_t* out, int64_t n, char* ws, int write_total,
+                    cudaStream_t s) {
+  if (n <= 0) {
+    if (write_total) {
+      k_zero_one<<<1, 1, 0, s>>>(out);
+      GDR_LAUNCHED();
+    }
+    return GDR_OK;
+  }
+  int64_t nb = cdiv(n, SCAN_TILE);
+  if (nb == 1) {
+    k_scan_apply<<<1, SCAN_THREADS, 0, s>>>(in, nullptr, out, n, write_total);
+    GDR_LAUNCHED();
+    return GDR_OK;
+  }
+  int32_t* bs = (int32_t*)ws;
+  char* ws_next = ws + ws_need(nb + 1, 4);
+  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, bs, n);
+  GDR_LAUNCHED();
+  int rc = scan_rec(bs, bs, nb, ws_next, 0, s);
+  if (rc) return rc;
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, bs, out, n, write_total);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, int64_t ws_bytes,
+                       cudaStream_t s) {
+  if (ws_bytes < scan_ws_bytes(n)) {
+    set_error("exclusive_scan: workspace %lld < %lld", (long long)ws_bytes,
+              (long long)scan_ws_bytes(n));
+    return GDR_EWORKSPACE;
+  }
+  return scan_rec(in, out, n, (char*)ws, 1, s);
+}
+
+// ----------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits
+// ----------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 16;                      // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;    // 4096 keys per CTA
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n,
+                                                        int shift, int32_t* __restrict__ table,
+                                                        int nblocks) {
+  __shared__ int hist[RS_BINS];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int64_t idx = base + r * RS_THREADS + threadIdx.x;
+    if (idx < n) {
+      int d = (int)((keys[idx] >> shift) & 0xff);
+      atomicAdd(&hist[d], 1);
+    }
+  }
+  __syncthreads();
+  table[(int64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in,
+                                                           const uint32_t* __restrict__ vals_in,
+                                                           uint64_t* __restrict__ keys_out,
+                                                           uint32_t* __restrict__ vals_out, int64_t n,
+                                                           int shift,
+                                                           const int32_t* __restrict__ table_scanned,
+                                                           int nblocks) {
+  __shared__ int cnt[RS_WARPS][RS_BINS];
+  for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_ROUNDS * 32);
+  uint64_t k[RS_ROUNDS];
+  uint32_t v[RS_ROUNDS];
+  int rank[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int64_t idx = base + r * 32 + lane;
+    bool valid = idx < n;
+    k[r] = valid ? keys_in[idx] : 0ull;
+    v[r] = (valid && vals_in) ? vals_in[idx] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int64_t idx = base + r * 32 + lane;
+    bool valid = idx < n;
+    int d = valid ? (int)((k[r] >> shift) & 0xff) : RS_BINS;  // sentinel digit for padding lanes
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int before = __popc(peers & lt_mask);
+    int leader = __ffs(peers) - 1;
+    int basecnt = 0;
+    if (valid && lane == leader) {
+      basecnt = cnt[w][d];
+      cnt[w][d] = basecnt + __popc(peers);
+    }
+    basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
+    rank[r] = basecnt + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    int d = threadIdx.x;
+    int run = table_scanned[(int64_t)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) {
+      int t = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int64_t idx = base + r * 32 + lane;
+    if (idx < n) {
+      int d = (int)((k[r] >> shift) & 0xff);
+      int64_t pos = (int64_t)cnt[w][d] + rank[r];
+      keys_out[pos] = k[r];
+      if (vals_out) vals_out[pos] = v[r];
+    }
+  }
+}
+
+int64_t sort_pairs_ws_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  int64_t nb = cdiv(n, RS_TILE);
+  int64_t tbl = (int64_t)RS_BINS * nb;
+  return ws_need(n, 8) + ws_need(n, 4) + ws_need(tbl + 1, 4) + scan_ws_bytes(tbl) + 256;
+}
+
+int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
+               cudaStream_t s) {
+  if (n <= 1 || key_bits <= 0) return GDR_OK;
+  if (ws_bytes < sort_pairs_ws_bytes(n)) {
+    set_error("sort_pairs: workspace %lld < %lld", (long long)ws_bytes,
+              (long long)sort_pairs_ws_bytes(n));
+    return GDR_EWORKSPACE;
+  }
+  if (n >= (1ll << 31)) {
+    set_error("sort_pairs: n=%lld exceeds int32 positions", (long long)n);
+    return GDR_ERANGE;
+  }
+  int64_t nb = cdiv(n, RS_TILE);
+  int64_t tbl = (int64_t)RS_BINS * nb;
+  Workspace W(ws, ws_bytes);
+  uint64_t* kalt = W.take<uint64_t>(n);
+  uint32_t* valt = W.take<uint32_t>(n);
+  int32_t* table = W.take<int32_t>(tbl + 1);
+  void* sws = W.take<char>(scan_ws_bytes(tbl));
+  int passes = (key_bits + 7) / 8;
+  uint64_t* kin = keys;
+  uint32_t* vin = vals;
+  uint64_t* kout = kalt;
+  uint32_t* vout = vals ? valt : nullptr;
+  for (int p = 0; p < passes; ++p) {
+    int shift = 8 * p;
+    k_rs_hist<<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
+    GDR_LAUNCHED();
+    int rc = exclusive_scan_i32(table, table, tbl, sws, scan_ws_bytes(tbl), s);
+    if (rc) return rc;
+    k_rs_scatter<<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
+    GDR_LAUNCHED();
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  if (kin != keys) {
+    GDR_CUDA(cudaMemcpyAsync(keys, kin, n * 8, cudaMemcpyDeviceToDevice, s));
+    if (vals) GDR_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return GDR_OK;
+}
+
+}  // namespace gdr
+
+extern "C" {
+
+int64_t gdr_sort_pairs_ws_bytes(int64_t n) { return gdr::sort_pairs_ws_bytes(n); }
+
+int gdr_sort_pairs(int64_t n, int key_bits, uint64_t* keys_io, uint32_t* vals_io, void* ws,
+                   int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n >= 0 && key_bits >= 0 && key_bits <= 64, "sort_pairs: bad n/key_bits");
+  GDR_CHECK_ARG(n == 0 || keys_io, "sort_pairs: null keys");
+  return gdr::sort_pairs(n, key_bits, keys_io, vals_io, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

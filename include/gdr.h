@@ -1,0 +1,266 @@
+/*
+ * gdr.h — C ABI of the B200-native graph-distillation core (libgdr_b200.so).
+ *
+ * The reference (Tyler-Linchenwei/Graph-Distillation-for-Recommendation) is pure
+ * Python and has no FFI surface; its hot path is reached through Python call
+ * sites that hand torch / numpy / scipy objects to torch-sparse, scipy
+ * sparsetools and scikit-learn.  This header is the boundary a maintainer would
+ * bind instead (ctypes stub: see INTEGRATION.md).  Every entry point names the
+ * reference call site it replaces as  file:line  relative to
+ * /root/reference/ClustGDD/ ("sklearn/" = scikit-learn's cluster package, the
+ * third-party dependency that owns stage 3's arithmetic).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns int: 0 = ok, <0 = GDR_E* ; text via gdr_last_error().
+ *   - all data pointers are DEVICE pointers owned by the caller unless the
+ *     parameter name ends in _host.  The library never frees caller memory and
+ *     never allocates outputs; scratch comes from the caller through the
+ *     two-phase  *_ws_bytes() / run(ws, ws_bytes)  pattern.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises unless the doc of the function says so.
+ *   - dense matrices are row-major float32 with an explicit leading dimension
+ *     in ELEMENTS; CSR is (rowptr int32[n+1], colidx int32[nnz], vals f32[nnz]).
+ *   - thread-safe for distinct streams; no global mutable state except the
+ *     thread-local error string.
+ */
+#ifndef GDR_H_
+#define GDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* the library is built with -fvisibility=hidden; only this header is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define GDR_ABI_VERSION 1
+
+#define GDR_OK            0
+#define GDR_EINVAL      (-1)  /* bad argument (null pointer, negative size, misalignment) */
+#define GDR_EWORKSPACE  (-2)  /* ws_bytes smaller than *_ws_bytes() asked for            */
+#define GDR_ECUDA       (-3)  /* a CUDA runtime/driver call failed                        */
+#define GDR_ERANGE      (-4)  /* index out of range / size exceeds int32 CSR limits       */
+#define GDR_EUNSUPPORTED (-5) /* shape not supported by this kernel (see doc)             */
+
+typedef void* gdr_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------- */
+int         gdr_abi_version(void);
+const char* gdr_last_error(void);
+/* Fills sm_count / compute capability of the CURRENT device. */
+int         gdr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Counter of kernels this library has launched in the calling process since
+ * load (all threads); used by bench.py for "gpu_launches". */
+int64_t     gdr_launch_count(void);
+
+/* ---- generic device primitives (used by stages 1, 3, 4) -------------- */
+/* Stable LSD radix sort of (uint64 key, uint32 payload) pairs on the low
+ * `key_bits` bits.  Result is left in keys_io / vals_io. */
+int64_t gdr_sort_pairs_ws_bytes(int64_t n);
+int     gdr_sort_pairs(int64_t n, int key_bits, uint64_t* keys_io, uint32_t* vals_io,
+                       void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* ---- stage 1: adjacency build ---------------------------------------- */
+/* COO -> CSR with duplicate (row,col) entries SUMMED and column indices
+ * sorted inside each row.
+ *   replaces  scipy  sp.csr_matrix((ones,(r,c)))          utils.py:66-67
+ *             sp.coo_matrix((vals,(u,i))).tocsr()          distill_recsys.py:116-117
+ *             adj + adj.T ; adj[adj>1] = 1                 utils_graphsaint.py:20-22
+ *   val == NULL means all ones.  symmetrize: also insert (col,row) for every
+ *   entry (n_rows must equal n_cols).  binarize: every stored value becomes 1.
+ *   Capacity of colidx/vals must be nnz_in * (symmetrize ? 2 : 1).
+ *   *nnz_out_dev (device int64) receives the number of stored entries
+ *   (= rowptr[n_rows]).  Indices outside [0,n_rows)x[0,n_cols) set
+ *   status_dev[0] != 0 (device int32, caller checks after sync) and are dropped. */
+int64_t gdr_coo_to_csr_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz_in, int symmetrize);
+int     gdr_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz_in,
+                       const int64_t* row, const int64_t* col, const float* val,
+                       int symmetrize, int binarize,
+                       int32_t* rowptr, int32_t* colidx, float* vals,
+                       int64_t* nnz_out_dev, int32_t* status_dev,
+                       void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* Symmetric normalisation  D^-1/2 (A [+ I]) D^-1/2  of a CSR matrix.
+ *   replaces  normalize_adj_tensor(adj, sparse=True)       deep_robust_utils.py:245-256
+ *             -> to_scipy :408-417 -> normalize_adj :180-207
+ *   self_loop_mode: 0 never add I, 1 always add I, 2 = the reference's rule
+ *   "add I iff A[0,0] == 0" (deep_robust_utils.py:199-200).
+ *   Degrees are row sums in fp64 (deg_out, nullable); r = deg^-1/2 in fp64 with
+ *   inf -> 0; value = fp32((r_i * a_ij) * r_j)  — bit-exact with scipy.
+ *   Output capacity: nnz + n.  *nnz_out_dev = stored entries of the result. */
+int64_t gdr_sym_normalize_ws_bytes(int64_t n, int64_t nnz);
+int     gdr_sym_normalize(int64_t n, int64_t nnz,
+                          const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                          int self_loop_mode,
+                          int32_t* rowptr_out, int32_t* colidx_out, float* vals_out,
+                          double* deg_out, int64_t* nnz_out_dev,
+                          void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* Dense n x n variant:  D^-1/2 (A + I) D^-1/2  in fp32, O(n^2).
+ *   replaces  normalize_adj_tensor(adj) dense branch       deep_robust_utils.py:257-264 */
+int gdr_sym_normalize_dense(int64_t n, const float* A, int64_t lda, float* out, int64_t ldo,
+                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int64_t gdr_sym_normalize_dense_ws_bytes(int64_t n);
+
+/* Bipartite edge normalisation  norm_e = w_e / (sqrt(du[cu_e]+eps) * sqrt(di[ci_e]+eps)),
+ * du = scatter-sum of w over cu, di over ci (fp32, deterministic order = CSR order).
+ *   replaces  LightGCNCondensed.propagate degree/norm part distill_recsys.py:329-335
+ *   Input is the CSR of the cu x ci weight matrix (rowptr/colidx/w) plus the
+ *   transposed CSR built by gdr_csr_transpose; outputs norm in BOTH orders. */
+int gdr_bipartite_normalize(int64_t n_u, int64_t n_i, int64_t nnz,
+                            const int32_t* rowptr, const int32_t* colidx, const float* w,
+                            const int32_t* t_rowptr, const int32_t* t_perm,
+                            float eps, float* norm_out, float* t_norm_out,
+                            float* deg_u, float* deg_i, gdr_stream_t stream);
+
+/* CSR transpose: t_rowptr[n_cols+1], t_colidx[nnz] (= source row ids, ascending
+ * inside each transposed row), t_perm[nnz] = position of that entry in the input. */
+int64_t gdr_csr_transpose_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
+int     gdr_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                          const int32_t* rowptr, const int32_t* colidx,
+                          int32_t* t_rowptr, int32_t* t_colidx, int32_t* t_perm,
+                          void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* CSR -> COO index expansion (row-major, int64) — the layout the reference's
+ * sparse_mx_to_torch_sparse_tensor produces     deep_robust_utils.py:389-396.
+ * col_out nullable. */
+int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx,
+                   int64_t* row_out, int64_t* col_out, gdr_stream_t stream);
+
+/* ---- stage 2: propagation -------------------------------------------- */
+/* One hop of   Y = (alpha * A) @ X ;  T += beta * Y   (T nullable).
+ *   replaces  prop_feat = alpha*adj_norm @ prop_feat ;
+ *             target_feat = target_feat + (1-alpha)*prop_feat
+ *                                       clustgdd_agent_transduct.py:64-65
+ *                                       clustgdd_agent_induct.py:77-78,85-86,93-94
+ *   and the index_add_ message passing of distill_recsys.py:340-345 (alpha=1).
+ *   The stored value used is fp32(vals[e] * alpha) exactly as `alpha*adj_norm`
+ *   produces it.  A is rows_local x n_cols CSR; X has n_cols rows.
+ *   Requirements: ldx, ldy, ldt multiples of 4 and X/Y/T 16-byte aligned
+ *   (the host pads F up to a multiple of 4).  Row sums are accumulated in
+ *   CSR order, one fp32 chain per output element => deterministic. */
+int gdr_spmm_prop(int64_t rows_local, int64_t F,
+                  const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                  float alpha, const float* X, int64_t ldx,
+                  float* Y, int64_t ldy,
+                  float* T, int64_t ldt, float beta,
+                  gdr_stream_t stream);
+
+/* out = a * X  (dense, row-major; used for the t = 0 term (1-alpha)*X). */
+int gdr_scale_rows(int64_t rows, int64_t F, float a, const float* X, int64_t ldx,
+                   float* out, int64_t ldo, gdr_stream_t stream);
+
+/* ---- stage 3: k-means ------------------------------------------------- */
+/* Column mean / variance of X in fp64 -> mean_out f32[D], var_mean_out f64[1]
+ * (= mean over columns of the population variance; sklearn/_kmeans.py:285-293),
+ * and optionally Xc = X - mean (sklearn/_kmeans.py:1487-1489). */
+int64_t gdr_center_columns_ws_bytes(int64_t N, int64_t D);
+int     gdr_center_columns(int64_t N, int64_t D, const float* X, int64_t ldx,
+                           float* mean_out, double* var_mean_out,
+                           float* Xc /*nullable*/, int64_t ldxc,
+                           void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* E-step.  labels[i] = argmin_j ( |c_j|^2 - 2 x_i . c_j ), first index wins ties.
+ *   replaces  _update_chunk_dense                 sklearn/_k_means_lloyd.pyx:196-213
+ *   precision_mode 0: exact fp32 SIMT everywhere.
+ *   precision_mode 1: tcgen05 3xTF32 tensor-core screen, rows whose best/second
+ *                     margin is inside the error band are re-scored in exact fp32.
+ *   n_changed_dev (nullable, device int32) += #rows whose label differs from
+ *   labels_prev (nullable).  best_out (nullable) = the winning partial distance. */
+int64_t gdr_kmeans_assign_ws_bytes(int64_t N, int64_t K, int64_t D, int precision_mode);
+int     gdr_kmeans_assign(int64_t N, int64_t K, int64_t D,
+                          const float* X, int64_t ldx, const float* C, int64_t ldc,
+                          int32_t* labels, const int32_t* labels_prev,
+                          int32_t* n_changed_dev, float* best_out,
+                          int precision_mode,
+                          void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* M-step, part 1: per-cluster sums and counts.
+ *   replaces  centers_new[label] += X[i]; weight[label] += 1
+ *                                                 sklearn/_k_means_lloyd.pyx:215-218
+ *             and the Python cluster-mean loop    clustgdd_agent_transduct.py:121-125
+ *             and index_add_/bincount pooling     distill_recsys.py:628-636
+ *   Deterministic: members of a cluster are summed in ascending row order, one
+ *   fp32 chain per output element (== np.add.at order). */
+int64_t gdr_segment_sum_ws_bytes(int64_t N, int64_t K, int64_t D);
+int     gdr_segment_sum(int64_t N, int64_t K, int64_t D,
+                        const float* X, int64_t ldx, const int32_t* labels,
+                        float* sums, int64_t lds, int32_t* counts,
+                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* counts[k] = #{i : labels[i] == k}  (cluster sizes: torch.bincount at
+ * distill_recsys.py:630, column sums of the one-hot at transduct :238).
+ * Labels outside [0,K) set status_dev[0] (nullable) and are skipped. */
+int gdr_label_histogram(int64_t N, int64_t K, const int32_t* labels, int32_t* counts,
+                        int32_t* status_dev, gdr_stream_t stream);
+
+/* M-step, part 2: average + centre shift.
+ *   replaces  _average_centers / _center_shift    sklearn/_k_means_common.pyx:274-311
+ *   C_new[j] = sums[j] * (1.0f / counts[j]); an empty cluster takes the centre of
+ *   the (first) largest cluster.  stats_dev f64[2 + K]: [0] = sum_j |C_new_j-C_old_j|^2,
+ *   [1] = number of empty clusters, [2..] scratch (per-cluster shift).  mean_mode 1: empty -> NaN row, no shift
+ *   (the reference's torch `.mean(dim=0)` of an empty selection, transduct :122). */
+int gdr_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t lds,
+                        const int32_t* counts, const float* C_old, int64_t ldc_old,
+                        float* C_new, int64_t ldc_new, double* stats_dev, int mean_mode,
+                        gdr_stream_t stream);
+
+/* Empty-cluster relocation  (sklearn/_k_means_common.pyx:167-211): for the idx-th
+ * empty cluster move the idx-th farthest sample (distance to its centre in
+ * C_old) out of its cluster.  Mutates sums/counts in place.  SYNCHRONISES. */
+int64_t gdr_kmeans_relocate_ws_bytes(int64_t N, int64_t K, int64_t D);
+int     gdr_kmeans_relocate(int64_t N, int64_t K, int64_t D,
+                            const float* X, int64_t ldx, const float* C_old, int64_t ldc,
+                            const int32_t* labels, float* sums, int64_t lds, int32_t* counts,
+                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* inertia = sum_i |x_i - c_label(i)|^2  accumulated in fp64 (deterministic).
+ *   replaces  _inertia_dense                      sklearn/_k_means_common.pyx:94-124 */
+int64_t gdr_inertia_ws_bytes(int64_t N, int64_t D);
+int     gdr_inertia(int64_t N, int64_t D, const float* X, int64_t ldx,
+                    const float* C, int64_t ldc, const int32_t* labels, double* out_dev,
+                    void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* out[i, :] = X[i, :] + sign * v[:]   (centres += X_mean, sklearn/_kmeans.py:1546) */
+int gdr_add_row_vector(int64_t rows, int64_t D, float* X, int64_t ldx, const float* v,
+                       float sign, gdr_stream_t stream);
+
+/* ---- stage 4: cluster-coarsened graph -------------------------------- */
+/* Segmented edge counting:  for every input edge e (src,dst[,w]) form the key
+ * (labels_src[src], labels_dst[dst]); output the CSR (n_src x n_dst) of
+ *   counts[a,b] = #edges with that key   (int32, exact)
+ *   wsum[a,b]   = sum of w over them     (fp32, summed in input order; nullable)
+ *   replaces  build_condensed_bipartite           distill_recsys.py:184-201
+ *             graph_compress (P^T A P)            clustgdd_agent_transduct.py:234-250
+ *                                                 clustgdd_agent_induct.py:258-274
+ *   Edges come either as COO (src/dst int64) or, when src == NULL, as CSR
+ *   (csr_rowptr/csr_colidx int32 with n_rows rows).  drop_diag removes a == b.
+ *   Output capacity: min(E, n_src*n_dst).  *nnz_out_dev = stored entries. */
+int64_t gdr_coarsen_ws_bytes(int64_t E, int64_t n_src, int64_t n_dst);
+int     gdr_coarsen(int64_t E, const int64_t* src, const int64_t* dst,
+                    int64_t n_rows, const int32_t* csr_rowptr, const int32_t* csr_colidx,
+                    const float* w,
+                    const int32_t* labels_src, const int32_t* labels_dst,
+                    int64_t n_src, int64_t n_dst, int drop_diag,
+                    int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
+                    int64_t* nnz_out_dev,
+                    void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* graph_compress value pass: vals[e] = wsum[e] / (size[a] * size[b])  computed as
+ * fp32 (wsum * (1/size[a])) * (1/size[b])  (transduct :237-244). */
+int gdr_coarsen_scale(int64_t n_src, const int32_t* rowptr, const int32_t* colidx,
+                      const float* wsum, const int32_t* size_src, const int32_t* size_dst,
+                      float* vals_out, gdr_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDR_H_ */
