@@ -106,7 +106,7 @@ def test_normalize_adj_tensor_golden(gdr, dev, case):
     if case in ("plain", "isolated"):
         assert np.array_equal(np_(out._values()), g["out_val"])  # bit-exact with scipy's fp64 path
     else:
-        np.testing.assert_allclose(np_(out._values()), g["out_val"], rtol=2e-7, atol=0)
+        np.testing.assert_allclose(np_(out._values()), g["out_val"], rtol=5e-7, atol=0)  # numpy powf: <= 2 ulp
     back = gdr.to_scipy(out)
     assert back.nnz == g["out_val"].shape[0]
 
