@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — one "step" = one pass of the distillation core over a synthetic graph of a
+BASELINE.json shape:  stage 1 (CSR build + D^-1/2 A D^-1/2)  ->  stage 2 (K hops)  ->
+stage 3 (20 Lloyd iterations from a fixed init, tol = 0)  ->  stage 4 (P^T A P).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload B] [--precision fp32|tc]
+    python bench.py --impl reference ...        # the reference's CPU path on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = k-means iterations / s (whole job), the quantity
+BASELINE.json's speed-up target is quoted on; `prop` carries the A^K.X GB/s figure of the
+same metric string with its own HBM roofline.  See DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLOYD_ITERS = 20
+ALPHA = 0.8
+
+
+# ----------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=reasons)
+
+
+def make_workload(name):
+    from gdr import synth
+    cfg = dict(synth.CONFIGS[name])
+    idx = {"A": 0, "B": 1, "E": 4}[name]
+    seed = 1234 + idx
+    u, v = synth.uniform_graph(cfg["n"], cfg["pairs"], seed)
+    X = synth.features(cfg["n"], cfg["f"], seed + 100, kind="l1" if name == "A" else "zscore")
+    cfg.update(u=u, v=v, X=X, seed=seed)
+    return cfg
+
+
+def spmm_bytes(nnz, rows, xrows, F, fused=True, model="min"):
+    """compulsory (B_min) or gather (B_gather) bytes of one hop."""
+    if model == "min":
+        b = nnz * 8 + (rows + 1) * 4 + xrows * F * 4 + rows * F * 4
+    else:
+        b = nnz * (8 + 4 * F) + (rows + 1) * 4 + rows * F * 4
+    return b + (2 * rows * F * 4 if fused else 0)
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle/ref_port.py: scipy + torch CPU sparse + scikit-learn)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_port as rp
+    from gdr import synth
+    w = make_workload(args.workload)
+    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    info = rp.host_info()
+    t_s1, t_s2, t_s3, t_s4, per_step = [], [], [], [], []
+    it_lo, it_hi = 3, 3 + args.ref_kmeans_iters
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        A = rp.build_adjacency(w["u"], w["v"], n)
+        adj = rp.to_tensor_sparse(A)
+        adj_norm = rp.normalize_adj_tensor_sparse(adj)
+        t1 = time.perf_counter()
+        _, target = rp.propagate(adj_norm, torch.from_numpy(w["X"]), hops + 1, ALPHA)
+        t2 = time.perf_counter()
+        tn = target.numpy()
+        C0 = synth.kmeans_init(tn, K, w["seed"])
+        rp.kmeans_fit(tn, C0, 1)  # first call pays thread-pool start-up; keep it out of the difference
+        t3 = time.perf_counter()
+        rp.kmeans_fit(tn, C0, it_lo)
+        t3a = time.perf_counter()
+        km = rp.kmeans_fit(tn, C0, it_hi)
+        t3b = time.perf_counter()
+        S = rp.graph_compress_sparse(km.labels_.astype(np.int64), adj_norm)
+        t4 = time.perf_counter()
+        if s >= args.warmup:
+            t_s1.append(t1 - t0)
+            t_s2.append(t2 - t1)
+            # differenced: (fit with it_hi) - (fit with it_lo) cancels validation / centring / final E-step
+            t_s3.append(((t3b - t3a) - (t3a - t3)) / (it_hi - it_lo))
+            t_s4.append(t4 - t3b)
+            per_step.append(t4 - t0)
+    nnz = adj_norm._nnz()
+    s_iter = float(np.mean(t_s3))
+    iters_per_s = 1.0 / s_iter
+    prop_gbs = hops * spmm_bytes(nnz, n, n, F) / np.mean(t_s2) / 1e9
+    line = {
+        "impl": "reference", "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(per_step)) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, "
+                               f"F={F}, hops={hops}, K={K}, k-means D={F}",
+                   "lloyd_iters_timed": f"sklearn fit(max_iter={it_hi}) - fit(max_iter={it_lo})"},
+        "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "bytes_model": "B_min",
+                 "s_per_hop": float(np.mean(t_s2)) / hops},
+        "stages_ms": {"s1_build_normalize": np.mean(t_s1) * 1e3, "s2_propagate": np.mean(t_s2) * 1e3,
+                      "s3_kmeans_per_iter": s_iter * 1e3, "s4_coarsen": np.mean(t_s4) * 1e3},
+        "cpu_baseline": {"value": iters_per_s, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
+                         "sample": f"full config {args.workload}; sklearn/scipy/torch-CPU with all host threads", "host": info},
+        "e2e": {"value": iters_per_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    import torch
+    import gdr
+    from gdr import synth
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        from gdr import parallel
+        return parallel.bench_entry(args, rank, world, dev, dist)
+
+    w = make_workload(args.workload)
+    n, F, K, hops, seed = w["n"], w["f"], w["k"], w["hops"], w["seed"]
+    pk = peaks()
+
+    # inputs resident in HBM before the timed region
+    u_d = torch.from_numpy(w["u"]).to(dev)
+    v_d = torch.from_numpy(w["v"]).to(dev)
+    X_d = torch.from_numpy(w["X"]).to(dev)
+    X_pin = torch.from_numpy(w["X"]).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # k-means init: C0 = X_target[perm[:K]] needs the propagated features -> computed once, untimed
+    A0 = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
+    _, tgt0 = gdr.propagate(A0, X_d, hops + 1, ALPHA)
+    perm = torch.from_numpy(np.random.RandomState(seed).permutation(n)[:K].astype(np.int64)).to(dev)
+    C0 = tgt0[perm].clone()
+    nnz = A0.nnz
+    del A0, tgt0
+
+    def step(record):
+        e = [ev() for _ in range(5)]
+        e[0].record()
+        A = gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True)
+        An = gdr.sym_normalize(A, 2)
+        e[1].record()
+        prop, target = gdr.propagate(An, X_d, hops + 1, ALPHA)
+        e[2].record()
+        km = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision)
+        km._assign_events = [] if record else None
+        km.fit(target)
+        e[3].record()
+        _, adj_syn = gdr.graph_compress(km.labels_, An, [])
+        e[4].record()
+        return e, km, adj_syn
+
+    for _ in range(args.warmup):
+        step(False)
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = gdr.launch_count()
+    recs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)          # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        recs.append(step(True))
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = gdr.launch_count() - launches0
+    clocks = sampler.stop()
+
+    st = np.array([[r[0][i].elapsed_time(r[0][i + 1]) for i in range(4)] for r in recs])  # ms per stage
+    step_ms = st.sum(axis=1)
+    n_iter = [r[1].n_iter_ for r in recs]
+    assign_ms = np.array([a.elapsed_time(b) for r in recs for (a, b) in r[1]._assign_events])
+    km_ms = st[:, 2]
+    iters_per_s = float(np.sum(n_iter) / (km_ms.sum() / 1e3))
+    prop_ms = st[:, 1]
+    b_hop = spmm_bytes(nnz, n, n, F)
+    b_prop = hops * b_hop + 2 * n * F * 4  # + the t = 0 scale pass
+    prop_gbs = float(b_prop / (prop_ms.mean() / 1e3) / 1e9)
+
+    # ---- e2e through the public API with HOST buffers (H2D of X, D2H of labels + centres) ----
+    tn_host = recs[-1][1]  # keep last km for result checks
+    C0_host = C0.cpu().numpy()
+    target_host = torch.empty((n, F), dtype=torch.float32).pin_memory()
+    target_host.copy_(gdr.propagate(gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2), X_d, hops + 1, ALPHA)[1])
+    e2e_t = []
+    for i in range(2 if args.profile else max(3, args.steps)):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x_dev = target_host.to(dev, non_blocking=True)
+        km = gdr.KMeans(n_clusters=K, init=C0_host, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision).fit(x_dev)
+        lab_h = km.labels_.cpu()
+        cen_h = km.cluster_centers_.cpu()
+        torch.cuda.synchronize()
+        e2e_t.append((time.perf_counter() - t0, km.n_iter_))
+    e2e_t = e2e_t[1:]
+    e2e_val = float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t))
+    h2d = n * F * 4 + K * F * 4
+    d2h = n * 4 + K * F * 4
+
+    # ---- roofline of the dominant kernel (k-means E-step) ----
+    flops = 2.0 * n * K * F
+    a_tf = float(flops / (assign_ms.mean() / 1e3) / 1e12)
+    roofline = {"kernel": "k_assign_tc (tcgen05 3xTF32)" if args.precision == "tc" else "k_assign_simt (exact fp32 FFMA)",
+                "bound": "tensor", "achieved": a_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": a_tf / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "note": "useful flops 2NKD per launch; fp32 inputs: TF32 rate = 1/2 bf16, 3xTF32 emulation ceiling = peak/6",
+                "launch_ms": float(assign_ms.mean()), "share_of_step": float(assign_ms.sum() / step_ms.sum())}
+    spmm_ms = prop_ms.mean() * (hops * b_hop / b_prop) / hops
+    roofline_spmm = {"kernel": "k_spmm", "bound": "hbm", "achieved": float(b_hop / (spmm_ms / 1e3) / 1e9), "peak": pk["hbm"],
+                     "unit": "GB/s", "frac": float(b_hop / (spmm_ms / 1e3) / 1e9 / pk["hbm"]), "traffic": None,
+                     "bytes_model": "B_min (X fits L2)", "b_gather_gbs": float(spmm_bytes(nnz, n, n, F, model='gather') / (spmm_ms / 1e3) / 1e9),
+                     "peak_source": pk["src"]}
+
+    cpu = cpu_baseline(w, args) if not (args.no_cpu_baseline or args.profile) else None
+    line = {
+        "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
+                               f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
+                   "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
+        "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / pk["hbm"],
+                 "frac_hbm_8TBs": prop_gbs / 8000.0, "bytes_model": "B_min", "ms": float(prop_ms.mean())},
+        "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
+                      "s3_kmeans": float(km_ms.mean()), "s3_kmeans_per_iter": float(km_ms.sum() / np.sum(n_iter)),
+                      "s4_coarsen": float(st[:, 3].mean())},
+        "roofline": roofline, "roofline_spmm": roofline_spmm, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
+        "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2]._nnz())},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(w, args):
+    """Bounded CPU sample on this box's host cores (oracle-side port of the reference)."""
+    import torch
+    from oracle import ref_port as rp
+    from gdr import synth
+    n, K = w["n"], w["k"]
+    X = w["X"]
+    C0 = synth.kmeans_init(X, K, w["seed"])
+    rp.kmeans_fit(X[:20000], C0[: min(K, 100)], 2)  # warm the thread pools
+    t0 = time.perf_counter()
+    rp.kmeans_fit(X, C0, 2)
+    t1 = time.perf_counter()
+    rp.kmeans_fit(X, C0, 12)
+    t2 = time.perf_counter()
+    s_iter = ((t2 - t1) - (t1 - t0)) / 10.0
+    info = rp.host_info()
+    return {"value": 1.0 / s_iter, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
+            "sample": f"sklearn KMeans(init=C0,n_init=1,tol=0) on the full {n}x{X.shape[1]} matrix, K={K}: fit(12 it) - fit(2 it)",
+            "host": info}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--ref-kmeans-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no CPU baseline, minimal e2e leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.workload is None:
+        args.workload = "B"
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

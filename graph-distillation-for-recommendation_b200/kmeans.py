@@ -200,8 +200,15 @@ class KMeans:
         for i in range(int(self.max_iter)):
             n_iter = i + 1
             S.n_changed.zero_()
+            ev = getattr(self, "_assign_events", None)
+            if ev is not None:  # bench.py: CUDA-event pair around the dominant kernel
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             assign_labels(Xc, S.centers[cur], S.labels[lab_new], labels_prev=S.labels[lab_old],
                           n_changed=S.n_changed, precision_mode=S.mode, ws=S.ws_assign)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
             segment_sum(Xc, S.labels[lab_new], K, sums=S.sums, counts=S.counts, ws=S.ws_seg)
             self._finalize(S, cur, nxt)
             S.host[:2].copy_(S.stats[:2], non_blocking=True)
