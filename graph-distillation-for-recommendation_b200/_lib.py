@@ -39,6 +39,10 @@ _SIGNATURES = {
     "gdr_center_columns": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
     "gdr_kmeans_assign_ws_bytes": (i64, [i64, i64, i64, i32]),
     "gdr_kmeans_assign": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
+    "gdr_kmeans_tc_xsplit_bytes": (i64, [i64, i64]),
+    "gdr_kmeans_tc_prepare": (i32, [i64, i64, vp, i64, vp, i64, vp]),
+    "gdr_kmeans_assign_tc_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_kmeans_assign_tc": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_segment_sum_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_segment_sum": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
     "gdr_label_histogram": (i32, [i64, i64, vp, vp, vp, vp]),

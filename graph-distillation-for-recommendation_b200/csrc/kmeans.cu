@@ -16,7 +16,7 @@
 namespace gdr {
 
 // implemented in kmeans_tc.cu
-int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D);
+int64_t kmeans_assign_tc_total_ws_bytes(int64_t N, int64_t K, int64_t D);
 int kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const float* C,
                      int64_t ldc, int32_t* labels, const int32_t* labels_prev,
                      int32_t* n_changed_dev, float* best_out, void* ws, int64_t ws_bytes,
@@ -131,12 +131,19 @@ __global__ void __launch_bounds__(AS_THREADS, 2)
 k_assign_simt(int64_t N, int K, int D, const float* __restrict__ X, int64_t ldx,
               const float* __restrict__ C, int64_t ldc, const float* __restrict__ cnorm,
               int32_t* __restrict__ labels, const int32_t* __restrict__ labels_prev,
-              int32_t* __restrict__ n_changed, float* __restrict__ best_out) {
+              int32_t* __restrict__ n_changed, float* __restrict__ best_out,
+              const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows_dev) {
+  // rows != nullptr: re-score only the listed rows (the tensor-core path's ambiguous set);
+  // the list length lives on the device, surplus CTAs exit.
   __shared__ __align__(16) float As[AS_BK][AS_BM + 4];
   __shared__ __align__(16) float Bs[AS_BK][AS_BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t row0 = (int64_t)blockIdx.x * AS_BM;
+  if (rows) {
+    N = *n_rows_dev;
+    if (row0 >= N) return;
+  }
 
   float best[8];
   int bidx[8];
@@ -163,7 +170,8 @@ k_assign_simt(int64_t N, int K, int D, const float* __restrict__ X, int64_t ldx,
         float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), cb = xa;
         int64_t gr = row0 + r;
         if (gr < N && k < D) {
-          xa = *reinterpret_cast<const float4*>(X + gr * ldx + k);
+          int64_t xr = rows ? (int64_t)rows[gr] : gr;
+          xa = *reinterpret_cast<const float4*>(X + xr * ldx + k);
           if (k + 1 >= D) xa.y = 0.f;
           if (k + 2 >= D) xa.z = 0.f;
           if (k + 3 >= D) xa.w = 0.f;
@@ -237,6 +245,7 @@ k_assign_simt(int64_t N, int K, int D, const float* __restrict__ X, int64_t ldx,
       int r = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
       int64_t gr = row0 + r;
       if (gr < N) {
+        if (rows) gr = rows[gr];
         labels[gr] = bidx[i];
         if (best_out) best_out[gr] = best[i];
         if (labels_prev && labels_prev[gr] != bidx[i]) ++changed;
@@ -248,6 +257,24 @@ k_assign_simt(int64_t N, int K, int D, const float* __restrict__ X, int64_t ldx,
     for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
     if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
   }
+}
+
+int launch_row_sqnorm(int64_t K, int D, const float* C, int64_t ldc, float* out, cudaStream_t s) {
+  k_row_sqnorm<<<(unsigned)cdiv(K, 8), 256, 0, s>>>(K, D, C, ldc, out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// exact re-score of a device-side row list (max_rows = capacity of the list)
+int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float* X, int64_t ldx,
+                            const float* C, int64_t ldc, const float* cnorm, const int32_t* rows,
+                            const int32_t* n_rows_dev, int32_t* labels, const int32_t* labels_prev,
+                            int32_t* n_changed, float* best_out, cudaStream_t s) {
+  k_assign_simt<<<(unsigned)cdiv(max_rows, AS_BM), AS_THREADS, 0, s>>>(
+      max_rows, (int)K, (int)D, X, ldx, C, ldc, cnorm, labels, labels_prev, n_changed, best_out, rows,
+      n_rows_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
 }
 
 // ----------------------------------------------------------------------------
@@ -569,7 +596,7 @@ int gdr_add_row_vector(int64_t rows, int64_t D, float* X, int64_t ldx, const flo
 
 int64_t gdr_kmeans_assign_ws_bytes(int64_t N, int64_t K, int64_t D, int precision_mode) {
   int64_t b = ws_need(K, 4) + 256;
-  if (precision_mode == 1) b += kmeans_assign_tc_ws_bytes(N, K, D);
+  if (precision_mode == 1) b = kmeans_assign_tc_total_ws_bytes(N, K, D);
   return b;
 }
 
@@ -600,7 +627,7 @@ int gdr_kmeans_assign(int64_t N, int64_t K, int64_t D, const float* X, int64_t l
   GDR_LAUNCHED();
   k_assign_simt<<<(unsigned)cdiv(N, AS_BM), AS_THREADS, 0, s>>>(N, (int)K, (int)D, X, ldx, C, ldc, cnorm,
                                                                labels, labels_prev, n_changed_dev,
-                                                               best_out);
+                                                               best_out, nullptr, nullptr);
   GDR_LAUNCHED();
   return GDR_OK;
 }

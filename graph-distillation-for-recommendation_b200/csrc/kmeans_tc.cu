@@ -1,16 +1,578 @@
-// kmeans_tc.cu — tensor-core (tcgen05 + TMA, 3xTF32) E-step.  Placeholder until
-// the exact-fp32 path is parity-green on the GPU; precision_mode 1 reports
-// GDR_EUNSUPPORTED so that nothing silently falls back.
+// kmeans_tc.cu — stage 3 E-step on the 5th-gen tensor cores (precision_mode 1).
+//
+//   d(i,j) = |c_j|^2 - 2 x_i . c_j          (sklearn/_k_means_lloyd.pyx:196-213)
+//
+// X.C^T is the only dense contraction of the distillation core.  Inputs are fp32 and
+// the contract is "labels bit-exact wherever the distance margin exceeds 1e-6", so the
+// GEMM runs as 3xTF32:  x = x_hi + x_lo, c = c_hi + c_lo (each a TF32 value),
+//   x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi        (fp32 accumulation in TMEM)
+// and every row whose best/second-best margin falls inside a proven error band is
+// re-scored by the exact fp32 SIMT kernel of kmeans.cu (screen-then-refine).
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-blocks of 32 floats
+//   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, one lane
+//   warps 2-5 epilogue      tcgen05.ld 32x32b.x32 -> +|c|^2 -> running (best, second, argmin)
+//   * the 128-row X tile (hi and lo) stays resident in shared memory while all centre
+//     tiles stream past it through a 3-stage mbarrier ring;
+//   * two 128-column fp32 accumulators in TMEM, so the argmin epilogue of centre tile t
+//     overlaps the MMAs of tile t+1.
 #include "common.cuh"
+#include <cuda.h>
 
 namespace gdr {
 
-int64_t kmeans_assign_tc_ws_bytes(int64_t, int64_t, int64_t) { return 256; }
+int launch_row_sqnorm(int64_t K, int D, const float* C, int64_t ldc, float* out, cudaStream_t s);
+int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float* X, int64_t ldx,
+                            const float* C, int64_t ldc, const float* cnorm, const int32_t* rows,
+                            const int32_t* n_rows_dev, int32_t* labels, const int32_t* labels_prev,
+                            int32_t* n_changed, float* best_out, cudaStream_t s);
 
-int kmeans_assign_tc(int64_t, int64_t, int64_t, const float*, int64_t, const float*, int64_t, int32_t*,
-                     const int32_t*, int32_t*, float*, void*, int64_t, cudaStream_t) {
-  set_error("kmeans_assign: precision_mode 1 (tcgen05) is not built into this library yet");
-  return GDR_EUNSUPPORTED;
+constexpr int TC_BM = 128;        // rows per tile (UMMA M)
+constexpr int TC_BN = 128;        // centres per tile (UMMA N)
+constexpr int TC_BK = 32;         // floats per K-block = one 128-byte swizzle row
+constexpr int TC_MAX_KB = 4;      // D padded <= 128
+constexpr int TC_STAGES = 3;      // centre-tile ring
+constexpr int TC_THREADS = 192;
+constexpr int TC_KBLK_BYTES = TC_BM * TC_BK * 4;  // 16 KB: one [128][32] fp32 block
+constexpr int TC_TMEM_COLS = 256;                 // two 128-column accumulators
+// error band of the 3xTF32 screen, relative to |x_i| * max_j |c_j|
+constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4   [16,30) LBO >> 4 (= 1, unused under swizzle)
+//   [32,46) SBO >> 4 (8 rows * 128 B = 1024 -> 64)   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------
+// hi/lo TF32 split (+ optional row norms); output rows padded to Dp with zeros
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_pad, int D, int Dp,
+                                                    const float* __restrict__ X, int64_t ldx,
+                                                    float* __restrict__ hi, float* __restrict__ lo,
+                                                    float* __restrict__ norm_out /*|x| per row, nullable*/) {
+  // one warp per row
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows_pad) return;
+  float s = 0.f;
+  for (int c = lane_id(); c < Dp; c += 32) {
+    float x = (r < rows && c < D) ? X[r * ldx + c] : 0.f;
+    float h = to_tf32(x);
+    float l = to_tf32(__fsub_rn(x, h));
+    hi[r * Dp + c] = h;
+    lo[r * Dp + c] = l;
+    s = fmaf(x, x, s);
+  }
+  if (norm_out && r < rows) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane_id() == 0) norm_out[r] = sqrtf(s);
+  }
+}
+
+// cnorm[j] for j >= K = +inf (padding centres can never win); cmax = max_j |c_j|
+__global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, float* __restrict__ cnorm,
+                                                       float* __restrict__ cmax) {
+  __shared__ float s_m[1024];
+  float m = 0.f;
+  for (int64_t j = threadIdx.x; j < Kp; j += 1024) {
+    if (j >= K) cnorm[j] = INFINITY;
+    else m = fmaxf(m, cnorm[j]);
+  }
+  s_m[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_m[threadIdx.x] = fmaxf(s_m[threadIdx.x], s_m[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cmax[0] = sqrtf(s_m[0]);
+}
+
+// ---------------------------------------------------------------------------------
+// the tensor-core kernel
+// ---------------------------------------------------------------------------------
+struct TcSmem {
+  // offsets into the 1024-aligned dynamic shared memory
+  __host__ __device__ static constexpr int x_hi(int kb) { return kb * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int x_lo(int nkb, int kb) { return (nkb + kb) * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return (2 * nkb + 2 * s) * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int bars(int nkb) { return (2 * nkb + 2 * TC_STAGES) * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1024; }  // + barriers + alignment slack
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
+            const __grid_constant__ CUtensorMap map_chi, const __grid_constant__ CUtensorMap map_clo,
+            int64_t N, int n_row_tiles, int n_col_tiles, int nkb, const float* __restrict__ cnorm,
+            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars(nkb));
+  uint64_t* x_full = bars;                     // [TC_MAX_KB]
+  uint64_t* x_empty = bars + TC_MAX_KB;        // [TC_MAX_KB]
+  uint64_t* c_full = bars + 2 * TC_MAX_KB;     // [TC_STAGES]
+  uint64_t* c_empty = c_full + TC_STAGES;      // [TC_STAGES]
+  uint64_t* t_full = c_empty + TC_STAGES;      // [2]
+  uint64_t* t_empty = t_full + 2;              // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < TC_MAX_KB; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t cit = 0, tile_it = 0;
+      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+          mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
+          tma_load_2d(smem + TcSmem::x_hi(kb), &map_xhi, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+          tma_load_2d(smem + TcSmem::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+        }
+        for (int ct = 0; ct < n_col_tiles; ++ct) {
+          for (int kb = 0; kb < nkb; ++kb, ++cit) {
+            const int s = cit % TC_STAGES;
+            const uint32_t ph = (cit / TC_STAGES) & 1;
+            mbar_wait(&c_empty[s], ph ^ 1);
+            mbar_expect_tx(&c_full[s], 2 * TC_KBLK_BYTES);
+            uint8_t* dst = smem + TcSmem::c_stage(nkb, s);
+            tma_load_2d(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s]);
+            tma_load_2d(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      uint32_t cit = 0, tile_it = 0, g = 0;
+      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+        for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+          const uint32_t a = g & 1, aph = (g >> 1) & 1;
+          mbar_wait(&t_empty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + a * TC_BN;
+          for (int kb = 0; kb < nkb; ++kb, ++cit) {
+            if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
+            const int s = cit % TC_STAGES;
+            const uint32_t ph = (cit / TC_STAGES) & 1;
+            mbar_wait(&c_full[s], ph);
+            tc_fence_after();
+            const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + TcSmem::x_hi(kb)));
+            const uint64_t d_xlo = umma_desc_sw128(smem_u32(smem + TcSmem::x_lo(nkb, kb)));
+            const uint64_t d_chi = umma_desc_sw128(smem_u32(smem + TcSmem::c_stage(nkb, s)));
+            const uint64_t d_clo = umma_desc_sw128(smem_u32(smem + TcSmem::c_stage(nkb, s) + TC_KBLK_BYTES));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step
+              // small terms first, the dominant hi*hi product last
+              tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
+              tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
+              tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+            }
+            tc_commit(&c_empty[s]);                                  // frees the centre stage
+            if (ct == n_col_tiles - 1) tc_commit(&x_empty[kb]);      // X K-block no longer needed
+          }
+          tc_commit(&t_full[a]);                                     // accumulator ready
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: 4 warps, one TMEM lane quarter each =================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
+    uint32_t g = 0;
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      float best = INFINITY, second = INFINITY;
+      int bidx = 0;
+      for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+        const uint32_t a = g & 1, aph = (g >> 1) & 1;
+        mbar_wait(&t_full[a], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * TC_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          uint32_t v[32];
+          tc_ld_32x32(taddr + c0, v);
+          tc_wait_ld();
+          const int jbase = ct * TC_BN + c0;
+          const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 cn = __ldg(cn4 + q);
+            const float cc[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float d = fmaf(-2.f, __uint_as_float(v[q * 4 + u]), cc[u]);
+              second = fminf(second, fmaxf(d, best));
+              bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
+              best = fminf(best, d);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[a]);
+      }
+      const int64_t row = (int64_t)rt * TC_BM + quarter * 32 + lane;
+      if (row < N) {
+        best_out[row] = best;
+        second_out[row] = second;
+        idx_out[row] = bidx;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// rows whose margin is inside the error band go to the exact re-score list
+__global__ void __launch_bounds__(256) k_tc_select(int64_t N, const float* __restrict__ best,
+                                                   const float* __restrict__ second,
+                                                   const int32_t* __restrict__ idx,
+                                                   const float* __restrict__ xnorm,
+                                                   const float* __restrict__ cmax, float band,
+                                                   int32_t* __restrict__ labels,
+                                                   const int32_t* __restrict__ labels_prev,
+                                                   int32_t* __restrict__ n_changed, float* __restrict__ best_out,
+                                                   int32_t* __restrict__ amb_list, int32_t* __restrict__ amb_count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int changed = 0;
+  if (i < N) {
+    float tol = band * xnorm[i] * cmax[0];
+    float b = best[i], s2 = second[i];
+    bool ambiguous = !(s2 - b > tol);  // also catches NaN / inf - inf
+    if (ambiguous) {
+      int slot = atomicAdd(amb_count, 1);
+      amb_list[slot] = (int32_t)i;
+    } else {
+      int l = idx[i];
+      labels[i] = l;
+      if (best_out) best_out[i] = b;
+      if (labels_prev && labels_prev[i] != l) changed = 1;
+    }
+  }
+  if (n_changed) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+    if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+// [rows][Dp] fp32 row-major, box = [box_rows][32 floats], 128B swizzle, OOB rows read as zero
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int Dp, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return GDR_ECUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Dp * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
+    return GDR_ECUDA;
+  }
+  return GDR_OK;
+}
+
+static inline int dpad(int64_t D) { return (int)align_up(D, TC_BK); }
+
+int64_t kmeans_tc_xsplit_bytes(int64_t N, int64_t D) {
+  int Dp = dpad(D);
+  return 2 * ws_need(N * Dp, 4) + ws_need(N, 4) + 256;
+}
+
+struct XSplit {
+  float *hi, *lo, *norm;
+};
+static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
+  Workspace W(buf, kmeans_tc_xsplit_bytes(N, D));
+  XSplit x;
+  int Dp = dpad(D);
+  x.hi = W.take<float>(N * Dp);
+  x.lo = W.take<float>(N * Dp);
+  x.norm = W.take<float>(N);
+  return x;
+}
+
+int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, cudaStream_t s) {
+  XSplit x = carve_xsplit(xsplit, N, D);
+  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
+  int Dp = dpad(D);
+  int64_t Kp = align_up(K, TC_BN);
+  return 2 * ws_need(Kp * Dp, 4) + ws_need(Kp, 4) + 256 /*cmax*/ + 3 * ws_need(N, 4) /*best, second, idx*/ +
+         ws_need(N, 4) /*amb list*/ + 256 /*amb count*/ + 256;
+}
+
+int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const void* xsplit,
+                         const float* C, int64_t ldc, int32_t* labels, const int32_t* labels_prev,
+                         int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev, void* ws,
+                         int64_t ws_bytes, cudaStream_t s) {
+  if (D > TC_MAX_KB * TC_BK) {
+    set_error("kmeans_assign(tc): D=%lld > %d is not supported by the tensor-core path", (long long)D,
+              TC_MAX_KB * TC_BK);
+    return GDR_EUNSUPPORTED;
+  }
+  if (N >= (1ll << 31) - TC_BM || K >= (1ll << 31) - TC_BN) {
+    set_error("kmeans_assign(tc): N or K exceeds int32 tile coordinates");
+    return GDR_ERANGE;
+  }
+  const int Dp = dpad(D);
+  const int nkb = Dp / TC_BK;
+  const int64_t Kp = align_up(K, TC_BN);
+  XSplit xs = carve_xsplit(const_cast<void*>(xsplit), N, D);
+  Workspace W(ws, ws_bytes);
+  float* c_hi = W.take<float>(Kp * Dp);
+  float* c_lo = W.take<float>(Kp * Dp);
+  float* cnorm = W.take<float>(Kp);
+  float* cmax = W.take<float>(1);
+  float* best = W.take<float>(N);
+  float* second = W.take<float>(N);
+  int32_t* idx = W.take<int32_t>(N);
+  int32_t* amb_list = W.take<int32_t>(N);
+  int32_t* amb_count = n_refined_dev ? n_refined_dev : W.take<int32_t>(1);
+  if (!W.ok()) {
+    set_error("kmeans_assign(tc): workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  // per-iteration centre preparation: split, norms, padding
+  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr);
+  GDR_LAUNCHED();
+  int rc = launch_row_sqnorm(K, (int)D, C, ldc, cnorm, s);
+  if (rc) return rc;
+  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cmax);
+  GDR_LAUNCHED();
+  GDR_CUDA(cudaMemsetAsync(amb_count, 0, 4, s));
+
+  CUtensorMap m_xhi, m_xlo, m_chi, m_clo;
+  if ((rc = make_map(&m_xhi, xs.hi, N, Dp, TC_BM))) return rc;
+  if ((rc = make_map(&m_xlo, xs.lo, N, Dp, TC_BM))) return rc;
+  if ((rc = make_map(&m_chi, c_hi, Kp, Dp, TC_BN))) return rc;
+  if ((rc = make_map(&m_clo, c_lo, Kp, Dp, TC_BN))) return rc;
+
+  const int n_row_tiles = (int)cdiv(N, TC_BM);
+  const int n_col_tiles = (int)(Kp / TC_BN);
+  const int smem_bytes = TcSmem::total(nkb);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
+    attr_set = true;
+  }
+  int sms = kSMs;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = n_row_tiles < sms ? n_row_tiles : sms;
+  k_assign_tc<<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
+                                                  cnorm, best, second, idx);
+  GDR_LAUNCHED();
+  k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
+                                                    labels_prev, n_changed_dev, best_out, amb_list, amb_count);
+  GDR_LAUNCHED();
+  // exact fp32 re-score of the ambiguous rows (list length stays on the device)
+  return launch_assign_simt_rows(N, K, D, X, ldx, C, ldc, cnorm, amb_list, amb_count, labels, labels_prev,
+                                 n_changed_dev, best_out, s);
+}
+
+// gdr_kmeans_assign(precision_mode = 1): split X into the tail of the workspace, then run
+int64_t kmeans_assign_tc_total_ws_bytes(int64_t N, int64_t K, int64_t D) {
+  return kmeans_assign_tc_ws_bytes(N, K, D) + kmeans_tc_xsplit_bytes(N, D);
+}
+
+int kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const float* C, int64_t ldc,
+                     int32_t* labels, const int32_t* labels_prev, int32_t* n_changed_dev, float* best_out,
+                     void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < kmeans_assign_tc_total_ws_bytes(N, K, D)) {
+    set_error("kmeans_assign(tc): workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  char* xsplit = (char*)ws + kmeans_assign_tc_ws_bytes(N, K, D);
+  int rc = kmeans_tc_prepare(N, D, X, ldx, xsplit, s);
+  if (rc) return rc;
+  return kmeans_assign_tc_run(N, K, D, X, ldx, xsplit, C, ldc, labels, labels_prev, n_changed_dev, best_out,
+                              nullptr, ws, kmeans_assign_tc_ws_bytes(N, K, D), s);
 }
 
 }  // namespace gdr
+
+extern "C" {
+
+int64_t gdr_kmeans_tc_xsplit_bytes(int64_t N, int64_t D) { return gdr::kmeans_tc_xsplit_bytes(N, D); }
+
+int gdr_kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, int64_t xsplit_bytes,
+                          gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && D > 0 && X && xsplit && ldx >= D, "kmeans_tc_prepare: bad arguments");
+  GDR_CHECK_ARG(D <= gdr::TC_MAX_KB * gdr::TC_BK, "kmeans_tc_prepare: D > 128 is not supported by the tensor-core path");
+  if (xsplit_bytes < gdr::kmeans_tc_xsplit_bytes(N, D)) {
+    gdr::set_error("kmeans_tc_prepare: buffer too small");
+    return GDR_EWORKSPACE;
+  }
+  return gdr::kmeans_tc_prepare(N, D, X, ldx, xsplit, (cudaStream_t)stream);
+}
+
+int64_t gdr_kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
+  return gdr::kmeans_assign_tc_ws_bytes(N, K, D);
+}
+
+int gdr_kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const void* xsplit,
+                         const float* C, int64_t ldc, int32_t* labels, const int32_t* labels_prev,
+                         int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev, void* ws,
+                         int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && K > 0 && D > 0 && X && xsplit && C && labels && ws, "kmeans_assign_tc: bad arguments");
+  GDR_CHECK_ARG(ldx % 4 == 0 && ldc % 4 == 0 && ldx >= D && ldc >= D && ((uintptr_t)X & 15) == 0 &&
+                    ((uintptr_t)C & 15) == 0,
+                "kmeans_assign_tc: X/C need 16B alignment and ld %% 4 == 0");
+  if (ws_bytes < gdr::kmeans_assign_tc_ws_bytes(N, K, D)) {
+    gdr::set_error("kmeans_assign_tc: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  return gdr::kmeans_assign_tc_run(N, K, D, X, ldx, xsplit, C, ldc, labels, labels_prev, n_changed_dev, best_out,
+                                   n_refined_dev, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

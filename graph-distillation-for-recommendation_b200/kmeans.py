@@ -44,7 +44,12 @@ class _Scratch:
         self.counts = torch.zeros(K, dtype=torch.int32, device=device)
         self.n_changed = torch.zeros(1, dtype=torch.int32, device=device)
         self.stats = torch.zeros(2 + K, dtype=torch.float64, device=device)
-        self.ws_assign = workspace(_lib.query("gdr_kmeans_assign_ws_bytes", N, K, D, precision_mode), device)
+        if precision_mode == 1:
+            self.ws_assign = workspace(_lib.query("gdr_kmeans_assign_tc_ws_bytes", N, K, D), device)
+        else:
+            self.ws_assign = workspace(_lib.query("gdr_kmeans_assign_ws_bytes", N, K, D, 0), device)
+        self.tc = None           # TcOperand of the centred X (tensor-core mode)
+        self.n_refined = torch.zeros(1, dtype=torch.int32, device=device)
         self.ws_seg = workspace(_lib.query("gdr_segment_sum_ws_bytes", N, K, D), device)
         self.ws_misc = workspace(
             max(_lib.query("gdr_inertia_ws_bytes", N, D), _lib.query("gdr_kmeans_relocate_ws_bytes", N, K, D)),
@@ -53,12 +58,32 @@ class _Scratch:
         self.host_i = torch.empty(1, dtype=torch.int32).pin_memory()
 
 
+class TcOperand:
+    """Cached TF32 hi/lo split of X for the tensor-core E-step (X is constant across the
+    Lloyd iterations, so the split is done once per fit)."""
+
+    def __init__(self, X: torch.Tensor):
+        N, D = X.shape
+        self.N, self.D = N, D
+        self.buf = workspace(_lib.query("gdr_kmeans_tc_xsplit_bytes", N, D), X.device)
+        _lib.call("gdr_kmeans_tc_prepare", N, D, ptr(X), X.stride(0), ptr(self.buf), self.buf.numel(), stream())
+
+
 def assign_labels(X: torch.Tensor, C: torch.Tensor, labels: torch.Tensor, *, labels_prev=None,
-                  n_changed=None, best=None, precision_mode: int = 0, ws: Optional[torch.Tensor] = None):
+                  n_changed=None, best=None, precision_mode: int = 0, ws: Optional[torch.Tensor] = None,
+                  tc_operand: Optional[TcOperand] = None, n_refined=None):
     """E-step: labels[i] = argmin_j |c_j|^2 - 2 x_i.c_j (first index wins).  X, C must be
-    row-padded (see _dev.padded_rows)."""
+    row-padded (see _dev.padded_rows).  With ``tc_operand`` the tcgen05 3xTF32 kernel runs
+    on the cached split and ambiguous rows are re-scored in exact fp32."""
     N, D = X.shape
     K = C.shape[0]
+    if tc_operand is not None:
+        if ws is None:
+            ws = workspace(_lib.query("gdr_kmeans_assign_tc_ws_bytes", N, K, D), X.device)
+        _lib.call("gdr_kmeans_assign_tc", N, K, D, ptr(X), X.stride(0), ptr(tc_operand.buf), ptr(C), C.stride(0),
+                  ptr(labels), ptr(labels_prev), ptr(n_changed), ptr(best), ptr(n_refined), ptr(ws), ws.numel(),
+                  stream())
+        return labels
     if ws is None:
         ws = workspace(_lib.query("gdr_kmeans_assign_ws_bytes", N, K, D, precision_mode), X.device)
     _lib.call("gdr_kmeans_assign", N, K, D, ptr(X), X.stride(0), ptr(C), C.stride(0), ptr(labels),
@@ -205,7 +230,8 @@ class KMeans:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             assign_labels(Xc, S.centers[cur], S.labels[lab_new], labels_prev=S.labels[lab_old],
-                          n_changed=S.n_changed, precision_mode=S.mode, ws=S.ws_assign)
+                          n_changed=S.n_changed, precision_mode=S.mode, ws=S.ws_assign, tc_operand=S.tc,
+                          n_refined=S.n_refined if S.tc is not None else None)
             if ev is not None:
                 e1.record()
                 ev.append((e0, e1))
@@ -234,7 +260,7 @@ class KMeans:
         labels = S.labels[lab_new]
         if not strict:
             # rerun the E-step so that labels match the final centres (:742-754)
-            assign_labels(Xc, S.centers[cur], labels, precision_mode=S.mode, ws=S.ws_assign)
+            assign_labels(Xc, S.centers[cur], labels, precision_mode=S.mode, ws=S.ws_assign, tc_operand=S.tc)
         inertia_dev = S.stats[0:1]
         _lib.call("gdr_inertia", N, D, ptr(Xc), Xc.stride(0), ptr(S.centers[cur]), S.centers[cur].stride(0),
                   ptr(labels), ptr(inertia_dev), ptr(S.ws_misc), S.ws_misc.numel(), stream())
@@ -282,6 +308,8 @@ class KMeans:
         if init_is_array:
             n_init = 1
         S = _Scratch(N, K, D, dev, mode)
+        if mode == 1:
+            S.tc = TcOperand(Xc)
         best = None
         for _ in range(int(n_init)):
             C0 = self._init_centers(Xc, mean, rs)
@@ -309,7 +337,7 @@ class KMeans:
             raise ValueError("X has a different number of features than the fitted model")
         Xp = padded_rows(Xd)
         labels = torch.empty(Xd.shape[0], dtype=torch.int32, device=Xd.device)
-        assign_labels(Xp, padded_rows(self._centers_dev), labels, precision_mode=self._mode())
+        assign_labels(Xp, padded_rows(self._centers_dev), labels, precision_mode=0)
         return self._out(labels)
 
 

@@ -180,6 +180,24 @@ int     gdr_kmeans_assign(int64_t N, int64_t K, int64_t D,
                           int precision_mode,
                           void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
+/* Tensor-core E-step with a cached operand split (the Lloyd loop calls prepare once per
+ * fit, X being constant across iterations, then assign_tc every iteration):
+ *   prepare: X -> (X_hi, X_lo) TF32 pair, rows zero-padded to a multiple of 32 floats, + |x_i|.
+ *   assign_tc: 3xTF32 tcgen05/TMA GEMM with fused |c|^2 add and (best, second, argmin)
+ *   epilogue; rows whose margin second-best is within 2^-15 |x_i| max|c_j| are re-scored by
+ *   the exact fp32 kernel.  *n_refined_dev (nullable) receives how many rows that was.
+ *   Supports D <= 128 (GDR_EUNSUPPORTED otherwise). */
+int64_t gdr_kmeans_tc_xsplit_bytes(int64_t N, int64_t D);
+int     gdr_kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx,
+                              void* xsplit, int64_t xsplit_bytes, gdr_stream_t stream);
+int64_t gdr_kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D);
+int     gdr_kmeans_assign_tc(int64_t N, int64_t K, int64_t D,
+                             const float* X, int64_t ldx, const void* xsplit,
+                             const float* C, int64_t ldc,
+                             int32_t* labels, const int32_t* labels_prev,
+                             int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev,
+                             void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
 /* M-step, part 1: per-cluster sums and counts.
  *   replaces  centers_new[label] += X[i]; weight[label] += 1
  *                                                 sklearn/_k_means_lloyd.pyx:215-218

@@ -1,0 +1,69 @@
+"""Tensor-core (tcgen05 3xTF32 + exact re-score) E-step against the oracle.  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gdr():
+    import gdr as g
+    assert torch.cuda.is_available()
+    return g
+
+
+DEV = "cuda:0"
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("N,K,D", [(128, 128, 32), (300, 7, 3), (5000, 140, 7), (4099, 129, 100), (20000, 1000, 40),
+                                   (20000, 333, 128), (1, 1, 1)])
+def test_tc_assign_vs_oracle(gdr, oracle, N, K, D):
+    from gdr import synth
+    from gdr._dev import padded_rows
+    from gdr.kmeans import TcOperand
+    X = synth.clustered_features(N, D, max(2, K // 3), seed=N + K)
+    X -= X.mean(axis=0)
+    C = synth.kmeans_init(X, K, seed=1)
+    Xd, Cd = padded_rows(torch.from_numpy(X).to(DEV)), padded_rows(torch.from_numpy(C).to(DEV))
+    op = TcOperand(Xd)
+    labels = torch.full((N,), -7, dtype=torch.int32, device=DEV)
+    best = torch.full((N,), float("nan"), dtype=torch.float32, device=DEV)
+    n_ref = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(Xd, Cd, labels, best=best, tc_operand=op, n_refined=n_ref)
+    torch.cuda.synchronize()
+    lab = np_(labels)
+    assert lab.min() >= 0 and lab.max() < K
+    ok, n_band, n_bad = oracle.labels_match(lab, X, C, band=1e-6)
+    assert ok, f"{n_bad} rows outside the 1e-6 margin band disagree with the exact argmin"
+    l32, b32 = oracle.kmeans_assign(X, C)
+    np.testing.assert_allclose(np_(best), b32, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(b32).max()))
+    # the screen must decide most rows on its own (refine set small on well-separated data)
+    assert int(n_ref.item()) <= max(64, N // 5)
+    # and the result equals the exact-fp32 kernel's labels
+    lab32 = torch.empty(N, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(Xd, Cd, lab32)
+    assert np.array_equal(np_(lab32), lab)
+
+
+def test_tc_full_fit_matches_fp32_path(gdr):
+    from gdr import synth
+    N, K, D = 30000, 500, 64
+    X = synth.clustered_features(N, D, 200, seed=5)
+    C0 = synth.kmeans_init(X, K, seed=2)
+    a = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=8, tol=0, precision="fp32").fit(X)
+    b = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=8, tol=0, precision="tc").fit(X)
+    assert a.n_iter_ == b.n_iter_
+    assert np.array_equal(a.labels_, b.labels_)
+    np.testing.assert_array_equal(a.cluster_centers_, b.cluster_centers_)
+    assert a.inertia_ == b.inertia_
+
+
+def test_tc_unsupported_width_fails_loudly(gdr):
+    x = torch.randn(1000, 200, device=DEV)
+    with pytest.raises(gdr.GdrError):
+        gdr.KMeans(n_clusters=10, init="random", random_state=0, precision="tc", max_iter=2).fit(x)
