@@ -46,17 +46,47 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
+        self.nvml = None
+        try:  # in-process NVML: no fork, negligible GIL time (a forked nvidia-smi stalls the launch thread)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), str(pw), flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.05 if self.nvml is not None else 0.5)
 
     def stop(self):
         self._stop_ev.set()
@@ -197,7 +227,6 @@ def run_ours(args, rank, world):
         prop, target = gdr.propagate(An, X_d, hops + 1, ALPHA)
         e[2].record()
         km = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision)
-        km._assign_events = [] if record else None
         km.fit(target)
         e[3].record()
         _, adj_syn = gdr.graph_compress(km.labels_, An, [])
@@ -210,6 +239,9 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    import ctypes
+    from gdr import _lib
+    _lib.call("gdr_profile_enable", 1)   # CUDA-event pair around every E-step main-kernel launch (its own stream)
     launches0 = gdr.launch_count()
     recs = []
     t_wall0 = time.perf_counter()
@@ -221,12 +253,27 @@ def run_ours(args, rank, world):
     t_wall = time.perf_counter() - t_wall0
     launches = gdr.launch_count() - launches0
     clocks = sampler.stop()
+    tot_ms, n_l = ctypes.c_double(0), ctypes.c_int64(0)
+    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
+    _lib.call("gdr_profile_enable", 0)
+    assign_ms = np.array([tot_ms.value / max(1, n_l.value)])
+    assign_total_ms = tot_ms.value
 
     st = np.array([[r[0][i].elapsed_time(r[0][i + 1]) for i in range(4)] for r in recs])  # ms per stage
     step_ms = st.sum(axis=1)
     n_iter = [r[1].n_iter_ for r in recs]
-    assign_ms = np.array([a.elapsed_time(b) for r in recs for (a, b) in r[1]._assign_events])
     km_ms = st[:, 2]
+
+    # SpMM kernel time alone (same event mechanism, separate short loop: hops only)
+    A_t = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
+    _lib.call("gdr_profile_enable", 2)
+    for _ in range(5):
+        flush.fill_(1)
+        gdr.propagate(A_t, X_d, hops + 1, ALPHA)
+    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
+    _lib.call("gdr_profile_enable", 0)
+    spmm_kernel_ms = tot_ms.value / max(1, n_l.value)
+    del A_t
     iters_per_s = float(np.sum(n_iter) / (km_ms.sum() / 1e3))
     prop_ms = st[:, 1]
     b_hop = spmm_bytes(nnz, n, n, F)
@@ -261,8 +308,8 @@ def run_ours(args, rank, world):
                 "bound": "tensor", "achieved": a_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": a_tf / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
                 "note": "useful flops 2NKD per launch; fp32 inputs: TF32 rate = 1/2 bf16, 3xTF32 emulation ceiling = peak/6",
-                "launch_ms": float(assign_ms.mean()), "share_of_step": float(assign_ms.sum() / step_ms.sum())}
-    spmm_ms = prop_ms.mean() * (hops * b_hop / b_prop) / hops
+                "launch_ms": float(assign_ms.mean()), "share_of_step": float(assign_total_ms / step_ms.sum())}
+    spmm_ms = spmm_kernel_ms
     roofline_spmm = {"kernel": "k_spmm", "bound": "hbm", "achieved": float(b_hop / (spmm_ms / 1e3) / 1e9), "peak": pk["hbm"],
                      "unit": "GB/s", "frac": float(b_hop / (spmm_ms / 1e3) / 1e9 / pk["hbm"]), "traffic": None,
                      "bytes_model": "B_min (X fits L2)", "b_gather_gbs": float(spmm_bytes(nnz, n, n, F, model='gather') / (spmm_ms / 1e3) / 1e9),
@@ -313,11 +360,11 @@ def cpu_baseline(w, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no CPU baseline, minimal e2e leg")

@@ -21,6 +21,8 @@ _SIGNATURES = {
     "gdr_last_error": (cp, []),
     "gdr_device_info": (i32, [vp, vp, vp]),
     "gdr_launch_count": (i64, []),
+    "gdr_profile_enable": (i32, [i32]),
+    "gdr_profile_collect": (i32, [vp, vp]),
     "gdr_sort_pairs_ws_bytes": (i64, [i64]),
     "gdr_sort_pairs": (i32, [i64, i32, vp, vp, vp, i64, vp]),
     "gdr_coo_to_csr_ws_bytes": (i64, [i64, i64, i64, i32]),
@@ -43,6 +45,8 @@ _SIGNATURES = {
     "gdr_kmeans_tc_prepare": (i32, [i64, i64, vp, i64, vp, i64, vp]),
     "gdr_kmeans_assign_tc_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_kmeans_assign_tc": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_kmeans_lloyd_ws_bytes": (i64, [i64, i64, i64, i32]),
+    "gdr_kmeans_lloyd": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i32, C.c_double, i32, vp, vp, vp, i32, vp, i64, vp]),
     "gdr_segment_sum_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_segment_sum": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
     "gdr_label_histogram": (i32, [i64, i64, vp, vp, vp, vp]),

@@ -42,6 +42,16 @@ void count_launch(int n = 1);
     }                                                                             \
   } while (0)
 
+// kernel kinds for gdr_profile_enable()
+constexpr int PROF_ASSIGN = 1;  // the E-step main kernel (k_assign_tc / k_assign_simt over all rows)
+constexpr int PROF_SPMM = 2;    // k_spmm (propagation hops and the M-step gather-sum)
+struct ProfileScope {
+  ProfileScope(int kind, cudaStream_t s);
+  ~ProfileScope();
+  void* stop_;
+  cudaStream_t stream_;
+};
+
 constexpr int kSMs = 148;  // B200
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -625,9 +625,12 @@ int gdr_kmeans_assign(int64_t N, int64_t K, int64_t D, const float* X, int64_t l
   float* cnorm = W.take<float>(K);
   k_row_sqnorm<<<(unsigned)cdiv(K, 8), 256, 0, s>>>(K, (int)D, C, ldc, cnorm);
   GDR_LAUNCHED();
-  k_assign_simt<<<(unsigned)cdiv(N, AS_BM), AS_THREADS, 0, s>>>(N, (int)K, (int)D, X, ldx, C, ldc, cnorm,
-                                                               labels, labels_prev, n_changed_dev,
-                                                               best_out, nullptr, nullptr);
+  {
+    ProfileScope prof(PROF_ASSIGN, s);
+    k_assign_simt<<<(unsigned)cdiv(N, AS_BM), AS_THREADS, 0, s>>>(N, (int)K, (int)D, X, ldx, C, ldc, cnorm,
+                                                                 labels, labels_prev, n_changed_dev,
+                                                                 best_out, nullptr, nullptr);
+  }
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -508,8 +508,11 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = n_row_tiles < sms ? n_row_tiles : sms;
-  k_assign_tc<<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
-                                                  cnorm, best, second, idx);
+  {
+    ProfileScope prof(PROF_ASSIGN, s);
+    k_assign_tc<<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
+                                                    cnorm, best, second, idx);
+  }
   GDR_LAUNCHED();
   k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
                                                     labels_prev, n_changed_dev, best_out, amb_list, amb_count);

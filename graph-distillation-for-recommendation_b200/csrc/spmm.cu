@@ -146,8 +146,11 @@ static int launch_spmm(int64_t rows, int F4, const int32_t* rowptr, const int32_
                        int64_t ldy, float* T, int64_t ldt, float beta, int col4_base,
                        cudaStream_t s) {
   unsigned grid = (unsigned)cdiv(rows, SPMM_ROWS_PER_CTA);
-  k_spmm<LPR, NCH><<<grid, SPMM_THREADS, 0, s>>>(rows, F4, rowptr, colidx, vals, alpha, X, ldx, Y,
-                                                 ldy, T, ldt, beta, col4_base);
+  {
+    ProfileScope prof(PROF_SPMM, s);
+    k_spmm<LPR, NCH><<<grid, SPMM_THREADS, 0, s>>>(rows, F4, rowptr, colidx, vals, alpha, X, ldx, Y,
+                                                   ldy, T, ldt, beta, col4_base);
+  }
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -147,7 +147,7 @@ class KMeans:
     """
 
     def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4,
-                 verbose=0, random_state=None, copy_x=True, algorithm="lloyd", precision="fp32",
+                 verbose=0, random_state=None, copy_x=True, algorithm="lloyd", precision="auto",
                  device=None):
         self.n_clusters = n_clusters
         self.init = init
@@ -162,9 +162,14 @@ class KMeans:
         self.device = device
 
     # -- helpers -------------------------------------------------------------------
-    def _mode(self) -> int:
-        if self.precision not in ("fp32", "tc"):
-            raise ValueError("precision must be 'fp32' or 'tc'")
+    def _mode(self, D: Optional[int] = None) -> int:
+        """0 = exact fp32 SIMT E-step, 1 = tcgen05 3xTF32 screen + exact re-score.  "auto" picks
+        the tensor-core kernel whenever the feature width fits its shared-memory plan (D <= 128);
+        both produce the same labels (tests/test_gpu_tc.py)."""
+        if self.precision not in ("fp32", "tc", "auto"):
+            raise ValueError("precision must be 'auto', 'fp32' or 'tc'")
+        if self.precision == "auto":
+            return 1 if (D is not None and D <= 128) else 0
         return 1 if self.precision == "tc" else 0
 
     def _to_device(self, X):
@@ -267,6 +272,26 @@ class KMeans:
         inertia = float(inertia_dev.item())
         return labels.clone(), inertia, S.centers[cur].clone(), n_iter
 
+    def _lloyd_native(self, Xc: torch.Tensor, C0: torch.Tensor, tol_abs: float, mode: int):
+        """One Lloyd run inside libgdr_b200 (gdr_kmeans_lloyd): same control flow as
+        ``_lloyd`` below, but the ~20 launches per iteration are issued from C++."""
+        N, D = Xc.shape
+        K = int(self.n_clusters)
+        centers = new_padded(K, D, Xc.device, zero=True)
+        centers.copy_(C0)
+        labels = torch.empty(N, dtype=torch.int32, device=Xc.device)
+        ws = workspace(_lib.query("gdr_kmeans_lloyd_ws_bytes", N, K, D, mode), Xc.device)
+        import ctypes
+        inertia = ctypes.c_double(0.0)
+        n_iter = ctypes.c_int32(0)
+        info = (ctypes.c_int32 * 2)()
+        _lib.call("gdr_kmeans_lloyd", N, K, D, ptr(Xc), Xc.stride(0), ptr(centers), centers.stride(0), ptr(labels),
+                  int(self.max_iter), float(tol_abs), mode, ctypes.addressof(inertia), ctypes.addressof(n_iter),
+                  ctypes.addressof(info), int(bool(self.verbose)), ptr(ws), ws.numel(), stream())
+        self._strict_convergence = bool(info[0])
+        self._relocations = int(info[1])
+        return labels, float(inertia.value), centers, int(n_iter.value)
+
     @staticmethod
     def _finalize(S: _Scratch, cur: int, nxt: int):
         _lib.call("gdr_kmeans_finalize", S.K, S.D, ptr(S.sums), S.sums.stride(0), ptr(S.counts),
@@ -287,7 +312,7 @@ class KMeans:
         if N < K:
             raise ValueError(f"n_samples={N} should be >= n_clusters={K}.")
         dev = Xd.device
-        mode = self._mode()
+        mode = self._mode(D)
         rs = _check_random_state(self.random_state)
 
         # X -= X.mean(0) ; tol' = mean(var(X, axis=0)) * tol   (:1487-1489, :285-293)
@@ -307,13 +332,18 @@ class KMeans:
             n_init = 1 if (init_is_array or self.init == "k-means++") else 10
         if init_is_array:
             n_init = 1
-        S = _Scratch(N, K, D, dev, mode)
-        if mode == 1:
-            S.tc = TcOperand(Xc)
+        stepwise = getattr(self, "_assign_events", None) is not None  # Python loop only when instrumented
+        if stepwise:
+            S = _Scratch(N, K, D, dev, mode)
+            if mode == 1:
+                S.tc = TcOperand(Xc)
         best = None
         for _ in range(int(n_init)):
             C0 = self._init_centers(Xc, mean, rs)
-            labels, inertia, centers, n_iter = self._lloyd(Xc, C0, tol_abs, S)
+            if stepwise:
+                labels, inertia, centers, n_iter = self._lloyd(Xc, C0, tol_abs, S)
+            else:
+                labels, inertia, centers, n_iter = self._lloyd_native(Xc, C0, tol_abs, mode)
             if best is None or inertia < best[1]:
                 best = (labels, inertia, centers, n_iter)
         labels, inertia, centers, n_iter = best
@@ -356,7 +386,7 @@ def standard_scale(X: torch.Tensor) -> torch.Tensor:
 
 
 def kmeans_cluster(X, n_clusters: int, seed: int, minibatch: bool = True, batch_size: int = 2048,
-                   init="k-means++", device=None, precision: str = "fp32"):
+                   init="k-means++", device=None, precision: str = "auto"):
     """distill_recsys.py:158-181 — returns (labels int64[N], centers f32[K, D]) as numpy.
 
     z-scores the columns, then clusters.  The reference switches to MiniBatchKMeans above

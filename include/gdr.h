@@ -58,6 +58,13 @@ int         gdr_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * load (all threads); used by bench.py for "gpu_launches". */
 int64_t     gdr_launch_count(void);
 
+/* Optional kernel timing for bench.py's roofline leg: kind 1 = the k-means E-step main
+ * kernel, 2 = the CSR SpMM; 0 = off.  Every launch of that kind is bracketed by a CUDA
+ * event pair on its stream; collect() synchronises those events and returns the summed
+ * device time and the number of launches. */
+int gdr_profile_enable(int kind);
+int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
+
 /* ---- generic device primitives (used by stages 1, 3, 4) -------------- */
 /* Stable LSD radix sort of (uint64 key, uint32 payload) pairs on the low
  * `key_bits` bits.  Result is left in keys_io / vals_io. */
@@ -197,6 +204,19 @@ int     gdr_kmeans_assign_tc(int64_t N, int64_t K, int64_t D,
                              int32_t* labels, const int32_t* labels_prev,
                              int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev,
                              void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* One complete Lloyd run from given (already mean-centred) initial centres — the loop of
+ * _kmeans_single_lloyd (sklearn/_kmeans.py:630-758) behind KMeans(...).fit()
+ * (clustgdd_agent_transduct.py:105, distill_recsys.py:178).  C_inout holds the initial
+ * centres on entry and the final centres on return; labels_out int32[N] (device).
+ * inertia / n_iter / info[2] = {strict_convergence, relocation_rounds} are HOST outputs.
+ * SYNCHRONISES the stream once per iteration (24-byte convergence status). */
+int64_t gdr_kmeans_lloyd_ws_bytes(int64_t N, int64_t K, int64_t D, int precision_mode);
+int     gdr_kmeans_lloyd(int64_t N, int64_t K, int64_t D, const float* Xc, int64_t ldx,
+                         float* C_inout, int64_t ldc, int32_t* labels_out,
+                         int max_iter, double tol_abs, int precision_mode,
+                         double* inertia_out_host, int32_t* n_iter_out_host, int32_t* info_out_host,
+                         int verbose, void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
 /* M-step, part 1: per-cluster sums and counts.
  *   replaces  centers_new[label] += X[i]; weight[label] += 1
