@@ -265,16 +265,132 @@ int launch_row_sqnorm(int64_t K, int D, const float* C, int64_t ldc, float* out,
   return GDR_OK;
 }
 
-// exact re-score of a device-side row list (max_rows = capacity of the list)
+// Exact re-score of a short device-side row list: one CTA per listed row (persistent,
+// grid-strided), its threads split the K centres.  Every (row, centre) distance is the SAME
+// fp32 chain k_assign_simt evaluates — acc = fmaf(x_k, c_k, acc) for k ascending, then
+// fmaf(-2, acc, |c|^2) — so a re-scored row gets exactly the label the full exact kernel
+// would give it.  (The tiled kernel would put all listed rows into a few 128-row CTAs that
+// walk all K centres serially: 170 us for 50 rows at config B.)
+constexpr int RF_THREADS = 128;
+
+__global__ void __launch_bounds__(RF_THREADS) k_refine_rows(int K, int D, const float* __restrict__ X,
+                                                            int64_t ldx, const float* __restrict__ C,
+                                                            int64_t ldc, const float* __restrict__ cnorm,
+                                                            const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ n_rows_dev,
+                                                            int32_t* __restrict__ labels,
+                                                            const int32_t* __restrict__ labels_prev,
+                                                            int32_t* __restrict__ n_changed,
+                                                            float* __restrict__ best_out) {
+  extern __shared__ float s_x[];  // D floats (rounded up to 4)
+  __shared__ float s_best[RF_THREADS];
+  __shared__ int s_idx[RF_THREADS];
+  const int n_rows = *n_rows_dev;
+  const int D4 = (D + 3) / 4;
+  for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
+    const int64_t row = rows[q];
+    for (int k4 = threadIdx.x; k4 < D4; k4 += RF_THREADS) {
+      float4 v = *reinterpret_cast<const float4*>(X + row * ldx + 4 * k4);
+      if (4 * k4 + 1 >= D) v.y = 0.f;
+      if (4 * k4 + 2 >= D) v.z = 0.f;
+      if (4 * k4 + 3 >= D) v.w = 0.f;
+      *reinterpret_cast<float4*>(&s_x[4 * k4]) = v;
+    }
+    __syncthreads();
+    float best = INFINITY;
+    int bidx = 0x7fffffff;
+    for (int j = threadIdx.x; j < K; j += RF_THREADS) {
+      const float* c = C + (int64_t)j * ldc;
+      float acc = 0.f;
+      for (int k4 = 0; k4 < D4; ++k4) {
+        float4 cv = __ldg(reinterpret_cast<const float4*>(c + 4 * k4));
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[4 * k4]);
+        if (4 * k4 + 1 >= D) cv.y = 0.f;
+        if (4 * k4 + 2 >= D) cv.z = 0.f;
+        if (4 * k4 + 3 >= D) cv.w = 0.f;
+        acc = fmaf(xv.x, cv.x, acc);
+        acc = fmaf(xv.y, cv.y, acc);
+        acc = fmaf(xv.z, cv.z, acc);
+        acc = fmaf(xv.w, cv.w, acc);
+      }
+      const float d = fmaf(-2.f, acc, __ldg(cnorm + j));
+      if (d < best) {  // ascending j per thread: first minimum wins
+        best = d;
+        bidx = j;
+      }
+    }
+    s_best[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bidx;
+    __syncthreads();
+    for (int o = RF_THREADS / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        float ob = s_best[threadIdx.x + o];
+        int oi = s_idx[threadIdx.x + o];
+        if (ob < s_best[threadIdx.x] || (ob == s_best[threadIdx.x] && oi < s_idx[threadIdx.x])) {
+          s_best[threadIdx.x] = ob;
+          s_idx[threadIdx.x] = oi;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      int l = s_idx[0] == 0x7fffffff ? 0 : s_idx[0];
+      labels[row] = l;
+      if (best_out) best_out[row] = s_best[0];
+      if (n_changed && labels_prev && labels_prev[row] != l) atomicAdd(n_changed, 1);
+    }
+    __syncthreads();
+  }
+}
+
+// exact re-score of a device-side row list.  Short lists (the normal case) use the
+// row-per-CTA kernel; max_rows only bounds the grid.
 int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float* X, int64_t ldx,
                             const float* C, int64_t ldc, const float* cnorm, const int32_t* rows,
                             const int32_t* n_rows_dev, int32_t* labels, const int32_t* labels_prev,
                             int32_t* n_changed, float* best_out, cudaStream_t s) {
-  k_assign_simt<<<(unsigned)cdiv(max_rows, AS_BM), AS_THREADS, 0, s>>>(
-      max_rows, (int)K, (int)D, X, ldx, C, ldc, cnorm, labels, labels_prev, n_changed, best_out, rows,
-      n_rows_dev);
+  unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(max_rows, 1), kSMs * 8);
+  size_t smem = (size_t)align_up(D, 4) * 4;
+  k_refine_rows<<<grid, RF_THREADS, smem, s>>>((int)K, (int)D, X, ldx, C, ldc, cnorm, rows, n_rows_dev, labels,
+                                              labels_prev, n_changed, best_out);
   GDR_LAUNCHED();
   return GDR_OK;
+}
+
+// M-step gather-sum: one warp per (cluster, 32-column slab); lane = column; the member
+// rows of the cluster are added in ascending row order, one fp32 chain per output element
+// (== np.add.at / single-thread sklearn order).  K * ceil(D/32) warps instead of K, 8
+// independent 128-byte row reads in flight per warp.
+__global__ void __launch_bounds__(256) k_gather_sum(int64_t K, int Dp4, int nslab,
+                                                    const int32_t* __restrict__ mptr,
+                                                    const uint32_t* __restrict__ ids,
+                                                    const float* __restrict__ X, int64_t ldx,
+                                                    float* __restrict__ sums, int64_t lds) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= K * nslab) return;
+  const int64_t k = w / nslab;
+  const int col = (int)(w - k * nslab) * 32 + lane_id();
+  const bool live = col < Dp4;
+  const int b = mptr[k], e = mptr[k + 1];
+  float acc = 0.f;
+  for (int i = b; i < e; i += 32) {
+    const int my = i + lane_id();
+    const uint32_t id_l = my < e ? ids[my] : 0u;
+    const int cnt = min(32, e - i);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 8) {
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t id = __shfl_sync(0xffffffffu, id_l, (j + u) & 31);
+        xv[u] = (live && j + u < cnt) ? __ldg(X + (int64_t)id * ldx + col) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (j + u < cnt) acc = __fadd_rn(acc, xv[u]);
+    }
+  }
+  if (live) sums[k * lds + col] = acc;
 }
 
 // ----------------------------------------------------------------------------
@@ -540,6 +656,20 @@ __global__ void __launch_bounds__(256) k_relocate_one(int nparts, const float* _
   }
 }
 
+// fixed-order reduction of the per-block partials: out[c] = sum, out[D + c] = sum of squares
+__global__ void __launch_bounds__(256) k_colstats_reduce(int D, int nblocks, const double* __restrict__ part,
+                                                         double* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += part[((int64_t)i * D + c) * 2 + 0];
+    b += part[((int64_t)i * D + c) * 2 + 1];
+  }
+  out[c] = a;
+  out[D + c] = b;
+}
+
 }  // namespace gdr
 
 using namespace gdr;
@@ -675,8 +805,14 @@ int gdr_segment_sum(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx
     k_counts_from_rowptr<<<(unsigned)cdiv(K, 256), 256, 0, s>>>(K, mptr, counts);
     GDR_LAUNCHED();
   }
-  return spmm_launch(K, D, mptr, (const int32_t*)ids, nullptr, 1.0f, X, ldx, sums, lds, nullptr, 0,
-                     0.f, s);
+  {
+    const int Dp4 = (int)align_up(D, 4);
+    const int nslab = (int)cdiv(Dp4, 32);
+    ProfileScope prof(PROF_SPMM + 1, s);
+    k_gather_sum<<<(unsigned)cdiv(K * nslab * 32, 256), 256, 0, s>>>(K, Dp4, nslab, mptr, ids, X, ldx, sums, lds);
+  }
+  GDR_LAUNCHED();
+  return GDR_OK;
 }
 
 int gdr_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t lds, const int32_t* counts,

@@ -142,17 +142,19 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, int
 // ----------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;                      // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;    // 4096 keys per CTA
 constexpr int RS_BINS = 256;
+// keys per thread: 16 (4096-key tiles) for large inputs, 4 (1024-key tiles) below 2M keys so
+// that mid-size sorts (k-means membership lists, arxiv-sized graphs) still fill the 148 SMs
+static inline int rs_rounds(int64_t n) { return n >= (1ll << 21) ? 16 : 4; }
 
+template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n,
                                                         int shift, int32_t* __restrict__ table,
                                                         int nblocks) {
   __shared__ int hist[RS_BINS];
   hist[threadIdx.x] = 0;
   __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  int64_t base = (int64_t)blockIdx.x * (RS_THREADS * RS_ROUNDS);
 #pragma unroll 4
   for (int r = 0; r < RS_ROUNDS; ++r) {
     int64_t idx = base + r * RS_THREADS + threadIdx.x;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
   table[(int64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
+template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in,
                                                            const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out,
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (RS_ROUNDS * 32);
+  int64_t base = (int64_t)blockIdx.x * (RS_THREADS * RS_ROUNDS) + (int64_t)w * (RS_ROUNDS * 32);
   uint64_t k[RS_ROUNDS];
   uint32_t v[RS_ROUNDS];
   int rank[RS_ROUNDS];
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
 
 int64_t sort_pairs_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
-  int64_t nb = cdiv(n, RS_TILE);
+  int64_t nb = cdiv(n, RS_THREADS * rs_rounds(n));
   int64_t tbl = (int64_t)RS_BINS * nb;
   return ws_need(n, 8) + ws_need(n, 4) + ws_need(tbl + 1, 4) + scan_ws_bytes(tbl) + 256;
 }
@@ -248,7 +251,8 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
     set_error("sort_pairs: n=%lld exceeds int32 positions", (long long)n);
     return GDR_ERANGE;
   }
-  int64_t nb = cdiv(n, RS_TILE);
+  const int rounds = rs_rounds(n);
+  int64_t nb = cdiv(n, RS_THREADS * rounds);
   int64_t tbl = (int64_t)RS_BINS * nb;
   Workspace W(ws, ws_bytes);
   uint64_t* kalt = W.take<uint64_t>(n);
@@ -262,11 +266,15 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
   uint32_t* vout = vals ? valt : nullptr;
   for (int p = 0; p < passes; ++p) {
     int shift = 8 * p;
-    k_rs_hist<<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
+    if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
+    else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
     GDR_LAUNCHED();
     int rc = exclusive_scan_i32(table, table, tbl, sws, scan_ws_bytes(tbl), s);
     if (rc) return rc;
-    k_rs_scatter<<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
+    if (rounds == 16)
+      k_rs_scatter<16><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
+    else
+      k_rs_scatter<4><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
     GDR_LAUNCHED();
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
