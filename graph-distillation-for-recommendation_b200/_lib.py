@@ -39,6 +39,11 @@ _SIGNATURES = {
     "gdr_scale_rows": (i32, [i64, i64, f32, vp, i64, vp, i64, vp]),
     "gdr_center_columns_ws_bytes": (i64, [i64, i64]),
     "gdr_center_columns": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
+    "gdr_column_sums": (i32, [i64, i64, vp, i64, vp, vp, i64, vp]),
+    "gdr_center_apply": (i32, [i64, i64, vp, i64, vp, vp, i64, vp]),
+    "gdr_coarse_scatter_dense": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, vp]),
+    "gdr_dense_to_coarse_ws_bytes": (i64, [i64]),
+    "gdr_dense_to_coarse": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_kmeans_assign_ws_bytes": (i64, [i64, i64, i64, i32]),
     "gdr_kmeans_assign": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "gdr_kmeans_tc_xsplit_bytes": (i64, [i64, i64]),

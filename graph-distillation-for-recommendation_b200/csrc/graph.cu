@@ -476,6 +476,58 @@ __global__ void __launch_bounds__(256) k_coarsen_scale(int64_t n_src, const int3
   }
 }
 
+// sparse (rowptr, colidx, counts, wsum) -> dense n_src x n_dst (one writer per cell: no atomics)
+__global__ void k_scatter_dense(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr,
+                                const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts,
+                                const float* __restrict__ wsum, int32_t* __restrict__ dc,
+                                float* __restrict__ dw) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < n_src; r += nw) {
+    for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+      dc[r * n_dst + colidx[j]] = counts[j];
+      if (dw) dw[r * n_dst + colidx[j]] = wsum[j];
+    }
+  }
+}
+
+// one warp per row of the dense count matrix
+__global__ void __launch_bounds__(256) k_dense_row_nnz(int64_t n_src, int64_t n_dst,
+                                                       const int32_t* __restrict__ dc,
+                                                       int32_t* __restrict__ row_len) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_src) return;
+  int c = 0;
+  for (int64_t j = lane_id(); j < n_dst; j += 32) c += dc[r * n_dst + j] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane_id() == 0) row_len[r] = c;
+}
+
+__global__ void __launch_bounds__(256) k_dense_compact(int64_t n_src, int64_t n_dst,
+                                                       const int32_t* __restrict__ dc,
+                                                       const float* __restrict__ dw,
+                                                       const int32_t* __restrict__ rowptr,
+                                                       int32_t* __restrict__ colidx, int32_t* __restrict__ counts,
+                                                       float* __restrict__ wsum, int64_t* __restrict__ nnz_out) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_src) return;
+  if (r == n_src - 1 && lane_id() == 0) *nnz_out = rowptr[n_src];
+  int o = rowptr[r];
+  for (int64_t j0 = 0; j0 < n_dst; j0 += 32) {
+    int64_t j = j0 + lane_id();
+    int c = j < n_dst ? dc[r * n_dst + j] : 0;
+    unsigned m = __ballot_sync(0xffffffffu, c != 0);
+    if (c != 0) {
+      int p = o + __popc(m & ((1u << lane_id()) - 1u));
+      colidx[p] = (int32_t)j;
+      counts[p] = c;
+      if (wsum && dw) wsum[p] = dw[r * n_dst + j];
+    }
+    o += __popc(m);
+  }
+}
+
 __global__ void k_csr_to_coo(int64_t n_rows, const int32_t* __restrict__ rowptr,
                              const int32_t* __restrict__ colidx, int64_t* __restrict__ row_out,
                              int64_t* __restrict__ col_out) {
@@ -754,6 +806,46 @@ int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx,
   GDR_CHECK_ARG(rowptr && colidx && row_out, "csr_to_coo: null pointer");
   k_csr_to_coo<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, row_out,
                                                                        col_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- dense merge of per-rank coarsened graphs (multi-GPU stage 4) ----------------
+int gdr_coarse_scatter_dense(int64_t n_src, int64_t n_dst, const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* counts, const float* wsum, int32_t* dense_counts,
+                             float* dense_wsum, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_src > 0 && n_dst > 0 && rowptr && dense_counts, "coarse_scatter_dense: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  GDR_CUDA(cudaMemsetAsync(dense_counts, 0, n_src * n_dst * 4, s));
+  if (dense_wsum) GDR_CUDA(cudaMemsetAsync(dense_wsum, 0, n_src * n_dst * 4, s));
+  k_scatter_dense<<<grid_for(n_src * 32), 256, 0, s>>>(n_src, n_dst, rowptr, colidx, counts, wsum, dense_counts,
+                                                       dense_wsum);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_dense_to_coarse_ws_bytes(int64_t n_src) { return ws_need(n_src + 1, 4) + scan_ws_bytes(n_src) + 256; }
+
+int gdr_dense_to_coarse(int64_t n_src, int64_t n_dst, const int32_t* dense_counts, const float* dense_wsum,
+                        int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum, int64_t* nnz_out_dev,
+                        void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_src > 0 && n_dst > 0 && dense_counts && rowptr && colidx && counts && nnz_out_dev,
+                "dense_to_coarse: bad arguments");
+  if (ws_bytes < gdr_dense_to_coarse_ws_bytes(n_src)) {
+    set_error("dense_to_coarse: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  int32_t* row_len = W.take<int32_t>(n_src + 1);
+  void* sws = W.take<char>(scan_ws_bytes(n_src));
+  unsigned grid = (unsigned)cdiv(n_src * 32, 256);
+  k_dense_row_nnz<<<grid, 256, 0, s>>>(n_src, n_dst, dense_counts, row_len);
+  GDR_LAUNCHED();
+  int rc = exclusive_scan_i32(row_len, rowptr, n_src, sws, scan_ws_bytes(n_src), s);
+  if (rc) return rc;
+  k_dense_compact<<<grid, 256, 0, s>>>(n_src, n_dst, dense_counts, dense_wsum, rowptr, colidx, counts, wsum,
+                                       nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -713,6 +713,44 @@ int gdr_center_columns(int64_t N, int64_t D, const float* X, int64_t ldx, float*
   return GDR_OK;
 }
 
+// Column sums / sums of squares in fp64 (sums_out[0..D) = sum, [D..2D) = sum of squares) — the
+// per-rank half of the mean/variance when rows are partitioned across GPUs.
+int gdr_column_sums(int64_t N, int64_t D, const float* X, int64_t ldx, double* sums_out, void* ws,
+                    int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && D > 0 && sums_out && ldx >= D, "column_sums: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 0) {
+    GDR_CUDA(cudaMemsetAsync(sums_out, 0, 2 * D * 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(X, "column_sums: null X");
+  if (ws_bytes < gdr_center_columns_ws_bytes(N, D)) {
+    set_error("column_sums: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  int nb = (int)cdiv(N, CC_ROWS_PER_BLOCK);
+  double* part = (double*)ws;
+  k_colstats_partial<<<nb, dim3(32, 8), 0, s>>>(N, (int)D, X, ldx, part);
+  GDR_LAUNCHED();
+  k_colstats_reduce<<<(unsigned)cdiv(D, 256), 256, 0, s>>>((int)D, nb, part, sums_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// Xc = X - mean (fp32 subtract, padding columns zeroed) — sklearn/_kmeans.py:1489
+int gdr_center_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean, float* Xc,
+                     int64_t ldxc, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && D > 0 && mean && ldx >= D && ldxc >= D, "center_apply: bad arguments");
+  if (N == 0) return GDR_OK;
+  GDR_CHECK_ARG(X && Xc, "center_apply: null pointer");
+  int ldpad = (int)std::min<int64_t>(ldxc, align_up(D, 4));
+  int64_t total = N * ldpad;
+  unsigned grid = (unsigned)std::min<int64_t>(cdiv(total, 256), kSMs * 16);
+  k_sub_rowvec<<<grid, 256, 0, (cudaStream_t)stream>>>(N, (int)D, ldpad, X, ldx, mean, Xc, ldxc);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
 int gdr_add_row_vector(int64_t rows, int64_t D, float* X, int64_t ldx, const float* v, float sign,
                        gdr_stream_t stream) {
   GDR_CHECK_ARG(rows >= 0 && D >= 0, "add_row_vector: negative size");

@@ -1,0 +1,397 @@
+"""Row-partitioned multi-GPU execution of the distillation core.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the B200 box, gloo in the CPU
+tests).  Nodes are split into contiguous row blocks; the reference itself is single-device,
+so nothing is ported here — the exchanges are the ones the algorithm needs:
+
+  stage 2  all-gather of the propagated rows before each hop (every rank then runs the CSR
+           SpMM on its own rows of A_hat against the full feature matrix);
+  stage 3  per Lloyd iteration ONE all-reduce of the [K x D] partial sums and ONE of the
+           packed int32 [counts | n_changed]; every rank finalises identically, so the
+           replicated centres stay bit-identical across ranks;
+  stage 4  all-gather of the labels, local segmented edge counting, dense n x n all-reduce of
+           (int32 counts, f32 sums), compaction back to CSR.
+
+All arithmetic goes through an ``ops`` object.  ``CudaOps`` (default) calls libgdr_b200;
+the CPU tests inject an oracle-backed stand-in so that the partition / packing / collective
+logic is exercised with world_size 2 on gloo.  Integer outputs are independent of the
+number of ranks; float outputs agree to the §8c tolerances (the all-reduce order changes
+with the rank count).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+
+@dataclass
+class RowPartition:
+    n: int
+    world: int
+    rank: int
+
+    @property
+    def rows_per(self) -> int:
+        return (self.n + self.world - 1) // self.world
+
+    def bounds(self, rank: Optional[int] = None) -> Tuple[int, int]:
+        r = self.rank if rank is None else rank
+        lo = min(self.n, r * self.rows_per)
+        return lo, min(self.n, lo + self.rows_per)
+
+    @property
+    def lo(self) -> int:
+        return self.bounds()[0]
+
+    @property
+    def hi(self) -> int:
+        return self.bounds()[1]
+
+    @property
+    def n_local(self) -> int:
+        lo, hi = self.bounds()
+        return hi - lo
+
+
+class Comm:
+    """Thin wrapper over torch.distributed (or a no-op for world size 1)."""
+
+    def __init__(self, dist=None, group=None):
+        self.dist, self.group = dist, group
+        self.world = 1 if dist is None else dist.get_world_size(group)
+        self.rank = 0 if dist is None else dist.get_rank(group)
+        self.backend = None if dist is None else dist.get_backend(group)
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        if self.dist is not None and self.world > 1:
+            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX}
+            self.dist.all_reduce(t, op=ops[op], group=self.group)
+        return t
+
+    def all_gather_rows(self, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[(r*rows):(r+1)*rows] = local of rank r; all ranks pass equally shaped blocks."""
+        if self.dist is None or self.world == 1:
+            out[: local.shape[0]].copy_(local)
+            return out
+        if self.backend == "nccl":
+            self.dist.all_gather_into_tensor(out, local, group=self.group)
+        else:
+            chunks = list(out.chunk(self.world, dim=0))
+            self.dist.all_gather(chunks, local, group=self.group)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# compute backend on the GPU
+# ------------------------------------------------------------------------------------------
+class CudaOps:
+    """The kernels of libgdr_b200 behind the small interface the distributed drivers need."""
+
+    def __init__(self, precision: str = "auto"):
+        from . import _lib, coarsen, graph, kmeans, propagation
+        from ._dev import new_padded, padded_rows, ptr, stream, workspace
+        self._lib, self._g, self._km, self._pr, self._co = _lib, graph, kmeans, propagation, coarsen
+        self.new_padded, self.padded_rows, self.ptr, self.stream, self.workspace = new_padded, padded_rows, ptr, stream, workspace
+        self.precision = precision
+        self._tc = None
+
+    # -- stage 2 --
+    def empty_rows(self, rows, f, like):
+        return self.new_padded(rows, f, like.device, zero=True)
+
+    def scale(self, x, a):
+        out = self.new_padded(x.shape[0], x.shape[1], x.device)
+        self._lib.call("gdr_scale_rows", x.shape[0], x.shape[1], float(a), self.ptr(x), x.stride(0), self.ptr(out),
+                       out.stride(0), self.stream())
+        return out
+
+    def spmm(self, A_local, x_full, alpha, target, beta):
+        y = self.new_padded(A_local.shape[0], x_full.shape[1], x_full.device)
+        self._lib.call("gdr_spmm_prop", A_local.shape[0], x_full.shape[1], self.ptr(A_local.rowptr), self.ptr(A_local.colidx),
+                       self.ptr(A_local.vals), float(alpha), self.ptr(x_full), x_full.stride(0), self.ptr(y), y.stride(0),
+                       self.ptr(target), 0 if target is None else target.stride(0), float(beta), self.stream())
+        return y
+
+    def prep_rows(self, x):
+        return self.padded_rows(x.to(torch.float32))
+
+    # -- stage 3 --
+    def column_sums(self, X):
+        N, D = X.shape
+        out = torch.zeros(2 * D, dtype=torch.float64, device=X.device)
+        ws = self.workspace(self._lib.query("gdr_center_columns_ws_bytes", max(N, 1), D), X.device)
+        self._lib.call("gdr_column_sums", N, D, self.ptr(X), X.stride(0), self.ptr(out), self.ptr(ws), ws.numel(), self.stream())
+        return out
+
+    def center(self, X, mean):
+        N, D = X.shape
+        Xc = self.new_padded(N, D, X.device)
+        self._lib.call("gdr_center_apply", N, D, self.ptr(X), X.stride(0), self.ptr(mean), self.ptr(Xc), Xc.stride(0), self.stream())
+        return Xc
+
+    def prepare_kmeans(self, Xc, K):
+        D = Xc.shape[1]
+        use_tc = self.precision == "tc" or (self.precision == "auto" and D <= 128)
+        self._tc = self._km.TcOperand(Xc) if (use_tc and Xc.shape[0] > 0) else None
+
+    def centers_like(self, C, device):
+        out = self.new_padded(C.shape[0], C.shape[1], device, zero=True)
+        out.copy_(C)
+        return out
+
+    def assign(self, Xc, C, labels, labels_prev, n_changed):
+        if Xc.shape[0] == 0:
+            return
+        self._km.assign_labels(Xc, C, labels, labels_prev=labels_prev, n_changed=n_changed, tc_operand=self._tc)
+
+    def segment_sum(self, Xc, labels, K, sums, counts):
+        if Xc.shape[0] == 0:
+            sums.zero_()
+            counts.zero_()
+            return
+        self._km.segment_sum(Xc, labels, K, sums=sums, counts=counts)
+
+    def finalize(self, sums, counts, C_old, C_new):
+        K, D = C_old.shape
+        stats = torch.zeros(2 + K, dtype=torch.float64, device=C_old.device)
+        self._lib.call("gdr_kmeans_finalize", K, D, self.ptr(sums), sums.stride(0), self.ptr(counts), self.ptr(C_old),
+                       C_old.stride(0), self.ptr(C_new), C_new.stride(0), self.ptr(stats), 0, self.stream())
+        s = stats[:2].cpu()
+        return float(s[0]), int(s[1])
+
+    def inertia(self, Xc, C, labels):
+        out = torch.zeros(1, dtype=torch.float64, device=C.device)
+        if Xc.shape[0] == 0:
+            return out
+        ws = self.workspace(self._lib.query("gdr_inertia_ws_bytes", Xc.shape[0], Xc.shape[1]), Xc.device)
+        self._lib.call("gdr_inertia", Xc.shape[0], Xc.shape[1], self.ptr(Xc), Xc.stride(0), self.ptr(C), C.stride(0),
+                       self.ptr(labels), self.ptr(out), self.ptr(ws), ws.numel(), self.stream())
+        return out
+
+    def row_dist(self, Xc, C, labels):
+        return ((Xc - C[labels.long()]) ** 2).sum(dim=1)  # rare relocation path only
+
+    # -- stage 4 --
+    def label_counts(self, labels, n):
+        return self._co.label_counts(labels, n)
+
+    def coarsen_dense(self, A_local, labels_src, labels_dst, n):
+        rowptr, colidx, counts, wsum = self._co.coarsen_edges(labels_src, labels_dst, n, n, csr=A_local,
+                                                              weights=A_local.vals, drop_diag=True)
+        dev = labels_dst.device
+        dc = torch.empty((n, n), dtype=torch.int32, device=dev)
+        dw = torch.empty((n, n), dtype=torch.float32, device=dev)
+        self._lib.call("gdr_coarse_scatter_dense", n, n, self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum),
+                       self.ptr(dc), self.ptr(dw), self.stream())
+        return dc, dw
+
+    def dense_to_coo(self, dc, dw, sizes):
+        n = dc.shape[0]
+        dev = dc.device
+        cap = int(n) * int(n)
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        # count first so that the outputs are sized by the merged nnz, not n^2
+        m_est = int((dc != 0).sum().item())
+        colidx = torch.empty(max(m_est, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty(max(m_est, 1), dtype=torch.int32, device=dev)
+        wsum = torch.empty(max(m_est, 1), dtype=torch.float32, device=dev)
+        ws = self.workspace(self._lib.query("gdr_dense_to_coarse_ws_bytes", n), dev)
+        self._lib.call("gdr_dense_to_coarse", n, n, self.ptr(dc), self.ptr(dw), self.ptr(rowptr), self.ptr(colidx),
+                       self.ptr(counts), self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
+        m = int(nnz.item())
+        assert m == m_est and m <= cap
+        vals = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        if m:
+            self._lib.call("gdr_coarsen_scale", n, self.ptr(rowptr), self.ptr(colidx), self.ptr(wsum), self.ptr(sizes),
+                           self.ptr(sizes), self.ptr(vals), self.stream())
+        S = self._g.CSR(rowptr, colidx[:m], vals[:m], (n, n))
+        return S.to_torch_coo(), counts[:m]
+
+
+# ------------------------------------------------------------------------------------------
+# stage 1 (replicated build, local row slice)
+# ------------------------------------------------------------------------------------------
+def slice_rows(A, lo: int, hi: int):
+    """Rows [lo, hi) of a device CSR as a CSR with global column ids (views, no copy of colidx/vals)."""
+    from .graph import CSR
+    b, e = int(A.rowptr[lo].item()), int(A.rowptr[hi].item())
+    rowptr = (A.rowptr[lo: hi + 1] - A.rowptr[lo]).contiguous()
+    return CSR(rowptr, A.colidx[b:e], A.vals[b:e], (hi - lo, A.shape[1]))
+
+
+def build_local_adjacency(u, v, n: int, part: RowPartition, device):
+    """Round-1 form of the distributed stage 1: the (small, one-off) CSR build + normalisation
+    is replicated on every rank and each rank keeps its row block.  The exchange-based build
+    (edges bucketed by owner, all-to-all of reversed edges, all-gather of degrees) is the
+    listed next step."""
+    from .graph import coo_to_csr, sym_normalize
+    A = sym_normalize(coo_to_csr(u, v, None, (n, n), symmetrize=True, binarize=True, device=device), 2)
+    return slice_rows(A, part.lo, part.hi), A
+
+
+# ------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------
+def dist_propagate(comm: Comm, part: RowPartition, A_local, x_local: torch.Tensor, prop_num: int, alpha: float,
+                   ops=None):
+    """clustgdd_agent_transduct.py:59-65 on row-partitioned data.  Returns the local row blocks
+    (prop_local, target_local)."""
+    ops = ops or CudaOps()
+    T = int(prop_num)
+    if T < 1:
+        raise ValueError("prop_num must be >= 1")
+    x = ops.prep_rows(x_local)
+    f = x.shape[1]
+    one_minus = float(1.0 - alpha)
+    target = ops.scale(x, one_minus)
+    prop = x
+    rows_per = part.rows_per
+    x_full = ops.empty_rows(rows_per * part.world, f, x)
+    block = ops.empty_rows(rows_per, f, x)
+    for _ in range(1, T):
+        block[: prop.shape[0]].copy_(prop)
+        comm.all_gather_rows(block, x_full)
+        prop = ops.spmm(A_local, x_full, alpha, target, one_minus)
+    return prop, target
+
+
+# ------------------------------------------------------------------------------------------
+# stage 3
+# ------------------------------------------------------------------------------------------
+class DistKMeans:
+    """Lloyd k-means on row-partitioned X with replicated centres (init must be an array that
+    is identical on every rank)."""
+
+    def __init__(self, n_clusters: int, init, max_iter: int = 300, tol: float = 1e-4, ops=None, comm: Comm = None):
+        self.n_clusters, self.init, self.max_iter, self.tol = int(n_clusters), init, int(max_iter), tol
+        self.ops = ops or CudaOps()
+        self.comm = comm or Comm()
+
+    def fit(self, X_local: torch.Tensor):
+        ops, comm, K = self.ops, self.comm, self.n_clusters
+        X = ops.prep_rows(X_local)
+        n_local, D = X.shape
+        dev = X.device
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        comm.all_reduce(cnt)
+        N = int(cnt.item())
+        if N < K:
+            raise ValueError(f"n_samples={N} should be >= n_clusters={K}.")
+        sums = ops.column_sums(X)
+        comm.all_reduce(sums)
+        m64 = sums[:D] / N
+        var_mean = float(((sums[D:] / N - m64 * m64).clamp_min(0)).mean().item())
+        mean = m64.to(torch.float32)
+        tol_abs = 0.0 if self.tol == 0 else var_mean * float(self.tol)
+        Xc = ops.center(X, mean)
+        C0 = torch.as_tensor(np.asarray(self.init) if not isinstance(self.init, torch.Tensor) else self.init,
+                             dtype=torch.float32).to(dev)
+        if tuple(C0.shape) != (K, D):
+            raise ValueError("init has the wrong shape")
+        centers = [ops.centers_like(C0 - mean, dev), ops.centers_like(torch.zeros_like(C0), dev)]
+        labels = [torch.full((n_local,), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+        psums = ops.centers_like(torch.zeros_like(C0), dev)
+        ints = torch.zeros(K + 1, dtype=torch.int32, device=dev)   # [counts | n_changed]
+        ops.prepare_kmeans(Xc, K)
+        cur, nxt, ln, lo_ = 0, 1, 0, 1
+        strict, n_iter = False, 0
+        for i in range(self.max_iter):
+            n_iter = i + 1
+            ints.zero_()
+            ops.assign(Xc, centers[cur], labels[ln], labels[lo_], ints[K:])
+            ops.segment_sum(Xc, labels[ln], K, psums, ints[:K])
+            comm.all_reduce(psums)       # K x D partial sums
+            comm.all_reduce(ints)        # counts + changed-label count, exact
+            shift_tot, n_empty = ops.finalize(psums, ints[:K], centers[cur], centers[nxt])
+            n_changed = int(ints[K].item())
+            if n_empty > 0:
+                self._relocate(Xc, centers[cur], labels[ln], psums, ints[:K], part_lo=0)
+                shift_tot, _ = ops.finalize(psums, ints[:K], centers[cur], centers[nxt])
+            cur, nxt = nxt, cur
+            if n_changed == 0:
+                strict = True
+                break
+            if shift_tot <= tol_abs:
+                break
+            ln, lo_ = lo_, ln
+        lab = labels[ln]
+        if not strict:
+            ops.assign(Xc, centers[cur], lab, None, None)
+        inertia = ops.inertia(Xc, centers[cur], lab)
+        comm.all_reduce(inertia)
+        self.labels_ = lab
+        self.cluster_centers_ = (centers[cur] + mean).contiguous()
+        self.inertia_ = float(inertia.item())
+        self.n_iter_ = n_iter
+        self._centers_centered = centers[cur]
+        self._mean = mean
+        return self
+
+    def _relocate(self, Xc, C_old, labels, sums, counts, part_lo):
+        """_relocate_empty_clusters_dense across ranks: every rank proposes its n_empty farthest
+        samples, the proposals are all-gathered and all ranks apply the same global choice to
+        the (replicated, already reduced) sums / counts."""
+        comm, ops = self.comm, self.ops
+        empty = torch.nonzero(counts == 0).flatten()
+        ne = int(empty.numel())
+        if ne == 0:
+            return
+        D = Xc.shape[1]
+        dev = Xc.device
+        dist_local = ops.row_dist(Xc, C_old, labels) if Xc.shape[0] else torch.zeros(0, device=dev)
+        k = min(ne, int(dist_local.numel()))
+        rec = torch.full((ne, D + 3), -1.0, dtype=torch.float64, device=dev)  # [dist, rank, old label, row...]
+        if k:
+            val, idx = torch.topk(dist_local, k)
+            rec[:k, 0] = val.double()
+            rec[:k, 1] = float(comm.rank)
+            rec[:k, 2] = labels[idx].double()
+            rec[:k, 3:] = Xc[idx].double()
+        allrec = torch.empty((ne * comm.world, D + 3), dtype=torch.float64, device=dev)
+        comm.all_gather_rows(rec, allrec)
+        order = torch.argsort(allrec[:, 0], descending=True, stable=True)
+        if float(allrec[order[0], 0]) <= 0:
+            return
+        for e, j in zip(empty.tolist(), order[:ne].tolist()):
+            if float(allrec[j, 0]) < 0:
+                break
+            old = int(allrec[j, 2].item())
+            x = allrec[j, 3:].to(torch.float32)
+            sums[old] -= x
+            sums[e] = x
+            counts[e] = 1
+            counts[old] -= 1
+
+
+# ------------------------------------------------------------------------------------------
+# stage 4
+# ------------------------------------------------------------------------------------------
+MAX_DENSE_CELLS = 1 << 28   # 2^28 cells = 1 GiB int32 + 1 GiB f32 per rank
+
+
+def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None):
+    """graph_compress (clustgdd_agent_transduct.py:234-250) for a row-partitioned A_hat: returns
+    (adj_syn torch sparse COO n x n replicated on every rank, merged integer cell counts)."""
+    ops = ops or CudaOps()
+    dev = labels_local.device
+    rows_per = part.rows_per
+    block = torch.full((rows_per,), -1, dtype=torch.int32, device=dev)
+    block[: labels_local.shape[0]] = labels_local.to(torch.int32)
+    gathered = torch.empty(rows_per * part.world, dtype=torch.int32, device=dev)
+    comm.all_gather_rows(block, gathered)
+    # drop the padding of every rank's block
+    pieces = [gathered[r * rows_per: r * rows_per + (part.bounds(r)[1] - part.bounds(r)[0])] for r in range(part.world)]
+    labels_all = torch.cat(pieces).contiguous()
+    nmax = labels_all.max().to(torch.int64).reshape(1)
+    n = int(comm.all_reduce(nmax, "max").item()) + 1
+    if n * n > MAX_DENSE_CELLS:
+        raise NotImplementedError(f"dense merge needs n^2 <= {MAX_DENSE_CELLS}; key-range exchange is the next step")
+    sizes = ops.label_counts(labels_all, n)
+    dc, dw = ops.coarsen_dense(A_local, labels_local.to(torch.int32).contiguous(), labels_all, n)
+    comm.all_reduce(dc)
+    comm.all_reduce(dw)
+    return ops.dense_to_coo(dc, dw, sizes)

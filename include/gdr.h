@@ -172,6 +172,14 @@ int     gdr_center_columns(int64_t N, int64_t D, const float* X, int64_t ldx,
                            float* Xc /*nullable*/, int64_t ldxc,
                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
+/* Row-partitioned form of the two steps above (multi-GPU): per-rank fp64 column sums
+ * (sums_out[0..D) = sum, [D..2D) = sum of squares; all-reduced by the host, which derives
+ * mean and tol') and the centring pass with a given mean.  ws: gdr_center_columns_ws_bytes. */
+int gdr_column_sums(int64_t N, int64_t D, const float* X, int64_t ldx, double* sums_out,
+                    void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int gdr_center_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean,
+                     float* Xc, int64_t ldxc, gdr_stream_t stream);
+
 /* E-step.  labels[i] = argmin_j ( |c_j|^2 - 2 x_i . c_j ), first index wins ties.
  *   replaces  _update_chunk_dense                 sklearn/_k_means_lloyd.pyx:196-213
  *   precision_mode 0: exact fp32 SIMT everywhere.
@@ -288,6 +296,19 @@ int     gdr_coarsen(int64_t E, const int64_t* src, const int64_t* dst,
                     int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
                     int64_t* nnz_out_dev,
                     void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* Multi-GPU merge of per-rank coarsened graphs (row-partitioned stage 4): every rank scatters
+ * its local result into a dense n_src x n_dst pair (int32 counts, f32 weight sums; both are
+ * zeroed first), the host all-reduces them (NCCL sum), and dense_to_coarse compacts the
+ * merged matrices back to CSR (cells with count 0 are dropped, columns ascending). */
+int gdr_coarse_scatter_dense(int64_t n_src, int64_t n_dst, const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* counts, const float* wsum /*nullable*/,
+                             int32_t* dense_counts, float* dense_wsum /*nullable*/, gdr_stream_t stream);
+int64_t gdr_dense_to_coarse_ws_bytes(int64_t n_src);
+int gdr_dense_to_coarse(int64_t n_src, int64_t n_dst, const int32_t* dense_counts,
+                        const float* dense_wsum /*nullable*/, int32_t* rowptr, int32_t* colidx,
+                        int32_t* counts, float* wsum /*nullable*/, int64_t* nnz_out_dev,
+                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
 /* graph_compress value pass: vals[e] = wsum[e] / (size[a] * size[b])  computed as
  * fp32 (wsum * (1/size[a])) * (1/size[b])  (transduct :237-244). */

@@ -1,0 +1,70 @@
+"""2-rank NCCL run of the row-partitioned drivers with the real CUDA kernels; results must
+match the single-GPU path (integers bit-exact, floats within the §8c tolerances).
+Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import gdr
+        from gdr import parallel as par
+        from gdr import synth
+        n, f, k = 30011, 100, 257
+        u, v = synth.skewed_graph(n, 200000, seed=11)
+        X = synth.clustered_features(n, f, 60, seed=12)
+        part = par.RowPartition(n, world, rank)
+        comm = par.Comm(dist)
+        ops = par.CudaOps()
+        u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+        A_local, A_full = par.build_local_adjacency(u_d, v_d, n, part, dev)
+        # stage 2
+        x_local = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
+        prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)
+        p1, t1 = gdr.propagate(A_full, torch.from_numpy(X).to(dev), 4, 0.8)
+        assert torch.equal(prop, p1[part.lo:part.hi]) and torch.equal(target, t1[part.lo:part.hi])
+        # stage 3
+        tn = t1.cpu().numpy()
+        C0 = synth.kmeans_init(tn, k, seed=13)
+        km = par.DistKMeans(k, C0, max_iter=15, tol=0, ops=ops, comm=comm).fit(target)
+        ref = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=15, tol=0).fit(t1)
+        assert km.n_iter_ == ref.n_iter_
+        same = (km.labels_ == ref.labels_[part.lo:part.hi]).float().mean().item()
+        assert same > 0.999, same          # centres differ in the last bits across rank counts -> band flips only
+        torch.testing.assert_close(km.cluster_centers_, ref.cluster_centers_.contiguous(), rtol=1e-4, atol=1e-4)
+        assert abs(km.inertia_ - ref.inertia_) <= 1e-4 * ref.inertia_
+        # stage 4 (use the single-GPU labels so that the integer result is comparable bit for bit)
+        labels = ref.labels_
+        adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops)
+        _, syn1 = gdr.graph_compress(labels, A_full, [])
+        kk = int(labels.max()) + 1
+        _, _, cnt1, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_full, drop_diag=True)
+        assert torch.equal(adj_syn._indices(), syn1._indices())
+        assert torch.equal(counts, cnt1)
+        torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+        torch.cuda.synchronize()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_matches_single_gpu():
+    mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)

@@ -1,0 +1,195 @@
+"""world_size-2 tests of the row-partitioned drivers (gdr.parallel) over gloo on CPU.
+
+The product has no CPU kernels, so the compute backend is replaced by ``OracleOps`` — the
+oracle behind the same small interface as ``CudaOps`` — and what is under test is the
+multi-rank host logic: partition bounds, padded all-gathers, packed all-reduces, the
+replicated finalise / convergence decisions, the dense merge of stage 4 and the
+distributed empty-cluster relocation.  Results are compared with the single-process oracle.
+"""
+import os
+import socket
+from dataclasses import dataclass
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+@dataclass
+class CpuCSR:
+    rowptr: torch.Tensor
+    colidx: torch.Tensor
+    vals: torch.Tensor
+    shape: tuple
+
+
+class OracleOps:
+    """CPU stand-in for gdr.parallel.CudaOps (tests only)."""
+
+    def __init__(self):
+        from oracle import oracle as o
+        self.o = o
+
+    def prep_rows(self, x):
+        return x.to(torch.float32).contiguous()
+
+    def empty_rows(self, rows, f, like):
+        return torch.zeros((rows, f), dtype=torch.float32)
+
+    def scale(self, x, a):
+        return torch.from_numpy((np.float32(a) * x.numpy()).astype(np.float32))
+
+    def spmm(self, A, x_full, alpha, target, beta):
+        tn = None if target is None else target.numpy()
+        y = self.o.spmm_prop(A.rowptr.numpy(), A.colidx.numpy(), A.vals.numpy(), np.float32(alpha),
+                             x_full.numpy(), T=tn, beta=np.float32(beta))
+        return torch.from_numpy(y)
+
+    def column_sums(self, X):
+        x = X.numpy().astype(np.float64)
+        return torch.from_numpy(np.concatenate([x.sum(0), (x * x).sum(0)]))
+
+    def center(self, X, mean):
+        return X - mean
+
+    def prepare_kmeans(self, Xc, K):
+        pass
+
+    def centers_like(self, C, device):
+        return C.clone().contiguous()
+
+    def assign(self, Xc, C, labels, labels_prev, n_changed):
+        if Xc.shape[0] == 0:
+            return
+        lab, _ = self.o.kmeans_assign(Xc.numpy(), C.numpy())
+        if labels_prev is not None and n_changed is not None:
+            n_changed += int((lab != labels_prev.numpy()).sum())
+        labels.copy_(torch.from_numpy(lab))
+
+    def segment_sum(self, Xc, labels, K, sums, counts):
+        s, c = self.o.segment_sum(Xc.numpy(), labels.numpy(), K)
+        sums.copy_(torch.from_numpy(s))
+        counts.copy_(torch.from_numpy(c))
+
+    def finalize(self, sums, counts, C_old, C_new):
+        cn, shift = self.o.kmeans_finalize(sums.numpy(), counts.numpy(), C_old.numpy())
+        C_new.copy_(torch.from_numpy(cn))
+        return shift, int((counts == 0).sum())
+
+    def inertia(self, Xc, C, labels):
+        if Xc.shape[0] == 0:
+            return torch.zeros(1, dtype=torch.float64)
+        return torch.tensor([self.o.inertia(Xc.numpy(), C.numpy(), labels.numpy())], dtype=torch.float64)
+
+    def row_dist(self, Xc, C, labels):
+        return ((Xc - C[labels.long()]) ** 2).sum(dim=1)
+
+    def label_counts(self, labels, n):
+        return torch.bincount(labels.long(), minlength=n).to(torch.int32)
+
+    def coarsen_dense(self, A, labels_src, labels_dst, n):
+        rows = np.repeat(np.arange(A.shape[0]), np.diff(A.rowptr.numpy()))
+        rp, ci, cnt, wsum = self.o.coarsen_counts(rows, A.colidx.numpy(), labels_src.numpy(), labels_dst.numpy(), n, n,
+                                                  w=A.vals.numpy(), drop_diag=True)
+        dc = np.zeros((n, n), np.int32)
+        dw = np.zeros((n, n), np.float32)
+        rr = np.repeat(np.arange(n), np.diff(rp))
+        dc[rr, ci] = cnt
+        dw[rr, ci] = wsum
+        return torch.from_numpy(dc), torch.from_numpy(dw)
+
+    def dense_to_coo(self, dc, dw, sizes):
+        idx = torch.nonzero(dc).t()
+        s = sizes.to(torch.float32)
+        vals = dw[idx[0], idx[1]] * (1.0 / s[idx[0]]) * (1.0 / s[idx[1]])
+        return torch.sparse_coo_tensor(idx, vals, dc.shape), dc[idx[0], idx[1]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _inputs():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gdr import synth
+    from oracle import oracle as o
+    n, f, k = 1501, 12, 23          # odd sizes: ragged last block
+    u, v = synth.skewed_graph(n, 9000, seed=3)
+    rp, ci, va = o.coo_to_csr(u, v, None, (n, n), symmetrize=True, binarize=True)
+    rpo, cio, vo, _ = o.sym_normalize(rp, ci, va, n)
+    X = synth.clustered_features(n, f, 9, seed=4)
+    return n, f, k, rpo, cio, vo, X
+
+
+def _worker(rank, world, port, case):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gdr import parallel as par
+        from gdr import synth
+        from oracle import oracle as o
+        n, f, k, rpo, cio, vo, X = _inputs()
+        part = par.RowPartition(n, world, rank)
+        comm = par.Comm(dist)
+        ops = OracleOps()
+        lo, hi = part.lo, part.hi
+        b, e = int(rpo[lo]), int(rpo[hi])
+        A_local = CpuCSR(torch.from_numpy((rpo[lo:hi + 1] - rpo[lo]).astype(np.int32)), torch.from_numpy(cio[b:e].copy()),
+                         torch.from_numpy(vo[b:e].copy()), (hi - lo, n))
+        x_local = torch.from_numpy(X[lo:hi].copy())
+
+        if case == "propagate":
+            prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)
+            p_ref, t_ref = o.propagate(rpo, cio, vo, X, 4, 0.8)
+            assert np.array_equal(prop.numpy(), p_ref[lo:hi])      # row-wise independent: bit-identical
+            assert np.array_equal(target.numpy(), t_ref[lo:hi])
+        elif case in ("kmeans", "kmeans_empty"):
+            C0 = synth.kmeans_init(X, k, seed=5)
+            if case == "kmeans_empty":
+                C0[3] = C0[2]
+                C0[4] = C0[2]
+            km = par.DistKMeans(k, C0, max_iter=30, tol=1e-4, ops=ops, comm=comm).fit(x_local)
+            ref = o.kmeans_fit(X, C0, max_iter=30, tol=1e-4)
+            if case == "kmeans":
+                assert km.n_iter_ == ref["n_iter"]
+                assert np.array_equal(km.labels_.numpy(), ref["labels"][lo:hi])
+                np.testing.assert_allclose(km.cluster_centers_.numpy(), ref["centers"], rtol=1e-5, atol=1e-5)
+            assert abs(km.inertia_ - ref["inertia"]) <= (1e-4 if case == "kmeans" else 5e-2) * ref["inertia"]
+            # replicated centres are bit-identical on every rank
+            cc = km.cluster_centers_.clone()
+            mx = cc.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            assert torch.equal(cc, mx)
+        elif case == "coarsen":
+            labels = np.random.RandomState(6).randint(0, 17, n).astype(np.int32)
+            labels[labels == 11] = 10      # an empty cluster
+            adj_syn, counts = par.dist_graph_compress(comm, part, torch.from_numpy(labels[lo:hi].copy()), A_local, ops=ops)
+            S = o.graph_compress_dense(labels.astype(np.int64), rpo, cio, vo, int(labels.max()) + 1)
+            got = adj_syn.to_dense().numpy()
+            fin = np.isfinite(S)
+            np.testing.assert_allclose(got[fin], S[fin], rtol=1e-5, atol=1e-8)
+            rows = np.repeat(np.arange(n), np.diff(rpo))
+            _, _, cnt_ref, _ = o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)
+            assert np.array_equal(np.sort(counts.numpy()), np.sort(cnt_ref))
+            assert int(counts.sum()) == int(cnt_ref.sum())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["propagate", "kmeans", "kmeans_empty", "coarsen"])
+def test_world2_gloo(case, oracle):
+    mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
+
+
+def test_row_partition_bounds():
+    from gdr.parallel import RowPartition
+    for n, w in [(10, 3), (9, 3), (1, 4), (1501, 2), (169343, 8)]:
+        spans = [RowPartition(n, w, r).bounds() for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) == RowPartition(n, w, 0).rows_per
