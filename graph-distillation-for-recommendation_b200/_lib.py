@@ -21,6 +21,7 @@ _SIGNATURES = {
     "gdr_last_error": (cp, []),
     "gdr_device_info": (i32, [vp, vp, vp]),
     "gdr_launch_count": (i64, []),
+    "gdr_debug_set": (i32, [cp, i32]),
     "gdr_profile_enable": (i32, [i32]),
     "gdr_profile_collect": (i32, [vp, vp]),
     "gdr_sort_pairs_ws_bytes": (i64, [i64]),

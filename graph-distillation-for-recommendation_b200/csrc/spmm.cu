@@ -7,75 +7,102 @@
 // cuSPARSE/MKL SpMM, and the index_add_ message passing of
 // distill_recsys.py:340-345.
 //
-// Mapping (HBM/L2-gather bound, no tensor cores):
+// Mapping (HBM / L2-gather bound, no tensor cores):
 //   * a CTA owns a block of SPMM_ROWS_PER_CTA consecutive rows; their rowptr
 //     slice is staged in shared memory once, and the CTA's warps pull rows from
 //     it through a shared counter (dynamic balance inside the block);
-//   * a row is processed by a group of LPR lanes (8/16/32, chosen from F) so a
-//     gathered X row is one fully coalesced run of 128-bit loads;
+//   * a row is processed by a group of LPR lanes (8/16/32, chosen from the
+//     column window) so a gathered X row is one fully coalesced run of 128-bit
+//     loads;
 //   * the row's (colidx, val) pairs are read coalesced, LPR at a time, and
-//     broadcast with warp shuffles; 4 gathers are in flight per lane before
-//     the first FMA consumes one (MLP), accumulation order stays CSR order so
-//     the result is deterministic;
-//   * rows longer than HEAVY_NNZ are split across the CTA's warps and reduced
-//     through shared memory in fixed order.
+//     broadcast with warp shuffles; UNROLL gathers are in flight per lane
+//     before the first FMA consumes one (MLP); accumulation order stays CSR
+//     order, one fp32 chain per output element => deterministic;
+//   * streamed operands (colidx, vals, T, Y) use no-allocate / streaming cache
+//     hints so that they do not evict the gathered X rows from L1/L2;
+//   * wide feature matrices can be processed in column windows (col_split) so
+//     that the window of X stays L2-resident across the whole pass.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace gdr {
 
 constexpr int SPMM_THREADS = 256;
-constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 constexpr int SPMM_ROWS_PER_CTA = 64;
+constexpr int SPMM_HEAVY_NNZ = 1024;   // rows longer than this are processed by the whole CTA
 
-template <int LPR, int NCH>
+// run-time tuning (gdr_debug_set): 0 = automatic choice
+static int g_spmm_unroll = 0;     // 4 or 8
+static int g_spmm_hints = -1;     // 0 off, 1 streaming hints on colidx/vals/T/Y
+static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
+
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_cs_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_cs_f4(float* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int LPR, int NCH, int UNROLL, bool HINTS>
 __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ colidx,
                                          const float* __restrict__ vals, float alpha,
                                          const float* __restrict__ X, int64_t ldx, int start, int end,
-                                         int F4, int gl /*lane in group*/, unsigned gmask,
+                                         int c4_end, int gl /*lane in group*/, unsigned gmask,
                                          int col4_base, float4 (&acc)[NCH]) {
 #pragma unroll
   for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // every lane of the WARP must execute the same number of shuffle rounds:
-  // the caller passes a warp-uniform trip count through start/end of the
-  // longest row in the warp when LPR < 32 (see below); here start/end are
-  // per-group and inactive iterations are predicated.
+  // start/end are uniform inside a lane group; groups of one warp may diverge (the
+  // shuffles below name only the group's own lanes in gmask).
   for (int k = start; k < end; k += LPR) {
     int my = k + gl;
     int c_l = 0;
     float v_l = 0.f;
     if (my < end) {
-      c_l = __ldg(colidx + my);
-      v_l = vals ? __fmul_rn(__ldg(vals + my), alpha) : alpha;
+      c_l = HINTS ? ld_stream_i32(colidx + my) : __ldg(colidx + my);
+      v_l = vals ? __fmul_rn(HINTS ? ld_stream_f32(vals + my) : __ldg(vals + my), alpha) : alpha;
     }
     int cnt = min(LPR, end - k);
 #pragma unroll 1
-    for (int j = 0; j < cnt; j += 4) {
-      int cj[4];
-      float vj[4];
-      float4 xv[4][NCH];
+    for (int j = 0; j < cnt; j += UNROLL) {
+      int cj[UNROLL];
+      float vj[UNROLL];
+      float4 xv[UNROLL][NCH];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         cj[u] = __shfl_sync(gmask, c_l, (j + u) & (LPR - 1), LPR);
         vj[u] = __shfl_sync(gmask, v_l, (j + u) & (LPR - 1), LPR);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         if (j + u < cnt) {
           const float* xr = X + (int64_t)cj[u] * ldx;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             int c4 = col4_base + c * LPR + gl;
-            if (c4 < F4) xv[u][c] = ldg_f4(xr + 4 * c4);
+            if (c4 < c4_end) xv[u][c] = ldg_f4(xr + 4 * c4);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         if (j + u < cnt) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             int c4 = col4_base + c * LPR + gl;
-            if (c4 < F4) {
+            if (c4 < c4_end) {
               acc[c].x = fmaf(vj[u], xv[u][c].x, acc[c].x);
               acc[c].y = fmaf(vj[u], xv[u][c].y, acc[c].y);
               acc[c].z = fmaf(vj[u], xv[u][c].z, acc[c].z);
@@ -88,23 +115,46 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ colidx,
   }
 }
 
-template <int LPR, int NCH>
-__global__ void __launch_bounds__(SPMM_THREADS)
-k_spmm(int64_t rows, int F4, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+template <int LPR, int NCH, int UNROLL, bool HINTS>
+__global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && UNROLL <= 4) ? 5 : 1)
+k_spmm(int64_t rows, int c4_end, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
        const float* __restrict__ vals, float alpha, const float* __restrict__ X, int64_t ldx,
        float* __restrict__ Y, int64_t ldy, float* __restrict__ T, int64_t ldt, float beta,
        int col4_base) {
   __shared__ int s_rowptr[SPMM_ROWS_PER_CTA + 1];
-  __shared__ int s_next;
+  __shared__ int s_heavy[SPMM_ROWS_PER_CTA];
+  __shared__ int s_next, s_nheavy;
   constexpr int GROUPS = 32 / LPR;  // rows processed concurrently by one warp
   const int64_t row0 = (int64_t)blockIdx.x * SPMM_ROWS_PER_CTA;
   const int nrows = (int)min((int64_t)SPMM_ROWS_PER_CTA, rows - row0);
   for (int i = threadIdx.x; i <= nrows; i += SPMM_THREADS) s_rowptr[i] = rowptr[row0 + i];
-  if (threadIdx.x == 0) s_next = 0;
+  if (threadIdx.x == 0) {
+    s_next = 0;
+    s_nheavy = 0;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, gl = lane % LPR;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+
+  // epilogue of one float4 column chunk: Y = acc ; T += beta * acc (two roundings, as the reference)
+  auto store = [&](int64_t row, int c4, const float4& a) {
+    float* yp = Y + row * ldy + 4 * c4;
+    if (HINTS) st_cs_f4(yp, a);
+    else *reinterpret_cast<float4*>(yp) = a;
+    if (T) {
+      float* tp = T + row * ldt + 4 * c4;
+      float4 t = HINTS ? ld_cs_f4(tp) : *reinterpret_cast<float4*>(tp);
+      t.x = __fadd_rn(t.x, __fmul_rn(beta, a.x));
+      t.y = __fadd_rn(t.y, __fmul_rn(beta, a.y));
+      t.z = __fadd_rn(t.z, __fmul_rn(beta, a.z));
+      t.w = __fadd_rn(t.w, __fmul_rn(beta, a.w));
+      if (HINTS) st_cs_f4(tp, t);
+      else *reinterpret_cast<float4*>(tp) = t;
+    }
+  };
+
+  // ---- phase 1: light rows, one lane group per row; heavy rows are deferred ----
   while (true) {
     int r_base = 0;
     if (lane == 0) r_base = atomicAdd(&s_next, GROUPS);
@@ -112,46 +162,114 @@ k_spmm(int64_t rows, int F4, const int32_t* __restrict__ rowptr, const int32_t* 
     if (r_base >= nrows) break;
     int r = r_base + g;
     int start = 0, end = 0;
-    if (r < nrows) {
+    bool live = r < nrows;
+    if (live) {
       start = s_rowptr[r];
       end = s_rowptr[r + 1];
+      if (end - start > SPMM_HEAVY_NNZ) {
+        if (gl == 0) s_heavy[atomicAdd(&s_nheavy, 1)] = r;
+        live = false;
+        start = end = 0;
+      }
     }
     float4 acc[NCH];
-    spmm_row<LPR, NCH>(colidx, vals, alpha, X, ldx, start, end, F4, gl, gmask, col4_base, acc);
-    if (r < nrows) {
-      int64_t row = row0 + r;
+    spmm_row<LPR, NCH, UNROLL, HINTS>(colidx, vals, alpha, X, ldx, start, end, c4_end, gl, gmask, col4_base, acc);
+    if (live) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         int c4 = col4_base + c * LPR + gl;
-        if (c4 < F4) {
-          *reinterpret_cast<float4*>(Y + row * ldy + 4 * c4) = acc[c];
-          if (T) {
-            float4* tp = reinterpret_cast<float4*>(T + row * ldt + 4 * c4);
-            float4 t = *tp;
-            t.x = __fadd_rn(t.x, __fmul_rn(beta, acc[c].x));
-            t.y = __fadd_rn(t.y, __fmul_rn(beta, acc[c].y));
-            t.z = __fadd_rn(t.z, __fmul_rn(beta, acc[c].z));
-            t.w = __fadd_rn(t.w, __fmul_rn(beta, acc[c].w));
-            *tp = t;
-          }
-        }
+        if (c4 < c4_end) store(row0 + r, c4, acc[c]);
       }
     }
   }
+  __syncthreads();
+
+  // ---- phase 2: each heavy (hub) row is split over all lane groups of the CTA; the
+  //      partial sums are combined in fixed chunk order (deterministic) ----
+  const int nheavy = s_nheavy;
+  if (nheavy == 0) return;
+  constexpr int NPART = (SPMM_THREADS / 32) * GROUPS;
+  __shared__ float4 s_part[NPART][NCH * LPR];
+  const int part = (threadIdx.x >> 5) * GROUPS + g;
+  for (int h = 0; h < nheavy; ++h) {
+    const int r = s_heavy[h];
+    const int hs = s_rowptr[r], he = s_rowptr[r + 1];
+    int chunk = (he - hs + NPART - 1) / NPART;
+    chunk = (chunk + LPR - 1) / LPR * LPR;
+    const int cs = min(he, hs + part * chunk), ce = min(he, cs + chunk);
+    float4 acc[NCH];
+    spmm_row<LPR, NCH, UNROLL, HINTS>(colidx, vals, alpha, X, ldx, cs, ce, c4_end, gl, gmask, col4_base, acc);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s_part[part][c * LPR + gl] = acc[c];
+    __syncthreads();
+    for (int t = threadIdx.x; t < NCH * LPR; t += SPMM_THREADS) {
+      const int c4 = col4_base + t;
+      if (c4 < c4_end) {
+        float4 s = s_part[0][t];
+#pragma unroll 4
+        for (int p = 1; p < NPART; ++p) {
+          const float4 q = s_part[p][t];
+          s.x = __fadd_rn(s.x, q.x);
+          s.y = __fadd_rn(s.y, q.y);
+          s.z = __fadd_rn(s.z, q.z);
+          s.w = __fadd_rn(s.w, q.w);
+        }
+        store(row0 + r, c4, s);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct SpmmArgs {
+  int64_t rows;
+  const int32_t *rowptr, *colidx;
+  const float* vals;
+  float alpha;
+  const float* X;
+  int64_t ldx;
+  float* Y;
+  int64_t ldy;
+  float* T;
+  int64_t ldt;
+  float beta;
+  cudaStream_t s;
+};
+
+template <int LPR, int NCH, int UNROLL, bool HINTS>
+static int launch_spmm(const SpmmArgs& a, int col4_base, int c4_end) {
+  unsigned grid = (unsigned)cdiv(a.rows, SPMM_ROWS_PER_CTA);
+  {
+    ProfileScope prof(PROF_SPMM, a.s);
+    k_spmm<LPR, NCH, UNROLL, HINTS><<<grid, SPMM_THREADS, 0, a.s>>>(a.rows, c4_end, a.rowptr, a.colidx, a.vals, a.alpha,
+                                                                    a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt, a.beta, col4_base);
+  }
+  GDR_LAUNCHED();
+  return GDR_OK;
 }
 
 template <int LPR, int NCH>
-static int launch_spmm(int64_t rows, int F4, const int32_t* rowptr, const int32_t* colidx,
-                       const float* vals, float alpha, const float* X, int64_t ldx, float* Y,
-                       int64_t ldy, float* T, int64_t ldt, float beta, int col4_base,
-                       cudaStream_t s) {
-  unsigned grid = (unsigned)cdiv(rows, SPMM_ROWS_PER_CTA);
-  {
-    ProfileScope prof(PROF_SPMM, s);
-    k_spmm<LPR, NCH><<<grid, SPMM_THREADS, 0, s>>>(rows, F4, rowptr, colidx, vals, alpha, X, ldx, Y,
-                                                   ldy, T, ldt, beta, col4_base);
+static int dispatch_tuning(const SpmmArgs& a, int base, int c4_end, int unroll, bool hints) {
+  if constexpr (NCH <= 2) {
+    if (unroll >= 8)
+      return hints ? launch_spmm<LPR, NCH, 8, true>(a, base, c4_end) : launch_spmm<LPR, NCH, 8, false>(a, base, c4_end);
   }
-  GDR_LAUNCHED();
+  constexpr int U = NCH >= 8 ? 1 : (NCH >= 4 ? 2 : 4);
+  return hints ? launch_spmm<LPR, NCH, U, true>(a, base, c4_end) : launch_spmm<LPR, NCH, U, false>(a, base, c4_end);
+}
+
+// one column window [base, base + width) in float4 units
+static int spmm_window(const SpmmArgs& a, int base, int width, int unroll, bool hints) {
+  const int c4_end = base + width;
+  if (width <= 8) return dispatch_tuning<8, 1>(a, base, c4_end, unroll, hints);
+  if (width <= 16) return dispatch_tuning<16, 1>(a, base, c4_end, unroll, hints);
+  if (width <= 32) return dispatch_tuning<32, 1>(a, base, c4_end, unroll, hints);
+  if (width <= 64) return dispatch_tuning<32, 2>(a, base, c4_end, unroll, hints);
+  if (width <= 128) return dispatch_tuning<32, 4>(a, base, c4_end, unroll, hints);
+  for (int b = base; b < c4_end; b += 256) {
+    int rc = dispatch_tuning<32, 8>(a, b, std::min(c4_end, b + 256), unroll, hints);
+    if (rc) return rc;
+  }
   return GDR_OK;
 }
 
@@ -159,21 +277,20 @@ int spmm_launch(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* c
                 const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
                 float* T, int64_t ldt, float beta, cudaStream_t s) {
   if (rows == 0 || F == 0) return GDR_OK;
-  int F4 = (int)cdiv(F, 4);
-#define GDR_SPMM(LPR, NCH, base) \
-  launch_spmm<LPR, NCH>(rows, F4, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, base, s)
-  if (F4 <= 8) return GDR_SPMM(8, 1, 0);
-  if (F4 <= 16) return GDR_SPMM(16, 1, 0);
-  if (F4 <= 32) return GDR_SPMM(32, 1, 0);
-  if (F4 <= 64) return GDR_SPMM(32, 2, 0);
-  if (F4 <= 128) return GDR_SPMM(32, 4, 0);
-  // wide rows: column super-blocks of 8*32 float4 = 1024 floats
-  for (int base = 0; base < F4; base += 256) {
-    int rc = GDR_SPMM(32, 8, base);
-    if (rc) return rc;
+  const int F4 = (int)cdiv(F, 4);
+  SpmmArgs a{rows, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, s};
+  const int unroll = g_spmm_unroll > 0 ? g_spmm_unroll : 4;
+  const bool hints = g_spmm_hints >= 0 ? g_spmm_hints != 0 : false;
+  int split = g_spmm_split > 0 ? g_spmm_split : 1;
+  if (split > 1 && F4 >= 8 * split) {
+    const int w = (int)cdiv(F4, split);
+    for (int b = 0; b < F4; b += w) {
+      int rc = spmm_window(a, b, std::min(w, F4 - b), unroll, hints);
+      if (rc) return rc;
+    }
+    return GDR_OK;
   }
-#undef GDR_SPMM
-  return GDR_OK;
+  return spmm_window(a, 0, F4, unroll, hints);
 }
 
 __global__ void k_scale_rows(int64_t rows, int F4, float a, const float* __restrict__ X, int64_t ldx,
@@ -195,6 +312,19 @@ __global__ void k_scale_rows(int64_t rows, int F4, float a, const float* __restr
 }  // namespace gdr
 
 extern "C" {
+
+// Tuning / experiment knobs (not part of the stable surface; see tools/spmm_sweep.py).
+int gdr_debug_set(const char* key, int value) {
+  GDR_CHECK_ARG(key, "debug_set: null key");
+  if (!strcmp(key, "spmm_unroll")) gdr::g_spmm_unroll = value;
+  else if (!strcmp(key, "spmm_hints")) gdr::g_spmm_hints = value;
+  else if (!strcmp(key, "spmm_split")) gdr::g_spmm_split = value;
+  else {
+    gdr::set_error("debug_set: unknown key %s", key);
+    return GDR_EINVAL;
+  }
+  return GDR_OK;
+}
 
 int gdr_spmm_prop(int64_t rows_local, int64_t F, const int32_t* rowptr, const int32_t* colidx,
                   const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,

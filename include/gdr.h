@@ -65,6 +65,10 @@ int64_t     gdr_launch_count(void);
 int gdr_profile_enable(int kind);
 int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
 
+/* Experiment knobs for kernel tuning sweeps (tools/spmm_sweep.py); not a stable surface.
+ * keys: "spmm_unroll" (4|8), "spmm_hints" (0|1), "spmm_split" (1|2|4); value 0 / -1 = automatic. */
+int gdr_debug_set(const char* key, int value);
+
 /* ---- generic device primitives (used by stages 1, 3, 4) -------------- */
 /* Stable LSD radix sort of (uint64 key, uint32 payload) pairs on the low
  * `key_bits` bits.  Result is left in keys_io / vals_io. */
