@@ -40,6 +40,8 @@ _SIGNATURES = {
     "gdr_scale_rows": (i32, [i64, i64, f32, vp, i64, vp, i64, vp]),
     "gdr_center_columns_ws_bytes": (i64, [i64, i64]),
     "gdr_center_columns": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
+    "gdr_standard_scale_ws_bytes": (i64, [i64, i64]),
+    "gdr_standard_scale": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp]),
     "gdr_column_sums": (i32, [i64, i64, vp, i64, vp, vp, i64, vp]),
     "gdr_center_apply": (i32, [i64, i64, vp, i64, vp, vp, i64, vp]),
     "gdr_coarse_scatter_dense": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, vp]),
@@ -53,6 +55,8 @@ _SIGNATURES = {
     "gdr_kmeans_assign_tc": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_kmeans_lloyd_ws_bytes": (i64, [i64, i64, i64, i32]),
     "gdr_kmeans_lloyd": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i32, C.c_double, i32, vp, vp, vp, i32, vp, i64, vp]),
+    "gdr_kmeans_plusplus_ws_bytes": (i64, [i64, i64, i64, i32]),
+    "gdr_kmeans_plusplus": (i32, [i64, i64, i64, vp, i64, i64, vp, i32, vp, i64, vp, vp, i64, vp]),
     "gdr_segment_sum_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_segment_sum": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
     "gdr_label_histogram": (i32, [i64, i64, vp, vp, vp, vp]),

@@ -656,6 +656,71 @@ __global__ void __launch_bounds__(256) k_relocate_one(int nparts, const float* _
   }
 }
 
+// second pass of the variance: per-block sums of (x - mean) and (x - mean)^2
+__global__ void __launch_bounds__(256) k_colvar_partial(int64_t N, int D, const float* __restrict__ X, int64_t ldx,
+                                                        const double* __restrict__ mean, double* __restrict__ part) {
+  __shared__ double s_sum[8][33], s_sq[8][33];
+  int64_t r0 = (int64_t)blockIdx.x * CC_ROWS_PER_BLOCK;
+  int64_t r1 = min(N, r0 + CC_ROWS_PER_BLOCK);
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    int c = c0 + threadIdx.x;
+    double su = 0.0, sq = 0.0;
+    if (c < D) {
+      const double m = mean[c];
+      for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+        double x = (double)X[r * ldx + c] - m;
+        su += x;
+        sq += x * x;
+      }
+    }
+    s_sum[threadIdx.y][threadIdx.x] = su;
+    s_sq[threadIdx.y][threadIdx.x] = sq;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        a += s_sum[y][threadIdx.x];
+        b += s_sq[y][threadIdx.x];
+      }
+      part[((int64_t)blockIdx.x * D + c) * 2 + 0] = a;
+      part[((int64_t)blockIdx.x * D + c) * 2 + 1] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// params[0..D) = mean, params[D..2D) = scale (fp64); fp32 copies for the transform.
+// sums2 == nullptr: first pass (mean only).
+__global__ void k_scale_params(int64_t N, int D, const double* __restrict__ sums1, const double* __restrict__ sums2,
+                               double* __restrict__ params, float* __restrict__ mean32, float* __restrict__ scale32) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const double mean = sums1[c] / (double)N;
+  params[c] = mean;
+  mean32[c] = (float)mean;
+  if (sums2) {
+    const double var = sums2[D + c] / (double)N;
+    // sklearn.preprocessing._data._is_constant_feature: var <= N*eps*var + (N*mean*eps)^2
+    const double eps = 2.220446049250313e-16;
+    const double bound = (double)N * eps * var + ((double)N * mean * eps) * ((double)N * mean * eps);
+    double scale = sqrt(var);
+    if (var <= bound) scale = 1.0;
+    params[D + c] = scale;
+    scale32[c] = (float)scale;
+  }
+}
+
+__global__ void k_standardize(int64_t N, int D, const float* __restrict__ X, int64_t ldx, const float* __restrict__ mean,
+                              const float* __restrict__ scale, float* __restrict__ out, int64_t ldo) {
+  int64_t total = N * (int64_t)D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D;
+    int c = (int)(i - r * D);
+    out[r * ldo + c] = __fdiv_rn(__fsub_rn(X[r * ldx + c], mean[c]), scale[c]);
+  }
+}
+
 // fixed-order reduction of the per-block partials: out[c] = sum, out[D + c] = sum of squares
 __global__ void __launch_bounds__(256) k_colstats_reduce(int D, int nblocks, const double* __restrict__ part,
                                                          double* __restrict__ out) {
@@ -734,6 +799,52 @@ int gdr_column_sums(int64_t N, int64_t D, const float* X, int64_t ldx, double* s
   GDR_LAUNCHED();
   k_colstats_reduce<<<(unsigned)cdiv(D, 256), 256, 0, s>>>((int)D, nb, part, sums_out);
   GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// StandardScaler(with_mean=True, with_std=True).fit_transform (distill_recsys.py:172):
+// mean and population variance per column in fp64 (two passes: sum, then sum of squared
+// deviations), scale = sqrt(var) with constant columns -> 1 (sklearn _is_constant_feature),
+// out = fp32((x - fp32(mean)) / fp32(scale)) — bit-exact with sklearn on the golden vector.
+int64_t gdr_standard_scale_ws_bytes(int64_t N, int64_t D) {
+  return gdr_center_columns_ws_bytes(N, D) + 3 * ws_need(2 * D, 8) + 2 * ws_need(D, 4) + 256;
+}
+
+int gdr_standard_scale(int64_t N, int64_t D, const float* X, int64_t ldx, float* out, int64_t ldo,
+                       double* mean_out /*nullable, f64[D]*/, double* scale_out /*nullable, f64[D]*/, void* ws,
+                       int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N > 0 && D > 0 && X && out && ldx >= D && ldo >= D, "standard_scale: bad arguments");
+  if (ws_bytes < gdr_standard_scale_ws_bytes(N, D)) {
+    set_error("standard_scale: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = (int)cdiv(N, CC_ROWS_PER_BLOCK);
+  Workspace W(ws, ws_bytes);
+  double* part = (double*)W.take<char>(gdr_center_columns_ws_bytes(N, D));
+  double* sums1 = W.take<double>(2 * D);
+  double* sums2 = W.take<double>(2 * D);
+  double* mean64 = W.take<double>(2 * D);  // [mean | scale]
+  float* mean32 = W.take<float>(D);
+  float* scale32 = W.take<float>(D);
+  k_colstats_partial<<<nb, dim3(32, 8), 0, s>>>(N, (int)D, X, ldx, part);
+  GDR_LAUNCHED();
+  k_colstats_reduce<<<(unsigned)cdiv(D, 256), 256, 0, s>>>((int)D, nb, part, sums1);
+  GDR_LAUNCHED();
+  k_scale_params<<<(unsigned)cdiv(D, 256), 256, 0, s>>>(N, (int)D, sums1, nullptr, mean64, mean32, scale32);
+  GDR_LAUNCHED();
+  k_colvar_partial<<<nb, dim3(32, 8), 0, s>>>(N, (int)D, X, ldx, mean64, part);
+  GDR_LAUNCHED();
+  k_colstats_reduce<<<(unsigned)cdiv(D, 256), 256, 0, s>>>((int)D, nb, part, sums2);
+  GDR_LAUNCHED();
+  k_scale_params<<<(unsigned)cdiv(D, 256), 256, 0, s>>>(N, (int)D, sums1, sums2, mean64, mean32, scale32);
+  GDR_LAUNCHED();
+  int64_t total = N * D;
+  k_standardize<<<(unsigned)std::min<int64_t>(cdiv(total, 256), kSMs * 16), 256, 0, s>>>(N, (int)D, X, ldx, mean32,
+                                                                                      scale32, out, ldo);
+  GDR_LAUNCHED();
+  if (mean_out) GDR_CUDA(cudaMemcpyAsync(mean_out, mean64, D * 8, cudaMemcpyDeviceToDevice, s));
+  if (scale_out) GDR_CUDA(cudaMemcpyAsync(scale_out, mean64 + D, D * 8, cudaMemcpyDeviceToDevice, s));
   return GDR_OK;
 }
 

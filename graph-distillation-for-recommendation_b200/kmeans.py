@@ -376,13 +376,15 @@ def standard_scale(X: torch.Tensor) -> torch.Tensor:
     mean / population variance in fp64, scale = sqrt(var) with zero variance -> 1,
     result fp32((x - fp32(mean)) / fp32(scale))."""
     X = X.to(torch.float32)
+    if not X.is_cuda:
+        raise ValueError("standard_scale needs a CUDA tensor (no CPU path)")
     N, D = X.shape
-    X64 = X.to(torch.float64)
-    mean = X64.mean(dim=0)
-    var = X64.var(dim=0, unbiased=False)
-    scale = var.sqrt()
-    scale = torch.where(scale == 0, torch.ones_like(scale), scale)
-    return (X - mean.to(torch.float32)) / scale.to(torch.float32)
+    Xin = X if X.stride(1) == 1 else X.contiguous()
+    out = torch.empty((N, D), dtype=torch.float32, device=X.device)
+    ws = workspace(_lib.query("gdr_standard_scale_ws_bytes", N, D), X.device)
+    _lib.call("gdr_standard_scale", N, D, ptr(Xin), Xin.stride(0), ptr(out), out.stride(0), 0, 0, ptr(ws),
+              ws.numel(), stream())
+    return out
 
 
 def kmeans_cluster(X, n_clusters: int, seed: int, minibatch: bool = True, batch_size: int = 2048,

@@ -176,6 +176,14 @@ int     gdr_center_columns(int64_t N, int64_t D, const float* X, int64_t ldx,
                            float* Xc /*nullable*/, int64_t ldxc,
                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
+/* StandardScaler(with_mean, with_std).fit_transform of distill_recsys.py:172 — per-column mean and
+ * population variance in fp64 (two passes), constant columns get scale 1, then
+ * out = fp32((x - fp32(mean)) / fp32(scale)).  mean_out / scale_out: device f64[D], nullable. */
+int64_t gdr_standard_scale_ws_bytes(int64_t N, int64_t D);
+int     gdr_standard_scale(int64_t N, int64_t D, const float* X, int64_t ldx, float* out, int64_t ldo,
+                           double* mean_out, double* scale_out, void* ws, int64_t ws_bytes,
+                           gdr_stream_t stream);
+
 /* Row-partitioned form of the two steps above (multi-GPU): per-rank fp64 column sums
  * (sums_out[0..D) = sum, [D..2D) = sum of squares; all-reduced by the host, which derives
  * mean and tol') and the centring pass with a given mean.  ws: gdr_center_columns_ws_bytes. */
@@ -229,6 +237,20 @@ int     gdr_kmeans_lloyd(int64_t N, int64_t K, int64_t D, const float* Xc, int64
                          int max_iter, double tol_abs, int precision_mode,
                          double* inertia_out_host, int32_t* n_iter_out_host, int32_t* info_out_host,
                          int verbose, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
+/* Greedy k-means++ seeding (sklearn/_kmeans.py:180-278; the default init of the reference's
+ * KMeans(n_clusters=n) at clustgdd_agent_transduct.py:105 and distill_recsys.py:178).
+ * The caller draws the random numbers on the host exactly as sklearn consumes them:
+ * first_center = random_state.choice(N, p=uniform) and, for each of the K-1 further centres,
+ * rand_vals_host[(c-1)*n_trials ...] = random_state.uniform(size=n_trials), n_trials = 2 + int(ln K).
+ * All distance / potential / cumulative-sum arithmetic runs on the device (fp64 accumulation,
+ * fixed order).  centers_out [K][ldc] (device); indices_out_dev int64[K] nullable.
+ * n_trials <= 16.  Synchronises the stream once at the end. */
+int64_t gdr_kmeans_plusplus_ws_bytes(int64_t N, int64_t K, int64_t D, int n_trials);
+int     gdr_kmeans_plusplus(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx,
+                            int64_t first_center, const double* rand_vals_host, int n_trials,
+                            float* centers_out, int64_t ldc, int64_t* indices_out_dev,
+                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
 /* M-step, part 1: per-cluster sums and counts.
  *   replaces  centers_new[label] += X[i]; weight[label] += 1

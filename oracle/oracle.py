@@ -384,6 +384,37 @@ def kmeans_fit(X, C0, max_iter=300, tol=1e-4):
                 n_iter=n_iter, centers_centered=Cn, mean=mean)
 
 
+def kmeans_plusplus(X, n_clusters, random_state, n_local_trials=None, cumsum_dtype=np.float64):
+    """sklearn's greedy k-means++ (sklearn/_kmeans.py:180-278) with unit sample weights.
+    Consumes ``random_state`` exactly as sklearn does.  ``cumsum_dtype=np.float32`` reproduces
+    sklearn's own cumulative sum; float64 is what the CUDA kernel accumulates in.
+    Returns (centers, indices)."""
+    X = _f32(X)
+    n, d = X.shape
+    if n_local_trials is None:
+        n_local_trials = 2 + int(np.log(n_clusters))
+    centers = np.empty((n_clusters, d), dtype=np.float32)
+    indices = np.full(n_clusters, -1, dtype=np.int64)
+    cid = random_state.choice(n, p=np.full(n, 1.0 / n))
+    centers[0], indices[0] = X[cid], cid
+
+    def sqdist(C):  # [len(C), n] exact squared distances, fp32 result
+        return ((X[None, :, :].astype(np.float64) - C[:, None, :].astype(np.float64)) ** 2).sum(-1).astype(np.float32)
+
+    closest = sqdist(centers[:1])[0]
+    pot = closest.astype(np.float64).sum()
+    for c in range(1, n_clusters):
+        rand_vals = random_state.uniform(size=n_local_trials) * pot
+        cand = np.searchsorted(np.cumsum(closest.astype(cumsum_dtype)), rand_vals)
+        np.clip(cand, None, n - 1, out=cand)
+        dc = np.minimum(closest[None, :], sqdist(X[cand]))
+        pots = dc.astype(np.float64).sum(axis=1)
+        best = int(np.argmin(pots))
+        pot, closest = pots[best], dc[best]
+        centers[c], indices[c] = X[cand[best]], cand[best]
+    return centers, indices
+
+
 def standard_scale(X):
     """StandardScaler().fit_transform (distill_recsys.py:172): fp64 mean / population var,
     scale = sqrt(var) (0 -> 1), result fp32((x - fp32(mean)) / fp32(scale))."""

@@ -171,3 +171,13 @@ def test_lightgcn_propagate(oracle):
     u, i = oracle.lightgcn_propagate(rp, ci, w, g["u0"], g["i0"], int(g["layers"]))
     np.testing.assert_allclose(u, g["u_out"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(i, g["i_out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("k", [25, 60, 200])
+def test_kmeans_plusplus_matches_sklearn(oracle, k):
+    g = golden("kmeans_plusplus.npz")
+    seed = int(g[f"k{k}_seed"])
+    for dt in (np.float32, np.float64):
+        c, idx = oracle.kmeans_plusplus(g["x"], k, np.random.RandomState(seed), cumsum_dtype=dt)
+        assert np.array_equal(idx, g[f"k{k}_indices"])
+        assert np.array_equal(c, g[f"k{k}_centers"])
