@@ -265,132 +265,155 @@ int launch_row_sqnorm(int64_t K, int D, const float* C, int64_t ldc, float* out,
   return GDR_OK;
 }
 
-// Exact re-score of a short device-side row list: one CTA per listed row (persistent,
-// grid-strided), its threads split the K centres.  Every (row, centre) distance is the SAME
-// fp32 chain k_assign_simt evaluates — acc = fmaf(x_k, c_k, acc) for k ascending, then
-// fmaf(-2, acc, |c|^2) — so a re-scored row gets exactly the label the full exact kernel
-// would give it.  (The tiled kernel would put all listed rows into a few 128-row CTAs that
-// walk all K centres serially: 170 us for 50 rows at config B.)
+// Exact re-score of a short device-side row list.  grid = (row groups, centre slabs): a CTA
+// keeps RF_ROWS listed rows in shared memory and each of its threads owns ONE centre of its
+// slab; the centres are read through a TRANSPOSED copy CT[k][j] (consecutive threads ->
+// consecutive addresses) and every loaded value feeds RF_ROWS chains.  Each (row, centre)
+// distance is the SAME fp32 chain k_assign_simt evaluates — acc = fmaf(x_k, c_k, acc) for k
+// ascending, then fmaf(-2, acc, |c|^2) — and the slabs are combined with a 64-bit atomicMin on
+// (ordered distance bits << 32 | centre index): minimum distance, then lowest index, which is
+// order-independent, so a re-scored row gets exactly the label of the full exact kernel.
 constexpr int RF_THREADS = 128;
+constexpr int RF_ROWS = 8;
 
-__global__ void __launch_bounds__(RF_THREADS) k_refine_rows(int K, int D, const float* __restrict__ X,
-                                                            int64_t ldx, const float* __restrict__ C,
-                                                            int64_t ldc, const float* __restrict__ cnorm,
-                                                            const int32_t* __restrict__ rows,
-                                                            const int32_t* __restrict__ n_rows_dev,
-                                                            int32_t* __restrict__ labels,
-                                                            const int32_t* __restrict__ labels_prev,
-                                                            int32_t* __restrict__ n_changed,
-                                                            float* __restrict__ best_out) {
-  extern __shared__ float s_x[];  // D floats (rounded up to 4)
-  __shared__ float s_best[RF_THREADS];
-  __shared__ int s_idx[RF_THREADS];
+__device__ __forceinline__ unsigned long long rf_pack(float d, int j) {
+  unsigned u = __float_as_uint(d);
+  u = (u >> 31) ? ~u : (u | 0x80000000u);   // monotone map float -> uint32
+  return ((unsigned long long)u << 32) | (unsigned)j;
+}
+
+__global__ void __launch_bounds__(RF_THREADS) k_refine_partial(int K, int D, const float* __restrict__ X,
+                                                               int64_t ldx, const float* __restrict__ CT,
+                                                               int64_t ldct, const float* __restrict__ cnorm,
+                                                               const int32_t* __restrict__ rows,
+                                                               const int32_t* __restrict__ n_rows_dev,
+                                                               unsigned long long* __restrict__ packed) {
+  extern __shared__ float s_x[];  // [RF_ROWS][D]
   const int n_rows = *n_rows_dev;
-  const int D4 = (D + 3) / 4;
-  for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
-    const int64_t row = rows[q];
-    for (int k4 = threadIdx.x; k4 < D4; k4 += RF_THREADS) {
-      float4 v = *reinterpret_cast<const float4*>(X + row * ldx + 4 * k4);
-      if (4 * k4 + 1 >= D) v.y = 0.f;
-      if (4 * k4 + 2 >= D) v.z = 0.f;
-      if (4 * k4 + 3 >= D) v.w = 0.f;
-      *reinterpret_cast<float4*>(&s_x[4 * k4]) = v;
+  const int lane = threadIdx.x & 31;
+  for (int q0 = blockIdx.x * RF_ROWS; q0 < n_rows; q0 += gridDim.x * RF_ROWS) {
+    const int nr = min(RF_ROWS, n_rows - q0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < RF_ROWS * D; t += RF_THREADS) {
+      const int r = t / D, k = t - r * D;
+      s_x[t] = r < nr ? X[(int64_t)rows[q0 + r] * ldx + k] : 0.f;
     }
     __syncthreads();
-    float best = INFINITY;
-    int bidx = 0x7fffffff;
-    for (int j = threadIdx.x; j < K; j += RF_THREADS) {
-      const float* c = C + (int64_t)j * ldc;
-      float acc = 0.f;
-      for (int k4 = 0; k4 < D4; ++k4) {
-        float4 cv = __ldg(reinterpret_cast<const float4*>(c + 4 * k4));
-        const float4 xv = *reinterpret_cast<const float4*>(&s_x[4 * k4]);
-        if (4 * k4 + 1 >= D) cv.y = 0.f;
-        if (4 * k4 + 2 >= D) cv.z = 0.f;
-        if (4 * k4 + 3 >= D) cv.w = 0.f;
-        acc = fmaf(xv.x, cv.x, acc);
-        acc = fmaf(xv.y, cv.y, acc);
-        acc = fmaf(xv.z, cv.z, acc);
-        acc = fmaf(xv.w, cv.w, acc);
+    for (int j0 = blockIdx.y * RF_THREADS; j0 < K; j0 += gridDim.y * RF_THREADS) {
+      const int j = j0 + threadIdx.x;
+      const int jc = j < K ? j : K - 1;   // clamp the address; masked below
+      float acc[RF_ROWS];
+#pragma unroll
+      for (int r = 0; r < RF_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 16
+      for (int k = 0; k < D; ++k) {
+        const float c = __ldg(CT + (int64_t)k * ldct + jc);
+#pragma unroll
+        for (int r = 0; r < RF_ROWS; ++r) acc[r] = fmaf(s_x[r * D + k], c, acc[r]);
       }
-      const float d = fmaf(-2.f, acc, __ldg(cnorm + j));
-      if (d < best) {  // ascending j per thread: first minimum wins
-        best = d;
-        bidx = j;
-      }
-    }
-    s_best[threadIdx.x] = best;
-    s_idx[threadIdx.x] = bidx;
-    __syncthreads();
-    for (int o = RF_THREADS / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        float ob = s_best[threadIdx.x + o];
-        int oi = s_idx[threadIdx.x + o];
-        if (ob < s_best[threadIdx.x] || (ob == s_best[threadIdx.x] && oi < s_idx[threadIdx.x])) {
-          s_best[threadIdx.x] = ob;
-          s_idx[threadIdx.x] = oi;
+      const float cn = __ldg(cnorm + jc);
+#pragma unroll
+      for (int r = 0; r < RF_ROWS; ++r) {
+        const float d = fmaf(-2.f, acc[r], cn);
+        unsigned long long key = (j < K && d == d) ? rf_pack(d, j) : ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other < key ? other : key;
         }
+        if (lane == 0 && r < nr) atomicMin(&packed[q0 + r], key);
       }
-      __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      int l = s_idx[0] == 0x7fffffff ? 0 : s_idx[0];
-      labels[row] = l;
-      if (best_out) best_out[row] = s_best[0];
-      if (n_changed && labels_prev && labels_prev[row] != l) atomicAdd(n_changed, 1);
-    }
-    __syncthreads();
   }
 }
 
-// exact re-score of a device-side row list.  Short lists (the normal case) use the
-// row-per-CTA kernel; max_rows only bounds the grid.
+__global__ void __launch_bounds__(256) k_refine_commit(const int32_t* __restrict__ rows,
+                                                       const int32_t* __restrict__ n_rows_dev,
+                                                       const unsigned long long* __restrict__ packed,
+                                                       int32_t* __restrict__ labels,
+                                                       const int32_t* __restrict__ labels_prev,
+                                                       int32_t* __restrict__ n_changed, float* __restrict__ best_out) {
+  const int n_rows = *n_rows_dev;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_rows; q += gridDim.x * blockDim.x) {
+    const unsigned long long key = packed[q];
+    const int64_t row = rows[q];
+    int l = (int)(unsigned)(key & 0xffffffffull);
+    if (key == ~0ull) l = 0;
+    unsigned u = (unsigned)(key >> 32);
+    u = (u >> 31) ? (u & 0x7fffffffu) : ~u;
+    labels[row] = l;
+    if (best_out) best_out[row] = __uint_as_float(u);
+    if (n_changed && labels_prev && labels_prev[row] != l) atomicAdd(n_changed, 1);
+  }
+}
+
+// exact re-score of a device-side row list; CT = centres transposed [D][ldct], ldct >= K;
+// packed[q] must be ~0 for every listed slot (k_tc_select initialises it).  max_rows only
+// bounds the grid.
 int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float* X, int64_t ldx,
-                            const float* C, int64_t ldc, const float* cnorm, const int32_t* rows,
-                            const int32_t* n_rows_dev, int32_t* labels, const int32_t* labels_prev,
-                            int32_t* n_changed, float* best_out, cudaStream_t s) {
-  unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(max_rows, 1), kSMs * 8);
-  size_t smem = (size_t)align_up(D, 4) * 4;
-  k_refine_rows<<<grid, RF_THREADS, smem, s>>>((int)K, (int)D, X, ldx, C, ldc, cnorm, rows, n_rows_dev, labels,
-                                              labels_prev, n_changed, best_out);
+                            const float* CT, int64_t ldct, const float* cnorm, const int32_t* rows,
+                            const int32_t* n_rows_dev, unsigned long long* packed, int32_t* labels,
+                            const int32_t* labels_prev, int32_t* n_changed, float* best_out, cudaStream_t s) {
+  size_t smem = (size_t)RF_ROWS * D * 4;
+  if (smem > 48 * 1024) {
+    set_error("re-score kernel: D=%lld exceeds its shared-memory plan", (long long)D);
+    return GDR_EUNSUPPORTED;
+  }
+  const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(max_rows, RF_ROWS), 1), 256);
+  const unsigned gy = (unsigned)std::min<int64_t>(cdiv(K, RF_THREADS), 1024);
+  k_refine_partial<<<dim3(gx, gy), RF_THREADS, smem, s>>>((int)K, (int)D, X, ldx, CT, ldct, cnorm, rows, n_rows_dev,
+                                                          packed);
+  GDR_LAUNCHED();
+  k_refine_commit<<<64, 256, 0, s>>>(rows, n_rows_dev, packed, labels, labels_prev, n_changed, best_out);
   GDR_LAUNCHED();
   return GDR_OK;
 }
 
-// M-step gather-sum: one warp per (cluster, 32-column slab); lane = column; the member
-// rows of the cluster are added in ascending row order, one fp32 chain per output element
-// (== np.add.at / single-thread sklearn order).  K * ceil(D/32) warps instead of K, 8
-// independent 128-byte row reads in flight per warp.
-__global__ void __launch_bounds__(256) k_gather_sum(int64_t K, int Dp4, int nslab,
+// M-step gather-sum: one CTA per cluster.  The member rows are staged through shared memory in
+// chunks of R rows with fully parallel, coalesced 128-bit loads (8+ independent loads per thread
+// in flight), then thread c adds column c of the staged rows IN ASCENDING ROW ORDER — one fp32
+// chain per output element, exactly np.add.at / single-thread sklearn order — so the loads are
+// parallel while the summation order stays sequential (bit-identical to the oracle).
+__global__ void __launch_bounds__(256) k_gather_sum(int64_t K, int Dp4, int R,
                                                     const int32_t* __restrict__ mptr,
                                                     const uint32_t* __restrict__ ids,
                                                     const float* __restrict__ X, int64_t ldx,
                                                     float* __restrict__ sums, int64_t lds) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= K * nslab) return;
-  const int64_t k = w / nslab;
-  const int col = (int)(w - k * nslab) * 32 + lane_id();
-  const bool live = col < Dp4;
+  extern __shared__ __align__(16) float s_rows[];   // [R][Dp4]
+  const int64_t k = blockIdx.x;
   const int b = mptr[k], e = mptr[k + 1];
-  float acc = 0.f;
-  for (int i = b; i < e; i += 32) {
-    const int my = i + lane_id();
-    const uint32_t id_l = my < e ? ids[my] : 0u;
-    const int cnt = min(32, e - i);
-#pragma unroll 1
-    for (int j = 0; j < cnt; j += 8) {
-      float xv[8];
+  const int F4 = Dp4 >> 2;
+  constexpr int MAXC = 4;                            // columns per thread: Dp4 <= 1024 per pass
+  for (int c0 = 0; c0 < Dp4; c0 += 256 * MAXC) {
+    float acc[MAXC];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t id = __shfl_sync(0xffffffffu, id_l, (j + u) & 31);
-        xv[u] = (live && j + u < cnt) ? __ldg(X + (int64_t)id * ldx + col) : 0.f;
+    for (int q = 0; q < MAXC; ++q) acc[q] = 0.f;
+    const int w4 = min(F4 - (c0 >> 2), 64 * MAXC);   // float4 columns in this pass
+    for (int i = b; i < e; i += R) {
+      const int rc = min(R, e - i);
+      for (int t = threadIdx.x; t < rc * w4; t += 256) {
+        const int r = t / w4, c4 = t - r * w4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(X + (int64_t)ids[i + r] * ldx + c0) + c4);
+        *reinterpret_cast<float4*>(&s_rows[r * Dp4 + 4 * c4]) = v;
       }
+      __syncthreads();
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (j + u < cnt) acc = __fadd_rn(acc, xv[u]);
+      for (int q = 0; q < MAXC; ++q) {
+        const int c = threadIdx.x + 256 * q;
+        if (c < 4 * w4) {
+          float a = acc[q];
+          for (int r = 0; r < rc; ++r) a = __fadd_rn(a, s_rows[r * Dp4 + c]);
+          acc[q] = a;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      const int c = threadIdx.x + 256 * q;
+      if (c < 4 * w4) sums[k * lds + c0 + c] = acc[q];
     }
   }
-  if (live) sums[k * lds + col] = acc;
 }
 
 // ----------------------------------------------------------------------------
@@ -956,9 +979,9 @@ int gdr_segment_sum(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx
   }
   {
     const int Dp4 = (int)align_up(D, 4);
-    const int nslab = (int)cdiv(Dp4, 32);
+    const int R = (int)std::max<int64_t>(1, std::min<int64_t>(64, (48 * 1024) / ((int64_t)Dp4 * 4)));
     ProfileScope prof(PROF_SPMM + 1, s);
-    k_gather_sum<<<(unsigned)cdiv(K * nslab * 32, 256), 256, 0, s>>>(K, Dp4, nslab, mptr, ids, X, ldx, sums, lds);
+    k_gather_sum<<<(unsigned)K, 256, (size_t)R * Dp4 * 4, s>>>(K, Dp4, R, mptr, ids, X, ldx, sums, lds);
   }
   GDR_LAUNCHED();
   return GDR_OK;

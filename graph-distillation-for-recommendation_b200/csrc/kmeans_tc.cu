@@ -24,9 +24,9 @@ namespace gdr {
 
 int launch_row_sqnorm(int64_t K, int D, const float* C, int64_t ldc, float* out, cudaStream_t s);
 int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float* X, int64_t ldx,
-                            const float* C, int64_t ldc, const float* cnorm, const int32_t* rows,
-                            const int32_t* n_rows_dev, int32_t* labels, const int32_t* labels_prev,
-                            int32_t* n_changed, float* best_out, cudaStream_t s);
+                            const float* CT, int64_t ldct, const float* cnorm, const int32_t* rows,
+                            const int32_t* n_rows_dev, unsigned long long* packed, int32_t* labels,
+                            const int32_t* labels_prev, int32_t* n_changed, float* best_out, cudaStream_t s);
 
 constexpr int TC_BM = 128;        // rows per tile (UMMA M)
 constexpr int TC_BN = 128;        // centres per tile (UMMA N)
@@ -133,7 +133,8 @@ __device__ __forceinline__ float to_tf32(float x) {
 __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_pad, int D, int Dp,
                                                     const float* __restrict__ X, int64_t ldx,
                                                     float* __restrict__ hi, float* __restrict__ lo,
-                                                    float* __restrict__ norm_out /*|x| per row, nullable*/) {
+                                                    float* __restrict__ norm_out /*|x| per row, nullable*/,
+                                                    float* __restrict__ xt /*[Dp][rows_pad] transposed copy, nullable*/) {
   // one warp per row
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows_pad) return;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
     float l = to_tf32(__fsub_rn(x, h));
     hi[r * Dp + c] = h;
     lo[r * Dp + c] = l;
+    if (xt) xt[(int64_t)c * rows_pad + r] = x;
     s = fmaf(x, x, s);
   }
   if (norm_out && r < rows) {
@@ -348,7 +350,8 @@ __global__ void __launch_bounds__(256) k_tc_select(int64_t N, const float* __res
                                                    int32_t* __restrict__ labels,
                                                    const int32_t* __restrict__ labels_prev,
                                                    int32_t* __restrict__ n_changed, float* __restrict__ best_out,
-                                                   int32_t* __restrict__ amb_list, int32_t* __restrict__ amb_count) {
+                                                   int32_t* __restrict__ amb_list, int32_t* __restrict__ amb_count,
+                                                   unsigned long long* __restrict__ amb_packed) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int changed = 0;
   if (i < N) {
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(256) k_tc_select(int64_t N, const float* __res
     if (ambiguous) {
       int slot = atomicAdd(amb_count, 1);
       amb_list[slot] = (int32_t)i;
+      amb_packed[slot] = ~0ull;   // identity of the re-score kernel's atomicMin
     } else {
       int l = idx[i];
       labels[i] = l;
@@ -435,7 +439,7 @@ static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
 
 int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, cudaStream_t s) {
   XSplit x = carve_xsplit(xsplit, N, D);
-  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm);
+  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -443,8 +447,8 @@ int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* x
 int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
   int Dp = dpad(D);
   int64_t Kp = align_up(K, TC_BN);
-  return 2 * ws_need(Kp * Dp, 4) + ws_need(Kp, 4) + 256 /*cmax*/ + 3 * ws_need(N, 4) /*best, second, idx*/ +
-         ws_need(N, 4) /*amb list*/ + 256 /*amb count*/ + 256;
+  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need(Kp, 4) + 256 /*cmax*/ + 3 * ws_need(N, 4) /*best, second, idx*/ +
+         ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ + 256 /*amb count*/ + 256;
 }
 
 int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const void* xsplit,
@@ -467,19 +471,21 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   Workspace W(ws, ws_bytes);
   float* c_hi = W.take<float>(Kp * Dp);
   float* c_lo = W.take<float>(Kp * Dp);
+  float* c_t = W.take<float>(Kp * Dp);   // fp32 centres transposed [Dp][Kp] for the re-score kernel
   float* cnorm = W.take<float>(Kp);
   float* cmax = W.take<float>(1);
   float* best = W.take<float>(N);
   float* second = W.take<float>(N);
   int32_t* idx = W.take<int32_t>(N);
   int32_t* amb_list = W.take<int32_t>(N);
+  unsigned long long* amb_packed = W.take<unsigned long long>(N);
   int32_t* amb_count = n_refined_dev ? n_refined_dev : W.take<int32_t>(1);
   if (!W.ok()) {
     set_error("kmeans_assign(tc): workspace too small");
     return GDR_EWORKSPACE;
   }
   // per-iteration centre preparation: split, norms, padding
-  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr);
+  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t);
   GDR_LAUNCHED();
   int rc = launch_row_sqnorm(K, (int)D, C, ldc, cnorm, s);
   if (rc) return rc;
@@ -515,11 +521,11 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   }
   GDR_LAUNCHED();
   k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
-                                                    labels_prev, n_changed_dev, best_out, amb_list, amb_count);
+                                                    labels_prev, n_changed_dev, best_out, amb_list, amb_count, amb_packed);
   GDR_LAUNCHED();
   // exact fp32 re-score of the ambiguous rows (list length stays on the device)
-  return launch_assign_simt_rows(N, K, D, X, ldx, C, ldc, cnorm, amb_list, amb_count, labels, labels_prev,
-                                 n_changed_dev, best_out, s);
+  return launch_assign_simt_rows(N, K, D, X, ldx, c_t, Kp, cnorm, amb_list, amb_count, amb_packed, labels,
+                                 labels_prev, n_changed_dev, best_out, s);
 }
 
 // gdr_kmeans_assign(precision_mode = 1): split X into the tail of the workspace, then run

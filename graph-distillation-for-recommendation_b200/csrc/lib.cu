@@ -38,6 +38,8 @@ ProfileScope::ProfileScope(int kind, cudaStream_t s) : stop_(nullptr), stream_(s
   }
   stop_ = b;
 }
+bool profiling_enabled() { return g_prof_kind != 0; }
+
 ProfileScope::~ProfileScope() {
   if (stop_) cudaEventRecord((cudaEvent_t)stop_, stream_);
 }

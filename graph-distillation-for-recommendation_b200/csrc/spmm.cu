@@ -36,6 +36,7 @@ constexpr int SPMM_HEAVY_NNZ = 1024;   // rows longer than this are processed by
 static int g_spmm_unroll = 0;     // 4 or 8
 static int g_spmm_hints = -1;     // 0 off, 1 streaming hints on colidx/vals/T/Y
 static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
+extern int g_lloyd_graph;         // lloyd.cu
 
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
   int v;
@@ -319,6 +320,7 @@ int gdr_debug_set(const char* key, int value) {
   if (!strcmp(key, "spmm_unroll")) gdr::g_spmm_unroll = value;
   else if (!strcmp(key, "spmm_hints")) gdr::g_spmm_hints = value;
   else if (!strcmp(key, "spmm_split")) gdr::g_spmm_split = value;
+  else if (!strcmp(key, "lloyd_graph")) gdr::g_lloyd_graph = value;
   else {
     gdr::set_error("debug_set: unknown key %s", key);
     return GDR_EINVAL;
