@@ -20,18 +20,22 @@ from .graph import (  # noqa: E402
 )
 from .propagation import propagate, spmm  # noqa: E402
 from .kmeans import (  # noqa: E402
-    KMeans, kmeans_cluster, cluster_means, segment_mean_pool, segment_sum, assign_labels, standard_scale,
+    KMeans, MiniBatchKMeans, kmeans_cluster, cluster_means, segment_mean_pool, segment_sum, assign_labels, standard_scale,
 )
 from .coarsen import (  # noqa: E402
     graph_compress, build_condensed_bipartite, condensed_csr_to_edge_index, coarsen_edges, label_counts,
 )
-from .recsys import BipartiteGraph, lightgcn_propagate, BipartitePropagate  # noqa: E402
+from .recsys import (  # noqa: E402
+    BipartiteGraph, lightgcn_propagate, BipartitePropagate, RankformerGCNGraph, rankformer_gcn_forward,
+)
+from . import parallel  # noqa: E402
 
 __all__ = [
     "GdrError", "LIB_PATH", "launch_count", "CSR", "coo_to_csr", "sym_normalize", "is_sparse_tensor",
     "sparse_mx_to_torch_sparse_tensor", "to_tensor", "to_scipy", "normalize_adj_tensor", "normalize_adj",
-    "build_interaction_matrix", "propagate", "spmm", "KMeans", "kmeans_cluster", "cluster_means",
+    "build_interaction_matrix", "propagate", "spmm", "KMeans", "MiniBatchKMeans", "kmeans_cluster", "cluster_means",
     "segment_mean_pool", "segment_sum", "assign_labels", "standard_scale", "graph_compress",
     "build_condensed_bipartite", "condensed_csr_to_edge_index", "coarsen_edges", "label_counts",
-    "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate",
+    "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate", "RankformerGCNGraph",
+    "rankformer_gcn_forward", "parallel",
 ]

@@ -407,6 +407,22 @@ __global__ void __launch_bounds__(256) k_bip_norm(int64_t n_u, const int32_t* __
   }
 }
 
+// Rankformer GCN weights: out_e = w_e / (max(du,1)^a * max(di,1)^b)  (two divisions, as torch evaluates
+// ones / du.pow(a) / di.pow(b)); du / di are the (integer-valued) interaction counts.
+__global__ void __launch_bounds__(256) k_bip_pow_norm(int64_t n_u, const int32_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ colidx,
+                                                      const float* __restrict__ w, const float* __restrict__ deg_u,
+                                                      const float* __restrict__ deg_i, float a, float b,
+                                                      float* __restrict__ out) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_u) return;
+  const float pu = powf(fmaxf(deg_u[r], 1.f), a);
+  for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+    const float pi = powf(fmaxf(deg_i[colidx[j]], 1.f), b);
+    out[j] = __fmul_rn(w[j], __fdiv_rn(__fdiv_rn(1.f, pu), pi));
+  }
+}
+
 __global__ void k_gather_f32(int64_t n, const int32_t* __restrict__ perm, const float* __restrict__ in,
                              float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -726,6 +742,32 @@ int gdr_bipartite_normalize(int64_t n_u, int64_t n_i, int64_t nnz, const int32_t
     k_gather_f32<<<grid_for(nnz), 256, 0, s>>>(nnz, t_perm, norm_out, t_norm_out);
     GDR_LAUNCHED();
   }
+  return GDR_OK;
+}
+
+// Rankformer GCN edge weights (Rankformer/code/rec.py:118-124): degrees = row / column sums of the
+// interaction counts clamped to >= 1;  out = w / du^a / di^b  and, for the transposed matrix,
+// t_out = w / du^b / di^a  (written in transposed order through t_perm).
+int gdr_bipartite_pow_normalize(int64_t n_u, int64_t n_i, int64_t nnz, const int32_t* rowptr,
+                                const int32_t* colidx, const float* w, const int32_t* t_rowptr,
+                                const int32_t* t_perm, float a, float b, float* out, float* t_out,
+                                float* deg_u, float* deg_i, float* scratch /*nnz floats*/, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_u > 0 && n_i > 0 && nnz >= 0 && rowptr && t_rowptr && deg_u && deg_i,
+                "bipartite_pow_normalize: bad arguments");
+  GDR_CHECK_ARG(nnz == 0 || (colidx && w && t_perm && out && t_out && scratch), "bipartite_pow_normalize: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_rowsum_seq<<<grid_for(n_u), 256, 0, s>>>(n_u, rowptr, nullptr, w, deg_u);
+  GDR_LAUNCHED();
+  k_rowsum_seq<<<grid_for(n_i), 256, 0, s>>>(n_i, t_rowptr, t_perm, w, deg_i);
+  GDR_LAUNCHED();
+  if (nnz == 0) return GDR_OK;
+  unsigned grid = (unsigned)cdiv(n_u * 32, 256);
+  k_bip_pow_norm<<<grid, 256, 0, s>>>(n_u, rowptr, colidx, w, deg_u, deg_i, a, b, out);
+  GDR_LAUNCHED();
+  k_bip_pow_norm<<<grid, 256, 0, s>>>(n_u, rowptr, colidx, w, deg_u, deg_i, b, a, scratch);
+  GDR_LAUNCHED();
+  k_gather_f32<<<grid_for(nnz), 256, 0, s>>>(nnz, t_perm, scratch, t_out);
+  GDR_LAUNCHED();
   return GDR_OK;
 }
 

@@ -371,6 +371,24 @@ class KMeans:
         return self._out(labels)
 
 
+class MiniBatchKMeans(KMeans):
+    """Entry point for the reference's ``MiniBatchKMeans(n_clusters, random_state, batch_size)``
+    call sites (clustgdd_agent_transduct.py:103, clustgdd_agent_induct.py:132,
+    distill_recsys.py:174-176).  The reference switches to mini-batches only because full Lloyd
+    is slow on the host; on the B200 the full-batch Lloyd run is the fast path and gives a lower
+    WCSS, so this class accepts the mini-batch keywords and runs full Lloyd (SURVEY §8f item 2:
+    the mini-batch RNG stream cannot be reproduced, parity is judged on WCSS).  ``batch_size``,
+    ``init_size``, ``max_no_improvement`` and ``reassignment_ratio`` are accepted and ignored."""
+
+    def __init__(self, n_clusters=8, *, init="k-means++", max_iter=100, batch_size=1024, verbose=0,
+                 compute_labels=True, random_state=None, tol=0.0, max_no_improvement=10, init_size=None,
+                 n_init="auto", reassignment_ratio=0.01, precision="auto", device=None):
+        super().__init__(n_clusters=n_clusters, init=init, n_init=n_init, max_iter=max_iter, tol=tol, verbose=verbose,
+                         random_state=random_state, precision=precision, device=device)
+        self.batch_size, self.compute_labels, self.max_no_improvement = batch_size, compute_labels, max_no_improvement
+        self.init_size, self.reassignment_ratio = init_size, reassignment_ratio
+
+
 def standard_scale(X: torch.Tensor) -> torch.Tensor:
     """StandardScaler(with_mean=True, with_std=True).fit_transform (distill_recsys.py:172):
     mean / population variance in fp64, scale = sqrt(var) with zero variance -> 1,

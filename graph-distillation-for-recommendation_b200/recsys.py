@@ -66,6 +66,40 @@ def lightgcn_propagate(graph: BipartiteGraph, u0: torch.Tensor, i0: torch.Tensor
     return u_out, i_out
 
 
+class RankformerGCNGraph:
+    """CSR of the raw user-item interactions with the Rankformer GCN weights
+    (Rankformer/code/rec.py:92-140): du / di = interaction counts clamped to >= 1,
+    w1 = 1/du^alpha/di^beta (items -> users), w2 = 1/du^beta/di^alpha (users -> items).
+    Duplicate (u, i) lines are summed into the CSR value, which is what scattering every line
+    separately adds up to."""
+
+    def __init__(self, u: torch.Tensor, i: torch.Tensor, num_users: int, num_items: int, alpha: float = 1.0,
+                 beta: float = 0.0):
+        need_cuda(u, "u")
+        self.n, self.m = int(num_users), int(num_items)
+        R = coo_to_csr(u, i, None, (self.n, self.m), device=u.device)
+        RT, t_perm = R.transpose()
+        dev = R.device
+        self.deg_u = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.deg_i = torch.empty(self.m, dtype=torch.float32, device=dev)
+        w1 = torch.empty(R.nnz, dtype=torch.float32, device=dev)
+        w2t = torch.empty(R.nnz, dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(R.nnz, 1), dtype=torch.float32, device=dev)
+        _lib.call("gdr_bipartite_pow_normalize", self.n, self.m, R.nnz, ptr(R.rowptr), ptr(R.colidx), ptr(R.vals),
+                  ptr(RT.rowptr), ptr(t_perm), float(alpha), float(beta), ptr(w1), ptr(w2t), ptr(self.deg_u),
+                  ptr(self.deg_i), ptr(scratch), stream())
+        self.A = CSR(R.rowptr, R.colidx, w1, R.shape)         # zu = A @ xi
+        self.AT = CSR(RT.rowptr, RT.colidx, w2t, RT.shape)    # zi = AT @ xu
+
+
+def rankformer_gcn_forward(graph: RankformerGCNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GCN.forward of Rankformer/code/rec.py:92-140: x = [users; items] -> [zu; zi]."""
+    xu, xi = x[: graph.n], x[graph.n:]
+    zu = spmm(graph.A, xi.contiguous())
+    zi = spmm(graph.AT, xu.contiguous())
+    return torch.cat([zu, zi], dim=0)
+
+
 class BipartitePropagate(torch.autograd.Function):
     """Differentiable (w.r.t. the embeddings) wrapper: the backward of a layer-mean of
     alternating SpMMs is the same propagation with A and A^T swapped."""

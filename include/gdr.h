@@ -129,6 +129,16 @@ int gdr_bipartite_normalize(int64_t n_u, int64_t n_i, int64_t nnz,
                             float eps, float* norm_out, float* t_norm_out,
                             float* deg_u, float* deg_i, gdr_stream_t stream);
 
+/* Rankformer GCN edge weights (Rankformer/code/rec.py:118-124, the teacher's propagation the
+ * reference's LightGCN mirrors): du / di = interaction counts clamped to >= 1,
+ *   out_e = w_e / du^a / di^b   (users <- items),   t_out = w_e / du^b / di^a (items <- users,
+ *   in transposed order).  scratch: nnz floats. */
+int gdr_bipartite_pow_normalize(int64_t n_u, int64_t n_i, int64_t nnz,
+                                const int32_t* rowptr, const int32_t* colidx, const float* w,
+                                const int32_t* t_rowptr, const int32_t* t_perm, float a, float b,
+                                float* out, float* t_out, float* deg_u, float* deg_i,
+                                float* scratch, gdr_stream_t stream);
+
 /* CSR transpose: t_rowptr[n_cols+1], t_colidx[nnz] (= source row ids, ascending
  * inside each transposed row), t_perm[nnz] = position of that entry in the input. */
 int64_t gdr_csr_transpose_ws_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
