@@ -29,7 +29,10 @@
 namespace gdr {
 
 constexpr int SPMM_THREADS = 256;
-constexpr int SPMM_ROWS_PER_CTA = 64;
+constexpr int SPMM_ROWS_PER_CTA = 64;     // row blocks without a plan
+constexpr int SPMM_MAX_ROWS = 128;        // rows per block with an nnz-balanced plan
+constexpr int SPMM_BLOCK_WEIGHT = 2048;   // plan: weight(row) = nnz(row) + SPMM_ROW_COST, blocks of equal weight
+constexpr int SPMM_ROW_COST = 16;         // => at most SPMM_BLOCK_WEIGHT / SPMM_ROW_COST = 128 rows per block
 constexpr int SPMM_HEAVY_NNZ = 1024;   // rows longer than this are processed by the whole CTA
 
 // run-time tuning (gdr_debug_set): 0 = automatic choice
@@ -121,13 +124,16 @@ __global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && UNROLL <= 4) ? 5 : 
 k_spmm(int64_t rows, int c4_end, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
        const float* __restrict__ vals, float alpha, const float* __restrict__ X, int64_t ldx,
        float* __restrict__ Y, int64_t ldy, float* __restrict__ T, int64_t ldt, float beta,
-       int col4_base) {
-  __shared__ int s_rowptr[SPMM_ROWS_PER_CTA + 1];
-  __shared__ int s_heavy[SPMM_ROWS_PER_CTA];
+       int col4_base, const int32_t* __restrict__ bounds) {
+  __shared__ int s_rowptr[SPMM_MAX_ROWS + 1];
+  __shared__ int s_heavy[SPMM_MAX_ROWS];
   __shared__ int s_next, s_nheavy;
   constexpr int GROUPS = 32 / LPR;  // rows processed concurrently by one warp
-  const int64_t row0 = (int64_t)blockIdx.x * SPMM_ROWS_PER_CTA;
-  const int nrows = (int)min((int64_t)SPMM_ROWS_PER_CTA, rows - row0);
+  // row block of this CTA: from the nnz-balanced plan when there is one, else 64 consecutive rows
+  const int64_t row0 = bounds ? (int64_t)bounds[blockIdx.x] : (int64_t)blockIdx.x * SPMM_ROWS_PER_CTA;
+  const int nrows = bounds ? (bounds[blockIdx.x + 1] - (int)row0)
+                           : (int)min((int64_t)SPMM_ROWS_PER_CTA, rows - row0);
+  if (nrows <= 0) return;
   for (int i = threadIdx.x; i <= nrows; i += SPMM_THREADS) s_rowptr[i] = rowptr[row0 + i];
   if (threadIdx.x == 0) {
     s_next = 0;
@@ -235,15 +241,18 @@ struct SpmmArgs {
   int64_t ldt;
   float beta;
   cudaStream_t s;
+  const int32_t* bounds;   // nnz-balanced row-block plan (nullable)
+  int64_t n_blocks;
 };
 
 template <int LPR, int NCH, int UNROLL, bool HINTS>
 static int launch_spmm(const SpmmArgs& a, int col4_base, int c4_end) {
-  unsigned grid = (unsigned)cdiv(a.rows, SPMM_ROWS_PER_CTA);
+  unsigned grid = a.bounds ? (unsigned)a.n_blocks : (unsigned)cdiv(a.rows, SPMM_ROWS_PER_CTA);
   {
     ProfileScope prof(PROF_SPMM, a.s);
     k_spmm<LPR, NCH, UNROLL, HINTS><<<grid, SPMM_THREADS, 0, a.s>>>(a.rows, c4_end, a.rowptr, a.colidx, a.vals, a.alpha,
-                                                                    a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt, a.beta, col4_base);
+                                                                    a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt, a.beta, col4_base,
+                                                                    a.bounds);
   }
   GDR_LAUNCHED();
   return GDR_OK;
@@ -274,12 +283,41 @@ static int spmm_window(const SpmmArgs& a, int base, int width, int unroll, bool 
   return GDR_OK;
 }
 
+// bounds[c] = first row r with rowptr[r] + SPMM_ROW_COST * r >= c * SPMM_BLOCK_WEIGHT
+__global__ void k_spmm_plan(int64_t n_rows, const int32_t* __restrict__ rowptr, int64_t n_blocks,
+                            int32_t* __restrict__ bounds) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_blocks) return;
+  if (c == n_blocks) {
+    bounds[c] = (int32_t)n_rows;
+    return;
+  }
+  const int64_t target = c * SPMM_BLOCK_WEIGHT;
+  int64_t lo = 0, hi = n_rows;   // answer in [0, n_rows]
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)rowptr[mid] + SPMM_ROW_COST * mid >= target) hi = mid;
+    else lo = mid + 1;
+  }
+  bounds[c] = (int32_t)lo;
+}
+
+int spmm_launch_planned(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
+                        const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                        float* T, int64_t ldt, float beta, const int32_t* bounds, int64_t n_blocks, cudaStream_t s);
+
 int spmm_launch(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
                 const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
                 float* T, int64_t ldt, float beta, cudaStream_t s) {
+  return spmm_launch_planned(rows, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, nullptr, 0, s);
+}
+
+int spmm_launch_planned(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
+                        const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                        float* T, int64_t ldt, float beta, const int32_t* bounds, int64_t n_blocks, cudaStream_t s) {
   if (rows == 0 || F == 0) return GDR_OK;
   const int F4 = (int)cdiv(F, 4);
-  SpmmArgs a{rows, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, s};
+  SpmmArgs a{rows, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, s, bounds, n_blocks};
   const int unroll = g_spmm_unroll > 0 ? g_spmm_unroll : 4;
   const bool hints = g_spmm_hints >= 0 ? g_spmm_hints != 0 : false;
   int split = g_spmm_split > 0 ? g_spmm_split : 1;
@@ -345,6 +383,39 @@ int gdr_spmm_prop(int64_t rows_local, int64_t F, const int32_t* rowptr, const in
   GDR_CHECK_ARG(X != Y, "spmm_prop: in-place propagation is not supported");
   return gdr::spmm_launch(rows_local, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta,
                           (cudaStream_t)stream);
+}
+
+int64_t gdr_spmm_plan_blocks(int64_t n_rows, int64_t nnz) {
+  if (n_rows <= 0) return 0;
+  return gdr::cdiv(nnz + (int64_t)gdr::SPMM_ROW_COST * n_rows, gdr::SPMM_BLOCK_WEIGHT) + 1;
+}
+
+int gdr_spmm_plan(int64_t n_rows, int64_t nnz, const int32_t* rowptr, int32_t* bounds_out, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0 && nnz >= 0, "spmm_plan: negative size");
+  if (n_rows == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && bounds_out, "spmm_plan: null pointer");
+  const int64_t nb = gdr_spmm_plan_blocks(n_rows, nnz);
+  gdr::k_spmm_plan<<<(unsigned)gdr::cdiv(nb + 1, 256), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, nb, bounds_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int gdr_spmm_prop_planned(int64_t rows_local, int64_t F, const int32_t* rowptr, const int32_t* colidx,
+                          const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                          float* T, int64_t ldt, float beta, const int32_t* bounds, int64_t n_blocks,
+                          gdr_stream_t stream) {
+  GDR_CHECK_ARG(rows_local >= 0 && F >= 0, "spmm_prop: negative size");
+  if (rows_local == 0 || F == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && colidx && X && Y && bounds && n_blocks > 0, "spmm_prop_planned: null pointer");
+  GDR_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= gdr::align_up(F, 4) && ldy >= gdr::align_up(F, 4),
+                "spmm_prop: ldx/ldy must be multiples of 4 and >= F rounded up to 4");
+  GDR_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Y & 15) == 0, "spmm_prop: X/Y not 16B aligned");
+  if (T) {
+    GDR_CHECK_ARG(ldt % 4 == 0 && ldt >= gdr::align_up(F, 4) && ((uintptr_t)T & 15) == 0, "spmm_prop: T misaligned");
+  }
+  GDR_CHECK_ARG(X != Y, "spmm_prop: in-place propagation is not supported");
+  return gdr::spmm_launch_planned(rows_local, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, bounds,
+                                  n_blocks, (cudaStream_t)stream);
 }
 
 int gdr_scale_rows(int64_t rows, int64_t F, float a, const float* X, int64_t ldx, float* out,

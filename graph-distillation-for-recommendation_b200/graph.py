@@ -31,9 +31,20 @@ class CSR:
     shape: Tuple[int, int]
     deg: Optional[torch.Tensor] = None  # fp64 degrees when produced by sym_normalize
 
+    _plan: Optional[torch.Tensor] = None  # nnz-balanced row blocks of the SpMM (pattern-only, cached)
+
     @property
     def nnz(self) -> int:
         return int(self.colidx.shape[0])
+
+    def spmm_plan(self) -> torch.Tensor:
+        """int32 block bounds for gdr_spmm_prop_planned (built once per sparsity pattern)."""
+        if self._plan is None:
+            nb = _lib.query("gdr_spmm_plan_blocks", self.shape[0], self.nnz)
+            bounds = torch.empty(nb + 1, dtype=torch.int32, device=self.device)
+            _lib.call("gdr_spmm_plan", self.shape[0], self.nnz, ptr(self.rowptr), ptr(bounds), stream())
+            self._plan = bounds
+        return self._plan
 
     @property
     def device(self) -> torch.device:

@@ -110,9 +110,11 @@ class CudaOps:
 
     def spmm(self, A_local, x_full, alpha, target, beta):
         y = self.new_padded(A_local.shape[0], x_full.shape[1], x_full.device)
-        self._lib.call("gdr_spmm_prop", A_local.shape[0], x_full.shape[1], self.ptr(A_local.rowptr), self.ptr(A_local.colidx),
-                       self.ptr(A_local.vals), float(alpha), self.ptr(x_full), x_full.stride(0), self.ptr(y), y.stride(0),
-                       self.ptr(target), 0 if target is None else target.stride(0), float(beta), self.stream())
+        plan = A_local.spmm_plan()
+        self._lib.call("gdr_spmm_prop_planned", A_local.shape[0], x_full.shape[1], self.ptr(A_local.rowptr),
+                       self.ptr(A_local.colidx), self.ptr(A_local.vals), float(alpha), self.ptr(x_full), x_full.stride(0),
+                       self.ptr(y), y.stride(0), self.ptr(target), 0 if target is None else target.stride(0), float(beta),
+                       self.ptr(plan), plan.numel() - 1, self.stream())
         return y
 
     def prep_rows(self, x):

@@ -36,9 +36,10 @@ def spmm(adj: Union[CSR, torch.Tensor], x: torch.Tensor, alpha: float = 1.0, out
     n, f = A.shape[0], x.shape[1]
     y = out if out is not None else new_padded(n, f, x.device)
     t = accumulate_into
-    _lib.call("gdr_spmm_prop", n, f, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), float(alpha),
+    plan = A.spmm_plan()
+    _lib.call("gdr_spmm_prop_planned", n, f, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), float(alpha),
               ptr(xs), xs.stride(0), ptr(y), y.stride(0), ptr(t), 0 if t is None else t.stride(0),
-              float(beta), stream())
+              float(beta), ptr(plan), plan.numel() - 1, stream())
     return y
 
 
@@ -66,11 +67,12 @@ def propagate(adj_norm: Union[CSR, torch.Tensor], features: torch.Tensor, prop_n
               stream())
     prop = x
     bufs = [new_padded(n, f, x.device) for _ in range(min(2, T - 1))]
+    plan = A.spmm_plan() if T > 1 else None
     for t in range(1, T):
         y = bufs[(t - 1) % len(bufs)]
-        _lib.call("gdr_spmm_prop", n, f, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), float(alpha),
+        _lib.call("gdr_spmm_prop_planned", n, f, ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), float(alpha),
                   ptr(prop), prop.stride(0), ptr(y), y.stride(0), ptr(target), target.stride(0),
-                  one_minus, stream())
+                  one_minus, ptr(plan), plan.numel() - 1, stream())
         prop = y
     if T == 1:
         prop = features

@@ -172,6 +172,20 @@ int gdr_spmm_prop(int64_t rows_local, int64_t F,
                   float* T, int64_t ldt, float beta,
                   gdr_stream_t stream);
 
+/* nnz-balanced row blocks for the SpMM (hub-heavy graphs): block c owns the rows r with
+ * rowptr[r] + 16 r in [2048 c, 2048 (c+1)) — equal work per CTA, at most 128 rows each.  The plan
+ * depends on the sparsity pattern only; build it once per matrix (bounds_out: int32
+ * [gdr_spmm_plan_blocks() + 1]) and pass it to gdr_spmm_prop_planned.  Same arithmetic and the
+ * same results as gdr_spmm_prop. */
+int64_t gdr_spmm_plan_blocks(int64_t n_rows, int64_t nnz);
+int     gdr_spmm_plan(int64_t n_rows, int64_t nnz, const int32_t* rowptr, int32_t* bounds_out,
+                      gdr_stream_t stream);
+int     gdr_spmm_prop_planned(int64_t rows_local, int64_t F,
+                              const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                              float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                              float* T, int64_t ldt, float beta,
+                              const int32_t* bounds, int64_t n_blocks, gdr_stream_t stream);
+
 /* out = a * X  (dense, row-major; used for the t = 0 term (1-alpha)*X). */
 int gdr_scale_rows(int64_t rows, int64_t F, float a, const float* X, int64_t ldx,
                    float* out, int64_t ldo, gdr_stream_t stream);
