@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
                                                     const float* __restrict__ X, int64_t ldx,
                                                     float* __restrict__ hi, float* __restrict__ lo,
                                                     float* __restrict__ norm_out /*|x| per row, nullable*/,
-                                                    float* __restrict__ xt /*[Dp][rows_pad] transposed copy, nullable*/) {
+                                                    float* __restrict__ xt /*[Dp][rows_pad] transposed copy, nullable*/,
+                                                    float* __restrict__ sqnorm_out /*|x|^2, +inf on padding rows, nullable*/) {
   // one warp per row
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows_pad) return;
@@ -148,22 +149,24 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
     if (xt) xt[(int64_t)c * rows_pad + r] = x;
     s = fmaf(x, x, s);
   }
-  if (norm_out && r < rows) {
+  if (norm_out || sqnorm_out) {
+    // same per-lane fmaf order and xor-shuffle tree as k_row_sqnorm: bit-identical |row|^2
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane_id() == 0) norm_out[r] = sqrtf(s);
+    if (lane_id() == 0) {
+      if (norm_out && r < rows) norm_out[r] = sqrtf(s);
+      if (sqnorm_out) sqnorm_out[r] = r < rows ? s : INFINITY;   // padding rows can never win the argmin
+    }
   }
 }
 
-// cnorm[j] for j >= K = +inf (padding centres can never win); cmax = max_j |c_j|
+// cmax = max_j |c_j| over the real centres; also resets the re-score list length
 __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, float* __restrict__ cnorm,
-                                                       float* __restrict__ cmax) {
+                                                       float* __restrict__ cmax, int32_t* __restrict__ amb_count) {
   __shared__ float s_m[1024];
   float m = 0.f;
-  for (int64_t j = threadIdx.x; j < Kp; j += 1024) {
-    if (j >= K) cnorm[j] = INFINITY;
-    else m = fmaxf(m, cnorm[j]);
-  }
+  if (threadIdx.x == 0 && amb_count) amb_count[0] = 0;
+  for (int64_t j = threadIdx.x; j < K; j += 1024) m = fmaxf(m, cnorm[j]);
   s_m[threadIdx.x] = m;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
@@ -439,7 +442,7 @@ static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
 
 int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, cudaStream_t s) {
   XSplit x = carve_xsplit(xsplit, N, D);
-  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr);
+  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr, nullptr);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -485,13 +488,11 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     return GDR_EWORKSPACE;
   }
   // per-iteration centre preparation: split, norms, padding
-  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t);
+  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t, cnorm);
   GDR_LAUNCHED();
-  int rc = launch_row_sqnorm(K, (int)D, C, ldc, cnorm, s);
-  if (rc) return rc;
-  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cmax);
+  int rc;
+  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cmax, amb_count);
   GDR_LAUNCHED();
-  GDR_CUDA(cudaMemsetAsync(amb_count, 0, 4, s));
 
   CUtensorMap m_xhi, m_xlo, m_chi, m_clo;
   if ((rc = make_map(&m_xhi, xs.hi, N, Dp, TC_BM))) return rc;

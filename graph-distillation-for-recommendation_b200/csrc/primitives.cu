@@ -88,6 +88,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int32_t* __re
   }
 }
 
+// one-launch scan for small inputs (n <= SCAN_SMALL_MAX): a single CTA, each thread owns a
+// contiguous run of ceil(n / 1024) elements; out may alias in.
+constexpr int SCAN_SMALL_MAX = 1 << 17;
+__global__ void __launch_bounds__(1024) k_scan_small(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                     int n, int write_total) {
+  __shared__ int sw[33];
+  const int per = (n + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += in[i];
+  int total;
+  int run = block_excl_scan(s, sw, &total);
+  for (int i = b; i < e; ++i) {
+    int v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (write_total && threadIdx.x == 0) out[n] = total;
+}
+
 __global__ void k_zero_one(int32_t* out) { out[0] = 0; }
 
 int64_t scan_ws_bytes(int64_t n) {
@@ -111,6 +131,11 @@ static int scan_rec(const int32_t* in, int32_t* out, int64_t n, char* ws, int wr
     return GDR_OK;
   }
   int64_t nb = cdiv(n, SCAN_TILE);
+  if (n <= SCAN_SMALL_MAX && nb > 1) {
+    k_scan_small<<<1, 1024, 0, s>>>(in, out, (int)n, write_total);
+    GDR_LAUNCHED();
+    return GDR_OK;
+  }
   if (nb == 1) {
     k_scan_apply<<<1, SCAN_THREADS, 0, s>>>(in, nullptr, out, n, write_total);
     GDR_LAUNCHED();
