@@ -74,7 +74,19 @@ class ClockSampler(threading.Thread):
         flag = lambda bit: "Active" if (r & bit) else "Not Active"
         return [str(sm), str(mx), str(pw), flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
+    def sample_now(self):
+        """One sample from the CALLING thread (used between timed steps: an NVML query running
+        concurrently with the launch thread contends on the driver lock and was measured to
+        double the step time)."""
+        try:
+            if self.nvml is not None:
+                self.rows.append(self._sample_nvml())
+        except Exception:
+            pass
+
     def run(self):
+        if self.nvml is not None:
+            return   # NVML available: samples are taken by sample_now() from the main thread
         while not self._stop_ev.is_set():
             try:
                 if self.nvml is not None:
@@ -227,7 +239,12 @@ def run_ours(args, rank, world):
         e[3].record()
         _, adj_syn = gdr.graph_compress(km.labels_, An, [])
         e[4].record()
-        return e, km, adj_syn
+        # keep only scalars: holding km / adj_syn of every step alive fragments the caching allocator
+        # and forces cudaMalloc (a device-wide sync) inside later timed steps
+        import types
+        nnz_syn = int(adj_syn._nnz())
+        return (e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_),
+                types.SimpleNamespace(_nnz=lambda v=nnz_syn: v))
 
     # W warm-up steps, continued until the GPU has been busy for >= 2 s: a fresh process starts
     # with the GPU in its idle power state and the first ~0.5 s of work runs at about half speed
@@ -249,6 +266,7 @@ def run_ours(args, rank, world):
         flush.fill_(1)          # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
         recs.append(step(True))
+        sampler.sample_now()    # clocks / throttle reasons while the GPU is still under load
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     launches = gdr.launch_count() - launches0
@@ -401,7 +419,12 @@ def run_ours_multi(args, rank, world, dev):
         e[3].record()
         adj_syn, _ = par.dist_graph_compress(comm, part, km.labels_, A_local, ops=ops)
         e[4].record()
-        return e, km, adj_syn
+        # keep only scalars: holding km / adj_syn of every step alive fragments the caching allocator
+        # and forces cudaMalloc (a device-wide sync) inside later timed steps
+        import types
+        nnz_syn = int(adj_syn._nnz())
+        return (e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_),
+                types.SimpleNamespace(_nnz=lambda v=nnz_syn: v))
 
     t_warm = time.perf_counter()
     n_warm = 0
@@ -425,6 +448,7 @@ def run_ours_multi(args, rank, world, dev):
         torch.cuda.synchronize()
         dist.barrier()
         recs.append(step())
+        sampler.sample_now()
     torch.cuda.synchronize()
     dist.barrier()
     t_wall = time.perf_counter() - t0
