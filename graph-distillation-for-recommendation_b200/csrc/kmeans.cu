@@ -288,30 +288,38 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_partial(int K, int D, con
                                                                const int32_t* __restrict__ rows,
                                                                const int32_t* __restrict__ n_rows_dev,
                                                                unsigned long long* __restrict__ packed) {
-  extern __shared__ float s_x[];  // [RF_ROWS][D]
+  extern __shared__ float s_mem[];   // [RF_ROWS][D] listed rows, then [D][RF_THREADS] centre slab
+  float* s_x = s_mem;
+  float* s_ct = s_mem + RF_ROWS * D;
   const int n_rows = *n_rows_dev;
   const int lane = threadIdx.x & 31;
-  for (int q0 = blockIdx.x * RF_ROWS; q0 < n_rows; q0 += gridDim.x * RF_ROWS) {
-    const int nr = min(RF_ROWS, n_rows - q0);
+  if ((int)blockIdx.x * RF_ROWS >= n_rows) return;   // no row group for this CTA
+  // outer loop: centre slabs (staged once, all D loads per thread in flight together);
+  // inner loop: the row groups of this CTA
+  for (int j0 = blockIdx.y * RF_THREADS; j0 < K; j0 += gridDim.y * RF_THREADS) {
+    const int j = j0 + threadIdx.x;
+    const int jc = j < K ? j : K - 1;   // clamp the address; masked below
     __syncthreads();
-    for (int t = threadIdx.x; t < RF_ROWS * D; t += RF_THREADS) {
-      const int r = t / D, k = t - r * D;
-      s_x[t] = r < nr ? X[(int64_t)rows[q0 + r] * ldx + k] : 0.f;
-    }
-    __syncthreads();
-    for (int j0 = blockIdx.y * RF_THREADS; j0 < K; j0 += gridDim.y * RF_THREADS) {
-      const int j = j0 + threadIdx.x;
-      const int jc = j < K ? j : K - 1;   // clamp the address; masked below
+#pragma unroll 32
+    for (int k = 0; k < D; ++k) s_ct[k * RF_THREADS + threadIdx.x] = __ldg(CT + (int64_t)k * ldct + jc);
+    const float cn = __ldg(cnorm + jc);
+    for (int q0 = blockIdx.x * RF_ROWS; q0 < n_rows; q0 += gridDim.x * RF_ROWS) {
+      const int nr = min(RF_ROWS, n_rows - q0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < RF_ROWS * D; t += RF_THREADS) {
+        const int r = t / D, k = t - r * D;
+        s_x[t] = r < nr ? X[(int64_t)rows[q0 + r] * ldx + k] : 0.f;
+      }
+      __syncthreads();
       float acc[RF_ROWS];
 #pragma unroll
       for (int r = 0; r < RF_ROWS; ++r) acc[r] = 0.f;
-#pragma unroll 16
+#pragma unroll 4
       for (int k = 0; k < D; ++k) {
-        const float c = __ldg(CT + (int64_t)k * ldct + jc);
+        const float c = s_ct[k * RF_THREADS + threadIdx.x];
 #pragma unroll
         for (int r = 0; r < RF_ROWS; ++r) acc[r] = fmaf(s_x[r * D + k], c, acc[r]);
       }
-      const float cn = __ldg(cnorm + jc);
 #pragma unroll
       for (int r = 0; r < RF_ROWS; ++r) {
         const float d = fmaf(-2.f, acc[r], cn);
@@ -354,13 +362,20 @@ int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float*
                             const float* CT, int64_t ldct, const float* cnorm, const int32_t* rows,
                             const int32_t* n_rows_dev, unsigned long long* packed, int32_t* labels,
                             const int32_t* labels_prev, int32_t* n_changed, float* best_out, cudaStream_t s) {
-  size_t smem = (size_t)RF_ROWS * D * 4;
-  if (smem > 48 * 1024) {
+  size_t smem = ((size_t)RF_ROWS * D + (size_t)D * RF_THREADS) * 4;
+  if (smem > 200 * 1024) {
     set_error("re-score kernel: D=%lld exceeds its shared-memory plan", (long long)D);
     return GDR_EUNSUPPORTED;
   }
-  const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(max_rows, RF_ROWS), 1), 256);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_refine_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  // centre slabs along y (each staged once per CTA), row groups along x: about two CTAs per SM in total
   const unsigned gy = (unsigned)std::min<int64_t>(cdiv(K, RF_THREADS), 1024);
+  const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(max_rows, RF_ROWS), 1),
+                                                  std::max<int64_t>(1, (2 * kSMs) / gy));
   k_refine_partial<<<dim3(gx, gy), RF_THREADS, smem, s>>>((int)K, (int)D, X, ldx, CT, ldct, cnorm, rows, n_rows_dev,
                                                           packed);
   GDR_LAUNCHED();
