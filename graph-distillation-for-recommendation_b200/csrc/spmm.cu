@@ -120,7 +120,7 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ colidx,
 }
 
 template <int LPR, int NCH, int UNROLL, bool HINTS>
-__global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && UNROLL <= 4) ? 5 : 1)
+__global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && UNROLL <= 2) ? 8 : ((NCH == 1 && UNROLL <= 4) ? 6 : 1))
 k_spmm(int64_t rows, int c4_end, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
        const float* __restrict__ vals, float alpha, const float* __restrict__ X, int64_t ldx,
        float* __restrict__ Y, int64_t ldy, float* __restrict__ T, int64_t ldt, float beta,
@@ -260,6 +260,10 @@ static int launch_spmm(const SpmmArgs& a, int col4_base, int c4_end) {
 
 template <int LPR, int NCH>
 static int dispatch_tuning(const SpmmArgs& a, int base, int c4_end, int unroll, bool hints) {
+  if constexpr (NCH == 1) {
+    if (unroll == 2)
+      return hints ? launch_spmm<LPR, NCH, 2, true>(a, base, c4_end) : launch_spmm<LPR, NCH, 2, false>(a, base, c4_end);
+  }
   if constexpr (NCH <= 2) {
     if (unroll >= 8)
       return hints ? launch_spmm<LPR, NCH, 8, true>(a, base, c4_end) : launch_spmm<LPR, NCH, 8, false>(a, base, c4_end);

@@ -23,7 +23,7 @@ b_min = nnz * 8 + (n + 1) * 4 + 4 * n * f * 4
 b_gather = nnz * (8 + 4 * f) + (n + 1) * 4 + 3 * n * f * 4
 ref = None
 print(f"# {which}: N={n} nnz={nnz} F={f}  B_min={b_min/1e6:.0f} MB  B_gather={b_gather/1e6:.0f} MB")
-for unroll, hints, split in itertools.product([4, 8], [0, 1], [1, 2, 4]):
+for unroll, hints, split in itertools.product([4, 2, 8], [0, 1], [1, 2]):
     _lib.call("gdr_debug_set", b"spmm_unroll", unroll)
     _lib.call("gdr_debug_set", b"spmm_hints", hints)
     _lib.call("gdr_debug_set", b"spmm_split", split)
