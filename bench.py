@@ -377,6 +377,16 @@ def run_ours(args, rank, world):
     print(json.dumps(line))
 
 
+def one_gpu_reference(workload):
+    """The committed single-GPU measurement of the same workload (for the strong-scaling ratio)."""
+    name = {"E": "r1_bench_configE_1gpu.json", "B": "r1_bench_tc_v10.json"}.get(workload)
+    try:
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "source": "profiles/" + name}
+    except Exception:
+        return None
+
+
 def run_ours_multi(args, rank, world, dev):
     """N > 1: the same step on the same graph, nodes row-partitioned over the ranks (strong
     scaling).  NCCL all-gather of the propagated rows per hop, all-reduce of the centroid
@@ -479,7 +489,7 @@ def run_ours_multi(args, rank, world, dev):
             "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
                           "s3_kmeans": float(km_ms.mean()), "s3_kmeans_per_iter": float(km_ms.sum() / np.sum(n_iter)),
                           "s4_coarsen": float(st[:, 3].mean())},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": None, "cpu_baseline": None, "same_workload_1gpu": one_gpu_reference(args.workload),
             "e2e": None, "gpu_launches": int(lt.item()), "clocks": clocks, "wall_s": t_wall,
             "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2]._nnz())},
         }
@@ -524,7 +534,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.workload is None:
-        args.workload = "B"
+        # BASELINE.json ties the shapes to GPU counts: configs[1] (ogbn-arxiv-shaped) is the 1-GPU
+        # config, configs[4] (ogbn-products-shaped) the row-partitioned multi-GPU one.  The same
+        # workload on one GPU is recorded in profiles/ (bench.py --workload E) for the scaling ratio.
+        args.workload = "B" if max(world, args.gpus) == 1 else "E"
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
