@@ -33,11 +33,13 @@ constexpr int TC_BN = 128;        // centres per tile (UMMA N)
 constexpr int TC_BK = 32;         // floats per K-block = one 128-byte swizzle row
 constexpr int TC_MAX_KB = 4;      // D padded <= 128
 constexpr int TC_STAGES = 3;      // centre-tile ring
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_KBLK_BYTES = TC_BM * TC_BK * 4;  // 16 KB: one [128][32] fp32 block
 constexpr int TC_TMEM_COLS = 256;                 // two 128-column accumulators
 // error band of the 3xTF32 screen, relative to |x_i| * max_j |c_j|
 constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
+int g_tc_cluster = 0;   // gdr_debug_set("tc_cluster", 1) forces the single-CTA kernel
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -74,11 +76,38 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in cta_mask and
+// completes tx bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                               uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)),
+        "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of cta_mask once the MMAs issued so far are done
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -185,9 +214,14 @@ struct TcSmem {
   __host__ __device__ static constexpr int x_lo(int nkb, int kb) { return (nkb + kb) * TC_KBLK_BYTES; }
   __host__ __device__ static constexpr int c_stage(int nkb, int s) { return (2 * nkb + 2 * s) * TC_KBLK_BYTES; }
   __host__ __device__ static constexpr int bars(int nkb) { return (2 * nkb + 2 * TC_STAGES) * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1024; }  // + barriers + alignment slack
+  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1536 + 1024; }  // + barriers + merge buffer + alignment slack
 };
 
+// CL = CTAs per cluster.  CL == 2: the two CTAs of a cluster work on two different row tiles but
+// walk the centre tiles in lockstep, and every centre K-block is fetched from L2 ONCE and
+// TMA-multicast into both CTAs' shared memory (CTA 0 issues the hi half, CTA 1 the lo half) —
+// the L2 -> SMEM stream of centre tiles, which bounds this kernel at large K, is halved.
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
             const __grid_constant__ CUtensorMap map_chi, const __grid_constant__ CUtensorMap map_clo,
@@ -206,6 +240,12 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // work units: a unit = CL consecutive row tiles, one per CTA of the cluster (a tile index past the
+  // end is a dummy: TMA zero-fills it and its results are never written)
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / CL, n_units_grid = (int)gridDim.x / CL;
+  const int n_units = (n_row_tiles + CL - 1) / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < TC_MAX_KB; ++i) {
@@ -214,11 +254,11 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     }
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], 1);
+      mbar_init(&c_empty[i], CL);   // released by the MMA thread of every CTA that reads the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 128);
+      mbar_init(&t_empty[i], TC_EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -230,6 +270,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -237,7 +278,8 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t cit = 0, tile_it = 0;
-      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+      for (int un = unit0; un < n_units; un += n_units_grid, ++tile_it) {
+        const int rt = un * CL + crank;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
           mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
@@ -251,8 +293,15 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
             mbar_wait(&c_empty[s], ph ^ 1);
             mbar_expect_tx(&c_full[s], 2 * TC_KBLK_BYTES);
             uint8_t* dst = smem + TcSmem::c_stage(nkb, s);
-            tma_load_2d(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s]);
-            tma_load_2d(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s]);
+            if (CL == 2) {
+              // c_empty[s] (count 2) says BOTH CTAs are done with the stage; this CTA fetches one half
+              // and multicasts it, the peer delivers the other half: each c_full[s] sees 2 x 16 KB
+              if (crank == 0) tma_load_2d_mc(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s], kMask);
+              else tma_load_2d_mc(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s], kMask);
+            } else {
+              tma_load_2d(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s]);
+              tma_load_2d(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s]);
+            }
           }
         }
       }
@@ -262,7 +311,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
       uint32_t cit = 0, tile_it = 0, g = 0;
-      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+      for (int un = unit0; un < n_units; un += n_units_grid, ++tile_it) {
         for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
           const uint32_t a = g & 1, aph = (g >> 1) & 1;
           mbar_wait(&t_empty[a], aph ^ 1);
@@ -286,7 +335,8 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
               tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
               tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
             }
-            tc_commit(&c_empty[s]);                                  // frees the centre stage
+            if (CL == 2) tc_commit_mc(&c_empty[s], kMask);           // frees the stage in BOTH CTAs
+            else tc_commit(&c_empty[s]);                             // frees the centre stage
             if (ct == n_col_tiles - 1) tc_commit(&x_empty[kb]);      // X K-block no longer needed
           }
           tc_commit(&t_full[a]);                                     // accumulator ready
@@ -294,23 +344,29 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
       }
     }
   } else {
-    // ================= epilogue: 4 warps, one TMEM lane quarter each =================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
+    // ================= epilogue: 8 warps; warp w reads TMEM lanes [32*(w%4), +32) and the
+    //                    column half (w-2)/4 of every accumulator (two warps per SM sub-partition
+    //                    hide each other's tcgen05.ld and min-chain latencies) =================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;            // 0: columns [0, 64), 1: columns [64, 128)
+    float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);   // [3][128] exchange buffer after the barriers
     uint32_t g = 0;
-    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+    for (int un = unit0; un < n_units; un += n_units_grid) {
+      const int rt = un * CL + crank;
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
         const uint32_t a = g & 1, aph = (g >> 1) & 1;
         mbar_wait(&t_full[a], aph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * TC_BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-          uint32_t v[32];
-          tc_ld_32x32(taddr + c0, v);
-          tc_wait_ld();
-          const int jbase = ct * TC_BN + c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * TC_BN + half * (TC_BN / 2);
+        uint32_t v[2][32];
+        tc_ld_32x32(taddr, v[0]);
+        tc_ld_32x32(taddr + 32, v[1]);          // both chunks in flight before the first is consumed
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int jbase = ct * TC_BN + half * (TC_BN / 2) + c * 32;
           const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -318,7 +374,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
             const float cc[4] = {cn.x, cn.y, cn.z, cn.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float d = fmaf(-2.f, __uint_as_float(v[q * 4 + u]), cc[u]);
+              const float d = fmaf(-2.f, __uint_as_float(v[c][q * 4 + u]), cc[u]);
               second = fminf(second, fmaxf(d, best));
               bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
               best = fminf(best, d);
@@ -328,16 +384,33 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
         tc_fence_before();
         mbar_arrive(&t_empty[a]);
       }
-      const int64_t row = (int64_t)rt * TC_BM + quarter * 32 + lane;
-      if (row < N) {
-        best_out[row] = best;
-        second_out[row] = second;
-        idx_out[row] = bidx;
+      // merge the two column halves of each row: lower columns win ties
+      const int rl = quarter * 32 + lane;
+      if (half == 1) {
+        s_merge[rl] = best;
+        s_merge[128 + rl] = second;
+        reinterpret_cast<int*>(s_merge)[256 + rl] = bidx;
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      if (half == 0) {
+        const float b1 = s_merge[rl], s1 = s_merge[128 + rl];
+        const int i1 = reinterpret_cast<int*>(s_merge)[256 + rl];
+        const float nb = fminf(best, b1);
+        const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
+        const int ni = b1 < best ? i1 : bidx;
+        const int64_t row = (int64_t)rt * TC_BM + rl;
+        if (row < N) {
+          best_out[row] = nb;
+          second_out[row] = ns;
+          idx_out[row] = ni;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // no CTA leaves while its peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -505,7 +578,8 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   const int smem_bytes = TcSmem::total(nkb);
   static bool attr_set = false;
   if (!attr_set) {
-    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
     attr_set = true;
   }
   int sms = kSMs;
@@ -514,11 +588,34 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = n_row_tiles < sms ? n_row_tiles : sms;
+  // 2-CTA clusters with multicast centre tiles whenever there are at least two row tiles
+  // (measured: multicast pairs are NOT faster — the kernel was epilogue-bound, not L2-bound — so the
+  //  2-CTA variant is opt-in: gdr_debug_set("tc_cluster", 2))
+  const int cl = (g_tc_cluster == 2 && n_row_tiles >= 2 && sms >= 2) ? 2 : 1;
   {
     ProfileScope prof(PROF_ASSIGN, s);
-    k_assign_tc<<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
-                                                    cnorm, best, second, idx);
+    if (cl == 2) {
+      const int n_units = (n_row_tiles + 1) / 2;
+      const int grid = 2 * (n_units < sms / 2 ? n_units : sms / 2);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = smem_bytes;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      GDR_CUDA(cudaLaunchKernelEx(&cfg, k_assign_tc<2>, m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
+                                  (const float*)cnorm, best, second, idx));
+    } else {
+      const int grid = n_row_tiles < sms ? n_row_tiles : sms;
+      k_assign_tc<1><<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
+                                                         cnorm, best, second, idx);
+    }
   }
   GDR_LAUNCHED();
   k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
