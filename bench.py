@@ -201,6 +201,9 @@ def run_ours(args, rank, world):
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.tc_screen:
+        from gdr import _lib as _l
+        _l.call("gdr_debug_set", b"tc_screen", int(args.tc_screen))
     if world > 1:
         return run_ours_multi(args, rank, world, dev)
 
@@ -337,11 +340,14 @@ def run_ours(args, rank, world):
     flops = 2.0 * n * K * F
     a_tf = float(flops / (assign_ms.mean() / 1e3) / 1e12)
     tc = args.precision in ("tc", "auto") and F <= 128
-    roofline = {"kernel": "k_assign_tc (tcgen05 3xTF32)" if tc else "k_assign_simt (exact fp32 FFMA)",
+    two_level = tc and (args.tc_screen >= 2 or (args.tc_screen == 0 and -(-n // 128) >= 4 * 148))
+    roofline = {"kernel": ("k_assign_tc two-level screen (tcgen05 1xTF32 all rows -> select -> compact -> 3xTF32 undecided rows)" if two_level
+                           else "k_assign_tc (tcgen05 3xTF32)") if tc else "k_assign_simt (exact fp32 FFMA)",
                 "bound": "tensor", "achieved": a_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": a_tf / pk["bf16_sustained"], "traffic": traffic.get("k_assign_tc") if tc else None,
                 "peak_source": pk["src"] + " bf16 sustained",
-                "note": "useful flops 2NKD per launch; fp32 inputs: TF32 rate = 1/2 bf16, 3xTF32 emulation ceiling = peak/6",
+                "note": "useful flops 2NKD per E-step over the time of the whole tensor-core screen; fp32 inputs: TF32 rate = 1/2 bf16, "
+                        "3xTF32 emulation ceiling = peak/6, two-level screen ceiling -> peak/2",
                 "frac_of_3xtf32_ceiling": a_tf / (pk["bf16_sustained"] / 6.0),
                 "launch_ms": float(assign_ms.mean()), "share_of_step": float(assign_total_ms / step_ms.sum())}
     spmm_ms = spmm_kernel_ms
@@ -363,7 +369,7 @@ def run_ours(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
                                f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
-                   "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
+                   "precision": args.precision, "tc_screen": args.tc_screen, "l2": "flushed between timed steps (256 MB write)"},
         "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / pk["hbm"],
                  "frac_hbm_8TBs": prop_gbs / 8000.0, "bytes_model": "B_min", "ms": float(prop_ms.mean())},
         "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
@@ -527,6 +533,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
+    ap.add_argument("--tc-screen", type=int, default=0, help="debug: 0 auto, 1 direct 3xTF32, 2/3 two-level screen (BN 128/256)")
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no CPU baseline, minimal e2e leg")

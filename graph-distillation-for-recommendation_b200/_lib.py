@@ -22,6 +22,7 @@ _SIGNATURES = {
     "gdr_device_info": (i32, [vp, vp, vp]),
     "gdr_launch_count": (i64, []),
     "gdr_debug_set": (i32, [cp, i32]),
+    "gdr_debug_get": (i32, [cp, vp]),
     "gdr_profile_enable": (i32, [i32]),
     "gdr_profile_collect": (i32, [vp, vp]),
     "gdr_sort_pairs_ws_bytes": (i64, [i64]),

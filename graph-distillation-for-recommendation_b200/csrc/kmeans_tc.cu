@@ -19,6 +19,7 @@
 //     overlaps the MMAs of tile t+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <string.h>
 
 namespace gdr {
 
@@ -39,7 +40,13 @@ constexpr int TC_KBLK_BYTES = TC_BM * TC_BK * 4;  // 16 KB: one [128][32] fp32 b
 constexpr int TC_TMEM_COLS = 256;                 // two 128-column accumulators
 // error band of the 3xTF32 screen, relative to |x_i| * max_j |c_j|
 constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
-int g_tc_cluster = 0;   // gdr_debug_set("tc_cluster", 1) forces the single-CTA kernel
+// first-level screen: one TF32 product.  |x.c - x_hi.c_hi| <= |x_hi||c - c_hi| + |c||x - x_hi| <= (2^-10 + 2^-22)|x||c|
+// (cvt.rna: unit round-off 2^-11 per operand), TMEM accumulation <= D 2^-23 |x||c| (D <= 128: 2^-16), so the
+// distance error |d^ - d| = 2|x.c error| <= 2^-9 (1 + 2^-6 + 2^-12)|x||c|; eps1 = 2^-9 * 1.0625 leaves 4 % for
+// the fp32 rounding of the norms and of the bound arithmetic itself.
+constexpr float TC_EPS1 = 1.0625f * 0.001953125f;
+static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
+int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with BN=128, 3 two-level with BN=256
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -76,38 +83,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
-// multicast variant: the box lands at the same shared-memory offset of every CTA in cta_mask and
-// completes tx bytes on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                               uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)),
-        "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-// arrive on the barrier at the same offset in every CTA of cta_mask once the MMAs issued so far are done
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -189,13 +169,21 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
   }
 }
 
-// cmax = max_j |c_j| over the real centres; also resets the re-score list length
-__global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, float* __restrict__ cnorm,
-                                                       float* __restrict__ cmax, int32_t* __restrict__ amb_count) {
+// cmax = max_j |c_j| over the real centres, |c_j| per centre (0 on padding); also resets the list lengths
+__global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, const float* __restrict__ cnorm,
+                                                       float* __restrict__ cnorm_sqrt, float* __restrict__ cmax,
+                                                       int32_t* __restrict__ amb_count, int32_t* __restrict__ count1) {
   __shared__ float s_m[1024];
   float m = 0.f;
-  if (threadIdx.x == 0 && amb_count) amb_count[0] = 0;
-  for (int64_t j = threadIdx.x; j < K; j += 1024) m = fmaxf(m, cnorm[j]);
+  if (threadIdx.x == 0) {
+    if (amb_count) amb_count[0] = 0;
+    if (count1) count1[0] = 0;
+  }
+  for (int64_t j = threadIdx.x; j < Kp; j += 1024) {
+    const float c2 = j < K ? cnorm[j] : 0.f;
+    m = fmaxf(m, c2);
+    cnorm_sqrt[j] = sqrtf(c2);
+  }
   s_m[threadIdx.x] = m;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
@@ -208,53 +196,60 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, fl
 // ---------------------------------------------------------------------------------
 // the tensor-core kernel
 // ---------------------------------------------------------------------------------
-struct TcSmem {
-  // offsets into the 1024-aligned dynamic shared memory
+// NPASS = 3: 3xTF32 (x_lo.c_hi + x_hi.c_lo + x_hi.c_hi), outputs (best, second, argmin) of the distances.
+// NPASS = 1: one TF32 product x_hi.c_hi per K-step — the first-level screen.  Its distances carry a
+//            proven error |d^ - d| <= eps1 |x_i| |c_j|, so the epilogue tracks the two smallest LOWER
+//            bounds L_ij = d^_ij - eps1 |x_i| |c_j| and their argmin; k_tc_select1 accepts the row when
+//            the upper bound of the argmin lies below every other lower bound.
+// BN      = centres per accumulator tile (UMMA N): 128 or 256.
+template <int NPASS, int BN>
+struct TcCfg {
+  static constexpr int kXCopies = NPASS == 3 ? 2 : 1;                        // hi (+ lo) copy of the row tile
+  static constexpr int kStageBytes = kXCopies * BN * TC_BK * 4;              // one centre K-block (hi [+ lo])
+  static constexpr int kStages = NPASS == 3 ? 3 : (BN == 256 ? 4 : 8);
+  static constexpr int kTmemCols = 2 * BN;                                   // two accumulators
   __host__ __device__ static constexpr int x_hi(int kb) { return kb * TC_KBLK_BYTES; }
   __host__ __device__ static constexpr int x_lo(int nkb, int kb) { return (nkb + kb) * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return (2 * nkb + 2 * s) * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int bars(int nkb) { return (2 * nkb + 2 * TC_STAGES) * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1536 + 1024; }  // + barriers + merge buffer + alignment slack
+  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return kXCopies * nkb * TC_KBLK_BYTES + s * kStageBytes; }
+  __host__ __device__ static constexpr int bars(int nkb) { return c_stage(nkb, kStages); }
+  // + barriers (256 B) + epilogue merge buffer (1536 B) + alignment slack
+  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1536 + 1024; }
 };
 
-// CL = CTAs per cluster.  CL == 2: the two CTAs of a cluster work on two different row tiles but
-// walk the centre tiles in lockstep, and every centre K-block is fetched from L2 ONCE and
-// TMA-multicast into both CTAs' shared memory (CTA 0 issues the hi half, CTA 1 the lo half) —
-// the L2 -> SMEM stream of centre tiles, which bounds this kernel at large K, is halved.
-template <int CL>
+template <int NPASS, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
             const __grid_constant__ CUtensorMap map_chi, const __grid_constant__ CUtensorMap map_clo,
-            int64_t N, int n_row_tiles, int n_col_tiles, int nkb, const float* __restrict__ cnorm,
-            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
+            int64_t N_host, const int32_t* __restrict__ n_rows_dev /*nullable: row count on the device*/,
+            int D, int n_col_tiles, int nkb, const float* __restrict__ cnorm,
+            const float* __restrict__ cnorm_sqrt /*NPASS 1: |c_j|*/, const float* __restrict__ xnorm /*NPASS 1: |x_i|*/,
+            float eps1, float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
+  using Cfg = TcCfg<NPASS, BN>;
+  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::bars(nkb));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bars(nkb));
   uint64_t* x_full = bars;                     // [TC_MAX_KB]
   uint64_t* x_empty = bars + TC_MAX_KB;        // [TC_MAX_KB]
-  uint64_t* c_full = bars + 2 * TC_MAX_KB;     // [TC_STAGES]
-  uint64_t* c_empty = c_full + TC_STAGES;      // [TC_STAGES]
-  uint64_t* t_full = c_empty + TC_STAGES;      // [2]
+  uint64_t* c_full = bars + 2 * TC_MAX_KB;     // [S]
+  uint64_t* c_empty = c_full + S;              // [S]
+  uint64_t* t_full = c_empty + S;              // [2]
   uint64_t* t_empty = t_full + 2;              // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // work units: a unit = CL consecutive row tiles, one per CTA of the cluster (a tile index past the
-  // end is a dummy: TMA zero-fills it and its results are never written)
-  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
-  const int unit0 = (int)blockIdx.x / CL, n_units_grid = (int)gridDim.x / CL;
-  const int n_units = (n_row_tiles + CL - 1) / CL;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  const int64_t N = n_rows_dev ? (int64_t)n_rows_dev[0] : N_host;
+  const int n_row_tiles = (int)((N + TC_BM - 1) / TC_BM);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < TC_MAX_KB; ++i) {
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
     }
-    for (int i = 0; i < TC_STAGES; ++i) {
+    for (int i = 0; i < S; ++i) {
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], CL);   // released by the MMA thread of every CTA that reads the stage
+      mbar_init(&c_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
@@ -264,13 +259,12 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)),
-                 "r"(TC_TMEM_COLS)
+                 "r"(Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -278,30 +272,22 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t cit = 0, tile_it = 0;
-      for (int un = unit0; un < n_units; un += n_units_grid, ++tile_it) {
-        const int rt = un * CL + crank;
+      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
-          mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
-          tma_load_2d(smem + TcSmem::x_hi(kb), &map_xhi, kb * TC_BK, rt * TC_BM, &x_full[kb]);
-          tma_load_2d(smem + TcSmem::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+          mbar_expect_tx(&x_full[kb], Cfg::kXCopies * TC_KBLK_BYTES);
+          tma_load_2d(smem + Cfg::x_hi(kb), &map_xhi, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+          if (NPASS == 3) tma_load_2d(smem + Cfg::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * TC_BM, &x_full[kb]);
         }
         for (int ct = 0; ct < n_col_tiles; ++ct) {
           for (int kb = 0; kb < nkb; ++kb, ++cit) {
-            const int s = cit % TC_STAGES;
-            const uint32_t ph = (cit / TC_STAGES) & 1;
+            const int s = cit % S;
+            const uint32_t ph = (cit / S) & 1;
             mbar_wait(&c_empty[s], ph ^ 1);
-            mbar_expect_tx(&c_full[s], 2 * TC_KBLK_BYTES);
-            uint8_t* dst = smem + TcSmem::c_stage(nkb, s);
-            if (CL == 2) {
-              // c_empty[s] (count 2) says BOTH CTAs are done with the stage; this CTA fetches one half
-              // and multicasts it, the peer delivers the other half: each c_full[s] sees 2 x 16 KB
-              if (crank == 0) tma_load_2d_mc(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s], kMask);
-              else tma_load_2d_mc(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s], kMask);
-            } else {
-              tma_load_2d(dst, &map_chi, kb * TC_BK, ct * TC_BN, &c_full[s]);
-              tma_load_2d(dst + TC_KBLK_BYTES, &map_clo, kb * TC_BK, ct * TC_BN, &c_full[s]);
-            }
+            mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
+            uint8_t* dst = smem + Cfg::c_stage(nkb, s);
+            tma_load_2d(dst, &map_chi, kb * TC_BK, ct * BN, &c_full[s]);
+            if (NPASS == 3) tma_load_2d(dst + BN * TC_BK * 4, &map_clo, kb * TC_BK, ct * BN, &c_full[s]);
           }
         }
       }
@@ -309,34 +295,41 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
       uint32_t cit = 0, tile_it = 0, g = 0;
-      for (int un = unit0; un < n_units; un += n_units_grid, ++tile_it) {
+      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
         for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
           const uint32_t a = g & 1, aph = (g >> 1) & 1;
           mbar_wait(&t_empty[a], aph ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + a * TC_BN;
+          const uint32_t tmem_d = tmem_base + a * BN;
           for (int kb = 0; kb < nkb; ++kb, ++cit) {
             if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
-            const int s = cit % TC_STAGES;
-            const uint32_t ph = (cit / TC_STAGES) & 1;
+            const int s = cit % S;
+            const uint32_t ph = (cit / S) & 1;
             mbar_wait(&c_full[s], ph);
             tc_fence_after();
-            const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + TcSmem::x_hi(kb)));
-            const uint64_t d_xlo = umma_desc_sw128(smem_u32(smem + TcSmem::x_lo(nkb, kb)));
-            const uint64_t d_chi = umma_desc_sw128(smem_u32(smem + TcSmem::c_stage(nkb, s)));
-            const uint64_t d_clo = umma_desc_sw128(smem_u32(smem + TcSmem::c_stage(nkb, s) + TC_KBLK_BYTES));
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step
-              // small terms first, the dominant hi*hi product last
-              tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
-              tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
-              tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+            const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(kb)));
+            const uint64_t d_chi = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s)));
+            // K = 8 steps that still hold real columns (the rest of the 32-float block is zero padding)
+            const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
+            if (NPASS == 3) {
+              const uint64_t d_xlo = umma_desc_sw128(smem_u32(smem + Cfg::x_lo(nkb, kb)));
+              const uint64_t d_clo = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s) + BN * TC_BK * 4));
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step
+                // small terms first, the dominant hi*hi product last
+                tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
+                tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
+                tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, (kb | k) != 0);
+              }
             }
-            if (CL == 2) tc_commit_mc(&c_empty[s], kMask);           // frees the stage in BOTH CTAs
-            else tc_commit(&c_empty[s]);                             // frees the centre stage
+            tc_commit(&c_empty[s]);                                  // frees the centre stage
             if (ct == n_col_tiles - 1) tc_commit(&x_empty[kb]);      // X K-block no longer needed
           }
           tc_commit(&t_full[a]);                                     // accumulator ready
@@ -348,36 +341,51 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     //                    column half (w-2)/4 of every accumulator (two warps per SM sub-partition
     //                    hide each other's tcgen05.ld and min-chain latencies) =================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;            // 0: columns [0, 64), 1: columns [64, 128)
+    const int half = (warp - 2) >> 2;            // 0: columns [0, BN/2), 1: columns [BN/2, BN)
     float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);   // [3][128] exchange buffer after the barriers
+    const int rl = quarter * 32 + lane;
     uint32_t g = 0;
-    for (int un = unit0; un < n_units; un += n_units_grid) {
-      const int rt = un * CL + crank;
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      const int64_t row = (int64_t)rt * TC_BM + rl;
+      float nexn = 0.f;                          // -eps1 |x_i|
+      if (NPASS == 1 && row < N) nexn = -eps1 * xnorm[row];
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
         const uint32_t a = g & 1, aph = (g >> 1) & 1;
         mbar_wait(&t_full[a], aph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * TC_BN + half * (TC_BN / 2);
-        uint32_t v[2][32];
-        tc_ld_32x32(taddr, v[0]);
-        tc_ld_32x32(taddr + 32, v[1]);          // both chunks in flight before the first is consumed
-        tc_wait_ld();
+#pragma unroll 1
+        for (int h2 = 0; h2 < BN / 128; ++h2) {
+          const int col0 = half * (BN / 2) + h2 * 64;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + col0;
+          uint32_t v[2][32];
+          tc_ld_32x32(taddr, v[0]);
+          tc_ld_32x32(taddr + 32, v[1]);          // both chunks in flight before the first is consumed
+          tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int jbase = ct * TC_BN + half * (TC_BN / 2) + c * 32;
-          const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
+          for (int c = 0; c < 2; ++c) {
+            const int jbase = ct * BN + col0 + c * 32;
+            const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
+            const float4* cr4 = reinterpret_cast<const float4*>(cnorm_sqrt + jbase);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 cn = __ldg(cn4 + q);
-            const float cc[4] = {cn.x, cn.y, cn.z, cn.w};
+            for (int q = 0; q < 8; ++q) {
+              const float4 cn = __ldg(cn4 + q);
+              float cc[4] = {cn.x, cn.y, cn.z, cn.w};
+              if (NPASS == 1) {
+                const float4 cr = __ldg(cr4 + q);
+                cc[0] = fmaf(nexn, cr.x, cc[0]);
+                cc[1] = fmaf(nexn, cr.y, cc[1]);
+                cc[2] = fmaf(nexn, cr.z, cc[2]);
+                cc[3] = fmaf(nexn, cr.w, cc[3]);
+              }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float d = fmaf(-2.f, __uint_as_float(v[c][q * 4 + u]), cc[u]);
-              second = fminf(second, fmaxf(d, best));
-              bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
-              best = fminf(best, d);
+              for (int u = 0; u < 4; ++u) {
+                const float d = fmaf(-2.f, __uint_as_float(v[c][q * 4 + u]), cc[u]);
+                second = fminf(second, fmaxf(d, best));
+                bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
+                best = fminf(best, d);
+              }
             }
           }
         }
@@ -385,7 +393,6 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
         mbar_arrive(&t_empty[a]);
       }
       // merge the two column halves of each row: lower columns win ties
-      const int rl = quarter * 32 + lane;
       if (half == 1) {
         s_merge[rl] = best;
         s_merge[128 + rl] = second;
@@ -398,7 +405,6 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
         const float nb = fminf(best, b1);
         const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
         const int ni = b1 < best ? i1 : bidx;
-        const int64_t row = (int64_t)rt * TC_BM + rl;
         if (row < N) {
           best_out[row] = nb;
           second_out[row] = ns;
@@ -410,10 +416,99 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();   // no CTA leaves while its peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// first-level decision: lower bounds L (best, second) and argmin idx from k_assign_tc<1, *>.
+// U_idx = L_idx + 2 eps1 |x||c_idx| is an upper bound of the true distance to idx; every other centre's true
+// distance is >= second.  second > U_idx  =>  idx is the unique exact argmin.  Everything else goes to the
+// second-level list (3xTF32 on the compacted rows).
+__global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __restrict__ best,
+                                                    const float* __restrict__ second,
+                                                    const int32_t* __restrict__ idx,
+                                                    const float* __restrict__ xnorm,
+                                                    const float* __restrict__ cnorm_sqrt, float eps1,
+                                                    int32_t* __restrict__ labels,
+                                                    const int32_t* __restrict__ labels_prev,
+                                                    int32_t* __restrict__ n_changed,
+                                                    int32_t* __restrict__ list1, int32_t* __restrict__ count1) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int changed = 0;
+  if (i < N) {
+    const int l = idx[i];
+    const float b = best[i], s2 = second[i];
+    // 2^-21 |.|: fp32 rounding of the two fmaf that formed each bound
+    const float tol = 2.f * eps1 * xnorm[i] * cnorm_sqrt[l] + 4.76837158e-07f * fmaxf(fabsf(b), fabsf(s2));
+    const bool ambiguous = !(s2 - b > tol);   // also catches NaN / inf - inf
+    if (ambiguous) {
+      list1[atomicAdd(count1, 1)] = (int32_t)i;
+    } else {
+      labels[i] = l;
+      if (labels_prev && labels_prev[i] != l) changed = 1;
+    }
+  }
+  if (n_changed) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+    if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
+  }
+}
+
+// compact the hi/lo operand rows (and |x|) of the second-level list; one warp per listed row
+__global__ void __launch_bounds__(256) k_tc_gather(const int32_t* __restrict__ list1, const int32_t* __restrict__ count1,
+                                                   int Dp, const float* __restrict__ hi, const float* __restrict__ lo,
+                                                   const float* __restrict__ xnorm, float* __restrict__ ghi,
+                                                   float* __restrict__ glo, float* __restrict__ gnorm) {
+  const int n = count1[0];
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  const int Dp4 = Dp >> 2;
+  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < n; slot += wpg) {
+    const int64_t r = list1[slot];
+    const float4* h = reinterpret_cast<const float4*>(hi + r * Dp);
+    const float4* l = reinterpret_cast<const float4*>(lo + r * Dp);
+    float4* gh = reinterpret_cast<float4*>(ghi + (int64_t)slot * Dp);
+    float4* gl = reinterpret_cast<float4*>(glo + (int64_t)slot * Dp);
+    for (int c = lane_id(); c < Dp4; c += 32) {
+      gh[c] = __ldg(h + c);
+      gl[c] = __ldg(l + c);
+    }
+    if (lane_id() == 0) gnorm[slot] = xnorm[r];
+  }
+}
+
+// second-level decision on the compacted rows (slot -> row through list1): same band as k_tc_select
+__global__ void __launch_bounds__(256) k_tc_select2(const int32_t* __restrict__ list1, const int32_t* __restrict__ count1,
+                                                    const float* __restrict__ best, const float* __restrict__ second,
+                                                    const int32_t* __restrict__ idx, const float* __restrict__ gnorm,
+                                                    const float* __restrict__ cmax, float band,
+                                                    int32_t* __restrict__ labels, const int32_t* __restrict__ labels_prev,
+                                                    int32_t* __restrict__ n_changed, int32_t* __restrict__ amb_list,
+                                                    int32_t* __restrict__ amb_count,
+                                                    unsigned long long* __restrict__ amb_packed) {
+  const int n = count1[0];
+  const int stride = gridDim.x * blockDim.x;
+  int changed = 0;
+  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += stride) {
+    const int32_t i = list1[slot];
+    const float tol = band * gnorm[slot] * cmax[0];
+    const float b = best[slot], s2 = second[slot];
+    if (!(s2 - b > tol)) {
+      const int a = atomicAdd(amb_count, 1);
+      amb_list[a] = i;
+      amb_packed[a] = ~0ull;
+    } else {
+      const int l = idx[slot];
+      labels[i] = l;
+      if (labels_prev && labels_prev[i] != l) ++changed;
+    }
+  }
+  if (n_changed) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+    if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
   }
 }
 
@@ -494,6 +589,7 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int Dp, int
 }
 
 static inline int dpad(int64_t D) { return (int)align_up(D, TC_BK); }
+constexpr int TC_KPAD = 256;   // centres padded to the widest accumulator tile
 
 int64_t kmeans_tc_xsplit_bytes(int64_t N, int64_t D) {
   int Dp = dpad(D);
@@ -520,11 +616,49 @@ int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* x
   return GDR_OK;
 }
 
+// two-level screen (1xTF32 over all rows, 3xTF32 over the compacted undecided rows) pays off once the
+// row tiles fill the machine a few times over; below that the direct 3xTF32 kernel is one launch instead of five
+static bool tc_two_level(int64_t N, bool want_best) {
+  if (want_best) return false;              // best_out is defined by the 3xTF32 / exact distances
+  if (g_tc_screen == 1) return false;
+  if (g_tc_screen >= 2) return true;
+  return cdiv(N, TC_BM) >= 4 * kSMs;
+}
+
 int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
   int Dp = dpad(D);
-  int64_t Kp = align_up(K, TC_BN);
-  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need(Kp, 4) + 256 /*cmax*/ + 3 * ws_need(N, 4) /*best, second, idx*/ +
-         ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ + 256 /*amb count*/ + 256;
+  int64_t Kp = align_up(K, TC_KPAD);
+  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + 2 * ws_need(Kp, 4) /*|c|^2, |c|*/ + 256 /*cmax*/ +
+         3 * ws_need(N, 4) /*best, second, idx*/ + ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ +
+         256 /*amb count*/ + ws_need(N, 4) /*second-level list*/ + 256 /*its count*/ +
+         2 * ws_need(N * Dp, 4) + ws_need(N, 4) /*compacted hi, lo, |x|*/ + 256;
+}
+
+template <int NPASS, int BN>
+static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, const CUtensorMap& m_chi,
+                            const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D, int64_t Kp,
+                            int nkb, const float* cnorm, const float* cnorm_sqrt, const float* xnorm, float* best,
+                            float* second, int32_t* idx, cudaStream_t s) {
+  using Cfg = TcCfg<NPASS, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<NPASS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::total(TC_MAX_KB)));
+    attr_set = true;
+  }
+  int sms = kSMs;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t tiles = cdiv(N_max, TC_BM);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  k_assign_tc<NPASS, BN><<<grid, TC_THREADS, Cfg::total(nkb), s>>>(m_xhi, m_xlo, m_chi, m_clo, N_max, n_rows_dev, D,
+                                                                  (int)(Kp / BN), nkb, cnorm, cnorm_sqrt, xnorm,
+                                                                  TC_EPS1, best, second, idx);
+  GDR_LAUNCHED();
+  return GDR_OK;
 }
 
 int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const void* xsplit,
@@ -536,26 +670,33 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
               TC_MAX_KB * TC_BK);
     return GDR_EUNSUPPORTED;
   }
-  if (N >= (1ll << 31) - TC_BM || K >= (1ll << 31) - TC_BN) {
+  if (N >= (1ll << 31) - TC_BM || K >= (1ll << 31) - TC_KPAD) {
     set_error("kmeans_assign(tc): N or K exceeds int32 tile coordinates");
     return GDR_ERANGE;
   }
   const int Dp = dpad(D);
   const int nkb = Dp / TC_BK;
-  const int64_t Kp = align_up(K, TC_BN);
+  const int64_t Kp = align_up(K, TC_KPAD);
   XSplit xs = carve_xsplit(const_cast<void*>(xsplit), N, D);
   Workspace W(ws, ws_bytes);
   float* c_hi = W.take<float>(Kp * Dp);
   float* c_lo = W.take<float>(Kp * Dp);
   float* c_t = W.take<float>(Kp * Dp);   // fp32 centres transposed [Dp][Kp] for the re-score kernel
   float* cnorm = W.take<float>(Kp);
+  float* cnorm_sqrt = W.take<float>(Kp);
   float* cmax = W.take<float>(1);
   float* best = W.take<float>(N);
   float* second = W.take<float>(N);
   int32_t* idx = W.take<int32_t>(N);
   int32_t* amb_list = W.take<int32_t>(N);
   unsigned long long* amb_packed = W.take<unsigned long long>(N);
-  int32_t* amb_count = n_refined_dev ? n_refined_dev : W.take<int32_t>(1);
+  int32_t* amb_count_ws = W.take<int32_t>(1);
+  int32_t* list1 = W.take<int32_t>(N);
+  int32_t* count1 = W.take<int32_t>(1);
+  float* g_hi = W.take<float>(N * Dp);
+  float* g_lo = W.take<float>(N * Dp);
+  float* g_norm = W.take<float>(N);
+  int32_t* amb_count = n_refined_dev ? n_refined_dev : amb_count_ws;
   if (!W.ok()) {
     set_error("kmeans_assign(tc): workspace too small");
     return GDR_EWORKSPACE;
@@ -564,63 +705,56 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t, cnorm);
   GDR_LAUNCHED();
   int rc;
-  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cmax, amb_count);
+  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cnorm_sqrt, cmax, amb_count, count1);
   GDR_LAUNCHED();
 
   CUtensorMap m_xhi, m_xlo, m_chi, m_clo;
   if ((rc = make_map(&m_xhi, xs.hi, N, Dp, TC_BM))) return rc;
   if ((rc = make_map(&m_xlo, xs.lo, N, Dp, TC_BM))) return rc;
-  if ((rc = make_map(&m_chi, c_hi, Kp, Dp, TC_BN))) return rc;
-  if ((rc = make_map(&m_clo, c_lo, Kp, Dp, TC_BN))) return rc;
+  if ((rc = make_map(&m_chi, c_hi, Kp, Dp, 128))) return rc;
+  if ((rc = make_map(&m_clo, c_lo, Kp, Dp, 128))) return rc;
 
-  const int n_row_tiles = (int)cdiv(N, TC_BM);
-  const int n_col_tiles = (int)(Kp / TC_BN);
-  const int smem_bytes = TcSmem::total(nkb);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
-    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(TC_MAX_KB)));
-    attr_set = true;
-  }
-  int sms = kSMs;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  // 2-CTA clusters with multicast centre tiles whenever there are at least two row tiles
-  // (measured: multicast pairs are NOT faster — the kernel was epilogue-bound, not L2-bound — so the
-  //  2-CTA variant is opt-in: gdr_debug_set("tc_cluster", 2))
-  const int cl = (g_tc_cluster == 2 && n_row_tiles >= 2 && sms >= 2) ? 2 : 1;
-  {
-    ProfileScope prof(PROF_ASSIGN, s);
-    if (cl == 2) {
-      const int n_units = (n_row_tiles + 1) / 2;
-      const int grid = 2 * (n_units < sms / 2 ? n_units : sms / 2);
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(TC_THREADS);
-      cfg.dynamicSmemBytes = smem_bytes;
-      cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      GDR_CUDA(cudaLaunchKernelEx(&cfg, k_assign_tc<2>, m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
-                                  (const float*)cnorm, best, second, idx));
-    } else {
-      const int grid = n_row_tiles < sms ? n_row_tiles : sms;
-      k_assign_tc<1><<<grid, TC_THREADS, smem_bytes, s>>>(m_xhi, m_xlo, m_chi, m_clo, N, n_row_tiles, n_col_tiles, nkb,
-                                                         cnorm, best, second, idx);
+  if (!tc_two_level(N, best_out != nullptr)) {
+    {
+      ProfileScope prof(PROF_ASSIGN, s);
+      if ((rc = launch_assign_tc<3, 128>(m_xhi, m_xlo, m_chi, m_clo, N, nullptr, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
+                                         xs.norm, best, second, idx, s)))
+        return rc;
     }
+    k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
+                                                      labels_prev, n_changed_dev, best_out, amb_list, amb_count,
+                                                      amb_packed);
+    GDR_LAUNCHED();
+  } else {
+    // the profile scope spans the whole tensor-core screen: level 1, decision, compaction, level 2
+    ProfileScope prof(PROF_ASSIGN, s);
+    if (g_tc_screen == 2) {
+      if ((rc = launch_assign_tc<1, 128>(m_xhi, m_xlo, m_chi, m_clo, N, nullptr, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
+                                         xs.norm, best, second, idx, s)))
+        return rc;
+    } else {
+      CUtensorMap m_chi256;
+      if ((rc = make_map(&m_chi256, c_hi, Kp, Dp, 256))) return rc;
+      if ((rc = launch_assign_tc<1, 256>(m_xhi, m_xlo, m_chi256, m_chi256, N, nullptr, (int)D, Kp, nkb, cnorm,
+                                         cnorm_sqrt, xs.norm, best, second, idx, s)))
+        return rc;
+    }
+    g_last_count1 = count1;
+    k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cnorm_sqrt, TC_EPS1, labels,
+                                                       labels_prev, n_changed_dev, list1, count1);
+    GDR_LAUNCHED();
+    k_tc_gather<<<4 * kSMs, 256, 0, s>>>(list1, count1, Dp, xs.hi, xs.lo, xs.norm, g_hi, g_lo, g_norm);
+    GDR_LAUNCHED();
+    CUtensorMap m_ghi, m_glo;
+    if ((rc = make_map(&m_ghi, g_hi, N, Dp, TC_BM))) return rc;
+    if ((rc = make_map(&m_glo, g_lo, N, Dp, TC_BM))) return rc;
+    if ((rc = launch_assign_tc<3, 128>(m_ghi, m_glo, m_chi, m_clo, N, count1, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
+                                       g_norm, best, second, idx, s)))
+      return rc;
+    k_tc_select2<<<2 * kSMs, 256, 0, s>>>(list1, count1, best, second, idx, g_norm, cmax, TC_BAND, labels,
+                                         labels_prev, n_changed_dev, amb_list, amb_count, amb_packed);
+    GDR_LAUNCHED();
   }
-  GDR_LAUNCHED();
-  k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
-                                                    labels_prev, n_changed_dev, best_out, amb_list, amb_count, amb_packed);
-  GDR_LAUNCHED();
   // exact fp32 re-score of the ambiguous rows (list length stays on the device)
   return launch_assign_simt_rows(N, K, D, X, ldx, c_t, Kp, cnorm, amb_list, amb_count, amb_packed, labels,
                                  labels_prev, n_changed_dev, best_out, s);
@@ -648,6 +782,19 @@ int kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ld
 }  // namespace gdr
 
 extern "C" {
+
+// debug read-back (synchronises the device): "tc_level2_rows" = rows the last two-level screen sent to level 2
+int gdr_debug_get(const char* key, int64_t* value_host) {
+  GDR_CHECK_ARG(key && value_host, "debug_get: bad arguments");
+  if (!strcmp(key, "tc_level2_rows")) {
+    int32_t v = -1;
+    if (gdr::g_last_count1) GDR_CUDA(cudaMemcpy(&v, gdr::g_last_count1, 4, cudaMemcpyDeviceToHost));
+    *value_host = v;
+    return GDR_OK;
+  }
+  gdr::set_error("debug_get: unknown key %s", key);
+  return GDR_EINVAL;
+}
 
 int64_t gdr_kmeans_tc_xsplit_bytes(int64_t N, int64_t D) { return gdr::kmeans_tc_xsplit_bytes(N, D); }
 

@@ -40,7 +40,7 @@ static int g_spmm_unroll = 0;     // 4 or 8
 static int g_spmm_hints = -1;     // 0 off, 1 streaming hints on colidx/vals/T/Y
 static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
 extern int g_lloyd_graph;         // lloyd.cu
-extern int g_tc_cluster;          // kmeans_tc.cu
+extern int g_tc_screen;           // kmeans_tc.cu
 
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
   int v;
@@ -364,7 +364,7 @@ int gdr_debug_set(const char* key, int value) {
   else if (!strcmp(key, "spmm_hints")) gdr::g_spmm_hints = value;
   else if (!strcmp(key, "spmm_split")) gdr::g_spmm_split = value;
   else if (!strcmp(key, "lloyd_graph")) gdr::g_lloyd_graph = value;
-  else if (!strcmp(key, "tc_cluster")) gdr::g_tc_cluster = value;
+  else if (!strcmp(key, "tc_screen")) gdr::g_tc_screen = value;
   else {
     gdr::set_error("debug_set: unknown key %s", key);
     return GDR_EINVAL;

@@ -66,8 +66,12 @@ int gdr_profile_enable(int kind);
 int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
 
 /* Experiment knobs for kernel tuning sweeps (tools/spmm_sweep.py); not a stable surface.
- * keys: "spmm_unroll" (4|8), "spmm_hints" (0|1), "spmm_split" (1|2|4); value 0 / -1 = automatic. */
+ * keys: "spmm_unroll" (4|8), "spmm_hints" (0|1), "spmm_split" (1|2|4), "lloyd_graph" (0|1),
+ * "tc_screen" (1 direct 3xTF32, 2 / 3 two-level screen with 128- / 256-centre tiles); value 0 / -1 = automatic. */
 int gdr_debug_set(const char* key, int value);
+/* Debug read-back (synchronises the device).  keys: "tc_level2_rows" = rows the last two-level
+ * tensor-core screen (gdr_kmeans_assign_tc) handed to its 3xTF32 second level; -1 if none ran. */
+int gdr_debug_get(const char* key, int64_t* value_host);
 
 /* ---- generic device primitives (used by stages 1, 3, 4) -------------- */
 /* Stable LSD radix sort of (uint64 key, uint32 payload) pairs on the low

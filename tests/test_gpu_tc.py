@@ -50,6 +50,60 @@ def test_tc_assign_vs_oracle(gdr, oracle, N, K, D):
     assert np.array_equal(np_(lab32), lab)
 
 
+@pytest.fixture
+def screen_mode():
+    """Force a tensor-core screen variant (gdr_debug_set "tc_screen"); reset to auto afterwards."""
+    from gdr import _lib
+    yield lambda v: _lib.call("gdr_debug_set", b"tc_screen", int(v))
+    _lib.call("gdr_debug_set", b"tc_screen", 0)
+
+
+@pytest.mark.parametrize("mode", [2, 3])   # two-level screen with 128- / 256-centre accumulator tiles
+@pytest.mark.parametrize("N,K,D,kind", [(300, 7, 3, "clustered"), (4099, 129, 100, "clustered"), (20000, 1000, 40, "clustered"),
+                                        (20000, 333, 128, "zscore"), (50000, 1000, 128, "zscore"), (30011, 700, 100, "zscore"),
+                                        (1, 1, 1, "clustered")])
+def test_tc_two_level_screen_equals_exact_kernel(gdr, oracle, screen_mode, mode, N, K, D, kind):
+    """1xTF32 lower-bound screen -> 3xTF32 on the compacted undecided rows -> exact re-score: the labels
+    are those of the exact fp32 kernel, also on unclustered data where many rows reach level 2."""
+    from gdr import synth
+    from gdr._dev import padded_rows
+    from gdr.kmeans import TcOperand
+    X = synth.clustered_features(N, D, max(2, K // 3), seed=N + K) if kind == "clustered" else synth.features(N, D, seed=N + K)
+    X -= X.mean(axis=0)
+    C = synth.kmeans_init(X, K, seed=1)
+    Xd, Cd = padded_rows(torch.from_numpy(X).to(DEV)), padded_rows(torch.from_numpy(C).to(DEV))
+    op = TcOperand(Xd)
+    prev = torch.zeros(N, dtype=torch.int32, device=DEV)
+    lab32 = torch.empty(N, dtype=torch.int32, device=DEV)
+    nch32 = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(Xd, Cd, lab32, labels_prev=prev, n_changed=nch32)
+    screen_mode(mode)
+    labels = torch.full((N,), -7, dtype=torch.int32, device=DEV)
+    nch = torch.zeros(1, dtype=torch.int32, device=DEV)
+    n_ref = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(Xd, Cd, labels, labels_prev=prev, n_changed=nch, tc_operand=op, n_refined=n_ref)
+    torch.cuda.synchronize()
+    assert np.array_equal(np_(lab32), np_(labels))
+    assert int(nch.item()) == int(nch32.item())
+    ok, n_band, n_bad = oracle.labels_match(np_(labels), X, C, band=1e-6)
+    assert ok, f"{n_bad} rows outside the 1e-6 margin band disagree with the exact argmin"
+    assert int(n_ref.item()) <= max(64, N // 5)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_tc_full_fit_same_for_every_screen(gdr, screen_mode, mode):
+    from gdr import synth
+    N, K, D = 40000, 300, 100
+    X = synth.features(N, D, seed=11)
+    C0 = synth.kmeans_init(X, K, seed=3)
+    a = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=6, tol=0, precision="fp32").fit(X)
+    screen_mode(mode)
+    b = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=6, tol=0, precision="tc").fit(X)
+    assert np.array_equal(a.labels_, b.labels_)
+    np.testing.assert_array_equal(a.cluster_centers_, b.cluster_centers_)
+    assert a.inertia_ == b.inertia_
+
+
 def test_tc_full_fit_matches_fp32_path(gdr):
     from gdr import synth
     N, K, D = 30000, 500, 64
