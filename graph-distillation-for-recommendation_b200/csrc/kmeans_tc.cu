@@ -33,6 +33,7 @@ constexpr int TC_BM = 128;        // rows per tile (UMMA M)
 constexpr int TC_BN = 128;        // centres per tile (UMMA N)
 constexpr int TC_BK = 32;         // floats per K-block = one 128-byte swizzle row
 constexpr int TC_MAX_KB = 4;      // D padded <= 128
+constexpr int TC_BAR_KB = 5;      // K-blocks of the augmented first-level operand (D + 3 padded <= 160)
 constexpr int TC_STAGES = 3;      // centre-tile ring
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int TC_EPI_THREADS = 256;
@@ -46,7 +47,7 @@ constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
 // the fp32 rounding of the norms and of the bound arithmetic itself.
 constexpr float TC_EPS1 = 1.0625f * 0.001953125f;
 static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
-int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with BN=128, 3 two-level with BN=256
+int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -139,12 +140,28 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// smallest TF32 value >= v (v finite); used where a bound must not shrink under the operand rounding
+__device__ __forceinline__ float tf32_up(float v) {
+  uint32_t u = __float_as_uint(v);
+  if (v >= 0.f) u = (u + 0x1FFFu) & ~0x1FFFu;   // magnitude up
+  else u &= ~0x1FFFu;                           // magnitude down
+  return __uint_as_float(u);
+}
+
+// aug_mode 1 (rows of X) / 2 (centres): additionally write the first-level operand row
+//   aug[r] = [ tf32(x_0..x_{D-1}), e, p, q, 0... ]   (Dp1 = D + 3 rounded up to 32 floats)
+//   X rows : e = up(eps1 |x|),  p = q = 1
+//   centres: e = up(|c| / 2),   p + q >= w = -|c|^2/2 (1 - 2^-15) split in two TF32 values; padding: p = -1e30
+// so that one TF32 GEMM over the augmented rows yields the SCORE
+//   s_ij = x^.c^ + (eps1/2)|x||c| - |c|^2/2 + slack  >=  t_ij = x.c - |c|^2/2  (= -d_ij / 2),
+// an upper bound of the true score that exceeds it by at most 2 rad_ij (k_tc_select1).
 __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_pad, int D, int Dp,
                                                     const float* __restrict__ X, int64_t ldx,
                                                     float* __restrict__ hi, float* __restrict__ lo,
                                                     float* __restrict__ norm_out /*|x| per row, nullable*/,
                                                     float* __restrict__ xt /*[Dp][rows_pad] transposed copy, nullable*/,
-                                                    float* __restrict__ sqnorm_out /*|x|^2, +inf on padding rows, nullable*/) {
+                                                    float* __restrict__ sqnorm_out /*|x|^2, +inf on padding rows, nullable*/,
+                                                    float* __restrict__ aug /*nullable*/, int Dp1, int aug_mode, float eps1) {
   // one warp per row
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows_pad) return;
@@ -156,16 +173,32 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
     hi[r * Dp + c] = h;
     lo[r * Dp + c] = l;
     if (xt) xt[(int64_t)c * rows_pad + r] = x;
+    if (aug && c < D) aug[r * Dp1 + c] = h;
     s = fmaf(x, x, s);
   }
-  if (norm_out || sqnorm_out) {
-    // same per-lane fmaf order and xor-shuffle tree as k_row_sqnorm: bit-identical |row|^2
+  // same per-lane fmaf order and xor-shuffle tree as k_row_sqnorm: bit-identical |row|^2
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane_id() == 0) {
-      if (norm_out && r < rows) norm_out[r] = sqrtf(s);
-      if (sqnorm_out) sqnorm_out[r] = r < rows ? s : INFINITY;   // padding rows can never win the argmin
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) {
+    if (norm_out && r < rows) norm_out[r] = sqrtf(s);
+    if (sqnorm_out) sqnorm_out[r] = r < rows ? s : INFINITY;   // padding rows can never win the argmin
+  }
+  if (aug) {
+    float e, p, q;
+    if (aug_mode == 1) {
+      e = tf32_up(eps1 * sqrtf(s));
+      p = q = 1.f;
+    } else if (r < rows) {
+      e = tf32_up(0.5f * sqrtf(s));
+      const float w = -0.5f * s * (1.f - 3.0517578125e-05f);
+      p = to_tf32(w);
+      q = tf32_up(__fsub_rn(w, p));
+    } else {
+      e = 0.f;
+      p = to_tf32(-1e30f);
+      q = 0.f;
     }
+    for (int c = D + lane_id(); c < Dp1; c += 32) aug[r * Dp1 + c] = c == D ? e : (c == D + 1 ? p : (c == D + 2 ? q : 0.f));
   }
 }
 
@@ -197,57 +230,70 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
 // the tensor-core kernel
 // ---------------------------------------------------------------------------------
 // NPASS = 3: 3xTF32 (x_lo.c_hi + x_hi.c_lo + x_hi.c_hi), outputs (best, second, argmin) of the distances.
-// NPASS = 1: one TF32 product x_hi.c_hi per K-step — the first-level screen.  Its distances carry a
-//            proven error |d^ - d| <= eps1 |x_i| |c_j|, so the epilogue tracks the two smallest LOWER
-//            bounds L_ij = d^_ij - eps1 |x_i| |c_j| and their argmin; k_tc_select1 accepts the row when
-//            the upper bound of the argmin lies below every other lower bound.
+// NPASS = 1: the first-level screen — ONE TF32 product per K-step over the augmented operands of
+//            k_split_tf32 (aug_mode 1 / 2), whose accumulator is directly the score s_ij >= x_i.c_j - |c_j|^2/2;
+//            the epilogue is a bare running (max, second max, argmax) — no norm add, no per-centre loads —
+//            and k_tc_select1 accepts the row when s_best - s_second exceeds twice the error radius.
 // BN      = centres per accumulator tile (UMMA N): 128 or 256.
-template <int NPASS, int BN>
+// SUB     = 128-row sub-tiles resident per CTA.  Every SM streams the WHOLE centre matrix from L2 once per row
+//           tile, so the L2 -> SMEM traffic of a launch is (N / (128 SUB)) * Kp * Dp * 4 bytes: at one TF32
+//           product per K-step that stream, not the tensor pipe, bounds the kernel (measured: 9.8 TB/s at
+//           SUB = 1), and SUB = 2 halves it — each centre K-block feeds the MMAs of both sub-tiles.
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+template <int NPASS, int BN, int SUB>
 struct TcCfg {
   static constexpr int kXCopies = NPASS == 3 ? 2 : 1;                        // hi (+ lo) copy of the row tile
   static constexpr int kStageBytes = kXCopies * BN * TC_BK * 4;              // one centre K-block (hi [+ lo])
-  static constexpr int kStages = NPASS == 3 ? 3 : (BN == 256 ? 4 : 8);
-  static constexpr int kTmemCols = 2 * BN;                                   // two accumulators
-  __host__ __device__ static constexpr int x_hi(int kb) { return kb * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int x_lo(int nkb, int kb) { return (nkb + kb) * TC_KBLK_BYTES; }
-  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return kXCopies * nkb * TC_KBLK_BYTES + s * kStageBytes; }
-  __host__ __device__ static constexpr int bars(int nkb) { return c_stage(nkb, kStages); }
-  // + barriers (256 B) + epilogue merge buffer (1536 B) + alignment slack
-  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + 256 + 1536 + 1024; }
+  static constexpr int kTmemCols = 2 * SUB * BN;                             // two buffers of SUB accumulators
+  static constexpr int kTail = 512 /*barriers*/ + 1536 /*epilogue merge buffer*/;
+  __host__ __device__ static constexpr int x_hi(int nkb, int sub, int kb) { return (sub * nkb + kb) * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int x_lo(int nkb, int kb) { return (nkb + kb) * TC_KBLK_BYTES; }   // NPASS 3, SUB 1
+  __host__ __device__ static constexpr int x_bytes(int nkb) { return SUB * kXCopies * nkb * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return x_bytes(nkb) + s * kStageBytes; }
+  // as many centre stages as fit beside the resident rows (<= TC_MAX_STAGES)
+  __host__ __device__ static constexpr int stages(int nkb) {
+    int n = (TC_SMEM_LIMIT - 1024 /*alignment slack*/ - kTail - x_bytes(nkb)) / kStageBytes;
+    return n > TC_MAX_STAGES ? TC_MAX_STAGES : n;
+  }
+  __host__ __device__ static constexpr int bars(int nkb) { return c_stage(nkb, stages(nkb)); }
+  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + kTail + 1024; }
 };
 
-template <int NPASS, int BN>
+template <int NPASS, int BN, int SUB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
             const __grid_constant__ CUtensorMap map_chi, const __grid_constant__ CUtensorMap map_clo,
             int64_t N_host, const int32_t* __restrict__ n_rows_dev /*nullable: row count on the device*/,
-            int D, int n_col_tiles, int nkb, const float* __restrict__ cnorm,
-            const float* __restrict__ cnorm_sqrt /*NPASS 1: |c_j|*/, const float* __restrict__ xnorm /*NPASS 1: |x_i|*/,
-            float eps1, float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
-  using Cfg = TcCfg<NPASS, BN>;
-  constexpr int S = Cfg::kStages;
+            int D /*contraction width incl. the 3 augmented columns for NPASS 1*/, int n_col_tiles, int nkb,
+            const float* __restrict__ cnorm /*NPASS 3: |c_j|^2*/,
+            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
+  using Cfg = TcCfg<NPASS, BN, SUB>;
+  static_assert(Cfg::kTmemCols <= 512 && (NPASS == 1 || SUB == 1) && (SUB == 1 || SUB == 2), "tile plan");
+  const int S = Cfg::stages(nkb);
+  constexpr int ROWS = TC_BM * SUB;            // rows per CTA tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bars(nkb));
-  uint64_t* x_full = bars;                     // [TC_MAX_KB]
-  uint64_t* x_empty = bars + TC_MAX_KB;        // [TC_MAX_KB]
-  uint64_t* c_full = bars + 2 * TC_MAX_KB;     // [S]
-  uint64_t* c_empty = c_full + S;              // [S]
-  uint64_t* t_full = c_empty + S;              // [2]
-  uint64_t* t_empty = t_full + 2;              // [2]
+  uint64_t* x_full = bars;                              // [TC_BAR_KB]
+  uint64_t* x_empty = bars + TC_BAR_KB;                 // [TC_BAR_KB]
+  uint64_t* c_full = bars + 2 * TC_BAR_KB;              // [TC_MAX_STAGES]
+  uint64_t* c_empty = c_full + TC_MAX_STAGES;           // [TC_MAX_STAGES]
+  uint64_t* t_full = c_empty + TC_MAX_STAGES;           // [2]
+  uint64_t* t_empty = t_full + 2;                       // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t N = n_rows_dev ? (int64_t)n_rows_dev[0] : N_host;
-  const int n_row_tiles = (int)((N + TC_BM - 1) / TC_BM);
+  const int n_row_tiles = (int)((N + ROWS - 1) / ROWS);
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < TC_MAX_KB; ++i) {
+    for (int i = 0; i < TC_BAR_KB; ++i) {
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
     }
-    for (int i = 0; i < S; ++i) {
+    for (int i = 0; i < TC_MAX_STAGES; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 1);
     }
@@ -275,9 +321,11 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
       for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
-          mbar_expect_tx(&x_full[kb], Cfg::kXCopies * TC_KBLK_BYTES);
-          tma_load_2d(smem + Cfg::x_hi(kb), &map_xhi, kb * TC_BK, rt * TC_BM, &x_full[kb]);
-          if (NPASS == 3) tma_load_2d(smem + Cfg::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+          mbar_expect_tx(&x_full[kb], SUB * Cfg::kXCopies * TC_KBLK_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < SUB; ++sub)
+            tma_load_2d(smem + Cfg::x_hi(nkb, sub, kb), &map_xhi, kb * TC_BK, rt * ROWS + sub * TC_BM, &x_full[kb]);
+          if (NPASS == 3) tma_load_2d(smem + Cfg::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * ROWS, &x_full[kb]);
         }
         for (int ct = 0; ct < n_col_tiles; ++ct) {
           for (int kb = 0; kb < nkb; ++kb, ++cit) {
@@ -302,18 +350,18 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
           const uint32_t a = g & 1, aph = (g >> 1) & 1;
           mbar_wait(&t_empty[a], aph ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + a * BN;
+          const uint32_t tmem_d = tmem_base + a * (SUB * BN);
           for (int kb = 0; kb < nkb; ++kb, ++cit) {
             if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
             const int s = cit % S;
             const uint32_t ph = (cit / S) & 1;
             mbar_wait(&c_full[s], ph);
             tc_fence_after();
-            const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(kb)));
             const uint64_t d_chi = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s)));
             // K = 8 steps that still hold real columns (the rest of the 32-float block is zero padding)
             const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
             if (NPASS == 3) {
+              const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(nkb, 0, kb)));
               const uint64_t d_xlo = umma_desc_sw128(smem_u32(smem + Cfg::x_lo(nkb, kb)));
               const uint64_t d_clo = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s) + BN * TC_BK * 4));
               for (int k = 0; k < ksteps; ++k) {
@@ -324,31 +372,37 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
                 tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
               }
             } else {
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-                tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, (kb | k) != 0);
+#pragma unroll
+              for (int sub = 0; sub < SUB; ++sub) {
+                const uint64_t d_x = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(nkb, sub, kb)));
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                  tc_mma_tf32(tmem_d + sub * BN, d_x + adv, d_chi + adv, idesc, (kb | k) != 0);
+                }
               }
             }
             tc_commit(&c_empty[s]);                                  // frees the centre stage
             if (ct == n_col_tiles - 1) tc_commit(&x_empty[kb]);      // X K-block no longer needed
           }
-          tc_commit(&t_full[a]);                                     // accumulator ready
+          tc_commit(&t_full[a]);                                     // accumulators ready
         }
       }
     }
   } else {
-    // ================= epilogue: 8 warps; warp w reads TMEM lanes [32*(w%4), +32) and the
-    //                    column half (w-2)/4 of every accumulator (two warps per SM sub-partition
-    //                    hide each other's tcgen05.ld and min-chain latencies) =================
+    // ================= epilogue: 8 warps; warp w reads TMEM lanes [32*(w%4), +32).  SUB = 1: the two
+    //                    warps of a lane quarter take one column half of the accumulator each (merged at the
+    //                    end of the row tile); SUB = 2: one row sub-tile each, no merge.  Two warps per SM
+    //                    sub-partition hide each other's tcgen05.ld and min-chain latencies =================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;            // 0: columns [0, BN/2), 1: columns [BN/2, BN)
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = SUB == 1 ? BN / 2 : BN;                       // columns per warp and accumulator
     float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);   // [3][128] exchange buffer after the barriers
     const int rl = quarter * 32 + lane;
     uint32_t g = 0;
     for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
-      const int64_t row = (int64_t)rt * TC_BM + rl;
-      float nexn = 0.f;                          // -eps1 |x_i|
-      if (NPASS == 1 && row < N) nexn = -eps1 * xnorm[row];
+      const int64_t row = (int64_t)rt * ROWS + (SUB == 2 ? half * TC_BM : 0) + rl;
+      // NPASS 3: (best, second) = two smallest distances; NPASS 1: two largest scores, stored negated so that
+      // both variants share the min-tracking code and the merge below
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
@@ -356,9 +410,10 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
         mbar_wait(&t_full[a], aph);
         tc_fence_after();
 #pragma unroll 1
-        for (int h2 = 0; h2 < BN / 128; ++h2) {
-          const int col0 = half * (BN / 2) + h2 * 64;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + col0;
+        for (int h2 = 0; h2 < COLS / 64; ++h2) {
+          const int col0 = (SUB == 1 ? half * COLS : 0) + h2 * 64;   // column inside the centre tile
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (SUB * BN) +
+                                 (SUB == 2 ? half * BN : 0) + col0;
           uint32_t v[2][32];
           tc_ld_32x32(taddr, v[0]);
           tc_ld_32x32(taddr + 32, v[1]);          // both chunks in flight before the first is consumed
@@ -366,25 +421,27 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int jbase = ct * BN + col0 + c * 32;
-            const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
-            const float4* cr4 = reinterpret_cast<const float4*>(cnorm_sqrt + jbase);
+            if (NPASS == 1) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 cn = __ldg(cn4 + q);
-              float cc[4] = {cn.x, cn.y, cn.z, cn.w};
-              if (NPASS == 1) {
-                const float4 cr = __ldg(cr4 + q);
-                cc[0] = fmaf(nexn, cr.x, cc[0]);
-                cc[1] = fmaf(nexn, cr.y, cc[1]);
-                cc[2] = fmaf(nexn, cr.z, cc[2]);
-                cc[3] = fmaf(nexn, cr.w, cc[3]);
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float d = fmaf(-2.f, __uint_as_float(v[c][q * 4 + u]), cc[u]);
+              for (int u = 0; u < 32; ++u) {
+                const float d = -__uint_as_float(v[c][u]);     // folded into the min / max operands by the compiler
                 second = fminf(second, fmaxf(d, best));
-                bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
+                bidx = d < best ? jbase + u : bidx;
                 best = fminf(best, d);
+              }
+            } else {
+              const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 cn = __ldg(cn4 + q);
+                const float cc[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float d = fmaf(-2.f, __uint_as_float(v[c][q * 4 + u]), cc[u]);
+                  second = fminf(second, fmaxf(d, best));
+                  bidx = d < best ? jbase + q * 4 + u : bidx;   // strict '<': first minimum wins
+                  best = fminf(best, d);
+                }
               }
             }
           }
@@ -392,26 +449,34 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
         tc_fence_before();
         mbar_arrive(&t_empty[a]);
       }
-      // merge the two column halves of each row: lower columns win ties
-      if (half == 1) {
-        s_merge[rl] = best;
-        s_merge[128 + rl] = second;
-        reinterpret_cast<int*>(s_merge)[256 + rl] = bidx;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
-      if (half == 0) {
-        const float b1 = s_merge[rl], s1 = s_merge[128 + rl];
-        const int i1 = reinterpret_cast<int*>(s_merge)[256 + rl];
-        const float nb = fminf(best, b1);
-        const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
-        const int ni = b1 < best ? i1 : bidx;
+      if (SUB == 2) {
         if (row < N) {
-          best_out[row] = nb;
-          second_out[row] = ns;
-          idx_out[row] = ni;
+          best_out[row] = best;
+          second_out[row] = second;
+          idx_out[row] = bidx;
         }
+      } else {
+        // merge the two column halves of each row: lower columns win ties
+        if (half == 1) {
+          s_merge[rl] = best;
+          s_merge[128 + rl] = second;
+          reinterpret_cast<int*>(s_merge)[256 + rl] = bidx;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+        if (half == 0) {
+          const float b1 = s_merge[rl], s1 = s_merge[128 + rl];
+          const int i1 = reinterpret_cast<int*>(s_merge)[256 + rl];
+          const float nb = fminf(best, b1);
+          const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
+          const int ni = b1 < best ? i1 : bidx;
+          if (row < N) {
+            best_out[row] = nb;
+            second_out[row] = ns;
+            idx_out[row] = ni;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
     }
   }
   tc_fence_before();
@@ -422,15 +487,19 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   }
 }
 
-// first-level decision: lower bounds L (best, second) and argmin idx from k_assign_tc<1, *>.
-// U_idx = L_idx + 2 eps1 |x||c_idx| is an upper bound of the true distance to idx; every other centre's true
-// distance is >= second.  second > U_idx  =>  idx is the unique exact argmin.  Everything else goes to the
-// second-level list (3xTF32 on the compacted rows).
+// first-level decision.  best = -s_idx, second = -s_second (negated scores of k_assign_tc<1, *>).  With
+//   rad_ij = 1.01 ((eps1/2)|x_i||c_j| + 2^-16 |c_j|^2)   and   t_ij <= s_ij <= t_ij + 2 rad_ij
+// (t = true score x.c - |c|^2/2), s_idx - s_second > 2 rad_idx implies t_idx > t_j for every other centre: idx is the
+// unique exact argmin.  eta = 2^-15 |x| cmax keeps the margin above the rounding noise of the exact fp32 kernel
+// (same term as the second-level band), 2^-21 |s| covers the last accumulator rounding.  Everything else goes
+// to the second-level list (3xTF32 on the compacted rows).
 __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __restrict__ best,
                                                     const float* __restrict__ second,
                                                     const int32_t* __restrict__ idx,
                                                     const float* __restrict__ xnorm,
-                                                    const float* __restrict__ cnorm_sqrt, float eps1,
+                                                    const float* __restrict__ cnorm,
+                                                    const float* __restrict__ cnorm_sqrt,
+                                                    const float* __restrict__ cmax, float eps1, float band,
                                                     int32_t* __restrict__ labels,
                                                     const int32_t* __restrict__ labels_prev,
                                                     int32_t* __restrict__ n_changed,
@@ -439,9 +508,9 @@ __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __re
   int changed = 0;
   if (i < N) {
     const int l = idx[i];
-    const float b = best[i], s2 = second[i];
-    // 2^-21 |.|: fp32 rounding of the two fmaf that formed each bound
-    const float tol = 2.f * eps1 * xnorm[i] * cnorm_sqrt[l] + 4.76837158e-07f * fmaxf(fabsf(b), fabsf(s2));
+    const float b = best[i], s2 = second[i], xn = xnorm[i];
+    const float tol = 1.01f * (eps1 * xn * cnorm_sqrt[l] + 3.0517578125e-05f * cnorm[l]) + band * xn * cmax[0] +
+                      4.76837158e-07f * fmaxf(fabsf(b), fabsf(s2));
     const bool ambiguous = !(s2 - b > tol);   // also catches NaN / inf - inf
     if (ambiguous) {
       list1[atomicAdd(count1, 1)] = (int32_t)i;
@@ -589,15 +658,15 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int Dp, int
 }
 
 static inline int dpad(int64_t D) { return (int)align_up(D, TC_BK); }
+static inline int dpad1(int64_t D) { return (int)align_up(D + 3, TC_BK); }   // first-level operand: 3 augmented columns
 constexpr int TC_KPAD = 256;   // centres padded to the widest accumulator tile
 
 int64_t kmeans_tc_xsplit_bytes(int64_t N, int64_t D) {
-  int Dp = dpad(D);
-  return 2 * ws_need(N * Dp, 4) + ws_need(N, 4) + 256;
+  return 2 * ws_need(N * dpad(D), 4) + ws_need(N, 4) + ws_need(N * dpad1(D), 4) + 256;
 }
 
 struct XSplit {
-  float *hi, *lo, *norm;
+  float *hi, *lo, *norm, *x1;
 };
 static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
   Workspace W(buf, kmeans_tc_xsplit_bytes(N, D));
@@ -606,12 +675,14 @@ static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
   x.hi = W.take<float>(N * Dp);
   x.lo = W.take<float>(N * Dp);
   x.norm = W.take<float>(N);
+  x.x1 = W.take<float>(N * dpad1(D));
   return x;
 }
 
 int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, cudaStream_t s) {
   XSplit x = carve_xsplit(xsplit, N, D);
-  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr, nullptr);
+  k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr,
+                                                          nullptr, x.x1, dpad1(D), 1, TC_EPS1);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -628,22 +699,23 @@ static bool tc_two_level(int64_t N, bool want_best) {
 int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
   int Dp = dpad(D);
   int64_t Kp = align_up(K, TC_KPAD);
-  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + 2 * ws_need(Kp, 4) /*|c|^2, |c|*/ + 256 /*cmax*/ +
+  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need(Kp * dpad1(D), 4) /*augmented centres*/ +
+         2 * ws_need(Kp, 4) /*|c|^2, |c|*/ + 256 /*cmax*/ +
          3 * ws_need(N, 4) /*best, second, idx*/ + ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ +
          256 /*amb count*/ + ws_need(N, 4) /*second-level list*/ + 256 /*its count*/ +
          2 * ws_need(N * Dp, 4) + ws_need(N, 4) /*compacted hi, lo, |x|*/ + 256;
 }
 
-template <int NPASS, int BN>
+// D_eff = contraction width (D, or D + 3 for the augmented first level); nkb = its 32-float K-blocks
+template <int NPASS, int BN, int SUB>
 static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, const CUtensorMap& m_chi,
-                            const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D, int64_t Kp,
-                            int nkb, const float* cnorm, const float* cnorm_sqrt, const float* xnorm, float* best,
-                            float* second, int32_t* idx, cudaStream_t s) {
-  using Cfg = TcCfg<NPASS, BN>;
+                            const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D_eff, int64_t Kp,
+                            int nkb, const float* cnorm, float* best, float* second, int32_t* idx, cudaStream_t s) {
+  using Cfg = TcCfg<NPASS, BN, SUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<NPASS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::total(TC_MAX_KB)));
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<NPASS, BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TC_SMEM_LIMIT));
     attr_set = true;
   }
   int sms = kSMs;
@@ -652,11 +724,10 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int64_t tiles = cdiv(N_max, TC_BM);
+  const int64_t tiles = cdiv(N_max, TC_BM * SUB);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  k_assign_tc<NPASS, BN><<<grid, TC_THREADS, Cfg::total(nkb), s>>>(m_xhi, m_xlo, m_chi, m_clo, N_max, n_rows_dev, D,
-                                                                  (int)(Kp / BN), nkb, cnorm, cnorm_sqrt, xnorm,
-                                                                  TC_EPS1, best, second, idx);
+  k_assign_tc<NPASS, BN, SUB><<<grid, TC_THREADS, Cfg::total(nkb), s>>>(m_xhi, m_xlo, m_chi, m_clo, N_max, n_rows_dev, D_eff,
+                                                                  (int)(Kp / BN), nkb, cnorm, best, second, idx);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -674,14 +745,15 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     set_error("kmeans_assign(tc): N or K exceeds int32 tile coordinates");
     return GDR_ERANGE;
   }
-  const int Dp = dpad(D);
-  const int nkb = Dp / TC_BK;
+  const int Dp = dpad(D), Dp1 = dpad1(D);
+  const int nkb = Dp / TC_BK, nkb1 = Dp1 / TC_BK;
   const int64_t Kp = align_up(K, TC_KPAD);
   XSplit xs = carve_xsplit(const_cast<void*>(xsplit), N, D);
   Workspace W(ws, ws_bytes);
   float* c_hi = W.take<float>(Kp * Dp);
   float* c_lo = W.take<float>(Kp * Dp);
   float* c_t = W.take<float>(Kp * Dp);   // fp32 centres transposed [Dp][Kp] for the re-score kernel
+  float* c1 = W.take<float>(Kp * Dp1);   // augmented first-level centres
   float* cnorm = W.take<float>(Kp);
   float* cnorm_sqrt = W.take<float>(Kp);
   float* cmax = W.take<float>(1);
@@ -701,24 +773,26 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     set_error("kmeans_assign(tc): workspace too small");
     return GDR_EWORKSPACE;
   }
-  // per-iteration centre preparation: split, norms, padding
-  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t, cnorm);
+  const bool two_level = tc_two_level(N, best_out != nullptr);
+  // per-iteration centre preparation: split, norms, padding (+ the augmented rows of the first level)
+  k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t, cnorm,
+                                                           two_level ? c1 : nullptr, Dp1, 2, TC_EPS1);
   GDR_LAUNCHED();
   int rc;
   k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cnorm_sqrt, cmax, amb_count, count1);
   GDR_LAUNCHED();
 
   CUtensorMap m_xhi, m_xlo, m_chi, m_clo;
-  if ((rc = make_map(&m_xhi, xs.hi, N, Dp, TC_BM))) return rc;
-  if ((rc = make_map(&m_xlo, xs.lo, N, Dp, TC_BM))) return rc;
   if ((rc = make_map(&m_chi, c_hi, Kp, Dp, 128))) return rc;
   if ((rc = make_map(&m_clo, c_lo, Kp, Dp, 128))) return rc;
 
-  if (!tc_two_level(N, best_out != nullptr)) {
+  if (!two_level) {
+    if ((rc = make_map(&m_xhi, xs.hi, N, Dp, TC_BM))) return rc;
+    if ((rc = make_map(&m_xlo, xs.lo, N, Dp, TC_BM))) return rc;
     {
       ProfileScope prof(PROF_ASSIGN, s);
-      if ((rc = launch_assign_tc<3, 128>(m_xhi, m_xlo, m_chi, m_clo, N, nullptr, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
-                                         xs.norm, best, second, idx, s)))
+      if ((rc = launch_assign_tc<3, 128, 1>(m_xhi, m_xlo, m_chi, m_clo, N, nullptr, (int)D, Kp, nkb, cnorm, best, second,
+                                         idx, s)))
         return rc;
     }
     k_tc_select<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cmax, TC_BAND, labels,
@@ -728,28 +802,30 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   } else {
     // the profile scope spans the whole tensor-core screen: level 1, decision, compaction, level 2
     ProfileScope prof(PROF_ASSIGN, s);
+    CUtensorMap m_x1, m_c1;
+    if ((rc = make_map(&m_x1, xs.x1, N, Dp1, TC_BM))) return rc;
     if (g_tc_screen == 2) {
-      if ((rc = launch_assign_tc<1, 128>(m_xhi, m_xlo, m_chi, m_clo, N, nullptr, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
-                                         xs.norm, best, second, idx, s)))
+      if ((rc = make_map(&m_c1, c1, Kp, Dp1, 128))) return rc;
+      if ((rc = launch_assign_tc<1, 128, 2>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
+                                         idx, s)))
         return rc;
     } else {
-      CUtensorMap m_chi256;
-      if ((rc = make_map(&m_chi256, c_hi, Kp, Dp, 256))) return rc;
-      if ((rc = launch_assign_tc<1, 256>(m_xhi, m_xlo, m_chi256, m_chi256, N, nullptr, (int)D, Kp, nkb, cnorm,
-                                         cnorm_sqrt, xs.norm, best, second, idx, s)))
+      if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
+      if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
+                                         idx, s)))
         return rc;
     }
     g_last_count1 = count1;
-    k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cnorm_sqrt, TC_EPS1, labels,
-                                                       labels_prev, n_changed_dev, list1, count1);
+    k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cnorm, cnorm_sqrt, cmax, TC_EPS1,
+                                                       TC_BAND, labels, labels_prev, n_changed_dev, list1, count1);
     GDR_LAUNCHED();
     k_tc_gather<<<4 * kSMs, 256, 0, s>>>(list1, count1, Dp, xs.hi, xs.lo, xs.norm, g_hi, g_lo, g_norm);
     GDR_LAUNCHED();
     CUtensorMap m_ghi, m_glo;
     if ((rc = make_map(&m_ghi, g_hi, N, Dp, TC_BM))) return rc;
     if ((rc = make_map(&m_glo, g_lo, N, Dp, TC_BM))) return rc;
-    if ((rc = launch_assign_tc<3, 128>(m_ghi, m_glo, m_chi, m_clo, N, count1, (int)D, Kp, nkb, cnorm, cnorm_sqrt,
-                                       g_norm, best, second, idx, s)))
+    if ((rc = launch_assign_tc<3, 128, 1>(m_ghi, m_glo, m_chi, m_clo, N, count1, (int)D, Kp, nkb, cnorm, best, second, idx,
+                                       s)))
       return rc;
     k_tc_select2<<<2 * kSMs, 256, 0, s>>>(list1, count1, best, second, idx, g_norm, cmax, TC_BAND, labels,
                                          labels_prev, n_changed_dev, amb_list, amb_count, amb_packed);
