@@ -47,7 +47,8 @@ constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
 // the fp32 rounding of the norms and of the bound arithmetic itself.
 constexpr float TC_EPS1 = 1.0625f * 0.001953125f;
 static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
-int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles
+int g_tc_ablate = 0;   // experiment: 1 no epilogue math, 2 no tcgen05.ld either, 3 no MMAs, 4 one K-block of MMAs only
+int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles, 4 two-level on CTA pairs (cta_group::2, 256 x 256)
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -267,7 +268,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
             int64_t N_host, const int32_t* __restrict__ n_rows_dev /*nullable: row count on the device*/,
             int D /*contraction width incl. the 3 augmented columns for NPASS 1*/, int n_col_tiles, int nkb,
             const float* __restrict__ cnorm /*NPASS 3: |c_j|^2*/,
-            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out) {
+            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate) {
   using Cfg = TcCfg<NPASS, BN, SUB>;
   static_assert(Cfg::kTmemCols <= 512 && (NPASS == 1 || SUB == 1) && (SUB == 1 || SUB == 2), "tile plan");
   const int S = Cfg::stages(nkb);
@@ -332,6 +333,10 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
             const int s = cit % S;
             const uint32_t ph = (cit / S) & 1;
             mbar_wait(&c_empty[s], ph ^ 1);
+            if (ablate == 5) {   // experiment: MMAs on stale shared memory, no centre stream
+              mbar_arrive(&c_full[s]);
+              continue;
+            }
             mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
             uint8_t* dst = smem + Cfg::c_stage(nkb, s);
             tma_load_2d(dst, &map_chi, kb * TC_BK, ct * BN, &c_full[s]);
@@ -375,7 +380,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
 #pragma unroll
               for (int sub = 0; sub < SUB; ++sub) {
                 const uint64_t d_x = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(nkb, sub, kb)));
-                for (int k = 0; k < ksteps; ++k) {
+                for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
                   const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
                   tc_mma_tf32(tmem_d + sub * BN, d_x + adv, d_chi + adv, idesc, (kb | k) != 0);
                 }
@@ -415,9 +420,14 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * (SUB * BN) +
                                  (SUB == 2 ? half * BN : 0) + col0;
           uint32_t v[2][32];
+          if (ablate == 2) continue;
           tc_ld_32x32(taddr, v[0]);
           tc_ld_32x32(taddr + 32, v[1]);          // both chunks in flight before the first is consumed
           tc_wait_ld();
+          if (ablate == 1) {
+            if (v[0][0] == 0x7fc12345u && v[1][31] == 0x7fc54321u) bidx = 1;   // keep the loads alive
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int jbase = ct * BN + col0 + c * 32;
@@ -484,6 +494,254 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// first level on CTA pairs: tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = 256
+// ---------------------------------------------------------------------------------
+// The single-CTA first level is bound by the stream of centre tiles (L2 -> SMEM at ~9 TB/s chip-wide and the
+// SMEM operand reads of N = 128 shapes).  A CTA pair shares every centre tile: each CTA loads HALF of it
+// (128 centres) and the pair's MMA reads both halves, so L2 traffic and B-operand SMEM reads per flop halve
+// while each CTA still owns a full 128 x 256 accumulator.  Protocol (leader = cluster rank 0):
+//   * both producers TMA into their own SMEM but complete the transaction bytes on the LEADER's full barriers;
+//   * only the leader's thread issues MMAs; its tcgen05.commit multicasts the arrive to both CTAs' barriers
+//     (stage free, row tile free, accumulator ready);
+//   * one lane per epilogue warp of BOTH CTAs arrives on the leader's accumulator-empty barrier (count 16).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory, transaction bytes completed on a barrier given by its cluster address
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Tc2Cfg {
+  static constexpr int BN = 256;                                  // centres per accumulator (pair-wide MMA N)
+  static constexpr int kStageBytes = (BN / 2) * TC_BK * 4;        // this CTA's half of one centre K-block: 16 KB
+  static constexpr int kStages = 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTail = 512;                               // barriers + TMEM base slot
+  __host__ __device__ static constexpr int x_blk(int kb) { return kb * TC_KBLK_BYTES; }
+  __host__ __device__ static constexpr int c_stage(int nkb, int s) { return nkb * TC_KBLK_BYTES + s * kStageBytes; }
+  __host__ __device__ static constexpr int bars(int nkb) { return c_stage(nkb, kStages); }
+  __host__ __device__ static constexpr int total(int nkb) { return bars(nkb) + kTail + 1024; }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
+                 int64_t N_host, const int32_t* __restrict__ n_rows_dev, int D, int n_col_tiles, int nkb,
+                 float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate) {
+  using Cfg = Tc2Cfg;
+  constexpr int S = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  // identical offsets in both CTAs: the dynamic shared memory base is the same for every CTA of a kernel
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bars(nkb));
+  uint64_t* x_full = bars;                              // [TC_BAR_KB]  used in the leader
+  uint64_t* x_empty = bars + TC_BAR_KB;                 // [TC_BAR_KB]  each CTA its own
+  uint64_t* c_full = bars + 2 * TC_BAR_KB;              // [S]          used in the leader
+  uint64_t* c_empty = c_full + S;                       // [S]          each CTA its own
+  uint64_t* t_full = c_empty + S;                       // [2]          each CTA its own
+  uint64_t* t_empty = t_full + 2;                       // [2]          used in the leader
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int64_t N = n_rows_dev ? (int64_t)n_rows_dev[0] : N_host;
+  const int n_row_tiles = (int)((N + TC_BM - 1) / TC_BM);
+  const int n_units = (n_row_tiles + 1) / 2;            // a unit = two consecutive row tiles, one per CTA
+  const int unit0 = (int)blockIdx.x >> 1, unit_stride = (int)gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < TC_BAR_KB; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 16);       // one lane of each of the 8 epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // peer barriers initialised, both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      uint32_t cit = 0, tile_it = 0;
+      for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
+        const int rt = 2 * un + (int)crank;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+          if (leader) mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
+          tma_load_2d_2sm(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, mapa_u32(smem_u32(&x_full[kb]), 0));
+        }
+        for (int ct = 0; ct < n_col_tiles; ++ct) {
+          for (int kb = 0; kb < nkb; ++kb, ++cit) {
+            const int s = cit % S;
+            const uint32_t ph = (cit / S) & 1;
+            mbar_wait(&c_empty[s], ph ^ 1);
+            if (ablate == 5) {
+              if (leader) mbar_arrive(&c_full[s]);
+              continue;
+            }
+            if (leader) mbar_expect_tx(&c_full[s], 2 * Cfg::kStageBytes);
+            tma_load_2d_2sm(smem + Cfg::c_stage(nkb, s), &map_c, kb * TC_BK, ct * BN + (int)crank * (BN / 2),
+                            mapa_u32(smem_u32(&c_full[s]), 0));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_BM, BN);
+      uint32_t cit = 0, tile_it = 0, g = 0;
+      for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
+        for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+          const uint32_t a = g & 1, aph = (g >> 1) & 1;
+          mbar_wait(&t_empty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + a * BN;
+          for (int kb = 0; kb < nkb; ++kb, ++cit) {
+            if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
+            const int s = cit % S;
+            const uint32_t ph = (cit / S) & 1;
+            mbar_wait(&c_full[s], ph);
+            tc_fence_after();
+            const uint64_t d_x = umma_desc_sw128(smem_u32(smem + Cfg::x_blk(kb)));
+            const uint64_t d_c = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s)));
+            const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
+            for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+              tc_mma_tf32_2sm(tmem_d, d_x + adv, d_c + adv, idesc, (kb | k) != 0);
+            }
+            tc_commit_2sm(&c_empty[s], 3);                              // frees the stage in both CTAs
+            if (ct == n_col_tiles - 1) tc_commit_2sm(&x_empty[kb], 3);  // row-tile K-block free in both CTAs
+          }
+          tc_commit_2sm(&t_full[a], 3);                                 // accumulator ready in both CTAs
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): as k_assign_tc<1, 256, 1> =================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int rl = quarter * 32 + lane;
+    const uint32_t t_empty_leader[2] = {mapa_u32(smem_u32(&t_empty[0]), 0), mapa_u32(smem_u32(&t_empty[1]), 0)};
+    __shared__ float s_mb[3][TC_BM];
+    uint32_t g = 0;
+    for (int un = unit0; un < n_units; un += unit_stride) {
+      const int rt = 2 * un + (int)crank;
+      const int64_t row = (int64_t)rt * TC_BM + rl;
+      float best = INFINITY, second = INFINITY;   // negated scores
+      int bidx = 0;
+      for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+        const uint32_t a = g & 1, aph = (g >> 1) & 1;
+        mbar_wait(&t_full[a], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int h2 = 0; h2 < BN / 128; ++h2) {
+          const int col0 = half * (BN / 2) + h2 * 64;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + col0;
+          uint32_t v[2][32];
+          tc_ld_32x32(taddr, v[0]);
+          tc_ld_32x32(taddr + 32, v[1]);
+          tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int jbase = ct * BN + col0 + c * 32;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+              const float d = -__uint_as_float(v[c][u]);
+              second = fminf(second, fmaxf(d, best));
+              bidx = d < best ? jbase + u : bidx;
+              best = fminf(best, d);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(t_empty_leader[a]);
+      }
+      // merge the two column halves of each row
+      if (half == 1) {
+        s_mb[0][rl] = best;
+        s_mb[1][rl] = second;
+        reinterpret_cast<int*>(s_mb[2])[rl] = bidx;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      if (half == 0) {
+        const float b1 = s_mb[0][rl], s1 = s_mb[1][rl];
+        const int i1 = reinterpret_cast<int*>(s_mb[2])[rl];
+        const float nb = fminf(best, b1);
+        const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
+        const int ni = b1 < best ? i1 : bidx;
+        if (row < N) {
+          best_out[row] = nb;
+          second_out[row] = ns;
+          idx_out[row] = ni;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA frees TMEM / leaves while the pair's MMAs, multicasts or remote arrives can still land
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -727,7 +985,41 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
   const int64_t tiles = cdiv(N_max, TC_BM * SUB);
   const int grid = (int)(tiles < sms ? tiles : sms);
   k_assign_tc<NPASS, BN, SUB><<<grid, TC_THREADS, Cfg::total(nkb), s>>>(m_xhi, m_xlo, m_chi, m_clo, N_max, n_rows_dev, D_eff,
-                                                                  (int)(Kp / BN), nkb, cnorm, best, second, idx);
+                                                                  (int)(Kp / BN), nkb, cnorm, best, second, idx, g_tc_ablate);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c, int64_t N_max, const int32_t* n_rows_dev,
+                                 int D_eff, int64_t Kp, int nkb, float* best, float* second, int32_t* idx,
+                                 cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::total(TC_BAR_KB)));
+    attr_set = true;
+  }
+  int sms = kSMs;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t units = cdiv(cdiv(N_max, TC_BM), 2);
+  const int pairs = (int)(units < sms / 2 ? units : sms / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Tc2Cfg::total(nkb);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GDR_CUDA(cudaLaunchKernelEx(&cfg, k_assign_tc_pair, m_x, m_c, N_max, n_rows_dev, D_eff, (int)(Kp / Tc2Cfg::BN), nkb, best,
+                              second, idx, g_tc_ablate));
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -809,12 +1101,16 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
       if ((rc = launch_assign_tc<1, 128, 2>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
                                          idx, s)))
         return rc;
+    } else if (g_tc_screen == 4) {
+      if ((rc = make_map(&m_c1, c1, Kp, Dp1, 128))) return rc;   // each CTA of a pair loads 128 of the 256 centres
+      if ((rc = launch_assign_tc_pair(m_x1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, best, second, idx, s))) return rc;
     } else {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
       if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
                                          idx, s)))
         return rc;
     }
+    if (g_tc_ablate) return GDR_OK;   // timing experiment: first-level kernel only
     g_last_count1 = count1;
     k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cnorm, cnorm_sqrt, cmax, TC_EPS1,
                                                        TC_BAND, labels, labels_prev, n_changed_dev, list1, count1);

@@ -41,6 +41,7 @@ static int g_spmm_hints = -1;     // 0 off, 1 streaming hints on colidx/vals/T/Y
 static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
 extern int g_lloyd_graph;         // lloyd.cu
 extern int g_tc_screen;           // kmeans_tc.cu
+extern int g_tc_ablate;
 
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
   int v;
@@ -365,6 +366,7 @@ int gdr_debug_set(const char* key, int value) {
   else if (!strcmp(key, "spmm_split")) gdr::g_spmm_split = value;
   else if (!strcmp(key, "lloyd_graph")) gdr::g_lloyd_graph = value;
   else if (!strcmp(key, "tc_screen")) gdr::g_tc_screen = value;
+  else if (!strcmp(key, "tc_ablate")) gdr::g_tc_ablate = value;
   else {
     gdr::set_error("debug_set: unknown key %s", key);
     return GDR_EINVAL;

@@ -58,7 +58,7 @@ def screen_mode():
     _lib.call("gdr_debug_set", b"tc_screen", 0)
 
 
-@pytest.mark.parametrize("mode", [2, 3])   # two-level screen with 128- / 256-centre accumulator tiles
+@pytest.mark.parametrize("mode", [2, 3, 4])   # two-level screen: 256x128 / 128x256 CTA tiles, CTA pairs (cta_group::2)
 @pytest.mark.parametrize("N,K,D,kind", [(300, 7, 3, "clustered"), (4099, 129, 100, "clustered"), (20000, 1000, 40, "clustered"),
                                         (20000, 333, 128, "zscore"), (50000, 1000, 128, "zscore"), (30011, 700, 100, "zscore"),
                                         (1, 1, 1, "clustered")])
@@ -90,7 +90,7 @@ def test_tc_two_level_screen_equals_exact_kernel(gdr, oracle, screen_mode, mode,
     assert int(n_ref.item()) <= max(64, N // 5)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_tc_full_fit_same_for_every_screen(gdr, screen_mode, mode):
     from gdr import synth
     N, K, D = 40000, 300, 100
