@@ -388,7 +388,7 @@ def run_ours(args, rank, world):
 
 def one_gpu_reference(workload):
     """The committed single-GPU measurement of the same workload (for the strong-scaling ratio)."""
-    name = {"E": "r1_bench_configE_1gpu.json", "B": "r1_bench_tc_v10.json"}.get(workload)
+    name = {"E": "r1_bench_configE_1gpu_twolevel.json", "B": "r1_bench_tc_twolevel_v14.json"}.get(workload)
     try:
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "source": "profiles/" + name}
@@ -414,6 +414,9 @@ def run_ours_multi(args, rank, world, dev):
     u_d = torch.from_numpy(w["u"]).to(dev)
     v_d = torch.from_numpy(w["v"]).to(dev)
     x_local = torch.from_numpy(w["X"][part.lo:part.hi].copy()).to(dev)
+    per = (u_d.shape[0] + world - 1) // world
+    u_sl = u_d[rank * per: (rank + 1) * per].contiguous()      # this rank's slice of the undirected pair list
+    v_sl = v_d[rank * per: (rank + 1) * per].contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # fixed init: rows perm[:K] of the propagated features (computed once on every rank, untimed)
@@ -430,9 +433,9 @@ def run_ours_multi(args, rank, world, dev):
     def step():
         e = [ev() for _ in range(5)]
         e[0].record()
-        A_local, _ = par.build_local_adjacency(u_d, v_d, n, part, dev)
+        A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)   # exchange-based: 1/world of the pairs per rank
         e[1].record()
-        prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops)
+        prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs)
         e[2].record()
         km = par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target)
         e[3].record()
@@ -479,9 +482,59 @@ def run_ours_multi(args, rank, world, dev):
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     dist.all_reduce(lt)
     n_iter = [r[1].n_iter_ for r in recs]
+
+    # ---- roofline leg (per GPU): the E-step tensor-core screen of this rank's row block, timed by the
+    #      library's own CUDA-event pairs on its launch stream ----
+    import ctypes
+    from gdr import _lib
+    A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)
+    _, target_l = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops)
+    tot_ms, n_l = ctypes.c_double(0), ctypes.c_int64(0)
+    _lib.call("gdr_profile_enable", 1)
+    flush.fill_(1)
+    par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target_l)
+    torch.cuda.synchronize()
+    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
+    _lib.call("gdr_profile_enable", 0)
+    assign_ms = tot_ms.value / max(1, n_l.value)
+    am = torch.tensor([assign_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(am, op=dist.ReduceOp.MAX)
+    assign_ms = float(am.item())
+
+    # ---- e2e: DistKMeans.fit through the public API from pinned HOST rows (H2D of this rank's block of the
+    #      propagated features, D2H of its labels + the centres), max over ranks ----
+    target_host = torch.empty(tuple(target_l.shape), dtype=torch.float32).pin_memory()
+    target_host.copy_(target_l)
+    del target_l, A_local
+    C0_host = C0.cpu()
+    e2e_t = []
+    for i in range(max(3, min(args.steps, 5))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0e = time.perf_counter()
+        x_dev = target_host.to(dev, non_blocking=True)
+        km = par.DistKMeans(K, C0_host, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(x_dev)
+        lab_h = km.labels_.cpu()
+        cen_h = km.cluster_centers_.cpu()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_t.append((float(tt.item()), km.n_iter_))
+    e2e_t = e2e_t[1:]
+    e2e_val = float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t))
+
     if rank == 0:
         step_ms = st.sum(axis=1)
         km_ms, prop_ms = st[:, 2], st[:, 1]
+        flops_rank = 2.0 * part.rows_per * K * F
+        a_tf = flops_rank / (assign_ms / 1e3) / 1e12
+        roofline = {"kernel": "k_assign_tc two-level screen (per GPU, this rank's row block)", "bound": "tensor",
+                    "achieved": a_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": a_tf / pk["bf16_sustained"],
+                    "traffic": None, "peak_source": pk["src"] + " bf16 sustained", "launch_ms": assign_ms,
+                    "note": "useful flops 2*(N/world)*K*D per E-step over the slowest rank's screen time; fp32 inputs run as TF32"}
+        e2e = {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": n * F * 4 + world * K * F * 4,
+               "d2h_bytes_per_step": n * 4 + world * K * F * 4}
         prop_model = "gather" if n * F * 4 > 96e6 else "min"   # SURVEY §8(d) headline rule
         b_prop = hops * spmm_bytes(nnz, n, n, F, model=prop_model) + 2 * n * F * 4
         prop_gbs = float(b_prop / (prop_ms.mean() / 1e3) / 1e9)
@@ -492,15 +545,17 @@ def run_ours_multi(args, rank, world, dev):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
                                    f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
-                       "parallelism": f"row-partition x{world} (all-gather per hop, all-reduce per Lloyd iteration)",
+                       "parallelism": f"row-partition x{world} (stage 1: pair slices, all-to-all by owner, all-gather of degrees; "
+                                      f"stage 2: all-gather per hop, {par.default_slabs(world, F) if args.slabs is None else args.slabs} column slab(s); "
+                                      "stage 3: all-reduce of centroid sums/counts per Lloyd iteration; stage 4: dense n x n all-reduce)",
                        "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
             "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / (pk["hbm"] * world),
                      "bytes_model": ("B_gather" if prop_model == "gather" else "B_min") + " (whole job, incl. the all-gather time)", "ms": float(prop_ms.mean())},
             "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
                           "s3_kmeans": float(km_ms.mean()), "s3_kmeans_per_iter": float(km_ms.sum() / np.sum(n_iter)),
                           "s4_coarsen": float(st[:, 3].mean())},
-            "roofline": None, "cpu_baseline": None, "same_workload_1gpu": one_gpu_reference(args.workload),
-            "e2e": None, "gpu_launches": int(lt.item()), "clocks": clocks, "wall_s": t_wall,
+            "roofline": roofline, "cpu_baseline": None, "same_workload_1gpu": one_gpu_reference(args.workload),
+            "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "wall_s": t_wall,
             "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2]._nnz())},
         }
         print(json.dumps(line))
@@ -537,6 +592,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
+    ap.add_argument("--slabs", type=int, default=None, help="N > 1: column slabs of the pipelined hop (default: automatic)")
     ap.add_argument("--tc-screen", type=int, default=0, help="debug: 0 auto, 1 direct 3xTF32, 2/3 two-level screen (BN 128/256)")
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -31,6 +31,9 @@ _SIGNATURES = {
     "gdr_coo_to_csr": (i32, [i64, i64, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_sym_normalize_ws_bytes": (i64, [i64, i64]),
     "gdr_sym_normalize": (i32, [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_sym_normalize_block_ws_bytes": (i64, [i64]),
+    "gdr_sym_normalize_block_degrees": (i32, [i64, i64, vp, vp, vp, i32, vp, vp, vp, i64, vp]),
+    "gdr_sym_normalize_block_fill": (i32, [i64, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_sym_normalize_dense_ws_bytes": (i64, [i64]),
     "gdr_sym_normalize_dense": (i32, [i64, vp, i64, vp, i64, vp, i64, vp]),
     "gdr_bipartite_normalize": (i32, [i64, i64, i64, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp]),

@@ -269,10 +269,12 @@ __global__ void __launch_bounds__(256) k_row_degree(int64_t n, const int32_t* __
                                                     const int32_t* __restrict__ colidx,
                                                     const float* __restrict__ vals,
                                                     const int32_t* __restrict__ flag,
-                                                    double* __restrict__ deg, int32_t* __restrict__ out_len) {
+                                                    double* __restrict__ deg, int32_t* __restrict__ out_len,
+                                                    int64_t row_offset /*global id of local row 0 (row-block mode)*/) {
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const int add = flag[0];
+  const int32_t diag = (int32_t)(r + row_offset);
   int b = rowptr[r], e = rowptr[r + 1];
   double s = 0.0;
   float sf = 0.f;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(256) k_row_degree(int64_t n, const int32_t* __
     float v = vals[j];
     s += (double)v;
     sf += v;
-    has_diag |= (colidx[j] == (int32_t)r);
+    has_diag |= (colidx[j] == diag);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -300,40 +302,42 @@ __global__ void __launch_bounds__(256) k_norm_fill(int64_t n, const int32_t* __r
                                                    const int32_t* __restrict__ colidx,
                                                    const float* __restrict__ vals,
                                                    const int32_t* __restrict__ flag,
-                                                   const double* __restrict__ deg,
+                                                   const double* __restrict__ deg_row /*by local row*/,
+                                                   const double* __restrict__ deg /*by (global) column*/,
                                                    const int32_t* __restrict__ rowptr_out,
                                                    int32_t* __restrict__ colidx_out,
                                                    float* __restrict__ vals_out,
-                                                   int64_t* __restrict__ nnz_out) {
+                                                   int64_t* __restrict__ nnz_out, int64_t row_offset) {
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const int add = flag[0];
+  const int32_t diag = (int32_t)(r + row_offset);
   const int b = rowptr[r], e = rowptr[r + 1];
   const int ob = rowptr_out[r];
   const bool inserts = add && (rowptr_out[r + 1] - ob) > (e - b);
   if (r == n - 1 && lane_id() == 0) *nnz_out = rowptr_out[n];
   // r_i = deg^-1/2 ; inf -> 0   (deep_robust_utils.py:202-203)
-  const double di = deg[r];
+  const double di = deg_row[r];
   if (add) {
     const double ri = di == 0.0 ? 0.0 : 1.0 / sqrt(di);
     // entries left of the diagonal keep their slot; the rest shift by one when I inserts
     for (int j = b + lane_id(); j < e; j += 32) {
       int c = colidx[j];
-      double a = (double)vals[j] + (c == (int32_t)r ? 1.0 : 0.0);
+      double a = (double)vals[j] + (c == diag ? 1.0 : 0.0);
       double dj = deg[c];
       double rj = dj == 0.0 ? 0.0 : 1.0 / sqrt(dj);
-      int o = ob + (j - b) + ((inserts && c > (int32_t)r) ? 1 : 0);
+      int o = ob + (j - b) + ((inserts && c > diag) ? 1 : 0);
       colidx_out[o] = c;
       vals_out[o] = (float)((ri * a) * rj);
     }
     if (inserts) {
       // position of the new diagonal entry = #entries with col < r (one lane finds it)
       int cnt = 0;
-      for (int j = b + lane_id(); j < e; j += 32) cnt += (colidx[j] < (int32_t)r);
+      for (int j = b + lane_id(); j < e; j += 32) cnt += (colidx[j] < diag);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       if (lane_id() == 0) {
-        colidx_out[ob + cnt] = (int32_t)r;
+        colidx_out[ob + cnt] = diag;
         vals_out[ob + cnt] = (float)((ri * 1.0) * ri);
       }
     }
@@ -693,12 +697,68 @@ int gdr_sym_normalize(int64_t n, int64_t nnz, const int32_t* rowptr, const int32
   k_selfloop_flag<<<1, 32, 0, s>>>(nnz, rowptr, colidx, vals, self_loop_mode, flag);
   GDR_LAUNCHED();
   unsigned grid = (unsigned)cdiv(n * 32, 256);
-  k_row_degree<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, out_len);
+  k_row_degree<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, out_len, 0);
   GDR_LAUNCHED();
   int rc = exclusive_scan_i32(out_len, rowptr_out, n, sws, sws_b, s);
   if (rc) return rc;
-  k_norm_fill<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, rowptr_out, colidx_out, vals_out,
-                                   nnz_out_dev);
+  k_norm_fill<<<grid, 256, 0, s>>>(n, rowptr, colidx, vals, flag, deg, deg, rowptr_out, colidx_out, vals_out,
+                                   nnz_out_dev, 0);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---- row-block form for the row-partitioned build (SURVEY §8e stage 1): the caller owns rows
+//      [row_offset, row_offset + n_local) with GLOBAL column ids.  Phase 1 gives the block's degrees and the
+//      output row pointer; the caller all-gathers the degrees; phase 2 fills the normalised block.  The values
+//      are the ones gdr_sym_normalize produces for the same rows of the whole matrix (same kernels). ----
+__global__ void k_set_flag(int32_t* flag, int v) { flag[0] = v; }
+
+int64_t gdr_sym_normalize_block_ws_bytes(int64_t n_local) {
+  return ws_need(n_local + 1, 4) + 256 + scan_ws_bytes(n_local) + 256;
+}
+
+int gdr_sym_normalize_block_degrees(int64_t n_local, int64_t row_offset, const int32_t* rowptr,
+                                    const int32_t* colidx, const float* vals, int add_identity,
+                                    double* deg_local_out, int32_t* rowptr_out, void* ws, int64_t ws_bytes,
+                                    gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_local > 0 && row_offset >= 0 && rowptr && deg_local_out && rowptr_out && ws,
+                "sym_normalize_block_degrees: bad arguments");
+  if (ws_bytes < gdr_sym_normalize_block_ws_bytes(n_local)) {
+    set_error("sym_normalize_block_degrees: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace W(ws, ws_bytes);
+  int32_t* out_len = W.take<int32_t>(n_local + 1);
+  int32_t* flag = W.take<int32_t>(1);
+  int64_t sws_b = scan_ws_bytes(n_local);
+  void* sws = W.take<char>(sws_b);
+  k_set_flag<<<1, 1, 0, s>>>(flag, add_identity ? 1 : 0);
+  GDR_LAUNCHED();
+  k_row_degree<<<(unsigned)cdiv(n_local * 32, 256), 256, 0, s>>>(n_local, rowptr, colidx, vals, flag, deg_local_out,
+                                                                out_len, row_offset);
+  GDR_LAUNCHED();
+  return exclusive_scan_i32(out_len, rowptr_out, n_local, sws, sws_b, s);
+}
+
+int gdr_sym_normalize_block_fill(int64_t n_local, int64_t row_offset, const int32_t* rowptr, const int32_t* colidx,
+                                 const float* vals, int add_identity, const double* deg_global,
+                                 const int32_t* rowptr_out, int32_t* colidx_out, float* vals_out,
+                                 int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_local > 0 && row_offset >= 0 && rowptr && deg_global && rowptr_out && colidx_out && vals_out &&
+                    nnz_out_dev && ws,
+                "sym_normalize_block_fill: bad arguments");
+  if (ws_bytes < 256) {
+    set_error("sym_normalize_block_fill: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* flag = (int32_t*)ws;
+  k_set_flag<<<1, 1, 0, s>>>(flag, add_identity ? 1 : 0);
+  GDR_LAUNCHED();
+  k_norm_fill<<<(unsigned)cdiv(n_local * 32, 256), 256, 0, s>>>(n_local, rowptr, colidx, vals, flag,
+                                                               deg_global + row_offset, deg_global, rowptr_out,
+                                                               colidx_out, vals_out, nnz_out_dev, row_offset);
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -116,6 +116,23 @@ int     gdr_sym_normalize(int64_t n, int64_t nnz,
                           double* deg_out, int64_t* nnz_out_dev,
                           void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
+/* Row-block form of gdr_sym_normalize for the row-partitioned build (one rank owns rows
+ * [row_offset, row_offset + n_local) with GLOBAL column ids; replaces the same reference lines,
+ * deep_robust_utils.py:180-207, on a block).  Phase 1: degrees of the block (fp64, +1 when
+ * add_identity) and the output row pointer (a diagonal slot is inserted where the block has none).
+ * The caller all-gathers the degrees into deg_global[n].  Phase 2 writes the block of
+ * D^-1/2 (A [+ I]) D^-1/2 — bit-identical to the rows gdr_sym_normalize produces on the whole matrix.
+ * add_identity is the caller's global decision (self_loop_mode 2: A[0,0] == 0 on the owner of row 0). */
+int64_t gdr_sym_normalize_block_ws_bytes(int64_t n_local);
+int     gdr_sym_normalize_block_degrees(int64_t n_local, int64_t row_offset, const int32_t* rowptr,
+                                        const int32_t* colidx, const float* vals, int add_identity,
+                                        double* deg_local_out, int32_t* rowptr_out /* n_local + 1 */,
+                                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int     gdr_sym_normalize_block_fill(int64_t n_local, int64_t row_offset, const int32_t* rowptr,
+                                     const int32_t* colidx, const float* vals, int add_identity,
+                                     const double* deg_global, const int32_t* rowptr_out,
+                                     int32_t* colidx_out, float* vals_out, int64_t* nnz_out_dev,
+                                     void* ws, int64_t ws_bytes, gdr_stream_t stream);
 /* Dense n x n variant:  D^-1/2 (A + I) D^-1/2  in fp32, O(n^2).
  *   replaces  normalize_adj_tensor(adj) dense branch       deep_robust_utils.py:257-264 */
 int gdr_sym_normalize_dense(int64_t n, const float* A, int64_t lda, float* out, int64_t ldo,

@@ -36,6 +36,17 @@ def _worker(rank, world, port):
         ops = par.CudaOps()
         u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
         A_local, A_full = par.build_local_adjacency(u_d, v_d, n, part, dev)
+        # stage 1, exchange-based: each rank starts from a slice of the pair list; block == rows of the global build
+        per = (u.shape[0] + world - 1) // world
+        sl = slice(rank * per, min(u.shape[0], (rank + 1) * per))
+        A_x = par.dist_build_adjacency(comm, part, u_d[sl].contiguous(), v_d[sl].contiguous(), n, ops=ops)
+        assert torch.equal(A_x.rowptr, A_local.rowptr) and torch.equal(A_x.colidx, A_local.colidx)
+        assert torch.equal(A_x.vals, A_local.vals)
+        # pipelined hop (3 column slabs, async all-gathers) == one-pass hop
+        x_l = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
+        pa, ta = par.dist_propagate(comm, part, A_local, x_l, 3, 0.8, ops=ops, slabs=1)
+        pb, tb = par.dist_propagate(comm, part, A_x, x_l, 3, 0.8, ops=ops, slabs=3)
+        assert torch.equal(pa, pb) and torch.equal(ta, tb)
         # stage 2
         x_local = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
         prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)

@@ -335,3 +335,16 @@ def test_config_b_properties(gdr, dev):
     k = int(labels.max()) + 1
     rpc, cic, cnt, _ = gdr.coarsen_edges(labels, labels, k, k, csr=An)
     assert int(cnt.sum()) == An.nnz                        # every edge lands in exactly one cell
+
+
+def test_block_build_world1_equals_global_build(gdr, dev):
+    """dist_build_adjacency with a single rank (no collectives) runs the row-block kernels
+    (gdr_sym_normalize_block_*) on the whole matrix: same CSR as coo_to_csr + sym_normalize."""
+    from gdr import parallel as par
+    from gdr import synth
+    for n, pairs, seed in [(5003, 40000, 1), (2000, 300, 2)]:      # the second one has isolated nodes
+        u, v = synth.skewed_graph(n, pairs, seed=seed)
+        u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+        A = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
+        B = par.dist_build_adjacency(par.Comm(), par.RowPartition(n, 1, 0), u_d, v_d, n)
+        assert torch.equal(A.rowptr, B.rowptr) and torch.equal(A.colidx, B.colidx) and torch.equal(A.vals, B.vals)

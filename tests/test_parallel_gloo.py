@@ -32,6 +32,56 @@ class OracleOps:
         from oracle import oracle as o
         self.o = o
 
+    # -- stage 1 (block build): numpy restatement of the block kernels, tests only --
+    def bucket_by_owner(self, src, dst, rows_per, world):
+        owner = (src // rows_per).numpy()
+        order = np.argsort(owner, kind="stable")
+        counts = np.bincount(owner, minlength=world)[:world].tolist()
+        return torch.stack([src[order], dst[order]], dim=1).contiguous(), counts
+
+    def build_block_csr(self, rows_local, cols, n_local, n):
+        rp, ci, va = self.o.coo_to_csr(rows_local.numpy(), cols.numpy(), None, (n_local, n), symmetrize=False, binarize=True)
+        return CpuCSR(torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va), (n_local, n))
+
+    def block_degrees(self, A, row_offset, add_identity):
+        rp, ci, va = A.rowptr.numpy().astype(np.int64), A.colidx.numpy().astype(np.int64), A.vals.numpy()
+        nl = A.shape[0]
+        rows = np.repeat(np.arange(nl), np.diff(rp))
+        has_diag = np.zeros(nl, bool)
+        has_diag[rows[ci == rows + row_offset]] = True
+        if add_identity:
+            deg = np.bincount(rows, weights=va.astype(np.float64), minlength=nl) + 1.0
+            out_len = np.diff(rp) + (~has_diag)
+        else:
+            d32 = np.zeros(nl, np.float32)
+            np.add.at(d32, rows, va)
+            deg, out_len = d32.astype(np.float64), np.diff(rp)
+        return torch.from_numpy(deg), torch.from_numpy(np.concatenate([[0], np.cumsum(out_len)]).astype(np.int32))
+
+    def block_fill(self, A, row_offset, add_identity, deg_global, rowptr_out):
+        assert add_identity, "the synthetic graphs of these tests take the +I path"
+        rp, ci, va = A.rowptr.numpy().astype(np.int64), A.colidx.numpy().astype(np.int64), A.vals.numpy()
+        nl = A.shape[0]
+        deg = deg_global.numpy()
+        rows = np.repeat(np.arange(nl), np.diff(rp))
+        v64 = va.astype(np.float64)
+        on_diag = ci == rows + row_offset
+        v64[on_diag] += 1.0
+        has_diag = np.zeros(nl, bool)
+        has_diag[rows[on_diag]] = True
+        new_r = np.flatnonzero(~has_diag)
+        r_all = np.concatenate([rows, new_r])
+        c_all = np.concatenate([ci, new_r + row_offset])
+        v_all = np.concatenate([v64, np.ones(new_r.shape[0])])
+        order = np.lexsort((c_all, r_all))
+        r_all, c_all, v_all = r_all[order], c_all[order], v_all[order]
+        with np.errstate(divide="ignore"):
+            r_inv = np.power(deg, -0.5)
+        r_inv[np.isinf(r_inv)] = 0.0
+        out = ((r_inv[r_all + row_offset] * v_all) * r_inv[c_all]).astype(np.float32)
+        assert np.array_equal(np.bincount(r_all, minlength=nl), np.diff(rowptr_out.numpy()))
+        return CpuCSR(rowptr_out, torch.from_numpy(c_all.astype(np.int32)), torch.from_numpy(out), A.shape)
+
     def prep_rows(self, x):
         return x.to(torch.float32).contiguous()
 
@@ -46,6 +96,15 @@ class OracleOps:
         y = self.o.spmm_prop(A.rowptr.numpy(), A.colidx.numpy(), A.vals.numpy(), np.float32(alpha),
                              x_full.numpy(), T=tn, beta=np.float32(beta))
         return torch.from_numpy(y)
+
+    def spmm_slab(self, A, x_slab, alpha, y, target, beta, c0):
+        w = x_slab.shape[1]
+        tn = None if target is None else np.ascontiguousarray(target[:, c0:c0 + w].numpy())
+        out = self.o.spmm_prop(A.rowptr.numpy(), A.colidx.numpy(), A.vals.numpy(), np.float32(alpha),
+                               np.ascontiguousarray(x_slab.numpy()), T=tn, beta=np.float32(beta))
+        y[:, c0:c0 + w] = torch.from_numpy(out)
+        if target is not None:
+            target[:, c0:c0 + w] = torch.from_numpy(tn)
 
     def column_sums(self, X):
         x = X.numpy().astype(np.float64)
@@ -143,8 +202,19 @@ def _worker(rank, world, port, case):
                          torch.from_numpy(vo[b:e].copy()), (hi - lo, n))
         x_local = torch.from_numpy(X[lo:hi].copy())
 
-        if case == "propagate":
-            prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)
+        if case == "build":
+            # every rank holds a slice of the undirected pair list; exchange-based build == rows of the global build
+            u, v = synth.skewed_graph(n, 9000, seed=3)
+            per = (u.shape[0] + world - 1) // world
+            sl = slice(rank * per, min(u.shape[0], (rank + 1) * per))
+            A_blk = par.dist_build_adjacency(comm, part, torch.from_numpy(u[sl].copy()), torch.from_numpy(v[sl].copy()), n, ops=ops)
+            assert np.array_equal(A_blk.rowptr.numpy(), A_local.rowptr.numpy())
+            assert np.array_equal(A_blk.colidx.numpy(), A_local.colidx.numpy())
+            assert np.array_equal(A_blk.vals.numpy(), A_local.vals.numpy())        # bit-identical values
+        elif case in ("propagate", "propagate_slabs"):
+            # one-pass hop / hop pipelined over 3 column slabs (async all-gathers): same bits
+            prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops,
+                                              slabs=1 if case == "propagate" else 3)
             p_ref, t_ref = o.propagate(rpo, cio, vo, X, 4, 0.8)
             assert np.array_equal(prop.numpy(), p_ref[lo:hi])      # row-wise independent: bit-identical
             assert np.array_equal(target.numpy(), t_ref[lo:hi])
@@ -181,9 +251,18 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["propagate", "kmeans", "kmeans_empty", "coarsen"])
+@pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "kmeans", "kmeans_empty", "coarsen"])
 def test_world2_gloo(case, oracle):
     mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
+
+
+def test_slab_bounds_cover_the_columns():
+    from gdr.parallel import slab_bounds, default_slabs
+    for f, s in [(100, 4), (128, 4), (12, 3), (7, 4), (1433, 4), (64, 2), (3, 2)]:
+        b = slab_bounds(f, s)
+        assert b[0][0] == 0 and b[-1][1] == f and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(c0 % 4 == 0 for c0, _ in b) and len(b) <= s
+    assert default_slabs(1, 128) == 1 and default_slabs(8, 100) >= 1
 
 
 def test_row_partition_bounds():
