@@ -44,9 +44,17 @@ def _worker(rank, world, port):
         assert torch.equal(A_x.vals, A_local.vals)
         # pipelined hop (3 column slabs, async all-gathers) == one-pass hop
         x_l = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
-        pa, ta = par.dist_propagate(comm, part, A_local, x_l, 3, 0.8, ops=ops, slabs=1)
-        pb, tb = par.dist_propagate(comm, part, A_x, x_l, 3, 0.8, ops=ops, slabs=3)
-        assert torch.equal(pa, pb) and torch.equal(ta, tb)
+        # ONE hop: rows on the sequential path (<= 1024 non-zeros) are the same fp32 chain whatever the slab width;
+        # hub rows are summed as fixed-order partials whose grouping follows the lane-group width (1e-5 contract)
+        pa, ta = par.dist_propagate(comm, part, A_local, x_l, 2, 0.8, ops=ops, slabs=1)
+        pb, tb = par.dist_propagate(comm, part, A_x, x_l, 2, 0.8, ops=ops, slabs=3)
+        light = (A_local.rowptr[1:] - A_local.rowptr[:-1]) <= 1024
+        assert torch.equal(pa[light], pb[light]) and torch.equal(ta[light], tb[light])
+        # several hops: the hub rows' last-bit differences reach their neighbours
+        pa, ta = par.dist_propagate(comm, part, A_local, x_l, 4, 0.8, ops=ops, slabs=1)
+        pb, tb = par.dist_propagate(comm, part, A_x, x_l, 4, 0.8, ops=ops, slabs=3)
+        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(ta, tb, rtol=1e-5, atol=1e-6)
         # stage 2
         x_local = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
         prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)
