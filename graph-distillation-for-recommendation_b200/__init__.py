@@ -5,6 +5,7 @@ Four stages behind the reference's own call signatures:
   2. K-hop propagation      propagation.py  (clustgdd_agent_transduct.py:55-65)
   3. k-means / WCSS         kmeans.py       (sklearn KMeans call sites)
   4. coarsened graph        coarsen.py      (graph_compress, build_condensed_bipartite)
+  +  edge scoring / top-k   sparsify.py     (ER_estimator, attaw_ER_estimator, graph_sparse)
 All arithmetic runs in libgdr_b200.so (hand-written sm_100a CUDA, C ABI in include/gdr.h).
 Importing this package loads that library and fails if it has not been built.
 """
@@ -25,6 +26,10 @@ from .kmeans import (  # noqa: E402
 from .coarsen import (  # noqa: E402
     graph_compress, build_condensed_bipartite, condensed_csr_to_edge_index, coarsen_edges, label_counts,
 )
+from .sparsify import (  # noqa: E402
+    ER_estimator, attaw_ER_estimator, graph_sparse, er_lower, cosine_reweight, softmax_rows, class_edge_weight,
+    topk_filter, row_degree,
+)
 from .recsys import (  # noqa: E402
     BipartiteGraph, lightgcn_propagate, BipartitePropagate, RankformerGCNGraph, rankformer_gcn_forward,
 )
@@ -36,6 +41,7 @@ __all__ = [
     "build_interaction_matrix", "propagate", "spmm", "KMeans", "MiniBatchKMeans", "kmeans_cluster", "cluster_means",
     "segment_mean_pool", "segment_sum", "assign_labels", "standard_scale", "graph_compress",
     "build_condensed_bipartite", "condensed_csr_to_edge_index", "coarsen_edges", "label_counts",
-    "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate", "RankformerGCNGraph",
+    "ER_estimator", "attaw_ER_estimator", "graph_sparse", "er_lower", "cosine_reweight", "softmax_rows",
+    "class_edge_weight", "topk_filter", "row_degree", "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate", "RankformerGCNGraph",
     "rankformer_gcn_forward", "parallel",
 ]

@@ -55,6 +55,13 @@ _SIGNATURES = {
     "gdr_coarse_scatter_dense": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, vp]),
     "gdr_dense_to_coarse_ws_bytes": (i64, [i64]),
     "gdr_dense_to_coarse": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_row_sums_f32": (i32, [i64, vp, vp, vp, vp]),
+    "gdr_er_lower": (i32, [i64, i64, vp, vp, vp, vp, vp, vp]),
+    "gdr_edge_cosine_scale": (i32, [i64, i64, i64, vp, vp, vp, vp, i64, f32, vp, vp, vp]),
+    "gdr_softmax_rows": (i32, [i64, i64, vp, i64, vp, i64, vp]),
+    "gdr_class_edge_weight": (i32, [i64, i64, vp, vp, vp, vp, i64, i64, vp, vp]),
+    "gdr_topk_filter_ws_bytes": (i64, [i64, i64]),
+    "gdr_topk_filter_csr": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_kmeans_assign_ws_bytes": (i64, [i64, i64, i64, i32]),
     "gdr_kmeans_assign": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp, i32, vp, i64, vp]),
     "gdr_kmeans_tc_xsplit_bytes": (i64, [i64, i64]),

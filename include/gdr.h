@@ -387,9 +387,41 @@ int gdr_coarsen_scale(int64_t n_src, const int32_t* rowptr, const int32_t* colid
                       const float* wsum, const int32_t* size_src, const int32_t* size_dst,
                       float* vals_out, gdr_stream_t stream);
 
+/* ---- edge scoring + top-k sparsification (between stages 3 and 4) ----
+ * All on a device CSR whose stored order is the reference's coalesced COO order
+ * (rows = src, colidx = dst).
+ *   gdr_row_sums_f32        degree = adj @ ones, fp32, stored order   utils_clustgdd.py:153-154
+ *   gdr_er_lower            ER_estimator  v/deg[src] + v/deg[dst]      utils_clustgdd.py:151-162
+ *                           (deg_scratch: n floats, receives the degrees)
+ *   gdr_edge_cosine_scale   vals_out = vals * cosine_similarity(ebd[src], ebd[dst], eps)
+ *                           (attaw_ER_estimator, utils_clustgdd.py:168-172; inv_norm_scratch: n floats)
+ *   gdr_softmax_rows        F.softmax(ebd, dim=-1)                     clustgdd_agent_transduct.py:158
+ *   gdr_class_edge_weight   (prob[src,cls] * prob[dst,cls]) * er       clustgdd_agent_transduct.py:164-167
+ *   gdr_topk_filter_csr     torch.topk(weight, k) + COO rebuild        clustgdd_agent_transduct.py:142-151,168-181
+ *                           keeps every entry above the k-th largest weight plus the first entries (stored
+ *                           order) equal to it, exactly k in total; output is a sorted CSR (capacity k);
+ *                           radix select + two scans, no host synchronisation, no sort. */
+int gdr_row_sums_f32(int64_t n, const int32_t* rowptr, const float* vals, float* deg_out, gdr_stream_t stream);
+int gdr_er_lower(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                 float* deg_scratch, float* er_out, gdr_stream_t stream);
+int gdr_edge_cosine_scale(int64_t n, int64_t nnz, int64_t C, const int32_t* rowptr, const int32_t* colidx,
+                          const float* vals, const float* ebd, int64_t ld, float eps,
+                          float* inv_norm_scratch, float* vals_out, gdr_stream_t stream);
+int gdr_softmax_rows(int64_t n, int64_t C, const float* X, int64_t ld, float* out, int64_t ldo,
+                     gdr_stream_t stream);
+int gdr_class_edge_weight(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                          const float* er, const float* prob, int64_t ldp, int64_t cls, float* w_out,
+                          gdr_stream_t stream);
+int64_t gdr_topk_filter_ws_bytes(int64_t n, int64_t nnz);
+int     gdr_topk_filter_csr(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                            const float* vals, const float* weight, int64_t k, int32_t* rowptr_out,
+                            int32_t* colidx_out, float* vals_out, int64_t* nnz_out_dev,
+                            void* ws, int64_t ws_bytes, gdr_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
+
 #ifdef __cplusplus
 }
 #endif

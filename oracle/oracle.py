@@ -477,3 +477,101 @@ def graph_compress_dense(labels, rowptr, colidx, vals, n):
         S = S / sizes[:, None] / sizes[None, :]
     np.fill_diagonal(S, 0.0)
     return S
+
+
+# ---------------------------------------------------------------------------------------
+# edge scoring + top-k sparsification (between stages 3 and 4)
+# ---------------------------------------------------------------------------------------
+def _rows_of(rowptr):
+    return np.repeat(np.arange(rowptr.shape[0] - 1, dtype=np.int64), np.diff(rowptr))
+
+
+def row_degree_f32(rowptr, vals):
+    """``adj @ ones`` (utils_clustgdd.py:153-154): fp32 row sums in stored order."""
+    n = rowptr.shape[0] - 1
+    deg = np.zeros(n, dtype=np.float32)
+    np.add.at(deg, _rows_of(rowptr), np.asarray(vals, dtype=np.float32))
+    return deg
+
+
+def er_lower(rowptr, colidx, vals):
+    """ER_estimator (utils_clustgdd.py:151-162): values/deg[src] + values/deg[dst] in fp32."""
+    vals = np.asarray(vals, dtype=np.float32)
+    deg = row_degree_f32(rowptr, vals)
+    rows = _rows_of(rowptr)
+    return (vals / deg[rows] + vals / deg[np.asarray(colidx, dtype=np.int64)]).astype(np.float32)
+
+
+def edge_cosine(rowptr, colidx, ebd, eps=1e-8):
+    """F.cosine_similarity(ebd[src], ebd[dst], dim=-1) (utils_clustgdd.py:171): ATen divides each vector
+    by max(|x|, eps) and then takes the dot product; evaluated here in float64 and rounded (the contract
+    on this value is 1e-6 relative, the summation order inside ATen is not specified)."""
+    e = np.asarray(ebd, dtype=np.float64)
+    nrm = np.maximum(np.sqrt((e * e).sum(1)), eps)
+    en = e / nrm[:, None]
+    rows = _rows_of(rowptr)
+    return (en[rows] * en[np.asarray(colidx, dtype=np.int64)]).sum(1).astype(np.float32)
+
+
+def attaw_er_lower(rowptr, colidx, vals, ebd):
+    """attaw_ER_estimator (utils_clustgdd.py:165-184): values re-weighted by the cosine similarity of the
+    end points' embeddings, then ER_lower on the re-weighted graph.  Returns (ER_lower, reweighted values)."""
+    rew = (np.asarray(vals, dtype=np.float32) * edge_cosine(rowptr, colidx, ebd)).astype(np.float32)
+    return er_lower(rowptr, colidx, rew), rew
+
+
+def softmax_rows(x):
+    """F.softmax(ebd, dim=-1) (clustgdd_agent_transduct.py:158) in fp32."""
+    x = np.asarray(x, dtype=np.float32)
+    m = x.max(axis=1, keepdims=True)
+    ex = np.exp(x - m, dtype=np.float32)
+    return (ex / ex.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+
+
+def class_edge_weight(rowptr, colidx, er, prob_col):
+    """src_prob * dst_prob * ER_low (clustgdd_agent_transduct.py:164-167), left to right in fp32."""
+    rows = _rows_of(rowptr)
+    p = np.asarray(prob_col, dtype=np.float32)
+    return ((p[rows] * p[np.asarray(colidx, dtype=np.int64)]).astype(np.float32) * np.asarray(er, dtype=np.float32)).astype(np.float32)
+
+
+def topk_edges(weight, k):
+    """torch.topk(weight, k) as an index SET (clustgdd_agent_transduct.py:142,168): every entry above the
+    k-th largest value, plus the first entries (in index order) equal to it.  torch leaves the choice among
+    equal values unspecified; the multiset of selected weights is what both must agree on."""
+    w = np.asarray(weight, dtype=np.float32)
+    k = int(k)
+    if k <= 0:
+        return np.zeros(0, dtype=np.int64)
+    thr = np.partition(w, w.shape[0] - k)[w.shape[0] - k]
+    gt = np.flatnonzero(w > thr)
+    eq = np.flatnonzero(w == thr)[: k - gt.shape[0]]
+    return np.sort(np.concatenate([gt, eq]))
+
+
+def filter_csr(rowptr, colidx, vals, keep_idx):
+    """coo_matrix((values[idx], (src[idx], dst[idx]))) (clustgdd_agent_transduct.py:146-151) as a sorted CSR."""
+    n = rowptr.shape[0] - 1
+    rows = _rows_of(rowptr)[keep_idx]
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rp, rows + 1, 1)
+    return np.cumsum(rp).astype(np.int32), np.asarray(colidx)[keep_idx].astype(np.int32), np.asarray(vals, dtype=np.float32)[keep_idx]
+
+
+def graph_sparse(rowptr, colidx, vals, ratio, ebd=None, sp_type="vanilla"):
+    """ClustGDD.graph_sparse (clustgdd_agent_transduct.py:131-203) for 'vanilla', 'attaw', 'single', 'no_sp':
+    list of (rowptr, colidx, vals) CSR triplets."""
+    nnz = int(np.asarray(vals).shape[0])
+    k = int(nnz * ratio)
+    if sp_type == "no_sp":
+        return [(rowptr, colidx, vals)]
+    if sp_type == "vanilla":
+        return [filter_csr(rowptr, colidx, vals, topk_edges(er_lower(rowptr, colidx, vals), k))]
+    er, rew = attaw_er_lower(rowptr, colidx, vals, ebd)
+    if sp_type == "single":
+        return [filter_csr(rowptr, colidx, rew, topk_edges(er, k))]
+    if sp_type == "attaw":
+        P = softmax_rows(ebd)
+        return [filter_csr(rowptr, colidx, rew, topk_edges(class_edge_weight(rowptr, colidx, er, P[:, i]), k))
+                for i in range(P.shape[1])]
+    raise ValueError(f"unknown sp_type {sp_type!r}")

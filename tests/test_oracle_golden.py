@@ -181,3 +181,49 @@ def test_kmeans_plusplus_matches_sklearn(oracle, k):
         c, idx = oracle.kmeans_plusplus(g["x"], k, np.random.RandomState(seed), cumsum_dtype=dt)
         assert np.array_equal(idx, g[f"k{k}_indices"])
         assert np.array_equal(c, g[f"k{k}_centers"])
+
+
+# ---------------------------------------------------------------- sparsification
+def _sparsify_case():
+    g = golden("sparsify.npz")
+    n = int(g["n"])
+    rp = np.zeros(n + 1, np.int64)
+    np.add.at(rp, g["src"] + 1, 1)
+    return g, n, np.cumsum(rp).astype(np.int32), g["dst"].astype(np.int32), g["val"]
+
+
+def _edge_set(rp, ci):
+    rows = np.repeat(np.arange(rp.shape[0] - 1), np.diff(rp))
+    return set(zip(rows.tolist(), ci.tolist()))
+
+
+def test_er_estimator_matches_reference(oracle):
+    g, n, rp, ci, va = _sparsify_case()
+    assert np.array_equal(oracle.er_lower(rp, ci, va), g["er"])                 # utils_clustgdd.ER_estimator, bit-exact
+    er_att, rew = oracle.attaw_er_lower(rp, ci, va, g["ebd"])                   # attaw_ER_estimator
+    np.testing.assert_allclose(rew, g["rew_val"], rtol=0, atol=2e-7 * np.abs(va).max())
+    # degrees of the re-weighted graph are sums with cancellation: compare against their magnitude
+    np.testing.assert_allclose(er_att, g["er_att"], rtol=1e-3, atol=1e-4 * np.abs(g["er_att"]).max())
+
+
+def test_graph_sparse_matches_reference(oracle):
+    g, n, rp, ci, va = _sparsify_case()
+    ratio = float(g["ratio"])
+    k = int(va.shape[0] * ratio)
+    for tag, tp in (("van", "vanilla"), ("sin", "single")):
+        rpo, cio, vo = oracle.graph_sparse(rp, ci, va, ratio, ebd=g["ebd"], sp_type=tp)[0]
+        assert cio.shape[0] == k
+        ref = set(zip(g[tag + "_row"].tolist(), g[tag + "_col"].tolist()))
+        assert len(_edge_set(rpo, cio) ^ ref) <= 2        # only edges AT the threshold may differ (ties / last-bit weights)
+    gl = oracle.graph_sparse(rp, ci, va, ratio, ebd=g["ebd"], sp_type="attaw")
+    assert len(gl) == int(g["C"])
+    for i, (rpo, cio, vo) in enumerate(gl):
+        ref = set(zip(g[f"att{i}_row"].tolist(), g[f"att{i}_col"].tolist()))
+        assert cio.shape[0] == k and len(_edge_set(rpo, cio) ^ ref) <= 4
+
+
+def test_topk_edges_ties_take_first_in_index_order(oracle):
+    w = np.array([1, 3, 3, 2, 3, 0, 3], np.float32)
+    assert oracle.topk_edges(w, 3).tolist() == [1, 2, 4]
+    assert oracle.topk_edges(w, 5).tolist() == [1, 2, 3, 4, 6]
+    assert oracle.topk_edges(w, 0).tolist() == []
