@@ -165,33 +165,44 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, int
 }
 
 // ----------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits
+// stable LSD radix sort, digits of up to 11 bits
 // ----------------------------------------------------------------------------
+// The pass count is what the sort costs (every pass streams the keys and payloads through HBM once in, once
+// out), so the key bits are cut into as few digits as fit: ceil(bits / 11) passes of equal width — 10-bit
+// cluster labels (K = 1000) sort in ONE pass, the 36-bit (row, col) keys of an arxiv-sized graph in 4 instead
+// of 5, the 44-bit keys of a products-sized graph in 4 instead of 6.  Bins live in dynamic shared memory
+// (8 warp-private counter rows of 2^bits ints: 64 KB at 11 bits).
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_BINS = 256;
+constexpr int RS_MAX_BITS = 11;
+constexpr int RS_MAX_BINS = 1 << RS_MAX_BITS;
 // keys per thread: 16 (4096-key tiles) for large inputs, 4 (1024-key tiles) below 2M keys so
 // that mid-size sorts (k-means membership lists, arxiv-sized graphs) still fill the 148 SMs
 static inline int rs_rounds(int64_t n) { return n >= (1ll << 21) ? 16 : 4; }
+static inline int rs_passes(int key_bits) { return (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS; }
+static inline int rs_digit_bits(int key_bits) { return (key_bits + rs_passes(key_bits) - 1) / rs_passes(key_bits); }
 
 template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n,
-                                                        int shift, int32_t* __restrict__ table,
+                                                        int shift, int bits, int32_t* __restrict__ table,
                                                         int nblocks) {
-  __shared__ int hist[RS_BINS];
-  hist[threadIdx.x] = 0;
+  extern __shared__ int rs_smem[];
+  int* hist = rs_smem;
+  const int bins = 1 << bits;
+  const uint32_t dmask = (uint32_t)bins - 1u;
+  for (int i = threadIdx.x; i < bins; i += RS_THREADS) hist[i] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * (RS_THREADS * RS_ROUNDS);
 #pragma unroll 4
   for (int r = 0; r < RS_ROUNDS; ++r) {
     int64_t idx = base + r * RS_THREADS + threadIdx.x;
     if (idx < n) {
-      int d = (int)((keys[idx] >> shift) & 0xff);
+      int d = (int)((uint32_t)(keys[idx] >> shift) & dmask);
       atomicAdd(&hist[d], 1);
     }
   }
   __syncthreads();
-  table[(int64_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+  for (int d = threadIdx.x; d < bins; d += RS_THREADS) table[(int64_t)d * nblocks + blockIdx.x] = hist[d];
 }
 
 template <int RS_ROUNDS>
@@ -199,14 +210,18 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
                                                            const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out,
                                                            uint32_t* __restrict__ vals_out, int64_t n,
-                                                           int shift,
+                                                           int shift, int bits,
                                                            const int32_t* __restrict__ table_scanned,
                                                            int nblocks) {
-  __shared__ int cnt[RS_WARPS][RS_BINS];
-  for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  extern __shared__ int rs_smem[];
+  const int bins = 1 << bits;
+  const uint32_t dmask = (uint32_t)bins - 1u;
+  int* cnt = rs_smem;   // [RS_WARPS][bins]
+  for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
+  int* mycnt = cnt + w * bins;
   int64_t base = (int64_t)blockIdx.x * (RS_THREADS * RS_ROUNDS) + (int64_t)w * (RS_ROUNDS * 32);
   uint64_t k[RS_ROUNDS];
   uint32_t v[RS_ROUNDS];
@@ -222,27 +237,26 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   for (int r = 0; r < RS_ROUNDS; ++r) {
     int64_t idx = base + r * 32 + lane;
     bool valid = idx < n;
-    int d = valid ? (int)((k[r] >> shift) & 0xff) : RS_BINS;  // sentinel digit for padding lanes
+    int d = valid ? (int)((uint32_t)(k[r] >> shift) & dmask) : bins;  // sentinel digit for padding lanes
     unsigned peers = __match_any_sync(0xffffffffu, d);
     int before = __popc(peers & lt_mask);
     int leader = __ffs(peers) - 1;
     int basecnt = 0;
     if (valid && lane == leader) {
-      basecnt = cnt[w][d];
-      cnt[w][d] = basecnt + __popc(peers);
+      basecnt = mycnt[d];
+      mycnt[d] = basecnt + __popc(peers);
     }
     basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
     rank[r] = basecnt + before;
     __syncwarp();
   }
   __syncthreads();
-  {
-    int d = threadIdx.x;
+  for (int d = threadIdx.x; d < bins; d += RS_THREADS) {
     int run = table_scanned[(int64_t)d * nblocks + blockIdx.x];
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) {
-      int t = cnt[ww][d];
-      cnt[ww][d] = run;
+      int t = cnt[ww * bins + d];
+      cnt[ww * bins + d] = run;
       run += t;
     }
   }
@@ -251,8 +265,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   for (int r = 0; r < RS_ROUNDS; ++r) {
     int64_t idx = base + r * 32 + lane;
     if (idx < n) {
-      int d = (int)((k[r] >> shift) & 0xff);
-      int64_t pos = (int64_t)cnt[w][d] + rank[r];
+      int d = (int)((uint32_t)(k[r] >> shift) & dmask);
+      int64_t pos = (int64_t)mycnt[d] + rank[r];
       keys_out[pos] = k[r];
       if (vals_out) vals_out[pos] = v[r];
     }
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
 int64_t sort_pairs_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
   int64_t nb = cdiv(n, RS_THREADS * rs_rounds(n));
-  int64_t tbl = (int64_t)RS_BINS * nb;
+  int64_t tbl = (int64_t)RS_MAX_BINS * nb;
   return ws_need(n, 8) + ws_need(n, 4) + ws_need(tbl + 1, 4) + scan_ws_bytes(tbl) + 256;
 }
 
@@ -278,30 +292,40 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
     set_error("sort_pairs: n=%lld exceeds int32 positions", (long long)n);
     return GDR_ERANGE;
   }
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int max_smem = RS_WARPS * RS_MAX_BINS * 4;
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
   const int rounds = rs_rounds(n);
   int64_t nb = cdiv(n, RS_THREADS * rounds);
-  int64_t tbl = (int64_t)RS_BINS * nb;
+  const int passes = rs_passes(key_bits);
+  const int bits = rs_digit_bits(key_bits);
+  const int bins = 1 << bits;
+  int64_t tbl = (int64_t)bins * nb;
   Workspace W(ws, ws_bytes);
   uint64_t* kalt = W.take<uint64_t>(n);
   uint32_t* valt = W.take<uint32_t>(n);
-  int32_t* table = W.take<int32_t>(tbl + 1);
-  void* sws = W.take<char>(scan_ws_bytes(tbl));
-  int passes = (key_bits + 7) / 8;
+  int32_t* table = W.take<int32_t>((int64_t)RS_MAX_BINS * nb + 1);
+  void* sws = W.take<char>(scan_ws_bytes((int64_t)RS_MAX_BINS * nb));
   uint64_t* kin = keys;
   uint32_t* vin = vals;
   uint64_t* kout = kalt;
   uint32_t* vout = vals ? valt : nullptr;
+  const size_t hist_smem = (size_t)bins * 4, scat_smem = (size_t)RS_WARPS * bins * 4;
   for (int p = 0; p < passes; ++p) {
-    int shift = 8 * p;
-    if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
-    else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, n, shift, table, (int)nb);
+    int shift = bits * p;
+    if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
+    else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
     GDR_LAUNCHED();
     int rc = exclusive_scan_i32(table, table, tbl, sws, scan_ws_bytes(tbl), s);
     if (rc) return rc;
     if (rounds == 16)
-      k_rs_scatter<16><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
+      k_rs_scatter<16><<<(unsigned)nb, RS_THREADS, scat_smem, s>>>(kin, vin, kout, vout, n, shift, bits, table, (int)nb);
     else
-      k_rs_scatter<4><<<(unsigned)nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, table, (int)nb);
+      k_rs_scatter<4><<<(unsigned)nb, RS_THREADS, scat_smem, s>>>(kin, vin, kout, vout, n, shift, bits, table, (int)nb);
     GDR_LAUNCHED();
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

@@ -314,4 +314,36 @@ int gdr_topk_filter_csr(int64_t n, int64_t nnz, const int32_t* rowptr, const int
   return GDR_OK;
 }
 
+/* All classes of the 'attaw' sparsifier in ONE call (clustgdd_agent_transduct.py:160-181): for class c the edge
+ * weights (prob[src,c] * prob[dst,c]) * er, their top-k and the rebuilt CSR, written to slice c of the outputs
+ * (rowptr_out [C][n+1], colidx_out / vals_out [C][k]).  ~20 launches per class issued back to back from here. */
+int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz) {
+  return ws_need(nnz, 4) + gdr_topk_filter_ws_bytes(n, nnz) + 256;
+}
+
+int gdr_sparsify_classes(int64_t n, int64_t nnz, int64_t C, const int32_t* rowptr, const int32_t* colidx,
+                         const float* vals, const float* er, const float* prob, int64_t ldp, int64_t k,
+                         int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, int64_t* nnz_out_dev /*[C]*/,
+                         void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n > 0 && nnz >= 0 && C > 0 && C <= ldp && k >= 0 && k <= nnz && rowptr && prob && rowptr_out &&
+                    nnz_out_dev && ws,
+                "sparsify_classes: bad arguments");
+  if (ws_bytes < gdr_sparsify_classes_ws_bytes(n, nnz)) {
+    set_error("sparsify_classes: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  float* w = W.take<float>(nnz);
+  const int64_t fws_b = gdr_topk_filter_ws_bytes(n, nnz);
+  void* fws = W.take<char>(fws_b);
+  for (int64_t c = 0; c < C; ++c) {
+    int rc = gdr_class_edge_weight(n, nnz, rowptr, colidx, er, prob, ldp, c, w, stream);
+    if (rc) return rc;
+    rc = gdr_topk_filter_csr(n, nnz, rowptr, colidx, vals, w, k, rowptr_out + c * (n + 1), colidx_out + c * k,
+                             vals_out + c * k, nnz_out_dev + c, fws, fws_b, stream);
+    if (rc) return rc;
+  }
+  return GDR_OK;
+}
+
 }  // extern "C"

@@ -87,6 +87,22 @@ def topk_filter(A: CSR, weight: torch.Tensor, k: int, values: Optional[torch.Ten
     return CSR(rowptr, colidx[:k], vout[:k], A.shape)   # exactly k entries by construction
 
 
+def sparsify_classes(R: CSR, er: torch.Tensor, prob: torch.Tensor, k: int) -> List[CSR]:
+    """One sparsified graph per class (column of ``prob``): top-k of (prob[src,c] * prob[dst,c]) * er, all classes
+    in a single library call."""
+    n, dev, C, k = R.shape[0], R.device, int(prob.shape[1]), int(k)
+    if not 0 <= k <= R.nnz:
+        raise ValueError("k out of range")
+    rowptr = torch.empty((C, n + 1), dtype=torch.int32, device=dev)
+    colidx = torch.empty((C, max(k, 1)), dtype=torch.int32, device=dev)
+    vals = torch.empty((C, max(k, 1)), dtype=torch.float32, device=dev)
+    nnz_out = torch.zeros(C, dtype=torch.int64, device=dev)
+    ws = workspace(_lib.query("gdr_sparsify_classes_ws_bytes", n, R.nnz), dev)
+    _lib.call("gdr_sparsify_classes", n, R.nnz, C, ptr(R.rowptr), ptr(R.colidx), ptr(R.vals), ptr(er), ptr(prob),
+              prob.stride(0), k, ptr(rowptr), ptr(colidx), ptr(vals), ptr(nnz_out), ptr(ws), ws.numel(), stream())
+    return [CSR(rowptr[c], colidx[c, :k], vals[c, :k], R.shape) for c in range(C)]
+
+
 # ---------------------------------------------------------------------------------
 # reference-signature functions
 # ---------------------------------------------------------------------------------
@@ -128,6 +144,5 @@ def graph_sparse(adj, ratio: float, ebd: Optional[torch.Tensor] = None, sp_type:
     if sp_type == "single":
         return [topk_filter(R, er, k).to_torch_coo()]
     if sp_type == "attaw":
-        prob = softmax_rows(ebd)
-        return [topk_filter(R, class_edge_weight(R, er, prob, i), k).to_torch_coo() for i in range(prob.shape[1])]
+        return [g.to_torch_coo() for g in sparsify_classes(R, er, softmax_rows(ebd), k)]
     raise ValueError(f"unknown sp_type {sp_type!r}")

@@ -412,6 +412,13 @@ int gdr_softmax_rows(int64_t n, int64_t C, const float* X, int64_t ld, float* ou
 int gdr_class_edge_weight(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                           const float* er, const float* prob, int64_t ldp, int64_t cls, float* w_out,
                           gdr_stream_t stream);
+/* every class of the 'attaw' sparsifier in one call: slice c of rowptr_out [C][n+1], colidx_out / vals_out [C][k],
+ * nnz_out_dev [C] receives the graph of class c (weights = (prob[src,c] * prob[dst,c]) * er, top-k, rebuild). */
+int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz);
+int     gdr_sparsify_classes(int64_t n, int64_t nnz, int64_t C, const int32_t* rowptr, const int32_t* colidx,
+                             const float* vals, const float* er, const float* prob, int64_t ldp, int64_t k,
+                             int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, int64_t* nnz_out_dev,
+                             void* ws, int64_t ws_bytes, gdr_stream_t stream);
 int64_t gdr_topk_filter_ws_bytes(int64_t n, int64_t nnz);
 int     gdr_topk_filter_csr(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                             const float* vals, const float* weight, int64_t k, int32_t* rowptr_out,

@@ -99,6 +99,44 @@ def build_condensed_bipartite(train_u, train_i, u2cu, i2ci, num_cu, num_ci) -> s
     return C.tocsr()
 
 
+def er_estimator(adj: torch.Tensor, src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """utils_clustgdd.py:151-162."""
+    degree = adj @ torch.ones(adj.shape[0])
+    values = adj.coalesce().values()
+    return values / degree[src] + values / degree[dst]
+
+
+def attaw_er_estimator(adj: torch.Tensor, ebd: torch.Tensor, src: torch.Tensor, dst: torch.Tensor):
+    """utils_clustgdd.py:165-184 (cosine re-weighting, scipy COO rebuild, ER on the re-weighted graph)."""
+    import torch.nn.functional as F
+    values = adj.coalesce()._values() * F.cosine_similarity(ebd[src], ebd[dst], dim=-1)
+    rew = to_tensor_sparse(sp.coo_matrix((values.numpy(), (src.numpy(), dst.numpy())), shape=tuple(adj.shape)))
+    degree = rew @ torch.ones(adj.shape[0])
+    values = rew.coalesce().values()
+    return values / degree[src] + values / degree[dst], rew
+
+
+def graph_sparse_attaw(adj: torch.Tensor, ratio: float, ebd: torch.Tensor, max_classes: int = None):
+    """clustgdd_agent_transduct.py:155-183 ('attaw'): per class  src_prob * dst_prob * ER_low, torch.topk,
+    scipy COO rebuild -> torch sparse.  ``max_classes`` bounds the loop for the timed CPU sample."""
+    import torch.nn.functional as F
+    co = adj.coalesce()
+    src, dst = co._indices()[0], co._indices()[1]
+    nedges = co._values().shape[0]
+    er_low, rew = attaw_er_estimator(adj, ebd, src, dst)
+    prob = F.softmax(ebd, dim=-1)
+    k = int(nedges * ratio)
+    out = []
+    for i in range(prob.shape[-1] if max_classes is None else min(max_classes, prob.shape[-1])):
+        values = rew.coalesce()._values()
+        cp = prob[:, i]
+        w = cp[src] * cp[dst] * er_low
+        _, idx = torch.topk(w, k)
+        g = sp.coo_matrix((values[idx].numpy(), (src[idx].numpy(), dst[idx].numpy())), shape=tuple(adj.shape))
+        out.append(to_tensor_sparse(g))
+    return out
+
+
 def host_info() -> dict:
     import os
     info = dict(cpu_count=os.cpu_count(), affinity=len(os.sched_getaffinity(0)), torch_threads=torch.get_num_threads())
