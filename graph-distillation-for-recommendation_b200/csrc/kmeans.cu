@@ -306,19 +306,28 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine_partial(int K, int D, con
     for (int q0 = blockIdx.x * RF_ROWS; q0 < n_rows; q0 += gridDim.x * RF_ROWS) {
       const int nr = min(RF_ROWS, n_rows - q0);
       __syncthreads();
+      // listed rows transposed to [k][RF_ROWS]: one k of all 8 rows is two broadcast 128-bit loads
       for (int t = threadIdx.x; t < RF_ROWS * D; t += RF_THREADS) {
         const int r = t / D, k = t - r * D;
-        s_x[t] = r < nr ? X[(int64_t)rows[q0 + r] * ldx + k] : 0.f;
+        s_x[k * RF_ROWS + r] = r < nr ? X[(int64_t)rows[q0 + r] * ldx + k] : 0.f;
       }
       __syncthreads();
       float acc[RF_ROWS];
 #pragma unroll
       for (int r = 0; r < RF_ROWS; ++r) acc[r] = 0.f;
+      const float4* s_x4 = reinterpret_cast<const float4*>(s_x);
 #pragma unroll 4
       for (int k = 0; k < D; ++k) {
         const float c = s_ct[k * RF_THREADS + threadIdx.x];
-#pragma unroll
-        for (int r = 0; r < RF_ROWS; ++r) acc[r] = fmaf(s_x[r * D + k], c, acc[r]);
+        const float4 xa = s_x4[2 * k], xb = s_x4[2 * k + 1];
+        acc[0] = fmaf(xa.x, c, acc[0]);
+        acc[1] = fmaf(xa.y, c, acc[1]);
+        acc[2] = fmaf(xa.z, c, acc[2]);
+        acc[3] = fmaf(xa.w, c, acc[3]);
+        acc[4] = fmaf(xb.x, c, acc[4]);
+        acc[5] = fmaf(xb.y, c, acc[5]);
+        acc[6] = fmaf(xb.z, c, acc[6]);
+        acc[7] = fmaf(xb.w, c, acc[7]);
       }
 #pragma unroll
       for (int r = 0; r < RF_ROWS; ++r) {
@@ -372,10 +381,11 @@ int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float*
     GDR_CUDA(cudaFuncSetAttribute(k_refine_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  // centre slabs along y (each staged once per CTA), row groups along x: about two CTAs per SM in total
+  // centre slabs along y (each staged once per CTA), row groups along x: about four CTAs per SM in total
+  // (128 threads and <= 56 KB of shared memory each)
   const unsigned gy = (unsigned)std::min<int64_t>(cdiv(K, RF_THREADS), 1024);
   const unsigned gx = (unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(max_rows, RF_ROWS), 1),
-                                                  std::max<int64_t>(1, (2 * kSMs) / gy));
+                                                  std::max<int64_t>(1, cdiv(4 * kSMs, gy)));
   k_refine_partial<<<dim3(gx, gy), RF_THREADS, smem, s>>>((int)K, (int)D, X, ldx, CT, ldct, cnorm, rows, n_rows_dev,
                                                           packed);
   GDR_LAUNCHED();

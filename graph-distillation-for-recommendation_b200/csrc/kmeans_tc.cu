@@ -33,7 +33,7 @@ constexpr int TC_BM = 128;        // rows per tile (UMMA M)
 constexpr int TC_BN = 128;        // centres per tile (UMMA N)
 constexpr int TC_BK = 32;         // floats per K-block = one 128-byte swizzle row
 constexpr int TC_MAX_KB = 4;      // D padded <= 128
-constexpr int TC_BAR_KB = 5;      // K-blocks of the augmented first-level operand (D + 3 padded <= 160)
+constexpr int TC_BAR_KB = 5;      // K-blocks of the augmented first-level operand (D + 4 padded <= 160)
 constexpr int TC_STAGES = 3;      // centre-tile ring
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int TC_EPI_THREADS = 256;
@@ -41,11 +41,8 @@ constexpr int TC_KBLK_BYTES = TC_BM * TC_BK * 4;  // 16 KB: one [128][32] fp32 b
 constexpr int TC_TMEM_COLS = 256;                 // two 128-column accumulators
 // error band of the 3xTF32 screen, relative to |x_i| * max_j |c_j|
 constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
-// first-level screen: one TF32 product.  |x.c - x_hi.c_hi| <= |x_hi||c - c_hi| + |c||x - x_hi| <= (2^-10 + 2^-22)|x||c|
-// (cvt.rna: unit round-off 2^-11 per operand), TMEM accumulation <= D 2^-23 |x||c| (D <= 128: 2^-16), so the
-// distance error |d^ - d| = 2|x.c error| <= 2^-9 (1 + 2^-6 + 2^-12)|x||c|; eps1 = 2^-9 * 1.0625 leaves 4 % for
-// the fp32 rounding of the norms and of the bound arithmetic itself.
-constexpr float TC_EPS1 = 1.0625f * 0.001953125f;
+// first-level screen: one TF32 product over the augmented operands of k_split_tf32; its error radius is built
+// from the measured rounding residuals |x - tf32(x)|, |c - tf32(c)| (see k_split_tf32 / k_tc_select1).
 static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
 int g_tc_ablate = 0;   // experiment: 1 no epilogue math, 2 no tcgen05.ld either, 3 no MMAs, 4 one K-block of MMAs only
 int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles, 4 two-level on CTA pairs (cta_group::2, 256 x 256)
@@ -150,56 +147,69 @@ __device__ __forceinline__ float tf32_up(float v) {
 }
 
 // aug_mode 1 (rows of X) / 2 (centres): additionally write the first-level operand row
-//   aug[r] = [ tf32(x_0..x_{D-1}), e, p, q, 0... ]   (Dp1 = D + 3 rounded up to 32 floats)
-//   X rows : e = up(eps1 |x|),  p = q = 1
-//   centres: e = up(|c| / 2),   p + q >= w = -|c|^2/2 (1 - 2^-15) split in two TF32 values; padding: p = -1e30
-// so that one TF32 GEMM over the augmented rows yields the SCORE
-//   s_ij = x^.c^ + (eps1/2)|x||c| - |c|^2/2 + slack  >=  t_ij = x.c - |c|^2/2  (= -d_ij / 2),
-// an upper bound of the true score that exceeds it by at most 2 rad_ij (k_tc_select1).
+//   aug[r] = [ tf32(x_0..x_{D-1}), e1, e2, p, q, 0... ]   (Dp1 = D + 4 rounded up to 32 floats)
+//   X rows : e1 = up(|dx|),  e2 = up(|x|),             p = q = 1           (dx = x - tf32(x), exact in fp32)
+//   centres: e1 = up(|c|),   e2 = up(|dc| + 2^-15|c|), p + q >= w = -|c|^2/2 (1 - 2^-15) in two TF32 values
+//            (padding centres: p = -1e30)                       (the e's carry a 1.001 factor for the fp32 norms)
+// so that ONE TF32 GEMM over the augmented rows yields the SCORE
+//   s_ij = x^.c^ + E_ij - |c|^2/2 + slack,   E_ij = |dx_i||c_j| + |x_i||dc_j| + 2^-15|x_i||c_j|
+// E_ij bounds the error of the rounded dot product (|x^.c^ - x.c| <= |dx||c| + |x^||dc|) plus the TMEM
+// accumulation error, with the MEASURED rounding residuals of this row and this centre instead of the worst
+// case 2^-11 — about 2.4x tighter.  s_ij >= t_ij = x.c - |c|^2/2 (= -d_ij / 2) and s_ij - t_ij <= 2 rad_ij.
 __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_pad, int D, int Dp,
                                                     const float* __restrict__ X, int64_t ldx,
                                                     float* __restrict__ hi, float* __restrict__ lo,
                                                     float* __restrict__ norm_out /*|x| per row, nullable*/,
                                                     float* __restrict__ xt /*[Dp][rows_pad] transposed copy, nullable*/,
                                                     float* __restrict__ sqnorm_out /*|x|^2, +inf on padding rows, nullable*/,
-                                                    float* __restrict__ aug /*nullable*/, int Dp1, int aug_mode, float eps1) {
+                                                    float* __restrict__ aug /*nullable*/, int Dp1, int aug_mode,
+                                                    float* __restrict__ dnorm_out /*|x - tf32(x)|, with aug*/) {
   // one warp per row
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows_pad) return;
-  float s = 0.f;
+  float s = 0.f, sd = 0.f;
   for (int c = lane_id(); c < Dp; c += 32) {
     float x = (r < rows && c < D) ? X[r * ldx + c] : 0.f;
     float h = to_tf32(x);
-    float l = to_tf32(__fsub_rn(x, h));
+    float dx = __fsub_rn(x, h);
+    float l = to_tf32(dx);
     hi[r * Dp + c] = h;
     lo[r * Dp + c] = l;
     if (xt) xt[(int64_t)c * rows_pad + r] = x;
     if (aug && c < D) aug[r * Dp1 + c] = h;
     s = fmaf(x, x, s);
+    sd = fmaf(dx, dx, sd);
   }
   // same per-lane fmaf order and xor-shuffle tree as k_row_sqnorm: bit-identical |row|^2
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  }
   if (lane_id() == 0) {
     if (norm_out && r < rows) norm_out[r] = sqrtf(s);
     if (sqnorm_out) sqnorm_out[r] = r < rows ? s : INFINITY;   // padding rows can never win the argmin
   }
   if (aug) {
-    float e, p, q;
+    const float nrm = sqrtf(s), dn = sqrtf(sd);
+    float e1, e2, p, q;
     if (aug_mode == 1) {
-      e = tf32_up(eps1 * sqrtf(s));
+      e1 = tf32_up(1.001f * dn);
+      e2 = tf32_up(1.001f * nrm);
       p = q = 1.f;
     } else if (r < rows) {
-      e = tf32_up(0.5f * sqrtf(s));
+      e1 = tf32_up(1.001f * nrm);
+      e2 = tf32_up(1.001f * (dn + 3.0517578125e-05f * nrm));
       const float w = -0.5f * s * (1.f - 3.0517578125e-05f);
       p = to_tf32(w);
       q = tf32_up(__fsub_rn(w, p));
     } else {
-      e = 0.f;
+      e1 = e2 = q = 0.f;
       p = to_tf32(-1e30f);
-      q = 0.f;
     }
-    for (int c = D + lane_id(); c < Dp1; c += 32) aug[r * Dp1 + c] = c == D ? e : (c == D + 1 ? p : (c == D + 2 ? q : 0.f));
+    if (lane_id() == 0 && dnorm_out) dnorm_out[r] = r < rows ? dn : 0.f;
+    for (int c = D + lane_id(); c < Dp1; c += 32)
+      aug[r * Dp1 + c] = c == D ? e1 : (c == D + 1 ? e2 : (c == D + 2 ? p : (c == D + 3 ? q : 0.f)));
   }
 }
 
@@ -745,19 +755,23 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
-// first-level decision.  best = -s_idx, second = -s_second (negated scores of k_assign_tc<1, *>).  With
-//   rad_ij = 1.01 ((eps1/2)|x_i||c_j| + 2^-16 |c_j|^2)   and   t_ij <= s_ij <= t_ij + 2 rad_ij
-// (t = true score x.c - |c|^2/2), s_idx - s_second > 2 rad_idx implies t_idx > t_j for every other centre: idx is the
-// unique exact argmin.  eta = 2^-15 |x| cmax keeps the margin above the rounding noise of the exact fp32 kernel
-// (same term as the second-level band), 2^-21 |s| covers the last accumulator rounding.  Everything else goes
-// to the second-level list (3xTF32 on the compacted rows).
+// first-level decision.  best = -s_idx, second = -s_second (negated scores of the first-level kernel).  With
+//   E_ij   = |dx_i||c_j| + |x_i|(|dc_j| + 2^-15|c_j|)   (operand rounding incl. the dx.dc cross term; TMEM
+//            accumulation <= (D + 4) 2^-23 |x||c| <= 2^-15.9 |x||c| for D <= 128)
+//   rad_ij = 1.01 (E_ij + 2^-16 |c_j|^2)   and   t_ij <= s_ij <= t_ij + 2 rad_ij
+// (t = true score x.c - |c|^2/2; the factor 1.01 covers the 1.001 factors and the round-ups inside the operands),
+// s_idx - s_second > 2 rad_idx implies t_idx > t_j for every other centre: idx is the unique exact argmin.
+// eta = 2^-15 |x| cmax keeps the margin above the rounding noise of the exact fp32 kernel (same term as the
+// second-level band), 2^-21 |s| covers the last accumulator rounding.  Everything else goes to the
+// second-level list (3xTF32 on the compacted rows).
 __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __restrict__ best,
                                                     const float* __restrict__ second,
                                                     const int32_t* __restrict__ idx,
-                                                    const float* __restrict__ xnorm,
+                                                    const float* __restrict__ xnorm, const float* __restrict__ xdnorm,
                                                     const float* __restrict__ cnorm,
                                                     const float* __restrict__ cnorm_sqrt,
-                                                    const float* __restrict__ cmax, float eps1, float band,
+                                                    const float* __restrict__ cdnorm,
+                                                    const float* __restrict__ cmax, float band,
                                                     int32_t* __restrict__ labels,
                                                     const int32_t* __restrict__ labels_prev,
                                                     int32_t* __restrict__ n_changed,
@@ -766,8 +780,9 @@ __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __re
   int changed = 0;
   if (i < N) {
     const int l = idx[i];
-    const float b = best[i], s2 = second[i], xn = xnorm[i];
-    const float tol = 1.01f * (eps1 * xn * cnorm_sqrt[l] + 3.0517578125e-05f * cnorm[l]) + band * xn * cmax[0] +
+    const float b = best[i], s2 = second[i], xn = xnorm[i], cr = cnorm_sqrt[l];
+    const float E = xdnorm[i] * cr + xn * (cdnorm[l] + 3.0517578125e-05f * cr);
+    const float tol = 2.02f * (E + 1.52587890625e-05f * cnorm[l]) + band * xn * cmax[0] +
                       4.76837158e-07f * fmaxf(fabsf(b), fabsf(s2));
     const bool ambiguous = !(s2 - b > tol);   // also catches NaN / inf - inf
     if (ambiguous) {
@@ -916,15 +931,16 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int Dp, int
 }
 
 static inline int dpad(int64_t D) { return (int)align_up(D, TC_BK); }
-static inline int dpad1(int64_t D) { return (int)align_up(D + 3, TC_BK); }   // first-level operand: 3 augmented columns
+constexpr int TC_AUG = 4;   // augmented columns of the first-level operands
+static inline int dpad1(int64_t D) { return (int)align_up(D + TC_AUG, TC_BK); }
 constexpr int TC_KPAD = 256;   // centres padded to the widest accumulator tile
 
 int64_t kmeans_tc_xsplit_bytes(int64_t N, int64_t D) {
-  return 2 * ws_need(N * dpad(D), 4) + ws_need(N, 4) + ws_need(N * dpad1(D), 4) + 256;
+  return 2 * ws_need(N * dpad(D), 4) + 2 * ws_need(N, 4) + ws_need(N * dpad1(D), 4) + 256;
 }
 
 struct XSplit {
-  float *hi, *lo, *norm, *x1;
+  float *hi, *lo, *norm, *x1, *dnorm;
 };
 static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
   Workspace W(buf, kmeans_tc_xsplit_bytes(N, D));
@@ -934,13 +950,14 @@ static XSplit carve_xsplit(void* buf, int64_t N, int64_t D) {
   x.lo = W.take<float>(N * Dp);
   x.norm = W.take<float>(N);
   x.x1 = W.take<float>(N * dpad1(D));
+  x.dnorm = W.take<float>(N);
   return x;
 }
 
 int kmeans_tc_prepare(int64_t N, int64_t D, const float* X, int64_t ldx, void* xsplit, cudaStream_t s) {
   XSplit x = carve_xsplit(xsplit, N, D);
   k_split_tf32<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, N, (int)D, dpad(D), X, ldx, x.hi, x.lo, x.norm, nullptr,
-                                                          nullptr, x.x1, dpad1(D), 1, TC_EPS1);
+                                                          nullptr, x.x1, dpad1(D), 1, x.dnorm);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -958,13 +975,13 @@ int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
   int Dp = dpad(D);
   int64_t Kp = align_up(K, TC_KPAD);
   return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need(Kp * dpad1(D), 4) /*augmented centres*/ +
-         2 * ws_need(Kp, 4) /*|c|^2, |c|*/ + 256 /*cmax*/ +
+         3 * ws_need(Kp, 4) /*|c|^2, |c|, |c - tf32(c)|*/ + 256 /*cmax*/ +
          3 * ws_need(N, 4) /*best, second, idx*/ + ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ +
          256 /*amb count*/ + ws_need(N, 4) /*second-level list*/ + 256 /*its count*/ +
          2 * ws_need(N * Dp, 4) + ws_need(N, 4) /*compacted hi, lo, |x|*/ + 256;
 }
 
-// D_eff = contraction width (D, or D + 3 for the augmented first level); nkb = its 32-float K-blocks
+// D_eff = contraction width (D, or D + 4 for the augmented first level); nkb = its 32-float K-blocks
 template <int NPASS, int BN, int SUB>
 static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, const CUtensorMap& m_chi,
                             const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D_eff, int64_t Kp,
@@ -1048,6 +1065,7 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   float* c1 = W.take<float>(Kp * Dp1);   // augmented first-level centres
   float* cnorm = W.take<float>(Kp);
   float* cnorm_sqrt = W.take<float>(Kp);
+  float* cdnorm = W.take<float>(Kp);
   float* cmax = W.take<float>(1);
   float* best = W.take<float>(N);
   float* second = W.take<float>(N);
@@ -1068,7 +1086,7 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   const bool two_level = tc_two_level(N, best_out != nullptr);
   // per-iteration centre preparation: split, norms, padding (+ the augmented rows of the first level)
   k_split_tf32<<<(unsigned)cdiv(Kp * 32, 256), 256, 0, s>>>(K, Kp, (int)D, Dp, C, ldc, c_hi, c_lo, nullptr, c_t, cnorm,
-                                                           two_level ? c1 : nullptr, Dp1, 2, TC_EPS1);
+                                                           two_level ? c1 : nullptr, Dp1, 2, cdnorm);
   GDR_LAUNCHED();
   int rc;
   k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cnorm_sqrt, cmax, amb_count, count1);
@@ -1098,22 +1116,23 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
     if ((rc = make_map(&m_x1, xs.x1, N, Dp1, TC_BM))) return rc;
     if (g_tc_screen == 2) {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 128))) return rc;
-      if ((rc = launch_assign_tc<1, 128, 2>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
+      if ((rc = launch_assign_tc<1, 128, 2>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
                                          idx, s)))
         return rc;
     } else if (g_tc_screen == 4) {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 128))) return rc;   // each CTA of a pair loads 128 of the 256 centres
-      if ((rc = launch_assign_tc_pair(m_x1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, best, second, idx, s))) return rc;
+      if ((rc = launch_assign_tc_pair(m_x1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, best, second, idx, s))) return rc;
     } else {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
-      if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + 3, Kp, nkb1, cnorm, best, second,
+      if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
                                          idx, s)))
         return rc;
     }
     if (g_tc_ablate) return GDR_OK;   // timing experiment: first-level kernel only
     g_last_count1 = count1;
-    k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, cnorm, cnorm_sqrt, cmax, TC_EPS1,
-                                                       TC_BAND, labels, labels_prev, n_changed_dev, list1, count1);
+    k_tc_select1<<<(unsigned)cdiv(N, 256), 256, 0, s>>>(N, best, second, idx, xs.norm, xs.dnorm, cnorm, cnorm_sqrt,
+                                                       cdnorm, cmax, TC_BAND, labels, labels_prev, n_changed_dev,
+                                                       list1, count1);
     GDR_LAUNCHED();
     k_tc_gather<<<4 * kSMs, 256, 0, s>>>(list1, count1, Dp, xs.hi, xs.lo, xs.norm, g_hi, g_lo, g_norm);
     GDR_LAUNCHED();
