@@ -3,8 +3,12 @@
 BASELINE.json shape:  stage 1 (CSR build + D^-1/2 A D^-1/2)  ->  stage 2 (K hops)  ->
 stage 3 (20 Lloyd iterations from a fixed init, tol = 0)  ->  stage 4 (P^T A P).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload B] [--precision fp32|tc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload E|B|A] [--precision fp32|tc]
     python bench.py --impl reference ...        # the reference's CPU path on the host cores
+
+The default workload is config E (BASELINE.json configs[4], ogbn-products-shaped: the shape the target is
+quoted on; it fits one GPU) for EVERY N, so the N = 1, 2, 4, 8 lines are one strong-scaling experiment;
+--workload B is configs[1] (ogbn-arxiv-shaped).
 
 Prints ONE JSON line (rank 0).  `value` = k-means iterations / s (whole job), the quantity
 BASELINE.json's speed-up target is quoted on; `prop` carries the A^K.X GB/s figure of the
@@ -142,6 +146,8 @@ def run_reference(args, rank, world):
     w = make_workload(args.workload)
     n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
     info = rp.host_info()
+    if n * K > 1e9:
+        return run_reference_bounded(args, w, info)
     t_s1, t_s2, t_s3, t_s4, per_step = [], [], [], [], []
     it_lo, it_hi = 3, 3 + args.ref_kmeans_iters
     for s in range(args.warmup + args.steps):
@@ -187,6 +193,38 @@ def run_reference(args, rank, world):
                       "s3_kmeans_per_iter": s_iter * 1e3, "s4_coarsen": np.mean(t_s4) * 1e3},
         "cpu_baseline": {"value": iters_per_s, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
                          "sample": f"full config {args.workload}; sklearn/scipy/torch-CPU with all host threads", "host": info},
+        "e2e": {"value": iters_per_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_reference_bounded(args, w, info):
+    """Large workload (config E): the reference's scipy build (`tolil` of 126 M entries) and 4.5 s k-means
+    iterations do not fit a few-minute run, so every step is a BOUNDED sample of the same workload: sklearn Lloyd
+    on the first CPU_SAMPLE_ROWS rows of the z-scored feature matrix against all K centres, differenced between
+    max_iter 1 and 3, the rate scaled by rows/N (an iteration costs the same flops whatever the rows hold, so the
+    un-propagated features stand in for the propagated ones; stages 1, 2 and 4 are not timed here)."""
+    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    rates, what, per_step = [], "", []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS)
+        if s >= args.warmup:
+            rates.append(rate)
+            per_step.append(time.perf_counter() - t0)
+    iters_per_s = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(per_step)) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, F={F}, hops={hops}, K={K}, "
+                               f"k-means D={F}", "bounded": what},
+        "stages_ms": {"s1_build_normalize": None, "s2_propagate": None, "s3_kmeans_per_iter": 1e3 / iters_per_s,
+                      "s4_coarsen": None},
+        "cpu_baseline": {"value": iters_per_s, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
+                         "sample": what, "host": info},
         "e2e": {"value": iters_per_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -563,31 +601,50 @@ def run_ours_multi(args, rank, world, dev):
     dist.destroy_process_group()
 
 
-def cpu_baseline(w, args):
-    """Bounded CPU sample on this box's host cores (oracle-side port of the reference)."""
-    import torch
+CPU_SAMPLE_ROWS = 200_000   # bounded k-means sample of the large workload (all K centres, first rows of X)
+
+
+def cpu_kmeans_rate(w, it_lo, it_hi, rows_cap=None):
+    """k-means iterations/s of the reference's CPU path (sklearn Lloyd, all host threads) on workload w,
+    differenced between two max_iter values so that validation / centring / the final E-step cancel.
+    With rows_cap the fit runs on the first rows_cap rows against all K centres and the rate is scaled by
+    rows_cap / N (the E-step is linear in the rows and dominates: 2*N*K*D flops per iteration)."""
     from oracle import ref_port as rp
     from gdr import synth
     n, K = w["n"], w["k"]
     X = w["X"]
     C0 = synth.kmeans_init(X, K, w["seed"])
-    rp.kmeans_fit(X[:20000], C0[: min(K, 100)], 2)  # warm the thread pools
+    m = n if rows_cap is None else min(n, int(rows_cap))
+    Xs = np.ascontiguousarray(X[:m])
+    if m < n:   # the init rows must lie inside the sample
+        C0 = synth.kmeans_init(Xs, K, w["seed"])
+    rp.kmeans_fit(Xs[:20000], C0[: min(K, 100)], 2)  # warm the thread pools
     t0 = time.perf_counter()
-    rp.kmeans_fit(X, C0, 2)
+    rp.kmeans_fit(Xs, C0, it_lo)
     t1 = time.perf_counter()
-    rp.kmeans_fit(X, C0, 12)
+    rp.kmeans_fit(Xs, C0, it_hi)
     t2 = time.perf_counter()
-    s_iter = ((t2 - t1) - (t1 - t0)) / 10.0
+    s_iter = ((t2 - t1) - (t1 - t0)) / float(it_hi - it_lo)
+    rate = (1.0 / s_iter) * (m / n)
+    what = (f"sklearn KMeans(init=C0,n_init=1,tol=0) on "
+            + (f"the full {n}x{X.shape[1]} matrix" if m == n else f"the first {m} of {n} rows (x{X.shape[1]}), rate scaled by {m}/{n}")
+            + f", K={K}: fit({it_hi} it) - fit({it_lo} it)")
+    return rate, what
+
+
+def cpu_baseline(w, args):
+    """Bounded CPU sample on this box's host cores (oracle-side port of the reference)."""
+    from oracle import ref_port as rp
+    big = w["n"] * w["k"] > 1e9
+    rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS) if big else cpu_kmeans_rate(w, 2, 12)
     info = rp.host_info()
-    return {"value": 1.0 / s_iter, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
-            "sample": f"sklearn KMeans(init=C0,n_init=1,tol=0) on the full {n}x{X.shape[1]} matrix, K={K}: fit(12 it) - fit(2 it)",
-            "host": info}
+    return {"value": rate, "unit": "iters/s", "cores": info["affinity"], "kind": "port", "sample": what, "host": info}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
@@ -601,10 +658,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.workload is None:
-        # BASELINE.json ties the shapes to GPU counts: configs[1] (ogbn-arxiv-shaped) is the 1-GPU
-        # config, configs[4] (ogbn-products-shaped) the row-partitioned multi-GPU one.  The same
-        # workload on one GPU is recorded in profiles/ (bench.py --workload E) for the scaling ratio.
-        args.workload = "B" if max(world, args.gpus) == 1 else "E"
+        # ONE workload for every N, so that the per-N lines are one strong-scaling experiment: config E
+        # (configs[4], ogbn-products-shaped), the shape BASELINE.json's target is quoted on; it fits one GPU
+        # (~6 GB resident).  `--workload B` is configs[1] (ogbn-arxiv-shaped), the shape of most parity tests.
+        args.workload = "E"
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
