@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace gdr {
 
@@ -75,6 +76,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// polling with back-off: the spinning warps otherwise issue a shared-memory barrier probe every few cycles and
+// compete with the tensor core's operand reads for the same shared-memory pipeline
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t addr = smem_u32(bar), ok;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(ns);
+  }
+}
+// one lane of the (converged) warp; the same lane every time, so its tcgen05.commit covers the MMAs it issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
                                             uint64_t* bar) {
   asm volatile(
@@ -94,6 +121,16 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// experiment only (tc_ablate 7): the same bytes issued as kind::f16 / BF16 operands — is the TF32 kind itself the slow part?
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -252,6 +289,9 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
 //           SUB = 1), and SUB = 2 halves it — each centre K-block feeds the MMAs of both sub-tiles.
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
+__device__ long long g_tc_probe[4];
+__device__ unsigned g_poll_ns_dev = 0;   // experiment: epilogue polling back-off in ns (0 = spin)   // ablation runs: MMA-thread cycles / nanoseconds / MMAs issued of CTA 0
+
 template <int NPASS, int BN, int SUB>
 struct TcCfg {
   static constexpr int kXCopies = NPASS == 3 ? 2 : 1;                        // hi (+ lo) copy of the row tile
@@ -325,83 +365,147 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
+  // Producer and MMA warps keep WARP-UNIFORM control flow and let one elected lane issue the asynchronous
+  // instructions.  (Running the loops inside `if (lane == 0)` makes every descriptor a per-thread value: the
+  // compiler then wraps each UTCHMMA in an ELECT / R2UR.BROADCAST waterfall and the issue path — ~350 cycles per
+  // MMA, measured with clock64 inside the kernel — becomes the bottleneck instead of the tensor pipe, which runs a
+  // 128 x 256 x 8 TF32 MMA in 171 cycles: tools/mma_issue_probe.py.)
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t cit = 0, tile_it = 0;
-      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+    uint32_t tile_it = 0;
+    int s = 0;
+    uint32_t ph = 0;   // ring position and its phase, advanced incrementally (no division on the issue path)
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&x_full[kb], SUB * Cfg::kXCopies * TC_KBLK_BYTES);
 #pragma unroll
           for (int sub = 0; sub < SUB; ++sub)
             tma_load_2d(smem + Cfg::x_hi(nkb, sub, kb), &map_xhi, kb * TC_BK, rt * ROWS + sub * TC_BM, &x_full[kb]);
           if (NPASS == 3) tma_load_2d(smem + Cfg::x_lo(nkb, kb), &map_xlo, kb * TC_BK, rt * ROWS, &x_full[kb]);
         }
-        for (int ct = 0; ct < n_col_tiles; ++ct) {
-          for (int kb = 0; kb < nkb; ++kb, ++cit) {
-            const int s = cit % S;
-            const uint32_t ph = (cit / S) & 1;
-            mbar_wait(&c_empty[s], ph ^ 1);
+        __syncwarp();
+      }
+      for (int ct = 0; ct < n_col_tiles; ++ct) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (ablate >= 6) continue;   // experiment: raw MMA issue rate, no stage barriers at all
+          mbar_wait(&c_empty[s], ph ^ 1);
+          if (elect_one()) {
             if (ablate == 5) {   // experiment: MMAs on stale shared memory, no centre stream
               mbar_arrive(&c_full[s]);
-              continue;
+            } else {
+              mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
+              uint8_t* dst = smem + Cfg::c_stage(nkb, s);
+              tma_load_2d(dst, &map_chi, kb * TC_BK, ct * BN, &c_full[s]);
+              if (NPASS == 3) tma_load_2d(dst + BN * TC_BK * 4, &map_clo, kb * TC_BK, ct * BN, &c_full[s]);
             }
-            mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
-            uint8_t* dst = smem + Cfg::c_stage(nkb, s);
-            tma_load_2d(dst, &map_chi, kb * TC_BK, ct * BN, &c_full[s]);
-            if (NPASS == 3) tma_load_2d(dst + BN * TC_BK * 4, &map_clo, kb * TC_BK, ct * BN, &c_full[s]);
+          }
+          __syncwarp();
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
-      uint32_t cit = 0, tile_it = 0, g = 0;
-      for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
-        for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
-          const uint32_t a = g & 1, aph = (g >> 1) & 1;
-          mbar_wait(&t_empty[a], aph ^ 1);
+    // The per-K-block issue path is kept to a handful of uniform instructions (descriptor = base + offset, ring
+    // position advanced incrementally, K steps unrolled): at ~128 cycles per 128 x 256 x 8 MMA the tensor pipe
+    // drains a K-block in ~500 cycles, and a path with integer divisions and descriptor rebuilds took longer
+    // than that (measured: 250 cycles per MMA with every wait removed, 128 in tools/mma_issue_probe.py).
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+    uint32_t tile_it = 0, g = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const uint64_t dx0 = umma_desc_sw128(smem_u32(smem));                                  // row tile, K-block 0
+    const uint64_t dc0 = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, 0)));             // centre stage 0
+    constexpr uint64_t kKb = TC_KBLK_BYTES >> 4, kStage = Cfg::kStageBytes >> 4, kLo = (uint64_t)(BN * TC_BK * 4) >> 4;
+    long long pc0 = 0, pn0 = 0, n_mma = 0;
+    if (ablate && blockIdx.x == 0) {
+      pc0 = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pn0));
+    }
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+      for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+        const uint32_t a = g & 1, aph = (g >> 1) & 1;
+        if (ablate != 8) mbar_wait(&t_empty[a], aph ^ 1);   // 8: no accumulator hand-shake with the epilogue either
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + a * (SUB * BN);
+        const bool last_ct = ct == n_col_tiles - 1;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
+          if (ablate < 6) mbar_wait(&c_full[s], ph);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + a * (SUB * BN);
-          for (int kb = 0; kb < nkb; ++kb, ++cit) {
-            if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
-            const int s = cit % S;
-            const uint32_t ph = (cit / S) & 1;
-            mbar_wait(&c_full[s], ph);
-            tc_fence_after();
-            const uint64_t d_chi = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s)));
-            // K = 8 steps that still hold real columns (the rest of the 32-float block is zero padding)
-            const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
+          const uint64_t d_chi = dc0 + (uint64_t)s * kStage;
+          // K = 8 steps that still hold real columns (the rest of the 32-float block is zero padding)
+          const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
+          if (ablate) n_mma += ksteps;
+          if (elect_one()) {
             if (NPASS == 3) {
-              const uint64_t d_xhi = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(nkb, 0, kb)));
-              const uint64_t d_xlo = umma_desc_sw128(smem_u32(smem + Cfg::x_lo(nkb, kb)));
-              const uint64_t d_clo = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s) + BN * TC_BK * 4));
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step
-                // small terms first, the dominant hi*hi product last
-                tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
-                tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
-                tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+              const uint64_t d_xhi = dx0 + (uint64_t)kb * kKb;
+              const uint64_t d_xlo = dx0 + (uint64_t)(nkb + kb) * kKb;
+              const uint64_t d_clo = d_chi + kLo;
+              if (ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K = 8 step
+                  // small terms first, the dominant hi*hi product last
+                  tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
+                  tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
+                  tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+                }
+              } else {
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                  tc_mma_tf32(tmem_d, d_xlo + adv, d_chi + adv, idesc, (kb | k) != 0);
+                  tc_mma_tf32(tmem_d, d_xhi + adv, d_clo + adv, idesc, 1);
+                  tc_mma_tf32(tmem_d, d_xhi + adv, d_chi + adv, idesc, 1);
+                }
               }
             } else {
 #pragma unroll
               for (int sub = 0; sub < SUB; ++sub) {
-                const uint64_t d_x = umma_desc_sw128(smem_u32(smem + Cfg::x_hi(nkb, sub, kb)));
-                for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
-                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-                  tc_mma_tf32(tmem_d + sub * BN, d_x + adv, d_chi + adv, idesc, (kb | k) != 0);
+                const uint64_t d_x = dx0 + (uint64_t)(sub * nkb + kb) * kKb;
+                const uint32_t td = tmem_d + sub * BN;
+                if (ablate == 0 && ksteps == 4) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                    tc_mma_tf32(td, d_x + adv, d_chi + adv, idesc, (kb | k) != 0);
+                  }
+                } else {
+                  for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                    if (ablate == 7) {   // D = F32, A = B = BF16 (format code 1), same N / M fields
+                      constexpr uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                      tc_mma_bf16(td, d_x + adv, d_chi + adv, idesc_bf16, (kb | k) != 0);
+                    } else {
+                      tc_mma_tf32(td, d_x + adv, d_chi + adv, idesc, (kb | k) != 0);
+                    }
+                  }
                 }
               }
             }
-            tc_commit(&c_empty[s]);                                  // frees the centre stage
-            if (ct == n_col_tiles - 1) tc_commit(&x_empty[kb]);      // X K-block no longer needed
+            if (ablate < 6) tc_commit(&c_empty[s]);                  // frees the centre stage
+            if (last_ct) tc_commit(&x_empty[kb]);                    // X K-block no longer needed
+            if (kb == nkb - 1 && ablate != 8) tc_commit(&t_full[a]); // accumulators ready
           }
-          tc_commit(&t_full[a]);                                     // accumulators ready
+          __syncwarp();
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
+    }
+    if (ablate && blockIdx.x == 0 && lane == 0) {
+      long long pn1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pn1));
+      g_tc_probe[0] = clock64() - pc0;
+      g_tc_probe[1] = pn1 - pn0;
+      g_tc_probe[2] = n_mma * (NPASS == 3 ? 3 : SUB);
     }
   } else {
     // ================= epilogue: 8 warps; warp w reads TMEM lanes [32*(w%4), +32).  SUB = 1: the two
@@ -414,7 +518,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);   // [3][128] exchange buffer after the barriers
     const int rl = quarter * 32 + lane;
     uint32_t g = 0;
-    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+    for (int rt = blockIdx.x; rt < (ablate == 8 ? 0 : n_row_tiles); rt += gridDim.x) {
       const int64_t row = (int64_t)rt * ROWS + (SUB == 2 ? half * TC_BM : 0) + rl;
       // NPASS 3: (best, second) = two smallest distances; NPASS 1: two largest scores, stored negated so that
       // both variants share the min-tracking code and the merge below
@@ -422,7 +526,8 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
       int bidx = 0;
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
         const uint32_t a = g & 1, aph = (g >> 1) & 1;
-        mbar_wait(&t_full[a], aph);
+        if (g_poll_ns_dev) mbar_wait_sleep(&t_full[a], aph, g_poll_ns_dev);
+        else mbar_wait(&t_full[a], aph);
         tc_fence_after();
 #pragma unroll 1
         for (int h2 = 0; h2 < COLS / 64; ++h2) {
@@ -627,60 +732,88 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp == 0) {
-    // ================= TMA producer (both CTAs) =================
-    if (lane == 0) {
-      uint32_t cit = 0, tile_it = 0;
-      for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
-        const int rt = 2 * un + (int)crank;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+    // ================= TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =================
+    uint32_t tile_it = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t x_full0 = mapa_u32(smem_u32(&x_full[0]), 0), c_full0 = mapa_u32(smem_u32(&c_full[0]), 0);   // leader's barriers
+    for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
+      const int rt = 2 * un + (int)crank;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
-          tma_load_2d_2sm(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, mapa_u32(smem_u32(&x_full[kb]), 0));
+          tma_load_2d_2sm(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, x_full0 + 8u * (uint32_t)kb);
         }
-        for (int ct = 0; ct < n_col_tiles; ++ct) {
-          for (int kb = 0; kb < nkb; ++kb, ++cit) {
-            const int s = cit % S;
-            const uint32_t ph = (cit / S) & 1;
-            mbar_wait(&c_empty[s], ph ^ 1);
+        __syncwarp();
+      }
+      for (int ct = 0; ct < n_col_tiles; ++ct) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&c_empty[s], ph ^ 1);
+          if (elect_one()) {
             if (ablate == 5) {
               if (leader) mbar_arrive(&c_full[s]);
-              continue;
+            } else {
+              if (leader) mbar_expect_tx(&c_full[s], 2 * Cfg::kStageBytes);
+              tma_load_2d_2sm(smem + Cfg::c_stage(nkb, s), &map_c, kb * TC_BK, ct * BN + (int)crank * (BN / 2),
+                              c_full0 + 8u * (uint32_t)s);
             }
-            if (leader) mbar_expect_tx(&c_full[s], 2 * Cfg::kStageBytes);
-            tma_load_2d_2sm(smem + Cfg::c_stage(nkb, s), &map_c, kb * TC_BK, ct * BN + (int)crank * (BN / 2),
-                            mapa_u32(smem_u32(&c_full[s]), 0));
+          }
+          __syncwarp();
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    // ================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) =================
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_BM, BN);
-      uint32_t cit = 0, tile_it = 0, g = 0;
+      uint32_t tile_it = 0, g = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t dx0 = umma_desc_sw128(smem_u32(smem));
+      const uint64_t dc0 = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, 0)));
+      constexpr uint64_t kKb = TC_KBLK_BYTES >> 4, kStage = Cfg::kStageBytes >> 4;
       for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
         for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
           const uint32_t a = g & 1, aph = (g >> 1) & 1;
           mbar_wait(&t_empty[a], aph ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + a * BN;
-          for (int kb = 0; kb < nkb; ++kb, ++cit) {
+          const bool last_ct = ct == n_col_tiles - 1;
+          for (int kb = 0; kb < nkb; ++kb) {
             if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
-            const int s = cit % S;
-            const uint32_t ph = (cit / S) & 1;
             mbar_wait(&c_full[s], ph);
             tc_fence_after();
-            const uint64_t d_x = umma_desc_sw128(smem_u32(smem + Cfg::x_blk(kb)));
-            const uint64_t d_c = umma_desc_sw128(smem_u32(smem + Cfg::c_stage(nkb, s)));
+            const uint64_t d_x = dx0 + (uint64_t)kb * kKb;
+            const uint64_t d_c = dc0 + (uint64_t)s * kStage;
             const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
-            for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
-              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-              tc_mma_tf32_2sm(tmem_d, d_x + adv, d_c + adv, idesc, (kb | k) != 0);
+            if (elect_one()) {
+              if (ablate == 0 && ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                  tc_mma_tf32_2sm(tmem_d, d_x + adv, d_c + adv, idesc, (kb | k) != 0);
+                }
+              } else {
+                for (int k = 0; k < ((ablate == 3 || (ablate == 4 && kb > 0)) ? 0 : ksteps); ++k) {
+                  const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                  tc_mma_tf32_2sm(tmem_d, d_x + adv, d_c + adv, idesc, (kb | k) != 0);
+                }
+              }
+              tc_commit_2sm(&c_empty[s], 3);                              // frees the stage in both CTAs
+              if (last_ct) tc_commit_2sm(&x_empty[kb], 3);                // row-tile K-block free in both CTAs
+              if (kb == nkb - 1) tc_commit_2sm(&t_full[a], 3);            // accumulator ready in both CTAs
             }
-            tc_commit_2sm(&c_empty[s], 3);                              // frees the stage in both CTAs
-            if (ct == n_col_tiles - 1) tc_commit_2sm(&x_empty[kb], 3);  // row-tile K-block free in both CTAs
+            __syncwarp();
+            if (++s == S) {
+              s = 0;
+              ph ^= 1;
+            }
           }
-          tc_commit_2sm(&t_full[a], 3);                                 // accumulator ready in both CTAs
         }
       }
     }
@@ -886,6 +1019,94 @@ __global__ void __launch_bounds__(256) k_tc_select(int64_t N, const float* __res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
     if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// tensor-pipe micro-probe (tools/mma_rate_probe.py): one CTA issues `iters` back-to-back tcgen05.mma of shape
+// 128 x N x (32 bytes of K) on zero-filled, 128B-swizzled operand tiles and reports the cycles until the
+// last one has completed.  variant bit 0: kind::f16 (BF16) instead of kind::tf32; bit 1: alternate between
+// two accumulators; bit 2: same K offset every time (no advance inside the swizzle atom).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_mma_probe(int N, int iters, int variant, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  // variant bit 3: non-zero operands (a hash of the index, |v| < 1)
+  for (int i = threadIdx.x; i < 4 * (128 + 256) * 128 / 4; i += blockDim.x)
+    reinterpret_cast<float*>(smem)[i] = (variant & 8) ? (float)((i * 2654435761u) >> 8) * 5.9604645e-8f - 0.5f : 0.f;
+  __shared__ uint64_t bar2;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar2, 1);
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill -> async-proxy MMA reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x < 32) {   // warp-uniform loop, one elected lane issues (as the production kernels do)
+    const uint32_t fmt = (variant & 1) ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const long long t0 = clock64();
+    if (variant & 256) {
+      // bit 8: the production pattern — per "tile" four elect blocks of 4, 4, 4 and 1 MMAs on four different A / B
+      // tiles, accumulator overwritten by the first, accumulators alternating per tile (+ bit 4: commits as there)
+      int issued = 0;
+      for (int t = 0; issued < iters; ++t) {
+        const uint32_t d = tmem_base + (uint32_t)(t & 1) * 256u;
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t da = umma_desc_sw128(smem_u32(smem + kb * 16384));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem + 65536 + ((t * 4 + kb) & 3) * 32768));
+          const int ks = kb < 3 ? 4 : ((variant & 512) ? 4 : 1);     // bit 9: no K tail (4, 4, 4, 4)
+          tc_fence_after();
+          if (elect_one()) {
+            for (int k = 0; k < ks; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              tc_mma_tf32(d, da + adv, db + adv, idesc, (kb | k) != 0);
+            }
+            if (variant & 16) tc_commit(&bar2);
+          }
+          __syncwarp();
+          issued += ks;
+        }
+      }
+    } else
+    for (int i = 0; i < iters; i += 4) {
+      // bit 7: a different A tile and B tile for every group of 4 MMAs (4 of each in shared memory), as a real
+      // K loop has; otherwise the same two tiles are re-used by every MMA
+      const int tsel = (variant & 128) ? ((i >> 2) & 3) : 0;
+      const uint64_t da = umma_desc_sw128(smem_u32(smem + tsel * 16384));
+      const uint64_t db = umma_desc_sw128(smem_u32(smem + 65536 + tsel * 32768));
+      if (variant & 64) tc_fence_after();                      // bit 6: tcgen05.fence::after_thread_sync every 4 MMAs
+      const uint32_t d = tmem_base + ((variant & 2) ? (uint32_t)((i >> 2) & 1) * 256u : 0u);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adv = (variant & 4) ? 0 : (uint64_t)((k * 32) >> 4);
+          const uint32_t acc = (variant & 32) ? (uint32_t)(((i + k) % 16) != 0) : (uint32_t)(i + k > 1);
+          if (variant & 1) tc_mma_bf16(d, da + adv, db + adv, idesc, acc);
+          else tc_mma_tf32(d, da + adv, db + adv, idesc, acc);
+        }
+        if (variant & 16) tc_commit(&bar2);                    // bit 4: a commit every 4 MMAs
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1177,6 +1398,18 @@ extern "C" {
 // debug read-back (synchronises the device): "tc_level2_rows" = rows the last two-level screen sent to level 2
 int gdr_debug_get(const char* key, int64_t* value_host) {
   GDR_CHECK_ARG(key && value_host, "debug_get: bad arguments");
+  if (!strcmp(key, "tc_probe_cycles") || !strcmp(key, "tc_probe_ns") || !strcmp(key, "tc_probe_mmas")) {
+    long long h[4] = {0, 0, 0, 0};
+    GDR_CUDA(cudaMemcpyFromSymbol(h, gdr::g_tc_probe, sizeof(h)));
+    *value_host = !strcmp(key, "tc_probe_cycles") ? h[0] : (!strcmp(key, "tc_probe_ns") ? h[1] : h[2]);
+    return GDR_OK;
+  }
+  if (!strncmp(key, "tc_poll_ns=", 11)) {   // setter smuggled through the getter: "tc_poll_ns=<ns>"
+    unsigned v = (unsigned)atoi(key + 11);
+    GDR_CUDA(cudaMemcpyToSymbol(gdr::g_poll_ns_dev, &v, sizeof(v)));
+    *value_host = v;
+    return GDR_OK;
+  }
   if (!strcmp(key, "tc_level2_rows")) {
     int32_t v = -1;
     if (gdr::g_last_count1) GDR_CUDA(cudaMemcpy(&v, gdr::g_last_count1, 4, cudaMemcpyDeviceToHost));
@@ -1185,6 +1418,22 @@ int gdr_debug_get(const char* key, int64_t* value_host) {
   }
   gdr::set_error("debug_get: unknown key %s", key);
   return GDR_EINVAL;
+}
+
+// cycles for `iters` back-to-back MMAs of shape 128 x N x 32 B on one SM (see k_mma_probe); synchronises
+int gdr_debug_mma_probe(int N, int iters, int variant, int64_t* cycles_host) {
+  GDR_CHECK_ARG((N == 64 || N == 128 || N == 256) && iters > 0 && cycles_host, "mma_probe: bad arguments");
+  long long* d = nullptr;
+  GDR_CUDA(cudaMalloc(&d, 8));
+  const int smem = 4 * (128 + 256) * 128 + 1024;
+  GDR_CUDA(cudaFuncSetAttribute(gdr::k_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  gdr::k_mma_probe<<<1, 128, smem>>>(N, iters, variant, d);
+  GDR_CUDA(cudaDeviceSynchronize());
+  long long h = 0;
+  GDR_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *cycles_host = h;
+  return GDR_OK;
 }
 
 int64_t gdr_kmeans_tc_xsplit_bytes(int64_t N, int64_t D) { return gdr::kmeans_tc_xsplit_bytes(N, D); }

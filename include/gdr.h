@@ -72,6 +72,9 @@ int gdr_debug_set(const char* key, int value);
 /* Debug read-back (synchronises the device).  keys: "tc_level2_rows" = rows the last two-level
  * tensor-core screen (gdr_kmeans_assign_tc) handed to its 3xTF32 second level; -1 if none ran. */
 int gdr_debug_get(const char* key, int64_t* value_host);
+/* Tensor-pipe micro-probe: SM cycles for `iters` back-to-back tcgen05.mma of shape 128 x N x (32 bytes of K)
+ * issued by one CTA (variant bit 0: kind::f16 instead of kind::tf32, bit 1: two accumulators, bit 2: no K advance). */
+int gdr_debug_mma_probe(int N, int iters, int variant, int64_t* cycles_host);
 
 /* ---- generic device primitives (used by stages 1, 3, 4) -------------- */
 /* Stable LSD radix sort of (uint64 key, uint32 payload) pairs on the low

@@ -54,7 +54,7 @@ if os.environ.get("PROBE_ABLATE"):
     # which role bounds the first-level kernel?  (results are garbage in these runs)
     for mode in MODES:
         _lib.call("gdr_debug_set", b"tc_screen", mode)
-        for ab in (0, 2, 3, 4, 5):
+        for ab in (0, 2, 3, 5, 8):
             _lib.call("gdr_debug_set", b"tc_ablate", ab)
             lab = torch.empty(n, dtype=torch.int32, device=dev)
             ts = []
