@@ -469,7 +469,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
               for (int sub = 0; sub < SUB; ++sub) {
                 const uint64_t d_x = dx0 + (uint64_t)(sub * nkb + kb) * kKb;
                 const uint32_t td = tmem_d + sub * BN;
-                if (ablate == 0 && ksteps == 4) {
+                if (ablate != 3 && ablate != 4 && ablate != 7 && ksteps == 4) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
