@@ -33,6 +33,10 @@ from .sparsify import (  # noqa: E402
 from .recsys import (  # noqa: E402
     BipartiteGraph, lightgcn_propagate, BipartitePropagate, RankformerGCNGraph, rankformer_gcn_forward,
 )
+from .io import (  # noqa: E402
+    induced_subgraph, load_graphsaint, load_rankformer_dataset, read_ui_txt, save_condensed, load_condensed,
+    RecDataset, GraphSaintData,
+)
 from . import parallel  # noqa: E402
 
 __all__ = [
@@ -43,5 +47,6 @@ __all__ = [
     "build_condensed_bipartite", "condensed_csr_to_edge_index", "coarsen_edges", "label_counts",
     "ER_estimator", "attaw_ER_estimator", "graph_sparse", "er_lower", "cosine_reweight", "softmax_rows",
     "class_edge_weight", "topk_filter", "row_degree", "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate", "RankformerGCNGraph",
-    "rankformer_gcn_forward", "parallel",
+    "rankformer_gcn_forward", "induced_subgraph", "load_graphsaint", "load_rankformer_dataset", "read_ui_txt",
+    "save_condensed", "load_condensed", "RecDataset", "GraphSaintData", "parallel",
 ]

@@ -679,7 +679,8 @@ struct Tc2Cfg {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                  int64_t N_host, const int32_t* __restrict__ n_rows_dev, int D, int n_col_tiles, int nkb,
-                 float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate) {
+                 float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate,
+                 int fwd /*1: ordinary 1-SM TMA on each CTA's own barriers, the peer forwards "stage landed" to the leader*/) {
   using Cfg = Tc2Cfg;
   constexpr int S = Cfg::kStages;
   constexpr int BN = Cfg::BN;
@@ -693,7 +694,9 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* c_empty = c_full + S;                       // [S]          each CTA its own
   uint64_t* t_full = c_empty + S;                       // [2]          each CTA its own
   uint64_t* t_empty = t_full + 2;                       // [2]          used in the leader
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* c_peer = t_empty + 2;                       // [S]          leader: "the peer's half of stage s has landed" (fwd)
+  uint64_t* x_peer = c_peer + S;                        // [TC_BAR_KB]  leader: same for the peer's row-tile K-blocks (fwd)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(x_peer + TC_BAR_KB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -717,6 +720,8 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_init(&t_full[i], 1);
       mbar_init(&t_empty[i], 16);       // one lane of each of the 8 epilogue warps of both CTAs
     }
+    for (int i = 0; i < S; ++i) mbar_init(&c_peer[i], 1);
+    for (int i = 0; i < TC_BAR_KB; ++i) mbar_init(&x_peer[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -742,8 +747,13 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&x_empty[kb], (tile_it & 1) ^ 1);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
-          tma_load_2d_2sm(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, x_full0 + 8u * (uint32_t)kb);
+          if (fwd) {
+            mbar_expect_tx(&x_full[kb], TC_KBLK_BYTES);
+            tma_load_2d(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, &x_full[kb]);
+          } else {
+            if (leader) mbar_expect_tx(&x_full[kb], 2 * TC_KBLK_BYTES);
+            tma_load_2d_2sm(smem + Cfg::x_blk(kb), &map_x, kb * TC_BK, rt * TC_BM, x_full0 + 8u * (uint32_t)kb);
+          }
         }
         __syncwarp();
       }
@@ -752,7 +762,10 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_wait(&c_empty[s], ph ^ 1);
           if (elect_one()) {
             if (ablate == 5) {
-              if (leader) mbar_arrive(&c_full[s]);
+              if (leader || fwd) mbar_arrive(&c_full[s]);
+            } else if (fwd) {
+              mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
+              tma_load_2d(smem + Cfg::c_stage(nkb, s), &map_c, kb * TC_BK, ct * BN + (int)crank * (BN / 2), &c_full[s]);
             } else {
               if (leader) mbar_expect_tx(&c_full[s], 2 * Cfg::kStageBytes);
               tma_load_2d_2sm(smem + Cfg::c_stage(nkb, s), &map_c, kb * TC_BK, ct * BN + (int)crank * (BN / 2),
@@ -785,8 +798,12 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           const uint32_t tmem_d = tmem_base + a * BN;
           const bool last_ct = ct == n_col_tiles - 1;
           for (int kb = 0; kb < nkb; ++kb) {
-            if (ct == 0) mbar_wait(&x_full[kb], tile_it & 1);
+            if (ct == 0) {
+              mbar_wait(&x_full[kb], tile_it & 1);
+              if (fwd) mbar_wait(&x_peer[kb], tile_it & 1);
+            }
             mbar_wait(&c_full[s], ph);
+            if (fwd) mbar_wait(&c_peer[s], ph);
             tc_fence_after();
             const uint64_t d_x = dx0 + (uint64_t)kb * kKb;
             const uint64_t d_c = dc0 + (uint64_t)s * kStage;
@@ -808,6 +825,30 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               if (last_ct) tc_commit_2sm(&x_empty[kb], 3);                // row-tile K-block free in both CTAs
               if (kb == nkb - 1) tc_commit_2sm(&t_full[a], 3);            // accumulator ready in both CTAs
             }
+            __syncwarp();
+            if (++s == S) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    } else if (fwd) {
+      // peer CTA: forward "my half of the stage / my row-tile K-block has landed" to the leader's barriers
+      uint32_t tile_it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t c_peer0 = mapa_u32(smem_u32(&c_peer[0]), 0), x_peer0 = mapa_u32(smem_u32(&x_peer[0]), 0);
+      for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
+        for (int ct = 0; ct < n_col_tiles; ++ct) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (ct == 0) {
+              mbar_wait(&x_full[kb], tile_it & 1);
+              if (elect_one()) mbar_arrive_cluster(x_peer0 + 8u * (uint32_t)kb);
+              __syncwarp();
+            }
+            mbar_wait(&c_full[s], ph);
+            if (elect_one()) mbar_arrive_cluster(c_peer0 + 8u * (uint32_t)s);
             __syncwarp();
             if (++s == S) {
               s = 0;
@@ -1229,7 +1270,7 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
 }
 
 static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c, int64_t N_max, const int32_t* n_rows_dev,
-                                 int D_eff, int64_t Kp, int nkb, float* best, float* second, int32_t* idx,
+                                 int D_eff, int64_t Kp, int nkb, float* best, float* second, int32_t* idx, int fwd,
                                  cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1257,7 +1298,7 @@ static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GDR_CUDA(cudaLaunchKernelEx(&cfg, k_assign_tc_pair, m_x, m_c, N_max, n_rows_dev, D_eff, (int)(Kp / Tc2Cfg::BN), nkb, best,
-                              second, idx, g_tc_ablate));
+                              second, idx, g_tc_ablate, fwd));
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -1340,9 +1381,11 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
       if ((rc = launch_assign_tc<1, 128, 2>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
                                          idx, s)))
         return rc;
-    } else if (g_tc_screen == 4) {
+    } else if (g_tc_screen == 4 || g_tc_screen == 5) {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 128))) return rc;   // each CTA of a pair loads 128 of the 256 centres
-      if ((rc = launch_assign_tc_pair(m_x1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, best, second, idx, s))) return rc;
+      if ((rc = launch_assign_tc_pair(m_x1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, best, second, idx,
+                                      g_tc_screen == 5 ? 1 : 0, s)))
+        return rc;
     } else {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
       if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,

@@ -201,6 +201,42 @@ __global__ void k_sel_compact(int64_t n_rows, int64_t nnz, const int32_t* __rest
   if (t0 == 0) *nnz_out = pos[nnz];
 }
 
+__global__ void k_copy_i32_to_i64(const int32_t* src, int64_t* dst) { dst[0] = src[0]; }
+
+// ---------------------------------------------------------------------------------
+// induced subgraph  adj[np.ix_(idx, idx)]  (utils_graphsaint.py:34-36, utils.py:127-129)
+// ---------------------------------------------------------------------------------
+__global__ void k_sub_map(int64_t m, const int64_t* __restrict__ idx, int32_t* __restrict__ map) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    map[idx[i]] = (int32_t)i;   // position of node idx[i] in the selection (a repeated node keeps one of its positions)
+}
+
+// one warp per selected row: how many of its entries stay (pass 0) / write them as relabelled COO (pass 1)
+__global__ void __launch_bounds__(256) k_sub_rows(int64_t m, const int64_t* __restrict__ idx,
+                                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                  const float* __restrict__ vals, const int32_t* __restrict__ map,
+                                                  int32_t* __restrict__ cnt_or_pos, int fill, int64_t* __restrict__ out_row,
+                                                  int64_t* __restrict__ out_col, float* __restrict__ out_val) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= m) return;
+  const int64_t r = idx[i];
+  const int b = rowptr[r], e = rowptr[r + 1];
+  int base = fill ? cnt_or_pos[i] : 0, total = 0;
+  for (int j0 = b; j0 < e; j0 += 32) {
+    const int j = j0 + lane_id();
+    const int c = j < e ? map[colidx[j]] : -1;
+    const unsigned keep = __ballot_sync(0xffffffffu, c >= 0);
+    if (fill && c >= 0) {
+      const int o = base + total + __popc(keep & ((1u << lane_id()) - 1u));
+      out_row[o] = i;
+      out_col[o] = c;
+      out_val[o] = vals[j];
+    }
+    total += __popc(keep);
+  }
+  if (!fill && lane_id() == 0) cnt_or_pos[i] = total;
+}
+
 }  // namespace gdr
 
 using namespace gdr;
@@ -310,6 +346,47 @@ int gdr_topk_filter_csr(int64_t n, int64_t nnz, const int32_t* rowptr, const int
   if ((rc = exclusive_scan_i32(b, b, nnz, sws, sws_b, s))) return rc;
   k_sel_compact<<<grid_for(std::max(nnz, n + 1)), 256, 0, s>>>(n, nnz, rowptr, colidx, vals, b, rowptr_out, colidx_out,
                                                               vals_out, nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+/* adj[np.ix_(idx, idx)] as relabelled COO triplets (row i of the result = node idx[i]); the caller sorts them
+ * into a CSR with gdr_coo_to_csr.  map_scratch: n int32, pos_scratch: m + 1 int32.  *nnz_out_dev = entries kept;
+ * capacity of the outputs: nnz of the source matrix. */
+int64_t gdr_induced_subgraph_ws_bytes(int64_t n, int64_t m) {
+  return ws_need(n, 4) + ws_need(m + 1, 4) + scan_ws_bytes(m) + 256;
+}
+
+int gdr_induced_subgraph_coo(int64_t n, const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t m,
+                             const int64_t* idx, int64_t* out_row, int64_t* out_col, float* out_val,
+                             int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n > 0 && m >= 0 && rowptr && nnz_out_dev && ws, "induced_subgraph: bad arguments");
+  if (ws_bytes < gdr_induced_subgraph_ws_bytes(n, m)) {
+    set_error("induced_subgraph: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0) {
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(idx && colidx && vals && out_row && out_col && out_val, "induced_subgraph: null pointer");
+  Workspace W(ws, ws_bytes);
+  int32_t* map = W.take<int32_t>(n);
+  int32_t* pos = W.take<int32_t>(m + 1);
+  const int64_t sws_b = scan_ws_bytes(m);
+  void* sws = W.take<char>(sws_b);
+  GDR_CUDA(cudaMemsetAsync(map, 0xff, n * 4, s));   // -1
+  k_sub_map<<<grid_for(m), 256, 0, s>>>(m, idx, map);
+  GDR_LAUNCHED();
+  const unsigned grid = (unsigned)cdiv(m * 32, 256);
+  k_sub_rows<<<grid, 256, 0, s>>>(m, idx, rowptr, colidx, vals, map, pos, 0, nullptr, nullptr, nullptr);
+  GDR_LAUNCHED();
+  int rc = exclusive_scan_i32(pos, pos, m, sws, sws_b, s);
+  if (rc) return rc;
+  k_sub_rows<<<grid, 256, 0, s>>>(m, idx, rowptr, colidx, vals, map, pos, 1, out_row, out_col, out_val);
+  GDR_LAUNCHED();
+  k_copy_i32_to_i64<<<1, 1, 0, s>>>(pos + m, nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -415,6 +415,14 @@ int gdr_softmax_rows(int64_t n, int64_t C, const float* X, int64_t ld, float* ou
 int gdr_class_edge_weight(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                           const float* er, const float* prob, int64_t ldp, int64_t cls, float* w_out,
                           gdr_stream_t stream);
+/* Induced subgraph  adj[np.ix_(idx, idx)]  (utils_graphsaint.py:34-36, utils.py:127-129) as relabelled COO
+ * triplets: row i of the result is node idx[i].  Outputs have the capacity of the source nnz; the caller turns
+ * them into a CSR with gdr_coo_to_csr.  idx entries must lie in [0, n). */
+int64_t gdr_induced_subgraph_ws_bytes(int64_t n, int64_t m);
+int     gdr_induced_subgraph_coo(int64_t n, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                                 int64_t m, const int64_t* idx, int64_t* out_row, int64_t* out_col,
+                                 float* out_val, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes,
+                                 gdr_stream_t stream);
 /* every class of the 'attaw' sparsifier in one call: slice c of rowptr_out [C][n+1], colidx_out / vals_out [C][k],
  * nnz_out_dev [C] receives the graph of class c (weights = (prob[src,c] * prob[dst,c]) * er, top-k, rebuild). */
 int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz);

@@ -26,7 +26,7 @@ C = padded_rows(Xc[perm].clone())
 op = TcOperand(Xc)
 ws = torch.empty(_lib.query("gdr_kmeans_assign_tc_ws_bytes", n, K, f), dtype=torch.uint8, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-MODES = tuple(int(m) for m in os.environ.get("PROBE_MODES", "1,2,3,4").split(","))
+MODES = tuple(int(m) for m in os.environ.get("PROBE_MODES", "1,2,3,4,5").split(","))
 for it in range(int(os.environ.get("PROBE_ITERS", "4"))):
     res = {}
     for mode in MODES:
