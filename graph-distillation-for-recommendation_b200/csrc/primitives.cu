@@ -179,8 +179,10 @@ constexpr int RS_MAX_BINS = 1 << RS_MAX_BITS;
 // keys per thread: 16 (4096-key tiles) for large inputs, 4 (1024-key tiles) below 2M keys so
 // that mid-size sorts (k-means membership lists, arxiv-sized graphs) still fill the 148 SMs
 static inline int rs_rounds(int64_t n) { return n >= (1ll << 21) ? 16 : 4; }
-static inline int rs_passes(int key_bits) { return (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS; }
-static inline int rs_digit_bits(int key_bits) { return (key_bits + rs_passes(key_bits) - 1) / rs_passes(key_bits); }
+static inline int rs_passes(int key_bits, int max_bits) { return (key_bits + max_bits - 1) / max_bits; }
+static inline int rs_digit_bits(int key_bits, int max_bits) {
+  return (key_bits + rs_passes(key_bits, max_bits) - 1) / rs_passes(key_bits, max_bits);
+}
 
 template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n,
@@ -205,6 +207,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
   for (int d = threadIdx.x; d < bins; d += RS_THREADS) table[(int64_t)d * nblocks + blockIdx.x] = hist[d];
 }
 
+// Scatter pass.  Every key gets its rank inside the tile (warp match + warp-private counters: no atomics, so the
+// sort is stable); the tile is then REORDERED IN SHARED MEMORY into digit order and written out with consecutive
+// threads on consecutive addresses of each digit's run.  Writing straight from registers sends every 8-byte key
+// to its own 32-byte sector (the runs of one tile in one bin are short), which cost 4.5 ms per pass at 124 M
+// keys = 0.66 TB/s; staged, a run of r keys is r * 8 contiguous bytes.
 template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in,
                                                            const uint32_t* __restrict__ vals_in,
@@ -213,16 +220,24 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
                                                            int shift, int bits,
                                                            const int32_t* __restrict__ table_scanned,
                                                            int nblocks) {
-  extern __shared__ int rs_smem[];
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  constexpr int TILE = RS_THREADS * RS_ROUNDS;
   const int bins = 1 << bits;
   const uint32_t dmask = (uint32_t)bins - 1u;
-  int* cnt = rs_smem;   // [RS_WARPS][bins]
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_raw);                 // [TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);          // [TILE]
+  int* cnt = reinterpret_cast<int*>(s_vals + TILE);                       // [RS_WARPS][bins] -> offsets inside the tile
+  int* tile_off = cnt + RS_WARPS * bins;                                  // [bins] first tile position of digit d
+  int* gbase = tile_off + bins;                                           // [bins] global position of that first key
+  __shared__ int s_wsum[RS_WARPS];
   for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   int* mycnt = cnt + w * bins;
-  int64_t base = (int64_t)blockIdx.x * (RS_THREADS * RS_ROUNDS) + (int64_t)w * (RS_ROUNDS * 32);
+  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+  const int tile_n = (int)min((int64_t)TILE, n - tile0);
+  const int64_t base = tile0 + (int64_t)w * (RS_ROUNDS * 32);
   uint64_t k[RS_ROUNDS];
   uint32_t v[RS_ROUNDS];
   int rank[RS_ROUNDS];
@@ -251,27 +266,69 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
     __syncwarp();
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < bins; d += RS_THREADS) {
-    int run = table_scanned[(int64_t)d * nblocks + blockIdx.x];
+  // per digit: counts of the warps -> exclusive offsets; tile-wide exclusive scan of the digit totals
+  const int per = (bins + RS_THREADS - 1) / RS_THREADS;      // digits owned by this thread (contiguous)
+  const int d0 = threadIdx.x * per, d1 = min(bins, d0 + per);
+  int mine = 0;
+  for (int d = d0; d < d1; ++d) {
+    int run = 0;
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) {
       int t = cnt[ww * bins + d];
       cnt[ww * bins + d] = run;
       run += t;
     }
+    tile_off[d] = run;          // digit total for now
+    mine += run;
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[w] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int ww = 0; ww < RS_WARPS; ++ww) woff += ww < w ? s_wsum[ww] : 0;
+  int run = woff + incl - mine;
+  for (int d = d0; d < d1; ++d) {
+    const int t = tile_off[d];
+    tile_off[d] = run;
+    gbase[d] = table_scanned[(int64_t)d * nblocks + blockIdx.x];
+    run += t;
   }
   __syncthreads();
+  // stage the tile in digit order
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
     int64_t idx = base + r * 32 + lane;
     if (idx < n) {
       int d = (int)((uint32_t)(k[r] >> shift) & dmask);
-      int64_t pos = (int64_t)mycnt[d] + rank[r];
-      keys_out[pos] = k[r];
-      if (vals_out) vals_out[pos] = v[r];
+      int p = tile_off[d] + mycnt[d] + rank[r];
+      s_keys[p] = k[r];
+      s_vals[p] = v[r];
     }
   }
+  __syncthreads();
+  // consecutive threads -> consecutive positions of a digit's run
+  for (int t = threadIdx.x; t < tile_n; t += RS_THREADS) {
+    const uint64_t kk = s_keys[t];
+    const int d = (int)((uint32_t)(kk >> shift) & dmask);
+    const int64_t pos = (int64_t)gbase[d] + (t - tile_off[d]);
+    keys_out[pos] = kk;
+    if (vals_out) vals_out[pos] = s_vals[t];
+  }
 }
+
+static inline size_t rs_scatter_smem(int rounds, int bits) {
+  return (size_t)RS_THREADS * rounds * 12 + (size_t)(RS_WARPS + 2) * (1 << bits) * 4;
+}
+// digit width: wide digits save passes, but a tile of T keys leaves runs of T / 2^bits keys per digit, and a run
+// is what one coalesced write covers: at most 9 bits for the 4096-key tiles of large sorts (runs of >= 8 keys =
+// two full 32-byte sectors), up to 11 for small ones (the whole output stays in L2)
+static inline int rs_max_bits(int64_t n) { return n >= (1ll << 21) ? 9 : RS_MAX_BITS; }
 
 int64_t sort_pairs_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
@@ -294,15 +351,16 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const int max_smem = RS_WARPS * RS_MAX_BINS * 4;
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rs_scatter_smem(4, RS_MAX_BITS)));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)rs_scatter_smem(16, RS_MAX_BITS)));
     attr_set = true;
   }
   const int rounds = rs_rounds(n);
   int64_t nb = cdiv(n, RS_THREADS * rounds);
-  const int passes = rs_passes(key_bits);
-  const int bits = rs_digit_bits(key_bits);
+  const int passes = rs_passes(key_bits, rs_max_bits(n));
+  const int bits = rs_digit_bits(key_bits, rs_max_bits(n));
   const int bins = 1 << bits;
   int64_t tbl = (int64_t)bins * nb;
   Workspace W(ws, ws_bytes);
@@ -314,7 +372,7 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
   uint32_t* vin = vals;
   uint64_t* kout = kalt;
   uint32_t* vout = vals ? valt : nullptr;
-  const size_t hist_smem = (size_t)bins * 4, scat_smem = (size_t)RS_WARPS * bins * 4;
+  const size_t hist_smem = (size_t)bins * 4, scat_smem = rs_scatter_smem(rounds, bits);
   for (int p = 0; p < passes; ++p) {
     int shift = bits * p;
     if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
