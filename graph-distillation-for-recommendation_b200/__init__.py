@@ -37,6 +37,7 @@ from .io import (  # noqa: E402
     induced_subgraph, load_graphsaint, load_rankformer_dataset, read_ui_txt, save_condensed, load_condensed,
     RecDataset, GraphSaintData,
 )
+from .svd import compute_svd_embeddings, truncated_svd  # noqa: E402
 from . import parallel  # noqa: E402
 
 __all__ = [
@@ -48,5 +49,6 @@ __all__ = [
     "ER_estimator", "attaw_ER_estimator", "graph_sparse", "er_lower", "cosine_reweight", "softmax_rows",
     "class_edge_weight", "topk_filter", "row_degree", "BipartiteGraph", "lightgcn_propagate", "BipartitePropagate", "RankformerGCNGraph",
     "rankformer_gcn_forward", "induced_subgraph", "load_graphsaint", "load_rankformer_dataset", "read_ui_txt",
-    "save_condensed", "load_condensed", "RecDataset", "GraphSaintData", "parallel",
+    "save_condensed", "load_condensed", "RecDataset", "GraphSaintData", "compute_svd_embeddings", "truncated_svd",
+    "parallel",
 ]
