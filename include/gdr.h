@@ -67,7 +67,10 @@ int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
 
 /* Experiment knobs for kernel tuning sweeps (tools/spmm_sweep.py); not a stable surface.
  * keys: "spmm_unroll" (4|8), "spmm_hints" (0|1), "spmm_split" (1|2|4), "lloyd_graph" (0|1),
- * "tc_screen" (1 direct 3xTF32, 2 / 3 two-level screen with 128- / 256-centre tiles); value 0 / -1 = automatic. */
+ * "tc_screen" (1 direct 3xTF32; two-level screen with 2: 256x128 CTA tiles, 3: 128x256 CTA tiles [default for large
+ * inputs], 4: CTA pairs with 2-SM TMA, 5: CTA pairs with forwarded 1-SM TMA), "tc_ablate" (role ablations of the
+ * first-level kernel for tools/estep_probe.py / tools/mma_rate_probe.py; results are garbage while it is set);
+ * value 0 / -1 = automatic. */
 int gdr_debug_set(const char* key, int value);
 /* Debug read-back (synchronises the device).  keys: "tc_level2_rows" = rows the last two-level
  * tensor-core screen (gdr_kmeans_assign_tc) handed to its 3xTF32 second level; -1 if none ran. */
