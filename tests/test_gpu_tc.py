@@ -121,3 +121,35 @@ def test_tc_unsupported_width_fails_loudly(gdr):
     x = torch.randn(1000, 200, device=DEV)
     with pytest.raises(gdr.GdrError):
         gdr.KMeans(n_clusters=10, init="random", random_state=0, precision="tc", max_iter=2).fit(x)
+
+
+@pytest.mark.parametrize("cfg_name", ["B", "E"])
+def test_tc_full_size_labels_equal_exact_kernel(gdr, cfg_name):
+    """BASELINE full sizes (config B: 169 343 x 128, K = 1 000; config E: 2 449 029 x 100, K = 10 000): one E-step of
+    the production path (automatic two-level tensor-core screen) gives exactly the labels of the exact fp32 SIMT
+    kernel, on unclustered z-scored data where thousands of rows reach the exact re-score."""
+    from gdr import synth, _lib
+    from gdr._dev import padded_rows
+    from gdr.kmeans import TcOperand
+    import ctypes
+    cfg = synth.CONFIGS[cfg_name]
+    n, d, k = cfg["n"], cfg["f"], cfg["k"]
+    X = torch.from_numpy(synth.features(n, d, seed=17)).to(DEV)
+    X = padded_rows((X - X.mean(0)).contiguous())
+    C = padded_rows(X[torch.from_numpy(np.random.RandomState(3).permutation(n)[:k].astype(np.int64)).to(DEV)].clone())
+    # one Lloyd update so that the centres are means (small norms, tight margins), not data points
+    lab0 = torch.empty(n, dtype=torch.int32, device=DEV)
+    op = TcOperand(X)
+    gdr.assign_labels(X, C, lab0, tc_operand=op)
+    sums, counts = gdr.segment_sum(X, lab0, k)
+    C = padded_rows((sums / counts.clamp_min(1).unsqueeze(1)).contiguous())
+    lab_tc = torch.empty(n, dtype=torch.int32, device=DEV)
+    n_ref = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(X, C, lab_tc, tc_operand=op, n_refined=n_ref)
+    lvl2 = ctypes.c_int64(-1)
+    _lib.call("gdr_debug_get", b"tc_level2_rows", ctypes.addressof(lvl2))
+    lab_32 = torch.empty(n, dtype=torch.int32, device=DEV)
+    gdr.assign_labels(X, C, lab_32)
+    torch.cuda.synchronize()
+    assert torch.equal(lab_tc, lab_32)
+    assert 0 < int(n_ref.item()) < n // 100 and 0 < lvl2.value < n // 5     # both refinement levels were exercised
