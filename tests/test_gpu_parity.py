@@ -348,3 +348,35 @@ def test_block_build_world1_equals_global_build(gdr, dev):
         A = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
         B = par.dist_build_adjacency(par.Comm(), par.RowPartition(n, 1, 0), u_d, v_d, n)
         assert torch.equal(A.rowptr, B.rowptr) and torch.equal(A.colidx, B.colidx) and torch.equal(A.vals, B.vals)
+
+
+def test_config_e_properties(gdr, dev):
+    """BASELINE full size (config E, ogbn-products-shaped: 2.45 M nodes, 61.9 M pairs): size-independent properties
+    of stages 1, 2 and 4 — sorted duplicate-free CSR, nnz(A_hat) = nnz(A) + N, symmetric pattern, the normalisation
+    identity sum_j A_hat_ij sqrt(d_j) = sqrt(d_i) through the SpMM kernel, and the coarsening checksum."""
+    from gdr import synth
+    cfg = synth.CONFIGS["E"]
+    n = cfg["n"]
+    u, v = synth.uniform_graph(n, cfg["pairs"], seed=1238)
+    A = gdr.coo_to_csr(torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev), None, (n, n), symmetrize=True, binarize=True)
+    rp = A.rowptr.long()
+    assert int(rp[0]) == 0 and int(rp[-1]) == A.nnz and bool((rp[1:] >= rp[:-1]).all())
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), rp[1:] - rp[:-1])
+    key = rows * n + A.colidx.long()
+    assert bool((key[1:] > key[:-1]).all())                                   # sorted, no duplicates
+    tkey = A.colidx.long() * n + rows                                         # pattern of the transpose
+    assert torch.equal(torch.sort(tkey).values, key)                          # symmetric
+    assert bool((A.vals == 1).all())
+    del key, tkey
+    An = gdr.sym_normalize(A, 2)
+    assert An.nnz == A.nnz + n
+    sq = An.deg.sqrt().to(torch.float32).unsqueeze(1)
+    lhs = gdr.spmm(An, sq.expand(n, 4).contiguous())[:, 0]
+    torch.testing.assert_close(lhs, sq[:, 0], rtol=2e-5, atol=2e-5)
+    labels = torch.from_numpy(np.random.RandomState(5).randint(0, cfg["k"], n).astype(np.int32)).to(dev)
+    k = cfg["k"]
+    rpc, cic, cnt, _ = gdr.coarsen_edges(labels, labels, k, k, csr=An)
+    assert int(cnt.long().sum()) == An.nnz                                     # every edge lands in exactly one cell
+    crow = torch.repeat_interleave(torch.arange(k, device=dev), (rpc[1:] - rpc[:-1]).long())
+    ckey = crow * k + cic.long()
+    assert bool((ckey[1:] > ckey[:-1]).all())
