@@ -426,7 +426,7 @@ def run_ours(args, rank, world):
 
 def one_gpu_reference(workload):
     """The committed single-GPU measurement of the same workload (for the strong-scaling ratio)."""
-    name = {"E": "r1_bench_default_configE_1gpu.json", "B": "r1_bench_configB_v17.json"}.get(workload)
+    name = {"E": "r1_bench_default_configE_1gpu.json", "B": "r1_bench_configB_v19.json"}.get(workload)
     try:
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "source": "profiles/" + name}

@@ -517,6 +517,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
     constexpr int COLS = SUB == 1 ? BN / 2 : BN;                       // columns per warp and accumulator
     float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);   // [3][128] exchange buffer after the barriers
     const int rl = quarter * 32 + lane;
+    const bool chunk_skip = n_col_tiles * BN >= 4096;   // the vote only pays once most chunks can be skipped
     uint32_t g = 0;
     for (int rt = blockIdx.x; rt < (ablate == 8 ? 0 : n_row_tiles); rt += gridDim.x) {
       const int64_t row = (int64_t)rt * ROWS + (SUB == 2 ? half * TC_BM : 0) + rl;
@@ -547,12 +548,23 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
           for (int c = 0; c < 2; ++c) {
             const int jbase = ct * BN + col0 + c * 32;
             if (NPASS == 1) {
+              // chunks of 8 columns: a row's running top-2 changes only ~2 ln(K) times, so most chunks hold nothing
+              // below any lane's `second` — one max-tree + one warp vote skips them (K = 10^4: ~80 % of the chunks)
 #pragma unroll
-              for (int u = 0; u < 32; ++u) {
-                const float d = -__uint_as_float(v[c][u]);     // folded into the min / max operands by the compiler
-                second = fminf(second, fmaxf(d, best));
-                bidx = d < best ? jbase + u : bidx;
-                best = fminf(best, d);
+              for (int u0 = 0; u0 < 32; u0 += 8) {
+                float m = fmaxf(fmaxf(__uint_as_float(v[c][u0]), __uint_as_float(v[c][u0 + 1])),
+                                fmaxf(__uint_as_float(v[c][u0 + 2]), __uint_as_float(v[c][u0 + 3])));
+                m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[c][u0 + 4]), __uint_as_float(v[c][u0 + 5])),
+                                   fmaxf(__uint_as_float(v[c][u0 + 6]), __uint_as_float(v[c][u0 + 7]))));
+                if (!chunk_skip || __any_sync(0xffffffffu, -m < second)) {     // scores are stored negated: d = -score
+#pragma unroll
+                  for (int u = u0; u < u0 + 8; ++u) {
+                    const float d = -__uint_as_float(v[c][u]);
+                    second = fminf(second, fmaxf(d, best));
+                    bidx = d < best ? jbase + u : bidx;
+                    best = fminf(best, d);
+                  }
+                }
               }
             } else {
               const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
@@ -887,11 +899,20 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int c = 0; c < 2; ++c) {
             const int jbase = ct * BN + col0 + c * 32;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              const float d = -__uint_as_float(v[c][u]);
-              second = fminf(second, fmaxf(d, best));
-              bidx = d < best ? jbase + u : bidx;
-              best = fminf(best, d);
+            for (int u0 = 0; u0 < 32; u0 += 8) {               // chunk skip as in k_assign_tc<1, *, *>
+              float m = fmaxf(fmaxf(__uint_as_float(v[c][u0]), __uint_as_float(v[c][u0 + 1])),
+                              fmaxf(__uint_as_float(v[c][u0 + 2]), __uint_as_float(v[c][u0 + 3])));
+              m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[c][u0 + 4]), __uint_as_float(v[c][u0 + 5])),
+                                 fmaxf(__uint_as_float(v[c][u0 + 6]), __uint_as_float(v[c][u0 + 7]))));
+              if (__any_sync(0xffffffffu, -m < second)) {
+#pragma unroll
+                for (int u = u0; u < u0 + 8; ++u) {
+                  const float d = -__uint_as_float(v[c][u]);
+                  second = fminf(second, fmaxf(d, best));
+                  bidx = d < best ? jbase + u : bidx;
+                  best = fminf(best, d);
+                }
+              }
             }
           }
         }
@@ -926,6 +947,64 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   cluster_sync_all();   // neither CTA frees TMEM / leaves while the pair's MMAs, multicasts or remote arrives can still land
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// micro-probe of the pair MMA (tools/mma_issue_probe.py): a 2-CTA cluster, the leader issues `iters`
+// tcgen05.mma.cta_group::2 of shape 256 x 256 x (32 bytes of K) in the production pattern (4-4-4-1 per tile, four
+// A / B tiles, alternating accumulators) on zero-filled operands; cycles until the last one has completed.
+__global__ void __launch_bounds__(128, 1) k_mma_probe_pair(int iters, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 8 * 128 * 128 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
+  const bool leader = cluster_ctarank() == 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (leader && threadIdx.x < 32) {
+    constexpr uint32_t idesc = umma_idesc_tf32(256, 256);
+    const long long t0 = clock64();
+    int issued = 0;
+    for (int t = 0; issued < iters; ++t) {
+      const uint32_t d = tmem_base + (uint32_t)(t & 1) * 256u;
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t da = umma_desc_sw128(smem_u32(smem + kb * 16384));
+        const uint64_t db = umma_desc_sw128(smem_u32(smem + 65536 + ((t * 4 + kb) & 3) * 16384));
+        const int ks = kb < 3 ? 4 : 1;
+        tc_fence_after();
+        if (elect_one()) {
+          for (int k = 0; k < ks; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            tc_mma_tf32_2sm(d, da + adv, db + adv, idesc, (kb | k) != 0);
+          }
+        }
+        __syncwarp();
+        issued += ks;
+      }
+    }
+    if (elect_one()) tc_commit_2sm(&bar, 1);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1468,6 +1547,28 @@ int gdr_debug_mma_probe(int N, int iters, int variant, int64_t* cycles_host) {
   GDR_CHECK_ARG((N == 64 || N == 128 || N == 256) && iters > 0 && cycles_host, "mma_probe: bad arguments");
   long long* d = nullptr;
   GDR_CUDA(cudaMalloc(&d, 8));
+  if (variant == 1024) {   // the CTA-pair probe (N is ignored: 256 x 256 x 8)
+    const int smem2 = 8 * 128 * 128 + 1024;
+    GDR_CUDA(cudaFuncSetAttribute(gdr::k_mma_probe_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem2;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GDR_CUDA(cudaLaunchKernelEx(&cfg, gdr::k_mma_probe_pair, iters, d));
+    GDR_CUDA(cudaDeviceSynchronize());
+    long long h2 = 0;
+    GDR_CUDA(cudaMemcpy(&h2, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *cycles_host = h2;
+    return GDR_OK;
+  }
   const int smem = 4 * (128 + 256) * 128 + 1024;
   GDR_CUDA(cudaFuncSetAttribute(gdr::k_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   gdr::k_mma_probe<<<1, 128, smem>>>(N, iters, variant, d);

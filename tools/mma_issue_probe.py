@@ -15,3 +15,8 @@ for variant, what in ((8, "tf32, same two operand tiles"), (8 + 256, "tf32, prod
         _lib.call("gdr_debug_mma_probe", N, iters, variant, ctypes.addressof(c))
         out.append(f"N={N}: {c.value / iters:.1f} clk/MMA")
     print(f"{what:40s}" + "   ".join(out), flush=True)
+
+c = ctypes.c_int64(0)
+_lib.call("gdr_debug_mma_probe", 256, iters, 1024, ctypes.addressof(c))
+_lib.call("gdr_debug_mma_probe", 256, iters, 1024, ctypes.addressof(c))
+print(f"CTA pair, cta_group::2, 256 x 256 x 8 tf32, production pattern: {c.value / iters:.1f} clk/MMA (two SMs)")
