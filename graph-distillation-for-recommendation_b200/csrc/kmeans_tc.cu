@@ -771,6 +771,7 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
       for (int ct = 0; ct < n_col_tiles; ++ct) {
         for (int kb = 0; kb < nkb; ++kb) {
+          if (ablate >= 6) continue;
           mbar_wait(&c_empty[s], ph ^ 1);
           if (elect_one()) {
             if (ablate == 5) {
@@ -805,7 +806,7 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int un = unit0; un < n_units; un += unit_stride, ++tile_it) {
         for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
           const uint32_t a = g & 1, aph = (g >> 1) & 1;
-          mbar_wait(&t_empty[a], aph ^ 1);
+          if (ablate != 8) mbar_wait(&t_empty[a], aph ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + a * BN;
           const bool last_ct = ct == n_col_tiles - 1;
@@ -814,14 +815,16 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               mbar_wait(&x_full[kb], tile_it & 1);
               if (fwd) mbar_wait(&x_peer[kb], tile_it & 1);
             }
-            mbar_wait(&c_full[s], ph);
-            if (fwd) mbar_wait(&c_peer[s], ph);
+            if (ablate < 6) {
+              mbar_wait(&c_full[s], ph);
+              if (fwd) mbar_wait(&c_peer[s], ph);
+            }
             tc_fence_after();
             const uint64_t d_x = dx0 + (uint64_t)kb * kKb;
             const uint64_t d_c = dc0 + (uint64_t)s * kStage;
             const int ksteps = min(TC_BK / 8, (D - kb * TC_BK + 7) >> 3);
             if (elect_one()) {
-              if (ablate == 0 && ksteps == 4) {
+              if (ablate != 3 && ablate != 4 && ksteps == 4) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
@@ -833,9 +836,9 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                   tc_mma_tf32_2sm(tmem_d, d_x + adv, d_c + adv, idesc, (kb | k) != 0);
                 }
               }
-              tc_commit_2sm(&c_empty[s], 3);                              // frees the stage in both CTAs
+              if (ablate < 6) tc_commit_2sm(&c_empty[s], 3);              // frees the stage in both CTAs
               if (last_ct) tc_commit_2sm(&x_empty[kb], 3);                // row-tile K-block free in both CTAs
-              if (kb == nkb - 1) tc_commit_2sm(&t_full[a], 3);            // accumulator ready in both CTAs
+              if (kb == nkb - 1 && ablate != 8) tc_commit_2sm(&t_full[a], 3);   // accumulator ready in both CTAs
             }
             __syncwarp();
             if (++s == S) {
@@ -878,7 +881,7 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t t_empty_leader[2] = {mapa_u32(smem_u32(&t_empty[0]), 0), mapa_u32(smem_u32(&t_empty[1]), 0)};
     __shared__ float s_mb[3][TC_BM];
     uint32_t g = 0;
-    for (int un = unit0; un < n_units; un += unit_stride) {
+    for (int un = unit0; un < (ablate == 8 ? 0 : n_units); un += unit_stride) {
       const int rt = 2 * un + (int)crank;
       const int64_t row = (int64_t)rt * TC_BM + rl;
       float best = INFINITY, second = INFINITY;   // negated scores
@@ -888,7 +891,7 @@ k_assign_tc_pair(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         mbar_wait(&t_full[a], aph);
         tc_fence_after();
 #pragma unroll 1
-        for (int h2 = 0; h2 < BN / 128; ++h2) {
+        for (int h2 = 0; h2 < (ablate == 2 ? 0 : BN / 128); ++h2) {
           const int col0 = half * (BN / 2) + h2 * 64;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + col0;
           uint32_t v[2][32];
