@@ -63,7 +63,7 @@ _SIGNATURES = {
     "gdr_class_edge_weight": (i32, [i64, i64, vp, vp, vp, vp, i64, i64, vp, vp]),
     "gdr_induced_subgraph_ws_bytes": (i64, [i64, i64]),
     "gdr_induced_subgraph_coo": (i32, [i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
-    "gdr_sparsify_classes_ws_bytes": (i64, [i64, i64]),
+    "gdr_sparsify_classes_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_sparsify_classes": (i32, [i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_topk_filter_ws_bytes": (i64, [i64, i64]),
     "gdr_topk_filter_csr": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),

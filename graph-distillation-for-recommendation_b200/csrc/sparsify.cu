@@ -201,6 +201,118 @@ __global__ void k_sel_compact(int64_t n_rows, int64_t nnz, const int32_t* __rest
   if (t0 == 0) *nnz_out = pos[nnz];
 }
 
+// ---------------------------------------------------------------------------------
+// class-batched variants (blockIdx.y = class inside the batch): at arxiv size one class is ~10 MB of
+// traffic per pass — a launch, not a bandwidth problem — so the per-class loop of ~20 short launches
+// is replaced by ~20 launches per BATCH of classes.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_class_weight_b(int64_t n, int64_t nnz, const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ colidx, const float* __restrict__ er,
+                                                        const float* __restrict__ P, int64_t ldp, int cls0,
+                                                        float* __restrict__ w /*[classes][nnz]*/) {
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int cls = cls0 + blockIdx.y;
+  float* wc = w + (int64_t)blockIdx.y * nnz;
+  const float pr = P[r * ldp + cls];
+  for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32)
+    wc[j] = __fmul_rn(__fmul_rn(pr, P[(int64_t)colidx[j] * ldp + cls]), er[j]);
+}
+
+__global__ void k_sel_init_b(SelState* st, int32_t* hist, int32_t k) {
+  if (threadIdx.x == 0) {
+    st[blockIdx.x].prefix = 0;
+    st[blockIdx.x].mask = 0;
+    st[blockIdx.x].k_rem = k;
+  }
+  hist[blockIdx.x * 256 + threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_sel_hist_b(int64_t n, const float* __restrict__ w, const SelState* __restrict__ st,
+                                                    int shift, int32_t* __restrict__ hist) {
+  __shared__ int sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const float* wc = w + (int64_t)blockIdx.y * n;
+  const uint32_t prefix = st[blockIdx.y].prefix, mask = st[blockIdx.y].mask;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = f32_key(wc[i]);
+    if ((u & mask) == prefix) atomicAdd(&sh[(u >> shift) & 0xff], 1);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[blockIdx.y * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void k_sel_pick_b(SelState* st, int32_t* hist, int shift) {
+  __shared__ int sh[256];
+  sh[threadIdx.x] = hist[blockIdx.x * 256 + threadIdx.x];
+  hist[blockIdx.x * 256 + threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SelState* s = st + blockIdx.x;
+    int k = s->k_rem, d = 255;
+    for (; d > 0; --d) {
+      if (sh[d] >= k) break;
+      k -= sh[d];
+    }
+    s->prefix |= (uint32_t)d << shift;
+    s->mask |= 0xffu << shift;
+    s->k_rem = k;
+  }
+}
+
+// flags of all classes into ONE array of classes * (n + 1) ints (the slot n of every class stays 0), so that a single
+// exclusive scan serves every class: position inside class c = scan[c (n+1) + i] - scan[c (n+1)]
+__global__ void k_sel_eqflag_b(int64_t n, const float* __restrict__ w, const SelState* __restrict__ st,
+                               int32_t* __restrict__ eq) {
+  const float* wc = w + (int64_t)blockIdx.y * n;
+  int32_t* e = eq + (int64_t)blockIdx.y * (n + 1);
+  const uint32_t T = st[blockIdx.y].prefix;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x)
+    e[i] = i < n ? (int32_t)(f32_key(wc[i]) == T) : 0;
+}
+
+__global__ void k_sel_flag_b(int64_t n, const float* __restrict__ w, const SelState* __restrict__ st,
+                             const int32_t* __restrict__ eqrank, int32_t* __restrict__ sel) {
+  const float* wc = w + (int64_t)blockIdx.y * n;
+  const int32_t* er = eqrank + (int64_t)blockIdx.y * (n + 1);
+  int32_t* sl = sel + (int64_t)blockIdx.y * (n + 1);
+  const uint32_t T = st[blockIdx.y].prefix;
+  const int k_rem = st[blockIdx.y].k_rem;
+  const int base = er[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+    int v = 0;
+    if (i < n) {
+      const uint32_t u = f32_key(wc[i]);
+      v = (u > T) || (u == T && er[i] - base < k_rem);
+    }
+    sl[i] = v;
+  }
+}
+
+__global__ void k_sel_compact_b(int64_t n_rows, int64_t nnz, int64_t k, const int32_t* __restrict__ rowptr,
+                                const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                const int32_t* __restrict__ pos /*[classes][nnz + 1]*/, int32_t* __restrict__ rowptr_out,
+                                int32_t* __restrict__ colidx_out, float* __restrict__ vals_out,
+                                int64_t* __restrict__ nnz_out) {
+  const int32_t* pc = pos + (int64_t)blockIdx.y * (nnz + 1);
+  const int base = pc[0];
+  int32_t* rp = rowptr_out + (int64_t)blockIdx.y * (n_rows + 1);
+  int32_t* co = colidx_out + (int64_t)blockIdx.y * k;
+  float* vo = vals_out + (int64_t)blockIdx.y * k;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < nnz; i += stride) {
+    const int p = pc[i];
+    if (pc[i + 1] != p) {
+      co[p - base] = colidx[i];
+      vo[p - base] = vals[i];
+    }
+  }
+  for (int64_t r = t0; r <= n_rows; r += stride) rp[r] = pc[rowptr[r]] - base;
+  if (t0 == 0) nnz_out[blockIdx.y] = pc[nnz] - base;
+}
+
 __global__ void k_copy_i32_to_i64(const int32_t* src, int64_t* dst) { dst[0] = src[0]; }
 
 // ---------------------------------------------------------------------------------
@@ -394,8 +506,18 @@ int gdr_induced_subgraph_coo(int64_t n, const int32_t* rowptr, const int32_t* co
 /* All classes of the 'attaw' sparsifier in ONE call (clustgdd_agent_transduct.py:160-181): for class c the edge
  * weights (prob[src,c] * prob[dst,c]) * er, their top-k and the rebuilt CSR, written to slice c of the outputs
  * (rowptr_out [C][n+1], colidx_out / vals_out [C][k]).  ~20 launches per class issued back to back from here. */
-int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz) {
-  return ws_need(nnz, 4) + gdr_topk_filter_ws_bytes(n, nnz) + 256;
+// classes per batch: bounded by ~1.5 GB of scratch (3 arrays of nnz + 1 words per class) and by int32 scan totals
+static int64_t sparsify_batch(int64_t nnz, int64_t C) {
+  int64_t by_mem = std::max<int64_t>(1, (int64_t)(1500ll << 20) / (12 * (nnz + 1)));
+  int64_t by_int = std::max<int64_t>(1, ((1ll << 31) - 1) / (nnz + 1));
+  return std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(by_mem, by_int), std::min<int64_t>(C, 65535)));
+}
+
+int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz, int64_t C) {
+  (void)n;
+  const int64_t b = sparsify_batch(nnz, C);
+  return ws_need(b * nnz, 4) + 2 * ws_need(b * (nnz + 1) + 1, 4) + ws_need(b * 256, 4) + ws_need(b * 16, 1) +
+         scan_ws_bytes(b * (nnz + 1)) + 256;
 }
 
 int gdr_sparsify_classes(int64_t n, int64_t nnz, int64_t C, const int32_t* rowptr, const int32_t* colidx,
@@ -405,20 +527,51 @@ int gdr_sparsify_classes(int64_t n, int64_t nnz, int64_t C, const int32_t* rowpt
   GDR_CHECK_ARG(n > 0 && nnz >= 0 && C > 0 && C <= ldp && k >= 0 && k <= nnz && rowptr && prob && rowptr_out &&
                     nnz_out_dev && ws,
                 "sparsify_classes: bad arguments");
-  if (ws_bytes < gdr_sparsify_classes_ws_bytes(n, nnz)) {
+  if (ws_bytes < gdr_sparsify_classes_ws_bytes(n, nnz, C)) {
     set_error("sparsify_classes: workspace too small");
     return GDR_EWORKSPACE;
   }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (k == 0 || nnz == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr_out, 0, C * (n + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, C * 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(colidx && vals && er && colidx_out && vals_out, "sparsify_classes: null pointer");
+  const int64_t bmax = sparsify_batch(nnz, C);
   Workspace W(ws, ws_bytes);
-  float* w = W.take<float>(nnz);
-  const int64_t fws_b = gdr_topk_filter_ws_bytes(n, nnz);
-  void* fws = W.take<char>(fws_b);
-  for (int64_t c = 0; c < C; ++c) {
-    int rc = gdr_class_edge_weight(n, nnz, rowptr, colidx, er, prob, ldp, c, w, stream);
+  float* w = W.take<float>(bmax * nnz);
+  int32_t* a = W.take<int32_t>(bmax * (nnz + 1) + 1);
+  int32_t* b = W.take<int32_t>(bmax * (nnz + 1) + 1);
+  int32_t* hist = W.take<int32_t>(bmax * 256);
+  SelState* st = (SelState*)W.take<char>(bmax * 16);
+  const int64_t sws_b = scan_ws_bytes(bmax * (nnz + 1));
+  void* sws = W.take<char>(sws_b);
+  const unsigned gx = grid_for(nnz);
+  for (int64_t c0 = 0; c0 < C; c0 += bmax) {
+    const unsigned nb = (unsigned)std::min<int64_t>(bmax, C - c0);
+    const int64_t tot = (int64_t)nb * (nnz + 1);
+    k_class_weight_b<<<dim3((unsigned)cdiv(n * 32, 256), nb), 256, 0, s>>>(n, nnz, rowptr, colidx, er, prob, ldp, (int)c0, w);
+    GDR_LAUNCHED();
+    k_sel_init_b<<<nb, 256, 0, s>>>(st, hist, (int32_t)k);
+    GDR_LAUNCHED();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      k_sel_hist_b<<<dim3(gx, nb), 256, 0, s>>>(nnz, w, st, shift, hist);
+      GDR_LAUNCHED();
+      k_sel_pick_b<<<nb, 256, 0, s>>>(st, hist, shift);
+      GDR_LAUNCHED();
+    }
+    k_sel_eqflag_b<<<dim3(gx, nb), 256, 0, s>>>(nnz, w, st, a);
+    GDR_LAUNCHED();
+    int rc = exclusive_scan_i32(a, a, tot, sws, sws_b, s);
     if (rc) return rc;
-    rc = gdr_topk_filter_csr(n, nnz, rowptr, colidx, vals, w, k, rowptr_out + c * (n + 1), colidx_out + c * k,
-                             vals_out + c * k, nnz_out_dev + c, fws, fws_b, stream);
-    if (rc) return rc;
+    k_sel_flag_b<<<dim3(gx, nb), 256, 0, s>>>(nnz, w, st, a, b);
+    GDR_LAUNCHED();
+    if ((rc = exclusive_scan_i32(b, b, tot, sws, sws_b, s))) return rc;
+    k_sel_compact_b<<<dim3(grid_for(std::max(nnz, n + 1)), nb), 256, 0, s>>>(
+        n, nnz, k, rowptr, colidx, vals, b, rowptr_out + c0 * (n + 1), colidx_out + c0 * k, vals_out + c0 * k,
+        nnz_out_dev + c0);
+    GDR_LAUNCHED();
   }
   return GDR_OK;
 }

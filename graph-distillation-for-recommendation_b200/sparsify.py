@@ -97,7 +97,7 @@ def sparsify_classes(R: CSR, er: torch.Tensor, prob: torch.Tensor, k: int) -> Li
     colidx = torch.empty((C, max(k, 1)), dtype=torch.int32, device=dev)
     vals = torch.empty((C, max(k, 1)), dtype=torch.float32, device=dev)
     nnz_out = torch.zeros(C, dtype=torch.int64, device=dev)
-    ws = workspace(_lib.query("gdr_sparsify_classes_ws_bytes", n, R.nnz), dev)
+    ws = workspace(_lib.query("gdr_sparsify_classes_ws_bytes", n, R.nnz, C), dev)
     _lib.call("gdr_sparsify_classes", n, R.nnz, C, ptr(R.rowptr), ptr(R.colidx), ptr(R.vals), ptr(er), ptr(prob),
               prob.stride(0), k, ptr(rowptr), ptr(colidx), ptr(vals), ptr(nnz_out), ptr(ws), ws.numel(), stream())
     return [CSR(rowptr[c], colidx[c, :k], vals[c, :k], R.shape) for c in range(C)]

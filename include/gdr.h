@@ -427,8 +427,9 @@ int     gdr_induced_subgraph_coo(int64_t n, const int32_t* rowptr, const int32_t
                                  float* out_val, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes,
                                  gdr_stream_t stream);
 /* every class of the 'attaw' sparsifier in one call: slice c of rowptr_out [C][n+1], colidx_out / vals_out [C][k],
- * nnz_out_dev [C] receives the graph of class c (weights = (prob[src,c] * prob[dst,c]) * er, top-k, rebuild). */
-int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz);
+ * nnz_out_dev [C] receives the graph of class c (weights = (prob[src,c] * prob[dst,c]) * er, top-k, rebuild).
+ * Classes are processed in batches (blockIdx.y = class) sized to ~1.5 GB of scratch: ~20 launches per batch. */
+int64_t gdr_sparsify_classes_ws_bytes(int64_t n, int64_t nnz, int64_t C);
 int     gdr_sparsify_classes(int64_t n, int64_t nnz, int64_t C, const int32_t* rowptr, const int32_t* colidx,
                              const float* vals, const float* er, const float* prob, int64_t ldp, int64_t k,
                              int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, int64_t* nnz_out_dev,
