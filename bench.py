@@ -135,6 +135,27 @@ def spmm_bytes(nnz, rows, xrows, F, fused=True, model="min"):
     return b + (2 * rows * F * 4 if fused else 0)
 
 
+_THREAD_LIMIT = None
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference's CPU path has to run on ALL the host cores
+    (the other ranks of the reference arm exit at once), so the BLAS / OpenMP / torch pools are raised at run time."""
+    global _THREAD_LIMIT
+    n = len(os.sched_getaffinity(0))
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        _THREAD_LIMIT = threadpool_limits(limits=n)   # kept alive for the rest of the process
+    except Exception:
+        pass
+    return n
+
+
 # ----------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """The reference's CPU path (oracle/ref_port.py: scipy + torch CPU sparse + scikit-learn)."""
@@ -143,6 +164,7 @@ def run_reference(args, rank, world):
     import torch
     from oracle import ref_port as rp
     from gdr import synth
+    use_all_host_threads()
     w = make_workload(args.workload)
     n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
     info = rp.host_info()
