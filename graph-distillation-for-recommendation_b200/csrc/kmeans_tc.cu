@@ -76,22 +76,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-// polling with back-off: the spinning warps otherwise issue a shared-memory barrier probe every few cycles and
-// compete with the tensor core's operand reads for the same shared-memory pipeline
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-  uint32_t addr = smem_u32(bar), ok;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    __nanosleep(ns);
-  }
-}
 // one lane of the (converged) warp; the same lane every time, so its tcgen05.commit covers the MMAs it issued
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -289,8 +273,7 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
 //           SUB = 1), and SUB = 2 halves it — each centre K-block feeds the MMAs of both sub-tiles.
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-__device__ long long g_tc_probe[4];
-__device__ unsigned g_poll_ns_dev = 0;   // experiment: epilogue polling back-off in ns (0 = spin)   // ablation runs: MMA-thread cycles / nanoseconds / MMAs issued of CTA 0
+__device__ long long g_tc_probe[4];   // ablation runs: MMA-thread cycles / nanoseconds / MMAs issued of CTA 0
 
 template <int NPASS, int BN, int SUB>
 struct TcCfg {
@@ -527,8 +510,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
       int bidx = 0;
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
         const uint32_t a = g & 1, aph = (g >> 1) & 1;
-        if (g_poll_ns_dev) mbar_wait_sleep(&t_full[a], aph, g_poll_ns_dev);
-        else mbar_wait(&t_full[a], aph);
+        mbar_wait(&t_full[a], aph);
         tc_fence_after();
 #pragma unroll 1
         for (int h2 = 0; h2 < COLS / 64; ++h2) {
@@ -1527,12 +1509,6 @@ int gdr_debug_get(const char* key, int64_t* value_host) {
     long long h[4] = {0, 0, 0, 0};
     GDR_CUDA(cudaMemcpyFromSymbol(h, gdr::g_tc_probe, sizeof(h)));
     *value_host = !strcmp(key, "tc_probe_cycles") ? h[0] : (!strcmp(key, "tc_probe_ns") ? h[1] : h[2]);
-    return GDR_OK;
-  }
-  if (!strncmp(key, "tc_poll_ns=", 11)) {   // setter smuggled through the getter: "tc_poll_ns=<ns>"
-    unsigned v = (unsigned)atoi(key + 11);
-    GDR_CUDA(cudaMemcpyToSymbol(gdr::g_poll_ns_dev, &v, sizeof(v)));
-    *value_host = v;
     return GDR_OK;
   }
   if (!strcmp(key, "tc_level2_rows")) {

@@ -16,11 +16,7 @@ X = padded_rows((X - X.mean(0)).contiguous())
 C = padded_rows(X[torch.randperm(X.shape[0], device=dev)[:K] % X.shape[0]].clone()) if X.shape[0] >= K else None
 C = padded_rows(torch.randn(K, D, device=dev))
 _lib.call("gdr_debug_set", b"tc_screen", 3)
-import ctypes as _ct
-for poll in (0,):
-  _v = _ct.c_int64(0)
-  _lib.call("gdr_debug_get", f"tc_poll_ns={poll}".encode(), _ct.addressof(_v))
-  print(f"--- epilogue polling back-off {poll} ns")
+if True:
   for ab, what in ((2, "TMA + MMA, no epilogue"), (5, "MMA only (no centre stream)"), (6, "MMA only, no stage barriers / commits"), (8, "MMA only, no barriers at all, no epilogue warps"), (7, "same, issued as kind::f16 BF16 (garbage numerics)"), (3, "TMA only (no MMA)")):
       if ab in (7,): continue
       _lib.call("gdr_debug_set", b"tc_ablate", ab)
