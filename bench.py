@@ -495,7 +495,8 @@ def run_ours_multi(args, rank, world, dev):
         e[0].record()
         A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)   # exchange-based: 1/world of the pairs per rank
         e[1].record()
-        prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs)
+        prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs,
+                                          row_chunks=args.row_chunks)
         e[2].record()
         km = par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target)
         e[3].record()
@@ -606,7 +607,7 @@ def run_ours_multi(args, rank, world, dev):
             "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
                                    f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
                        "parallelism": f"row-partition x{world} (stage 1: pair slices, all-to-all by owner, all-gather of degrees; "
-                                      f"stage 2: all-gather per hop, {par.default_slabs(world, F) if args.slabs is None else args.slabs} column slab(s); "
+                                      f"stage 2: all-gather per hop pipelined over {par.default_row_chunks(world) if args.row_chunks is None else args.row_chunks} row chunks; "
                                       "stage 3: all-reduce of centroid sums/counts per Lloyd iteration; stage 4: dense n x n all-reduce)",
                        "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
             "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / (pk["hbm"] * world),
@@ -672,6 +673,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
     ap.add_argument("--slabs", type=int, default=None, help="N > 1: column slabs of the pipelined hop (default: automatic)")
+    ap.add_argument("--row-chunks", type=int, default=None, help="N > 1: row chunks of the pipelined hop (default: 4)")
     ap.add_argument("--tc-screen", type=int, default=0, help="debug: 0 auto, 1 direct 3xTF32, 2/3 two-level screen (BN 128/256)")
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

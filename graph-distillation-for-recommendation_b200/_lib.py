@@ -46,6 +46,7 @@ _SIGNATURES = {
     "gdr_spmm_plan_blocks": (i64, [i64, i64]),
     "gdr_spmm_plan": (i32, [i64, i64, vp, vp, vp]),
     "gdr_spmm_prop_planned": (i32, [i64, i64, vp, vp, vp, f32, vp, i64, vp, i64, vp, i64, f32, vp, i64, vp]),
+    "gdr_remap_chunk_major": (i32, [i64, vp, i64, i64, i64, vp, vp]),
     "gdr_scale_rows": (i32, [i64, i64, f32, vp, i64, vp, i64, vp]),
     "gdr_center_columns_ws_bytes": (i64, [i64, i64]),
     "gdr_center_columns": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp]),

@@ -354,9 +354,34 @@ __global__ void k_scale_rows(int64_t rows, int F4, float a, const float* __restr
   }
 }
 
+// column ids of a row-partitioned matrix -> rows of the chunk-major gathered operand (parallel.py, row-chunk
+// pipelined hop): node (rank r, local row i = c*cr + o)  ->  c*world*cr + r*cr + o
+__global__ void k_remap_chunk_major(int64_t nnz, const int32_t* __restrict__ in, int rows_per, int cr, int world,
+                                    int32_t* __restrict__ out) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x) {
+    const int g = in[j];
+    const int r = g / rows_per, i = g - r * rows_per;
+    const int c = i / cr, o = i - c * cr;
+    out[j] = c * (world * cr) + r * cr + o;
+  }
+}
+
 }  // namespace gdr
 
 extern "C" {
+
+int gdr_remap_chunk_major(int64_t nnz, const int32_t* colidx_in, int64_t rows_per, int64_t chunk_rows, int64_t world,
+                          int32_t* colidx_out, gdr_stream_t stream) {
+  GDR_CHECK_ARG(nnz >= 0 && rows_per > 0 && chunk_rows > 0 && world > 0, "remap_chunk_major: bad sizes");
+  if (nnz == 0) return GDR_OK;
+  GDR_CHECK_ARG(colidx_in && colidx_out, "remap_chunk_major: null pointer");
+  GDR_CHECK_ARG(((rows_per + chunk_rows - 1) / chunk_rows) * chunk_rows * world < (1ll << 31), "remap_chunk_major: range");
+  unsigned grid = (unsigned)std::min<int64_t>(gdr::cdiv(nnz, 256), gdr::kSMs * 32);
+  gdr::k_remap_chunk_major<<<grid, 256, 0, (cudaStream_t)stream>>>(nnz, colidx_in, (int)rows_per, (int)chunk_rows,
+                                                                  (int)world, colidx_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
 
 // Tuning / experiment knobs (not part of the stable surface; see tools/spmm_sweep.py).
 int gdr_debug_set(const char* key, int value) {

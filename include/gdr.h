@@ -393,6 +393,12 @@ int gdr_coarsen_scale(int64_t n_src, const int32_t* rowptr, const int32_t* colid
                       const float* wsum, const int32_t* size_src, const int32_t* size_dst,
                       float* vals_out, gdr_stream_t stream);
 
+/* Multi-GPU propagation helper: remap the (global) column ids of a row block to the rows of the chunk-major
+ * gathered operand used by the row-chunk pipelined hop: node (rank r, local row i = c*chunk_rows + o) ->
+ * c*world*chunk_rows + r*chunk_rows + o. */
+int gdr_remap_chunk_major(int64_t nnz, const int32_t* colidx_in, int64_t rows_per, int64_t chunk_rows,
+                          int64_t world, int32_t* colidx_out, gdr_stream_t stream);
+
 /* ---- edge scoring + top-k sparsification (between stages 3 and 4) ----
  * All on a device CSR whose stored order is the reference's coalesced COO order
  * (rows = src, colidx = dst).

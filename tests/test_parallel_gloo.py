@@ -97,6 +97,32 @@ class OracleOps:
                              x_full.numpy(), T=tn, beta=np.float32(beta))
         return torch.from_numpy(y)
 
+    def remap_chunk_major(self, A, rows_per, cr, world):
+        g = A.colidx.to(torch.int64)
+        r, i = g // rows_per, g % rows_per
+        c = i // cr
+        return CpuCSR(A.rowptr, (c * (world * cr) + r * cr + (i - c * cr)).to(torch.int32), A.vals, A.shape)
+
+    def slice_row_chunks(self, A, bounds):
+        rp = A.rowptr.numpy()
+        out = []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            b, e = int(rp[lo]), int(rp[hi])
+            out.append(CpuCSR(torch.from_numpy((rp[lo:hi + 1] - rp[lo]).astype(np.int32)), A.colidx[b:e].clone(),
+                              A.vals[b:e].clone(), (hi - lo, A.shape[1])))
+        return out
+
+    def spmm_rows(self, A, x_full, alpha, y, target, beta, r0):
+        rows = A.shape[0]
+        if rows == 0:
+            return
+        tn = None if target is None else np.ascontiguousarray(target[r0:r0 + rows].numpy())
+        out = self.o.spmm_prop(A.rowptr.numpy(), A.colidx.numpy(), A.vals.numpy(), np.float32(alpha),
+                               np.ascontiguousarray(x_full.numpy()), T=tn, beta=np.float32(beta))
+        y[r0:r0 + rows] = torch.from_numpy(out)
+        if target is not None:
+            target[r0:r0 + rows] = torch.from_numpy(tn)
+
     def spmm_slab(self, A, x_slab, alpha, y, target, beta, c0):
         w = x_slab.shape[1]
         tn = None if target is None else np.ascontiguousarray(target[:, c0:c0 + w].numpy())
@@ -211,10 +237,11 @@ def _worker(rank, world, port, case):
             assert np.array_equal(A_blk.rowptr.numpy(), A_local.rowptr.numpy())
             assert np.array_equal(A_blk.colidx.numpy(), A_local.colidx.numpy())
             assert np.array_equal(A_blk.vals.numpy(), A_local.vals.numpy())        # bit-identical values
-        elif case in ("propagate", "propagate_slabs"):
-            # one-pass hop / hop pipelined over 3 column slabs (async all-gathers): same bits
+        elif case in ("propagate", "propagate_slabs", "propagate_rows"):
+            # one-pass hop / hop pipelined over 3 column slabs / over 3 row chunks (async all-gathers): same bits
             prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops,
-                                              slabs=1 if case == "propagate" else 3)
+                                              slabs=3 if case == "propagate_slabs" else 1,
+                                              row_chunks=3 if case == "propagate_rows" else 1)
             p_ref, t_ref = o.propagate(rpo, cio, vo, X, 4, 0.8)
             assert np.array_equal(prop.numpy(), p_ref[lo:hi])      # row-wise independent: bit-identical
             assert np.array_equal(target.numpy(), t_ref[lo:hi])
@@ -251,7 +278,7 @@ def _worker(rank, world, port, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "kmeans", "kmeans_empty", "coarsen"])
+@pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "propagate_rows", "kmeans", "kmeans_empty", "coarsen"])
 def test_world2_gloo(case, oracle):
     mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
 
