@@ -433,7 +433,7 @@ def default_slabs(world: int, f: int) -> int:
 def default_row_chunks(world: int) -> int:
     """Row chunks of the pipelined hop: the all-gather of chunk c overlaps the SpMM of chunks c+1.. (rows are
     independent, so nothing changes numerically and the SpMM keeps its full-width gathers).  Measured at config E:
-    8 GPUs 8.49 ms (one pass) -> 7.94 ms (4 chunks); 2 GPUs 19.1 -> 20.8 ms (the all-gather is only 0.8 ms of a
+    8 GPUs 8.49 ms (one pass) -> 7.94 ms (4 chunks); 4 GPUs 11.97 -> 11.75 ms; 2 GPUs 19.1 -> 20.8 ms (the all-gather is only 0.8 ms of a
     6.3 ms hop there and the extra launches / concurrent NCCL traffic cost more), hence 4 chunks from 4 ranks up."""
     return 4 if world >= 4 else 1
 
