@@ -507,7 +507,9 @@ int gdr_induced_subgraph_coo(int64_t n, const int32_t* rowptr, const int32_t* co
  * weights (prob[src,c] * prob[dst,c]) * er, their top-k and the rebuilt CSR, written to slice c of the outputs
  * (rowptr_out [C][n+1], colidx_out / vals_out [C][k]).  ~20 launches per class issued back to back from here. */
 // classes per batch: bounded by ~1.5 GB of scratch (3 arrays of nnz + 1 words per class) and by int32 scan totals
+int g_sparsify_batch_cap = 0;   // gdr_debug_set("sparsify_batch", v): cap the classes per batch (tests)
 static int64_t sparsify_batch(int64_t nnz, int64_t C) {
+  if (g_sparsify_batch_cap > 0) C = std::min<int64_t>(C, g_sparsify_batch_cap);
   int64_t by_mem = std::max<int64_t>(1, (int64_t)(1500ll << 20) / (12 * (nnz + 1)));
   int64_t by_int = std::max<int64_t>(1, ((1ll << 31) - 1) / (nnz + 1));
   return std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(by_mem, by_int), std::min<int64_t>(C, 65535)));

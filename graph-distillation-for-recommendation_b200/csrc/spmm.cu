@@ -42,6 +42,9 @@ static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
 extern int g_lloyd_graph;         // lloyd.cu
 extern int g_tc_screen;           // kmeans_tc.cu
 extern int g_tc_ablate;
+}  // namespace gdr
+extern "C" int g_sparsify_batch_cap;   // sparsify.cu
+namespace gdr {
 
 __device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
   int v;
@@ -392,6 +395,7 @@ int gdr_debug_set(const char* key, int value) {
   else if (!strcmp(key, "lloyd_graph")) gdr::g_lloyd_graph = value;
   else if (!strcmp(key, "tc_screen")) gdr::g_tc_screen = value;
   else if (!strcmp(key, "tc_ablate")) gdr::g_tc_ablate = value;
+  else if (!strcmp(key, "sparsify_batch")) g_sparsify_batch_cap = value;
   else {
     gdr::set_error("debug_set: unknown key %s", key);
     return GDR_EINVAL;

@@ -67,7 +67,7 @@ int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
 
 /* Experiment knobs for kernel tuning sweeps (tools/spmm_sweep.py); not a stable surface.
  * keys: "spmm_unroll" (4|8), "spmm_hints" (0|1), "spmm_split" (1|2|4), "lloyd_graph" (0|1),
- * "tc_screen" (1 direct 3xTF32; two-level screen with 2: 256x128 CTA tiles, 3: 128x256 CTA tiles [default for large
+ * "sparsify_batch" (cap on the classes per batch of gdr_sparsify_classes), "tc_screen" (1 direct 3xTF32; two-level screen with 2: 256x128 CTA tiles, 3: 128x256 CTA tiles [default for large
  * inputs], 4: CTA pairs with 2-SM TMA, 5: CTA pairs with forwarded 1-SM TMA), "tc_ablate" (role ablations of the
  * first-level kernel for tools/estep_probe.py / tools/mma_rate_probe.py; results are garbage while it is set);
  * value 0 / -1 = automatic. */

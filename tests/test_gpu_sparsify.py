@@ -126,3 +126,27 @@ def test_rand_sparsifier_follows_torch_randperm(gdr):
         ref = set(zip(coo[0][pick].tolist(), coo[1][pick].tolist()))
         i = t.coalesce()._indices().cpu()
         assert set(zip(i[0].tolist(), i[1].tolist())) == ref
+
+
+def test_sparsify_classes_multi_batch_equals_single_batch(gdr):
+    """Large graphs process the classes in several batches (scratch is bounded): force 3 classes per batch on a
+    7-class problem and compare with the single-batch result, entry for entry."""
+    from gdr import synth, _lib
+    n, C = 3000, 7
+    u, v = synth.uniform_graph(n, 25000, seed=9)
+    A = gdr.sym_normalize(gdr.coo_to_csr(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV), None, (n, n),
+                                         symmetrize=True, binarize=True), 2)
+    ebd = torch.randn(n, C, device=DEV)
+    R = gdr.cosine_reweight(A, ebd)
+    er, P, k = gdr.er_lower(R), gdr.softmax_rows(ebd), A.nnz // 5
+    from gdr.sparsify import sparsify_classes
+    one = sparsify_classes(R, er, P, k)
+    _lib.call("gdr_debug_set", b"sparsify_batch", 3)
+    try:
+        many = sparsify_classes(R, er, P, k)
+    finally:
+        _lib.call("gdr_debug_set", b"sparsify_batch", 0)
+    assert len(one) == len(many) == C
+    for a, b in zip(one, many):
+        assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.colidx, b.colidx) and torch.equal(a.vals, b.vals)
+        assert int(a.rowptr[-1]) == k
