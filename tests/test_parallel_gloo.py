@@ -299,3 +299,27 @@ def test_row_partition_bounds():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) == RowPartition(n, w, 0).rows_per
+
+
+@pytest.mark.parametrize("slabs,row_chunks", [(1, 1), (3, 1), (1, 3), (1, 5)])
+def test_world1_drivers_without_process_group(oracle, slabs, row_chunks):
+    """The drivers with a single rank and no process group (Comm() is a no-op): the pipelined hop variants, the
+    exchange-based build and the coarsening merge all reduce to the single-device result."""
+    from gdr import parallel as par
+    from gdr import synth
+    from oracle import oracle as o
+    n, f, k, rpo, cio, vo, X = _inputs()
+    part, comm, ops = par.RowPartition(n, 1, 0), par.Comm(), OracleOps()
+    A = CpuCSR(torch.from_numpy(rpo.astype(np.int32)), torch.from_numpy(cio.copy()), torch.from_numpy(vo.copy()), (n, n))
+    prop, target = par.dist_propagate(comm, part, A, torch.from_numpy(X.copy()), 4, 0.8, ops=ops, slabs=slabs,
+                                      row_chunks=row_chunks)
+    p_ref, t_ref = o.propagate(rpo, cio, vo, X, 4, 0.8)
+    assert np.array_equal(prop.numpy(), p_ref) and np.array_equal(target.numpy(), t_ref)
+    if (slabs, row_chunks) == (1, 1):
+        u, v = synth.skewed_graph(n, 9000, seed=3)
+        B = par.dist_build_adjacency(comm, part, torch.from_numpy(u), torch.from_numpy(v), n, ops=ops)
+        assert np.array_equal(B.rowptr.numpy(), rpo) and np.array_equal(B.colidx.numpy(), cio)
+        assert np.array_equal(B.vals.numpy(), vo)
+        send = torch.arange(12).reshape(6, 2)
+        out, counts = comm.all_to_all_rows(send, [6])
+        assert torch.equal(out, send) and counts == [6]
