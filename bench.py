@@ -194,7 +194,10 @@ def run_reference(args, rank, world):
             t_s1.append(t1 - t0)
             t_s2.append(t2 - t1)
             # differenced: (fit with it_hi) - (fit with it_lo) cancels validation / centring / final E-step
-            t_s3.append(((t3b - t3a) - (t3a - t3)) / (it_hi - it_lo))
+            d_it = ((t3b - t3a) - (t3a - t3)) / (it_hi - it_lo)
+            if d_it <= 0:   # tiny problems converge before it_lo: fall back to the undifferenced fit
+                d_it = (t3b - t3a) / max(1, int(km.n_iter_))
+            t_s3.append(d_it)
             t_s4.append(t4 - t3b)
             per_step.append(t4 - t0)
     nnz = adj_norm._nnz()
