@@ -10,13 +10,13 @@ OBJS     := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 
 all: $(OUT)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/gdr.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/comm.cuh include/gdr.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 
 $(OUT): $(OBJS)
 	@mkdir -p $(PKG)/lib
-	$(NVCC) -shared -o $@ $(OBJS) -lcuda
+	$(NVCC) -shared -o $@ $(OBJS) -lcuda -ldl
 
 clean:
 	rm -rf build $(OUT)

@@ -1,26 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — one "step" = one pass of the distillation core over a synthetic graph of a
-BASELINE.json shape:  stage 1 (CSR build + D^-1/2 A D^-1/2)  ->  stage 2 (K hops)  ->
-stage 3 (20 Lloyd iterations from a fixed init, tol = 0)  ->  stage 4 (P^T A P).
+"""bench.py — one "step" = one pass of the distillation core over a synthetic graph of a BASELINE.json shape:
+stage 1 (CSR build + D^-1/2 A D^-1/2)  ->  stage 2 (K hops)  ->  stage 3 (20 Lloyd iterations from a fixed
+init, tol = 0)  ->  stage 4 (P^T A P).  Bipartite workloads (C, D) run the distill_recsys form of the same four
+stages: interaction CSR + LightGCN normalisation -> L propagation layers -> per-side k-means -> condensed counts.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload E|B|A] [--precision fp32|tc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload E|B|A|C|D] [--precision fp32|tc]
     python bench.py --impl reference ...        # the reference's CPU path on the host cores
 
-The default workload is config E (BASELINE.json configs[4], ogbn-products-shaped: the shape the target is
-quoted on; it fits one GPU) for EVERY N, so the N = 1, 2, 4, 8 lines are one strong-scaling experiment;
---workload B is configs[1] (ogbn-arxiv-shaped).
+The default workload is config E (BASELINE.json configs[4], ogbn-products-shaped: the shape the target is quoted
+on; it fits one GPU) for EVERY N, so the N = 1, 2, 4, 8 lines are one strong-scaling experiment.
 
-Prints ONE JSON line (rank 0).  `value` = k-means iterations / s (whole job), the quantity
-BASELINE.json's speed-up target is quoted on; `prop` carries the A^K.X GB/s figure of the
-same metric string with its own HBM roofline.  See DESIGN.md §Measurement.
+Prints ONE JSON line (rank 0).  `value` = k-means iterations / s (whole job), the quantity BASELINE.json's
+speed-up target is quoted on; `prop` carries the A^K.X GB/s figure of the same metric string with its own HBM
+roofline.  See DESIGN.md §Measurement.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import types
 
 import numpy as np
 
@@ -29,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 LLOYD_ITERS = 20
 ALPHA = 0.8
+HOMOGENEOUS = {"A": 0, "B": 1, "E": 4}
+BIPARTITE = {"C": 2, "D": 3}
+CPU_SAMPLE_ROWS = 200_000   # bounded k-means sample of the large workload (all K centres, first rows of X)
 
 
 # ----------------------------------------------------------------------------------------
@@ -36,8 +41,26 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+def load_synth():
+    """The workload generators, loaded BY PATH: `import gdr` would map libgdr_b200.so into the process, and the
+    reference arm must stay a pure CPU process (no product code anywhere near it)."""
+    spec = importlib.util.spec_from_file_location(
+        "_bench_synth", os.path.join(ROOT, "graph-distillation-for-recommendation_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def product_so_mapped() -> bool:
+    try:
+        return "libgdr_b200" in open("/proc/self/maps").read()
+    except OSError:
+        return False
 
 
 class ClockSampler(threading.Thread):
@@ -93,16 +116,13 @@ class ClockSampler(threading.Thread):
             return   # NVML available: samples are taken by sample_now() from the main thread
         while not self._stop_ev.is_set():
             try:
-                if self.nvml is not None:
-                    self.rows.append(self._sample_nvml())
-                else:
-                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([x.strip() for x in out.split(",")])
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_ev.wait(0.05 if self.nvml is not None else 0.5)
+            self._stop_ev.wait(0.5)
 
     def stop(self):
         self._stop_ev.set()
@@ -115,15 +135,37 @@ class ClockSampler(threading.Thread):
                     samples=len(sm), reasons=reasons)
 
 
-def make_workload(name):
-    from gdr import synth
+def make_workload(name, synth, graph="uniform"):
+    """Host arrays of one BASELINE.json config (seed = 1234 + config index); the same arrays go to
+    the GPU path and to the CPU reference."""
+    if name in BIPARTITE:
+        cfg = dict(synth.BIPARTITE[name])
+        seed = 1234 + BIPARTITE[name]
+        u, i = synth.bipartite_interactions(cfg["users"], cfg["items"], cfg["inter"], seed)
+        rs = np.random.RandomState(seed + 100)
+        u0 = (0.1 * rs.standard_normal((cfg["users"], cfg["d"]))).astype(np.float32)   # nn.init.normal_(std=0.1)
+        i0 = (0.1 * rs.standard_normal((cfg["items"], cfg["d"]))).astype(np.float32)
+        cfg.update(u=u, i=i, u0=u0, i0=i0, seed=seed, ku=int(np.ceil(0.1 * cfg["users"])), ki=int(np.ceil(0.1 * cfg["items"])),
+                   bipartite=True)
+        return cfg
     cfg = dict(synth.CONFIGS[name])
-    idx = {"A": 0, "B": 1, "E": 4}[name]
-    seed = 1234 + idx
-    u, v = synth.uniform_graph(cfg["n"], cfg["pairs"], seed)
+    seed = 1234 + HOMOGENEOUS[name]
+    gen = synth.uniform_graph if graph == "uniform" else synth.skewed_graph
+    u, v = gen(cfg["n"], cfg["pairs"], seed)
     X = synth.features(cfg["n"], cfg["f"], seed + 100, kind="l1" if name == "A" else "zscore")
-    cfg.update(u=u, v=v, X=X, seed=seed)
+    cfg.update(u=u, v=v, X=X, seed=seed, bipartite=False)
     return cfg
+
+
+def workload_string(name, w, kmeans_d=None):
+    """ONE string for both arms (the driver compares the two lines' config.workload)."""
+    if w.get("bipartite"):
+        return (f"config {name}: {w['name']}-shaped user-item bipartite graph, users={w['users']}, items={w['items']}, "
+                f"interaction lines={w['inter']} (~4% duplicates), d={w['d']}, LightGCN layers={w['layers']}, "
+                f"K_users={w['ku']}, K_items={w['ki']}, {LLOYD_ITERS} Lloyd iterations per side tol=0")
+    d = w["f"] if kmeans_d is None else kmeans_d
+    return (f"config {name}: {w['name']}-shaped uniform graph, N={w['n']}, undirected input pairs={w['u'].shape[0]}, "
+            f"F={w['f']}, hops={w['hops']}, K={w['k']}, k-means D={d}, {LLOYD_ITERS} Lloyd iterations tol=0")
 
 
 def spmm_bytes(nnz, rows, xrows, F, fused=True, model="min"):
@@ -156,20 +198,25 @@ def use_all_host_threads():
     return n
 
 
-# ----------------------------------------------------------------------------------------
+# ========================================================================================
+# reference arm: the reference's own CPU path (oracle/ref_port.py restates its call sites on scipy /
+# torch-CPU sparse / scikit-learn, the libraries that own its arithmetic).  Pure CPU process.
+# ========================================================================================
 def run_reference(args, rank, world):
-    """The reference's CPU path (oracle/ref_port.py: scipy + torch CPU sparse + scikit-learn)."""
     if rank != 0:
         return
     import torch
     from oracle import ref_port as rp
-    from gdr import synth
+    synth = load_synth()
+    assert not product_so_mapped(), "the reference arm must not load the product library"
     use_all_host_threads()
-    w = make_workload(args.workload)
-    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    w = make_workload(args.workload, synth)
     info = rp.host_info()
+    if w["bipartite"]:
+        return run_reference_bipartite(args, w, info, rp, synth)
+    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
     if n * K > 1e9:
-        return run_reference_bounded(args, w, info)
+        return run_reference_bounded(args, w, info, rp, synth)
     t_s1, t_s2, t_s3, t_s4, per_step = [], [], [], [], []
     it_lo, it_hi = 3, 3 + args.ref_kmeans_iters
     for s in range(args.warmup + args.steps):
@@ -188,7 +235,7 @@ def run_reference(args, rank, world):
         t3a = time.perf_counter()
         km = rp.kmeans_fit(tn, C0, it_hi)
         t3b = time.perf_counter()
-        S = rp.graph_compress_sparse(km.labels_.astype(np.int64), adj_norm)
+        rp.graph_compress_sparse(km.labels_.astype(np.int64), adj_norm)
         t4 = time.perf_counter()
         if s >= args.warmup:
             t_s1.append(t1 - t0)
@@ -209,9 +256,8 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(per_step)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, "
-                               f"F={F}, hops={hops}, K={K}, k-means D={F}",
-                   "lloyd_iters_timed": f"sklearn fit(max_iter={it_hi}) - fit(max_iter={it_lo})"},
+        "config": {"workload": workload_string(args.workload, w), "nnz_a_hat": int(nnz),
+                   "lloyd_iters_timed": f"sklearn fit(max_iter={it_hi}) - fit(max_iter={it_lo})", "full_size": True},
         "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "bytes_model": "B_min",
                  "s_per_hop": float(np.mean(t_s2)) / hops},
         "stages_ms": {"s1_build_normalize": np.mean(t_s1) * 1e3, "s2_propagate": np.mean(t_s2) * 1e3,
@@ -219,44 +265,271 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": iters_per_s, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
                          "sample": f"full config {args.workload}; sklearn/scipy/torch-CPU with all host threads", "host": info},
         "e2e": {"value": iters_per_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "product_so_mapped": product_so_mapped(),
     }
     print(json.dumps(line))
 
 
-def run_reference_bounded(args, w, info):
-    """Large workload (config E): the reference's scipy build (`tolil` of 126 M entries) and 4.5 s k-means
-    iterations do not fit a few-minute run, so every step is a BOUNDED sample of the same workload: sklearn Lloyd
-    on the first CPU_SAMPLE_ROWS rows of the z-scored feature matrix against all K centres, differenced between
-    max_iter 1 and 3, the rate scaled by rows/N (an iteration costs the same flops whatever the rows hold, so the
-    un-propagated features stand in for the propagated ones; stages 1, 2 and 4 are not timed here)."""
+def reference_full_size_legs(w, rp, synth, budget_s):
+    """Config E at FULL size on the host, once per run (not per step): every stage of the reference's CPU path
+    as BASELINE.md §4 prescribes, each leg skipped (null + reason) when the remaining budget cannot hold it.
+      s1  utils_graphsaint.py:18-22 build + deep_robust_utils.to_tensor + normalize_adj_tensor(sparse=True).  The
+          reference's normalize_adj goes through scipy `tolil()` (Python-object lists: 126 M entries, hours and
+          > 60 GB) — timed here on a 1/32 row block and reported as infeasible at full size; the downstream legs use
+          the same arithmetic without the LIL detour (csr + diags products).
+      s2  ONE hop of clustgdd_agent_transduct.py:59-65 on torch-CPU sparse COO ((alpha*adj_norm) @ X), reported per hop
+      s3  sklearn KMeans(init=C0, n_init=1, tol=0): fit(max_iter=3) - fit(max_iter=1) on all 2.45 M rows
+      s4  graph_compress with a sparse one-hot (the dense N x n one-hot is 196 GB): scipy P^T A_hat P"""
+    import scipy.sparse as sp
+    import torch
     n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    t_start = time.perf_counter()
+    left = lambda: budget_s - (time.perf_counter() - t_start)
+    out = {"budget_s": budget_s, "notes": []}
+    adj_norm = None
+    if left() > 0:
+        t0 = time.perf_counter()
+        A = rp.build_adjacency(w["u"], w["v"], n)
+        t1 = time.perf_counter()
+        adj = rp.to_tensor_sparse(A)
+        t2 = time.perf_counter()
+        # normalize_adj (deep_robust_utils.py:180-207) without tolil(): identical arithmetic (fp64 rowsum, power -1/2,
+        # two diagonal products), then back to a torch COO as normalize_adj_tensor does
+        mx = sp.csr_matrix((adj._values().numpy(), adj._indices().numpy()), shape=(n, n))
+        if mx[0, 0] == 0:
+            mx = mx + sp.eye(n, format="csr")
+        rowsum = np.asarray(mx.sum(1)).ravel()
+        with np.errstate(divide="ignore"):
+            r_inv = np.power(rowsum, -0.5)
+        r_inv[np.isinf(r_inv)] = 0.0
+        mx = sp.diags(r_inv).dot(mx).dot(sp.diags(r_inv))
+        adj_norm = rp.to_tensor_sparse(mx.tocsr())
+        t3 = time.perf_counter()
+        out["s1_build_adjacency_s"] = t1 - t0
+        out["s1_to_tensor_s"] = t2 - t1
+        out["s1_normalize_without_tolil_s"] = t3 - t2
+        out["s1_build_normalize_s"] = t3 - t0
+        out["nnz_a_hat"] = int(adj_norm._nnz())
+        # the reference's own normalize_adj_tensor (with tolil) on a 1/32 row block, to document why it is not run whole
+        m = n // 32
+        blk = A[:m, :m].tocsr()
+        t4 = time.perf_counter()
+        rp.normalize_adj_tensor_sparse(rp.to_tensor_sparse(blk))
+        out["s1_reference_tolil_path_on_1_32_block_s"] = time.perf_counter() - t4
+        out["notes"].append("normalize_adj's tolil() detour is not run at full size (Python-object lists for 126 M entries); "
+                            "s1 uses the same fp64 arithmetic on CSR")
+        del A, adj, mx, blk
+    if adj_norm is not None and left() > 60:
+        X = torch.from_numpy(w["X"])
+        t0 = time.perf_counter()
+        prop = ALPHA * adj_norm @ X
+        _ = (1 - ALPHA) * X + (1 - ALPHA) * prop
+        out["s2_one_hop_s"] = time.perf_counter() - t0
+        out["s2_propagate_s"] = out["s2_one_hop_s"] * hops
+        out["s2_b_gather_gbs"] = spmm_bytes(out["nnz_a_hat"], n, n, F, model="gather") / out["s2_one_hop_s"] / 1e9
+        out["notes"].append(f"s2: one hop timed, s2_propagate_s = {hops} x that")
+        del prop
+    else:
+        out["notes"].append("s2 skipped: budget")
+    if left() > 45:
+        Xh = w["X"]
+        C0 = synth.kmeans_init(Xh, K, w["seed"])
+        rp.kmeans_fit(Xh[:20000], C0[:100], 2)
+        t0 = time.perf_counter()
+        rp.kmeans_fit(Xh, C0, 1)
+        t1 = time.perf_counter()
+        km = rp.kmeans_fit(Xh, C0, 3)
+        t2 = time.perf_counter()
+        s_iter = ((t2 - t1) - (t1 - t0)) / 2.0
+        out["s3_fit1_s"], out["s3_fit3_s"] = t1 - t0, t2 - t1
+        out["s3_kmeans_per_iter_s"] = s_iter
+        out["s3_kmeans_iters_per_s"] = 1.0 / s_iter if s_iter > 0 else None
+        labels = km.labels_.astype(np.int64)
+    else:
+        out["notes"].append("s3 skipped: budget")
+        labels = np.random.RandomState(0).randint(0, K, n).astype(np.int64)
+    if adj_norm is not None and left() > 45:
+        t0 = time.perf_counter()
+        S = rp.graph_compress_sparse(labels, adj_norm)
+        out["s4_coarsen_s"] = time.perf_counter() - t0
+        out["s4_syn_nnz"] = int(S.nnz)
+    else:
+        out["notes"].append("s4 skipped: budget")
+    out["wall_s"] = time.perf_counter() - t_start
+    return out
+
+
+def run_reference_bounded(args, w, info, rp, synth):
+    """Large workload (config E).  Per STEP: a bounded sample of the same workload — sklearn Lloyd on the first
+    CPU_SAMPLE_ROWS rows of the feature matrix against all K centres, differenced between max_iter 1 and 3, rate
+    scaled by rows/N (an iteration costs the same flops whatever the rows hold).  Once per RUN: every stage at full
+    size (reference_full_size_legs), printed beside the sampled rate."""
+    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    full = reference_full_size_legs(w, rp, synth, args.ref_full_budget) if args.ref_full_budget > 0 else None
     rates, what, per_step = [], "", []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS)
+        rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS, synth=synth)
         if s >= args.warmup:
             rates.append(rate)
             per_step.append(time.perf_counter() - t0)
     iters_per_s = float(np.mean(rates))
+    g = (lambda k, sc=1e3: (None if (full is None or full.get(k) is None) else full[k] * sc))
     line = {
         "impl": "reference", "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(per_step)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, F={F}, hops={hops}, K={K}, "
-                               f"k-means D={F}", "bounded": what},
-        "stages_ms": {"s1_build_normalize": None, "s2_propagate": None, "s3_kmeans_per_iter": 1e3 / iters_per_s,
-                      "s4_coarsen": None},
+        "config": {"workload": workload_string(args.workload, w), "per_step_sample": what,
+                   "full_size": "every stage once per run, see full_size"},
+        "stages_ms": {"s1_build_normalize": g("s1_build_normalize_s"), "s2_propagate": g("s2_propagate_s"),
+                      "s3_kmeans_per_iter": 1e3 / iters_per_s, "s3_kmeans_per_iter_full_size": g("s3_kmeans_per_iter_s"),
+                      "s4_coarsen": g("s4_coarsen_s")},
+        "full_size": full,
+        "prop": None if g("s2_one_hop_s") is None else {
+            "metric": "A^K.X", "value": full["s2_b_gather_gbs"], "unit": "GB/s", "bytes_model": "B_gather",
+            "s_per_hop": full["s2_one_hop_s"]},
         "cpu_baseline": {"value": iters_per_s, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
-                         "sample": what, "host": info},
+                         "sample": what, "full_size_iters_per_s": None if full is None else full.get("s3_kmeans_iters_per_s"),
+                         "host": info},
         "e2e": {"value": iters_per_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "product_so_mapped": product_so_mapped(),
     }
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------------------
+def run_reference_bipartite(args, w, info, rp, synth):
+    """distill_recsys on the host (configs C / D), full size every step: build_interaction_matrix, LightGCN
+    propagate (torch index_add_), StandardScaler + sklearn KMeans per side (init pinned), build_condensed_bipartite."""
+    import torch
+    nu, ni = w["users"], w["items"]
+    it_lo, it_hi = 2, 2 + max(2, args.ref_kmeans_iters // 2)
+    t_s1, t_s2, t_s3, t_s4, per_step = [], [], [], [], []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        R = rp.build_interaction_matrix(nu, ni, w["u"], w["i"])
+        coo = R.tocoo()
+        cu, ci = torch.from_numpy(coo.row.astype(np.int64)), torch.from_numpy(coo.col.astype(np.int64))
+        wgt = torch.from_numpy(coo.data.astype(np.float32))
+        t1 = time.perf_counter()
+        rp.lightgcn_propagate(cu, ci, wgt, torch.from_numpy(w["u0"]), torch.from_numpy(w["i0"]), w["layers"])
+        t2 = time.perf_counter()
+        d_it, maps = 0.0, []
+        for emb, K in ((w["u0"], w["ku"]), (w["i0"], w["ki"])):
+            Xs = rp.standard_scale(emb).astype(np.float32)
+            C0 = synth.kmeans_init(Xs, K, w["seed"])
+            ta = time.perf_counter()
+            rp.kmeans_fit(Xs, C0, it_lo)
+            tb = time.perf_counter()
+            km = rp.kmeans_fit(Xs, C0, it_hi)
+            tc = time.perf_counter()
+            d = ((tc - tb) - (tb - ta)) / (it_hi - it_lo)
+            d_it += d if d > 0 else (tc - tb) / max(1, int(km.n_iter_))
+            maps.append(km.labels_.astype(np.int64))
+        t3 = time.perf_counter()
+        rp.build_condensed_bipartite(w["u"], w["i"], maps[0], maps[1], w["ku"], w["ki"])
+        t4 = time.perf_counter()
+        if s >= args.warmup:
+            t_s1.append(t1 - t0)
+            t_s2.append(t2 - t1)
+            t_s3.append(d_it)
+            t_s4.append(t4 - t3)
+            per_step.append(t4 - t0)
+    s_iter = float(np.mean(t_s3))
+    line = {
+        "impl": "reference", "metric": "kmeans_iters_per_s", "value": 1.0 / s_iter, "unit": "iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(per_step)) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.workload, w), "full_size": True,
+                   "iteration": "one Lloyd iteration over BOTH sides (users + items)",
+                   "lloyd_iters_timed": f"sklearn fit(max_iter={it_hi}) - fit(max_iter={it_lo}) per side"},
+        "stages_ms": {"s1_build_normalize": np.mean(t_s1) * 1e3, "s2_propagate": np.mean(t_s2) * 1e3,
+                      "s3_kmeans_per_iter": s_iter * 1e3, "s4_coarsen": np.mean(t_s4) * 1e3},
+        "cpu_baseline": {"value": 1.0 / s_iter, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
+                         "sample": f"full config {args.workload}; scipy / torch-CPU index_add_ / sklearn with all host threads",
+                         "host": info},
+        "e2e": {"value": 1.0 / s_iter, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "product_so_mapped": product_so_mapped(),
+    }
+    print(json.dumps(line))
+
+
+def cpu_kmeans_rate(w, it_lo, it_hi, rows_cap=None, synth=None, X=None, K=None):
+    """k-means iterations/s of the reference's CPU path (sklearn Lloyd, all host threads) on workload w,
+    differenced between two max_iter values so that validation / centring / the final E-step cancel.
+    With rows_cap the fit runs on the first rows_cap rows against all K centres and the rate is scaled by
+    rows_cap / N (the E-step is linear in the rows and dominates: 2*N*K*D flops per iteration)."""
+    from oracle import ref_port as rp
+    synth = synth or load_synth()
+    X = w["X"] if X is None else X
+    K = w["k"] if K is None else K
+    n = X.shape[0]
+    m = n if rows_cap is None else min(n, int(rows_cap))
+    Xs = np.ascontiguousarray(X[:m])
+    C0 = synth.kmeans_init(Xs, K, w["seed"])       # the init rows lie inside the sample
+    rp.kmeans_fit(Xs[:20000], C0[: min(K, 100)], 2)  # warm the thread pools
+    t0 = time.perf_counter()
+    rp.kmeans_fit(Xs, C0, it_lo)
+    t1 = time.perf_counter()
+    km = rp.kmeans_fit(Xs, C0, it_hi)
+    t2 = time.perf_counter()
+    s_iter = ((t2 - t1) - (t1 - t0)) / float(it_hi - it_lo)
+    if s_iter <= 0:   # noisy or converged before it_lo: undifferenced fit
+        s_iter = (t2 - t1) / max(1, int(km.n_iter_))
+    rate = (1.0 / s_iter) * (m / n)
+    what = (f"sklearn KMeans(init=C0,n_init=1,tol=0) on "
+            + (f"the full {n}x{X.shape[1]} matrix" if m == n else f"the first {m} of {n} rows (x{X.shape[1]}), rate scaled by {m}/{n}")
+            + f", K={K}: fit({it_hi} it) - fit({it_lo} it)")
+    return rate, what
+
+
+def cpu_baseline(w, args, synth):
+    """Bounded CPU sample on this box's host cores (oracle-side port of the reference)."""
+    from oracle import ref_port as rp
+    info = rp.host_info()
+    if w.get("bipartite"):
+        s_iter, what = 0.0, []
+        for emb, K in ((w["u0"], w["ku"]), (w["i0"], w["ki"])):
+            Xs = rp.standard_scale(emb).astype(np.float32)
+            r, wh = cpu_kmeans_rate(w, 2, 6, synth=synth, X=Xs, K=K)
+            s_iter += 1.0 / r
+            what.append(wh)
+        return {"value": 1.0 / s_iter, "unit": "iters/s", "cores": info["affinity"], "kind": "port",
+                "sample": " + ".join(what), "host": info}
+    big = w["n"] * w["k"] > 1e9
+    rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS, synth=synth) if big else cpu_kmeans_rate(w, 2, 12, synth=synth)
+    return {"value": rate, "unit": "iters/s", "cores": info["affinity"], "kind": "port", "sample": what, "host": info}
+
+
+# ========================================================================================
+# our arm, one GPU
+# ========================================================================================
+def _profile_kernel(_lib, kind, fn, reps, flush):
+    """Average duration of the launches of one kernel kind inside fn(), by the CUDA-event pairs the library records
+    on its own launch stream (gdr_profile_enable): (ms per launch, launches)."""
+    import ctypes
+    import torch
+    tot_ms, n_l = ctypes.c_double(0), ctypes.c_int64(0)
+    _lib.call("gdr_profile_enable", kind)
+    for _ in range(reps):
+        flush.fill_(1)
+        fn()
+    torch.cuda.synchronize()
+    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
+    _lib.call("gdr_profile_enable", 0)
+    return tot_ms.value / max(1, n_l.value), int(n_l.value)
+
+
+def _ncu_traffic(workload):
+    """DRAM bytes per launch from the committed `ncu --set full` capture of this same command
+    (profiles/ncu_traffic.json: a constant of the profile, not a measurement of this run)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload, {})
+    except Exception:
+        return {}
+
+
 def run_ours(args, rank, world):
     import torch
     import gdr
@@ -267,10 +540,15 @@ def run_ours(args, rank, world):
     if args.tc_screen:
         from gdr import _lib as _l
         _l.call("gdr_debug_set", b"tc_screen", int(args.tc_screen))
+    w = make_workload(args.workload, synth)
     if world > 1:
-        return run_ours_multi(args, rank, world, dev)
+        if w["bipartite"]:
+            return run_ours_multi_bipartite(args, rank, world, dev, w)
+        return run_ours_multi(args, rank, world, dev, w)
+    if w["bipartite"]:
+        return run_ours_bipartite(args, dev, w)
 
-    w = make_workload(args.workload)
+    from gdr import _lib
     n, F, K, hops, seed = w["n"], w["f"], w["k"], w["hops"], w["seed"]
     pk = peaks()
 
@@ -278,25 +556,26 @@ def run_ours(args, rank, world):
     u_d = torch.from_numpy(w["u"]).to(dev)
     v_d = torch.from_numpy(w["v"]).to(dev)
     X_d = torch.from_numpy(w["X"]).to(dev)
-    X_pin = torch.from_numpy(w["X"]).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    def build():
+        return gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
+
     # k-means init: C0 = X_target[perm[:K]] needs the propagated features -> computed once, untimed
-    A0 = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
+    A0 = build()
     _, tgt0 = gdr.propagate(A0, X_d, hops + 1, ALPHA)
     perm = torch.from_numpy(np.random.RandomState(seed).permutation(n)[:K].astype(np.int64)).to(dev)
     C0 = tgt0[perm].clone()
     nnz = A0.nnz
     del A0, tgt0
 
-    def step(record):
+    def step():
         e = [ev() for _ in range(5)]
         e[0].record()
-        A = gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True)
-        An = gdr.sym_normalize(A, 2)
+        An = build()
         e[1].record()
         prop, target = gdr.propagate(An, X_d, hops + 1, ALPHA)
         e[2].record()
@@ -307,133 +586,89 @@ def run_ours(args, rank, world):
         e[4].record()
         # keep only scalars: holding km / adj_syn of every step alive fragments the caching allocator
         # and forces cudaMalloc (a device-wide sync) inside later timed steps
-        import types
-        nnz_syn = int(adj_syn._nnz())
-        return (e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_),
-                types.SimpleNamespace(_nnz=lambda v=nnz_syn: v))
+        return e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_), int(adj_syn._nnz())
 
     # W warm-up steps, continued until the GPU has been busy for >= 2 s: a fresh process starts
     # with the GPU in its idle power state and the first ~0.5 s of work runs at about half speed
     t_warm = time.perf_counter()
     n_warm = 0
     while n_warm < args.warmup or (not args.profile and time.perf_counter() - t_warm < 2.0):
-        step(False)
+        step()
         flush.fill_(1)
         n_warm += 1
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    import ctypes
-    from gdr import _lib
     launches0 = gdr.launch_count()
     recs = []
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)          # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
-        recs.append(step(True))
+        recs.append(step())
         sampler.sample_now()    # clocks / throttle reasons while the GPU is still under load
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     launches = gdr.launch_count() - launches0
     clocks = sampler.stop()
-    # roofline leg: the E-step main kernel alone, timed by CUDA-event pairs recorded inside the
-    # library on its launch stream (separate pass: event pairs cannot live inside the replayed graph)
-    tot_ms, n_l = ctypes.c_double(0), ctypes.c_int64(0)
-    _lib.call("gdr_profile_enable", 1)
-    for _ in range(3):
-        flush.fill_(1)
-        step(True)
-    torch.cuda.synchronize()
-    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
-    _lib.call("gdr_profile_enable", 0)
-    assign_ms = np.array([tot_ms.value / max(1, n_l.value)])
-    assign_total_ms = assign_ms[0] * (LLOYD_ITERS + 1) * args.steps   # launches per step: 20 iterations + final E-step
 
     st = np.array([[r[0][i].elapsed_time(r[0][i + 1]) for i in range(4)] for r in recs])  # ms per stage
     step_ms = st.sum(axis=1)
     n_iter = [r[1].n_iter_ for r in recs]
-    km_ms = st[:, 2]
-
-    # SpMM kernel time alone (same event mechanism, separate short loop: hops only)
-    A_t = gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2)
-    _lib.call("gdr_profile_enable", 2)
-    for _ in range(5):
-        flush.fill_(1)
-        gdr.propagate(A_t, X_d, hops + 1, ALPHA)
-    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
-    _lib.call("gdr_profile_enable", 0)
-    spmm_kernel_ms = tot_ms.value / max(1, n_l.value)
-    del A_t
+    km_ms, prop_ms = st[:, 2], st[:, 1]
     iters_per_s = float(np.sum(n_iter) / (km_ms.sum() / 1e3))
-    prop_ms = st[:, 1]
+
+    # roofline legs: the E-step screen and the SpMM kernel alone, timed by CUDA-event pairs recorded inside the
+    # library on its launch stream (separate passes: event pairs cannot live inside the replayed graph)
+    assign_ms, _ = _profile_kernel(_lib, 1, step, 3, flush)
+    assign_total_ms = assign_ms * (LLOYD_ITERS + 1) * args.steps   # launches per step: 20 iterations + final E-step
+    A_t = build()
+    spmm_ms, _ = _profile_kernel(_lib, 2, lambda: gdr.propagate(A_t, X_d, hops + 1, ALPHA), 5, flush)
     # SURVEY §8(d) headline rule: B_gather when X does not fit L2 (N*F*4 > 96 MB), else B_min
     prop_model = "gather" if n * F * 4 > 96e6 else "min"
     b_hop = spmm_bytes(nnz, n, n, F, model=prop_model)
     b_prop = hops * b_hop + 2 * n * F * 4  # + the t = 0 scale pass
     prop_gbs = float(b_prop / (prop_ms.mean() / 1e3) / 1e9)
 
-    # ---- e2e through the public API with HOST buffers (H2D of X, D2H of labels + centres) ----
-    tn_host = recs[-1][1]  # keep last km for result checks
-    C0_host = C0.cpu().numpy()
-    target_host = torch.empty((n, F), dtype=torch.float32).pin_memory()
-    target_host.copy_(gdr.propagate(gdr.sym_normalize(gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True), 2), X_d, hops + 1, ALPHA)[1])
-    e2e_t = []
-    for i in range(2 if args.profile else max(3, args.steps)):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        x_dev = target_host.to(dev, non_blocking=True)
-        km = gdr.KMeans(n_clusters=K, init=C0_host, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision).fit(x_dev)
-        lab_h = km.labels_.cpu()
-        cen_h = km.cluster_centers_.cpu()
-        torch.cuda.synchronize()
-        e2e_t.append((time.perf_counter() - t0, km.n_iter_))
-    e2e_t = e2e_t[1:]
-    e2e_val = float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t))
-    h2d = n * F * 4 + K * F * 4
-    d2h = n * 4 + K * F * 4
-
-    # ---- roofline of the dominant kernel (k-means E-step) ----
-    # DRAM traffic per launch comes from the committed ncu --set full capture of this same command
-    # (profiles/ncu_traffic.json); null when there is no capture for this workload.
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload, {})
-    except Exception:
-        pass
+    traffic = _ncu_traffic(args.workload)
     flops = 2.0 * n * K * F
-    a_tf = float(flops / (assign_ms.mean() / 1e3) / 1e12)
+    a_tf = float(flops / (assign_ms / 1e3) / 1e12)
     tc = args.precision in ("tc", "auto") and F <= 128
     two_level = tc and (args.tc_screen >= 2 or (args.tc_screen == 0 and -(-n // 128) >= 4 * 148))
     roofline = {"kernel": ("k_assign_tc two-level screen (tcgen05 1xTF32 all rows -> select -> compact -> 3xTF32 undecided rows)" if two_level
                            else "k_assign_tc (tcgen05 3xTF32)") if tc else "k_assign_simt (exact fp32 FFMA)",
                 "bound": "tensor", "achieved": a_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": a_tf / pk["bf16_sustained"], "traffic": traffic.get("k_assign_tc") if tc else None,
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this command; not measured in this run)",
                 "peak_source": pk["src"] + " bf16 sustained",
-                "note": "useful flops 2NKD per E-step over the time of the whole tensor-core screen; fp32 inputs: TF32 rate = 1/2 bf16, "
-                        "3xTF32 emulation ceiling = peak/6, two-level screen ceiling -> peak/2",
-                "frac_of_3xtf32_ceiling": a_tf / (pk["bf16_sustained"] / 6.0),
-                "launch_ms": float(assign_ms.mean()), "share_of_step": float(assign_total_ms / step_ms.sum())}
-    spmm_ms = spmm_kernel_ms
-    # SURVEY §8(d) headline rule: B_gather when X does not fit L2 (N*F*4 > 96 MB), else B_min
-    model = "gather" if n * F * 4 > 96e6 else "min"
-    b_head = spmm_bytes(nnz, n, n, F, model=model)
+                "note": "useful flops 2NKD per E-step over the time of the whole tensor-core screen; fp32 inputs run as TF32 "
+                        "(1/2 the bf16 rate), so 0.5 is the ceiling of this fraction",
+                "launch_ms": float(assign_ms), "share_of_step": float(assign_total_ms / step_ms.sum())}
+    b_head = spmm_bytes(nnz, n, n, F, model=prop_model)
     roofline_spmm = {"kernel": "k_spmm", "bound": "hbm", "achieved": float(b_head / (spmm_ms / 1e3) / 1e9), "peak": pk["hbm"],
                      "unit": "GB/s", "frac": float(b_head / (spmm_ms / 1e3) / 1e9 / pk["hbm"]),
                      "traffic": traffic.get("k_spmm"), "launch_ms": float(spmm_ms),
-                     "bytes_model": "B_gather (X exceeds L2)" if model == "gather" else "B_min (X fits L2; the gathers run out of L2)",
+                     "bytes_model": "B_gather (X exceeds L2)" if prop_model == "gather" else "B_min (X fits L2; the gathers run out of L2)",
                      "b_min_gbs": float(spmm_bytes(nnz, n, n, F) / (spmm_ms / 1e3) / 1e9),
                      "b_gather_gbs": float(spmm_bytes(nnz, n, n, F, model='gather') / (spmm_ms / 1e3) / 1e9),
                      "peak_source": pk["src"]}
+    del A_t
 
-    cpu = cpu_baseline(w, args) if not (args.no_cpu_baseline or args.profile) else None
+    # ---- §8(d) secondary legs: the reference-faithful logit-space k-means width and the skewed (hub-heavy) graph ----
+    legs = {}
+    if not args.profile and not args.no_extra_legs:
+        legs["kmeans_logit"] = logit_leg(args, gdr, _lib, synth, w, dev, flush, pk)
+        legs["prop_skewed"] = skewed_leg(args, gdr, _lib, synth, w, dev, flush, pk, X_d)
+
+    # ---- e2e through the public API with HOST buffers ----
+    e2e = e2e_homogeneous(args, gdr, w, dev, flush, C0, build, X_d)
+
+    cpu = cpu_baseline(w, args, synth) if not (args.no_cpu_baseline or args.profile) else None
     line = {
         "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
-                               f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
+        "config": {"workload": workload_string(args.workload, w), "nnz_a_hat": int(nnz),
                    "precision": args.precision, "tc_screen": args.tc_screen, "l2": "flushed between timed steps (256 MB write)"},
         "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / pk["hbm"],
                  "frac_hbm_8TBs": prop_gbs / 8000.0, "bytes_model": "B_gather" if prop_model == "gather" else "B_min",
@@ -441,17 +676,254 @@ def run_ours(args, rank, world):
         "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
                       "s3_kmeans": float(km_ms.mean()), "s3_kmeans_per_iter": float(km_ms.sum() / np.sum(n_iter)),
                       "s4_coarsen": float(st[:, 3].mean())},
-        "roofline": roofline, "roofline_spmm": roofline_spmm, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
-        "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2]._nnz())},
+        "stage_rooflines": {
+            "s1": {"bytes_model": "E_in*16 + nnz*8", "gbs": float((w["u"].shape[0] * 16 + nnz * 8) / (st[:, 0].mean() / 1e3) / 1e9),
+                   "edges_per_s": float(w["u"].shape[0] / (st[:, 0].mean() / 1e3))},
+            "s4": {"bytes_model": "nnz*24", "gbs": float(nnz * 24 / (st[:, 3].mean() / 1e3) / 1e9),
+                   "edges_per_s": float(nnz / (st[:, 3].mean() / 1e3))}},
+        "roofline": roofline, "roofline_spmm": roofline_spmm, **legs, "cpu_baseline": cpu,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
+        "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2])},
     }
     print(json.dumps(line))
 
 
+def logit_leg(args, gdr, _lib, synth, w, dev, flush, pk):
+    """k-means on the width ClustGDD actually clusters: the MLP probe's logits, N x nclass
+    (clustgdd_agent_transduct.py:88-105; 47 classes at ogbn-products, 40 at arxiv, 7 at Cora)."""
+    import torch
+    n, K, D = w["n"], w["k"], w["d_logit"]
+    Xl = torch.from_numpy(synth.clustered_features(n, D, D, seed=w["seed"] + 200)).to(dev)
+    perm = torch.from_numpy(np.random.RandomState(w["seed"]).permutation(n)[:K].astype(np.int64)).to(dev)
+    C0 = Xl[perm].clone()
+
+    def fit():
+        return gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision).fit(Xl)
+
+    fit()
+    ts, its = [], []
+    for _ in range(3):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        km = fit()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+        its.append(km.n_iter_)
+    screen_ms, _ = _profile_kernel(_lib, 1, fit, 2, flush)
+    tf = 2.0 * n * K * D / (screen_ms / 1e3) / 1e12
+    return {"D": D, "value": float(sum(its) / (sum(ts) / 1e3)), "unit": "iters/s", "ms_per_iter": float(sum(ts) / sum(its)),
+            "screen_ms": float(screen_ms), "tflops": float(tf), "frac": float(tf / pk["bf16_sustained"]),
+            "note": "synthetic logits: mixture of nclass Gaussians; same K, init rule and iteration count as the headline"}
+
+
+def skewed_leg(args, gdr, _lib, synth, w, dev, flush, pk, X_d):
+    """SURVEY §8(d) secondary graph: hub-biased destinations (v = floor(N r^3) for half of the pairs) — exercises the
+    load balancing of the SpMM; hub rows hit L2, so DRAM bytes < B_gather here."""
+    import torch
+    n, F, hops = w["n"], w["f"], w["hops"]
+    u, v = synth.skewed_graph(n, w["pairs"], w["seed"] + 7)
+    A = gdr.sym_normalize(gdr.coo_to_csr(torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev), None, (n, n),
+                                         symmetrize=True, binarize=True), 2)
+    deg = (A.rowptr[1:] - A.rowptr[:-1])
+    gdr.propagate(A, X_d, hops + 1, ALPHA)
+    ms, _ = _profile_kernel(_lib, 2, lambda: gdr.propagate(A, X_d, hops + 1, ALPHA), 5, flush)
+    model = "gather" if n * F * 4 > 96e6 else "min"
+    b = spmm_bytes(A.nnz, n, n, F, model=model)
+    return {"graph": "skewed (50% of destinations floor(N r^3))", "nnz": int(A.nnz), "max_degree": int(deg.max()),
+            "mean_degree": float(A.nnz / n), "ms_per_hop": float(ms), "gbs": float(b / (ms / 1e3) / 1e9),
+            "frac": float(b / (ms / 1e3) / 1e9 / pk["hbm"]), "bytes_model": "B_gather" if model == "gather" else "B_min"}
+
+
+def e2e_homogeneous(args, gdr, w, dev, flush, C0, build, X_d):
+    """The same metric through the public API from pinned HOST buffers.  `value`: KMeans.fit with the H2D copy of the
+    propagated rows and the D2H read of labels + centres inside the timed region.  `pipeline`: the WHOLE step from
+    host buffers — H2D of the pair list and the features, stages 1-4, D2H of labels, centres and the coarsened graph."""
+    import torch
+    n, F, K, hops = w["n"], w["f"], w["k"], w["hops"]
+    C0_host = C0.cpu().numpy()
+    target_host = torch.empty((n, F), dtype=torch.float32).pin_memory()
+    target_host.copy_(gdr.propagate(build(), X_d, hops + 1, ALPHA)[1])
+    e2e_t = []
+    for i in range(2 if args.profile else max(3, min(args.steps, 6))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x_dev = target_host.to(dev, non_blocking=True)
+        km = gdr.KMeans(n_clusters=K, init=C0_host, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision).fit(x_dev)
+        km.labels_.cpu()
+        km.cluster_centers_.cpu()
+        torch.cuda.synchronize()
+        e2e_t.append((time.perf_counter() - t0, km.n_iter_))
+    e2e_t = e2e_t[1:]
+    out = {"value": float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t)), "unit": "iters/s",
+           "h2d_bytes_per_step": n * F * 4 + K * F * 4, "d2h_bytes_per_step": n * 4 + K * F * 4}
+    if args.profile:
+        return out
+    del target_host
+    u_pin, v_pin = torch.from_numpy(w["u"]).pin_memory(), torch.from_numpy(w["v"]).pin_memory()
+    X_pin = torch.from_numpy(w["X"]).pin_memory()
+    ts = []
+    for i in range(3):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        u_e, v_e, X_e = u_pin.to(dev, non_blocking=True), v_pin.to(dev, non_blocking=True), X_pin.to(dev, non_blocking=True)
+        An = gdr.sym_normalize(gdr.coo_to_csr(u_e, v_e, None, (n, n), symmetrize=True, binarize=True), 2)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        _, target = gdr.propagate(An, X_e, hops + 1, ALPHA)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        km = gdr.KMeans(n_clusters=K, init=C0_host, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision).fit(target)
+        lab_h, cen_h = km.labels_.cpu(), km.cluster_centers_.cpu()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        _, adj_syn = gdr.graph_compress(km.labels_, An, [])
+        idx_h, val_h = adj_syn._indices().cpu(), adj_syn._values().cpu()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        ts.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3, int(val_h.numel())))
+    ts = np.array(ts[1:], dtype=np.float64)
+    m = ts.mean(axis=0)
+    out["pipeline"] = {
+        "ms": float(m[:4].sum() * 1e3),
+        "stages_ms": {"s1_h2d_pairs_features_build_normalize": float(m[0] * 1e3), "s2_propagate": float(m[1] * 1e3),
+                      "s3_kmeans_d2h_labels_centres": float(m[2] * 1e3), "s4_coarsen_d2h_graph": float(m[3] * 1e3)},
+        "h2d_bytes": int(w["u"].shape[0] * 16 + n * F * 4 + K * F * 4),
+        "d2h_bytes": int(n * 4 + K * F * 4 + m[4] * 20),
+        "note": "wall clock with a synchronize per stage; pinned host buffers; whole step incl. all copies"}
+    return out
+
+
+# ========================================================================================
+# our arm, one GPU, bipartite (configs C / D)
+# ========================================================================================
+def run_ours_bipartite(args, dev, w):
+    import torch
+    import gdr
+    from gdr import _lib, synth
+    pk = peaks()
+    nu, ni, d, L, ku, ki, seed = w["users"], w["items"], w["d"], w["layers"], w["ku"], w["ki"], w["seed"]
+    u_d, i_d = torch.from_numpy(w["u"]).to(dev), torch.from_numpy(w["i"]).to(dev)
+    u0, i0 = torch.from_numpy(w["u0"]).to(dev), torch.from_numpy(w["i0"]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # fixed init per side: rows perm[:K] of the z-scored embeddings (distill_recsys.py:172)
+    C0 = []
+    for emb, K in ((u0, ku), (i0, ki)):
+        Xs = gdr.standard_scale(emb)
+        perm = torch.from_numpy(np.random.RandomState(seed).permutation(emb.shape[0])[:K].astype(np.int64)).to(dev)
+        C0.append(Xs[perm].clone())
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step():
+        e = [ev() for _ in range(5)]
+        e[0].record()
+        R = gdr.coo_to_csr(u_d, i_d, None, (nu, ni))                 # build_interaction_matrix: duplicates summed
+        graph = gdr.BipartiteGraph(R.coo_indices(), R.vals, nu, ni)  # degrees + LightGCN edge norm, R and R^T
+        e[1].record()
+        gdr.lightgcn_propagate(graph, u0, i0, L)
+        e[2].record()
+        its, maps, inertia = 0, [], 0.0
+        for emb, K, c0 in ((u0, ku, C0[0]), (i0, ki, C0[1])):
+            km = gdr.KMeans(n_clusters=K, init=c0, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision)
+            km.fit(gdr.standard_scale(emb))
+            its += km.n_iter_
+            inertia += km.inertia_
+            maps.append(km.labels_)
+        e[3].record()
+        C = gdr.build_condensed_bipartite(u_d, i_d, maps[0], maps[1], ku, ki, device=dev, return_device=True)
+        e[4].record()
+        return e, types.SimpleNamespace(n_iter_=its / 2.0, inertia_=inertia), int(C.nnz)
+
+    t_warm, n_warm = time.perf_counter(), 0
+    while n_warm < args.warmup or (not args.profile and time.perf_counter() - t_warm < 2.0):
+        step()
+        flush.fill_(1)
+        n_warm += 1
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    launches0 = gdr.launch_count()
+    recs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        recs.append(step())
+        sampler.sample_now()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = gdr.launch_count() - launches0
+    clocks = sampler.stop()
+    st = np.array([[r[0][i].elapsed_time(r[0][i + 1]) for i in range(4)] for r in recs])
+    n_iter = [r[1].n_iter_ for r in recs]
+    iters_per_s = float(np.sum(n_iter) / (st[:, 2].sum() / 1e3))
+    assign_ms, n_l = _profile_kernel(_lib, 1, step, 3, flush)
+    flops = 2.0 * (nu * ku + ni * ki) * d / 2.0     # mean over the two sides' E-steps (launches alternate)
+    a_tf = float(flops / (assign_ms / 1e3) / 1e12)
+    R = gdr.coo_to_csr(u_d, i_d, None, (nu, ni))
+    graph = gdr.BipartiteGraph(R.coo_indices(), R.vals, nu, ni)
+    spmm_ms, _ = _profile_kernel(_lib, 2, lambda: gdr.lightgcn_propagate(graph, u0, i0, L), 5, flush)
+    nnz = R.nnz
+    b_layer = 2 * nnz * 8 + (nu + ni + 2) * 4 + 2 * (nu + ni) * d * 4 + 2 * (nu + ni) * d * 4   # both directions of one layer (B_min, fused accumulate)
+    prop_gbs = float(L * b_layer / (st[:, 1].mean() / 1e3) / 1e9)
+
+    # e2e: kmeans_cluster-style call from HOST arrays (H2D of the embeddings, D2H of labels + centres), both sides
+    e2e_t = []
+    u0_pin, i0_pin = torch.from_numpy(w["u0"]).pin_memory(), torch.from_numpy(w["i0"]).pin_memory()
+    c0_host = [c.cpu().numpy() for c in C0]
+    for _ in range(max(3, min(args.steps, 6))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        its = 0
+        for pin, K, c0 in ((u0_pin, ku, c0_host[0]), (i0_pin, ki, c0_host[1])):
+            km = gdr.KMeans(n_clusters=K, init=c0, n_init=1, max_iter=LLOYD_ITERS, tol=0, precision=args.precision)
+            km.fit(gdr.standard_scale(pin.to(dev, non_blocking=True)))
+            km.labels_.cpu()
+            km.cluster_centers_.cpu()
+            its += km.n_iter_
+        torch.cuda.synchronize()
+        e2e_t.append((time.perf_counter() - t0, its / 2.0))
+    e2e_t = e2e_t[1:]
+    cpu = cpu_baseline(w, args, synth) if not (args.no_cpu_baseline or args.profile) else None
+    line = {
+        "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(st.sum(axis=1).mean()), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.workload, w), "nnz_r": int(nnz),
+                   "iteration": "one Lloyd iteration over BOTH sides (users + items)", "precision": args.precision,
+                   "l2": "flushed between timed steps (256 MB write)"},
+        "prop": {"metric": "LightGCN layers on R / R^T", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / pk["hbm"],
+                 "bytes_model": "B_min (embeddings fit L2)", "ms": float(st[:, 1].mean())},
+        "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(st[:, 1].mean()),
+                      "s3_kmeans": float(st[:, 2].mean()), "s3_kmeans_per_iter": float(st[:, 2].sum() / np.sum(n_iter)),
+                      "s4_coarsen": float(st[:, 3].mean())},
+        "roofline": {"kernel": "k_assign_tc (tcgen05), mean over the users' and items' E-steps", "bound": "tensor", "achieved": a_tf,
+                     "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": a_tf / pk["bf16_sustained"], "traffic": None,
+                     "launch_ms": float(assign_ms), "peak_source": pk["src"] + " bf16 sustained"},
+        "roofline_spmm": {"kernel": "k_spmm", "bound": "hbm", "launch_ms": float(spmm_ms), "peak": pk["hbm"], "unit": "GB/s",
+                          "achieved": float(b_layer / 2 / (spmm_ms / 1e3) / 1e9), "frac": float(b_layer / 2 / (spmm_ms / 1e3) / 1e9 / pk["hbm"]),
+                          "bytes_model": "B_min per direction", "traffic": None},
+        "cpu_baseline": cpu,
+        "e2e": {"value": float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t)), "unit": "iters/s",
+                "h2d_bytes_per_step": (nu + ni) * d * 4 + (ku + ki) * d * 4, "d2h_bytes_per_step": (nu + ni) * 4 + (ku + ki) * d * 4},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s": t_wall,
+        "result": {"inertia": recs[-1][1].inertia_, "n_iter": float(n_iter[-1]), "condensed_nnz": int(recs[-1][2])},
+    }
+    print(json.dumps(line))
+
+
+# ========================================================================================
+# our arm, N > 1
+# ========================================================================================
 def one_gpu_reference(workload):
     """The committed single-GPU measurement of the same workload (for the strong-scaling ratio)."""
-    name = {"E": "r1_bench_default_configE_1gpu.json", "B": "r1_bench_configB_v19.json"}.get(workload)
+    name = {"E": "r2_bench_configE_1gpu.json", "B": "r2_bench_configB_1gpu.json"}.get(workload)
     try:
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "source": "profiles/" + name}
@@ -459,16 +931,68 @@ def one_gpu_reference(workload):
         return None
 
 
-def run_ours_multi(args, rank, world, dev):
+def multi_parity(gdr, par, comm, part, ops, dev, w, A_ref, tgt_ref, C0, u_sl, v_sl):
+    """N > 1 parity record, computed OUTSIDE the timed region on every rank and reduced with MIN: this rank's
+    block of each stage against the same rows of the single-GPU path run on this very GPU.
+      adj_block_equal   rows of A_hat built by the all-to-all exchange == rows of the one-GPU build (rowptr/colidx/vals)
+      prop_rows_equal   distributed hops == one-GPU hops on this rank's rows (bit-exact: same fp32 chains)
+      labels_equal      ONE Lloyd step from shared centres on bit-identical rows: labels torch.equal to the one-GPU labels
+      centres_close     centres after that step within 1e-5 (the all-reduce order changes the last bits)
+      counts_equal      integer cell counts of the coarsened graph == one-GPU counts (same labels in)"""
+    import torch
+    import torch.distributed as dist
+    n, K, hops = w["n"], w["k"], w["hops"]
+    lo, hi = part.lo, part.hi
+    out = {}
+    A_blk = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)
+    A_rows = par.slice_rows(A_ref, lo, hi)
+    out["adj_block_equal"] = bool(torch.equal(A_blk.rowptr, A_rows.rowptr) and torch.equal(A_blk.colidx, A_rows.colidx)
+                                  and torch.equal(A_blk.vals, A_rows.vals))
+    x_local = torch.from_numpy(w["X"][lo:hi].copy()).to(dev)
+    _, t_l = par.dist_propagate(comm, part, A_blk, x_local, hops + 1, ALPHA, ops=ops)
+    out["prop_rows_equal"] = bool(torch.equal(t_l, tgt_ref[lo:hi]))
+    out["prop_rows_max_rel_err"] = float(((t_l - tgt_ref[lo:hi]).abs().max() / tgt_ref.abs().max()).item())
+    km1 = par.DistKMeans(K, C0, max_iter=1, tol=0, ops=ops, comm=comm).fit(tgt_ref[lo:hi].contiguous())
+    ref1 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(tgt_ref)
+    out["labels_equal"] = bool(torch.equal(km1.labels_, ref1.labels_[lo:hi]))
+    out["labels_differ"] = int((km1.labels_ != ref1.labels_[lo:hi]).sum().item())
+    cdiff = (km1.cluster_centers_ - ref1.cluster_centers_).abs().max() / ref1.cluster_centers_.abs().max()
+    out["centres_close"] = bool(cdiff.item() <= 1e-5)
+    labels = ref1.labels_
+    adj_syn, counts = par.dist_graph_compress(comm, part, labels[lo:hi].contiguous(), A_blk, ops=ops)
+    kk = int(labels.max()) + 1
+    rp1, ci1, cnt1, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_ref, drop_diag=True)
+    _, syn1 = gdr.graph_compress(labels, A_ref, [])
+    out["counts_equal"] = bool(counts.shape == cnt1.shape and torch.equal(counts, cnt1)
+                               and torch.equal(adj_syn._indices(), syn1._indices()))
+    vdiff = (adj_syn._values() - syn1._values()).abs().max() / syn1._values().abs().max() if out["counts_equal"] else torch.tensor(1.0)
+    out["coarse_values_close"] = bool(vdiff.item() <= 1e-5)
+    flags = [k for k, v in out.items() if isinstance(v, bool)]
+    t = torch.tensor([1 if out[k] else 0 for k in flags], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    d = torch.tensor([out["labels_differ"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(d)
+    e = torch.tensor([out["prop_rows_max_rel_err"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    res = {k: bool(v) for k, v in zip(flags, t.tolist())}
+    res["labels_differ"] = int(d.item())
+    res["prop_rows_max_rel_err"] = float(e.item())
+    must = ["adj_block_equal", "labels_equal", "centres_close", "counts_equal", "coarse_values_close"]
+    res["status"] = "ok" if all(res[k] for k in must) and res["prop_rows_max_rel_err"] <= 1e-5 else "MISMATCH"
+    res["what"] = "each rank's block vs the same rows of the single-GPU path (MIN over ranks); single Lloyd step from shared centres"
+    return res
+
+
+def run_ours_multi(args, rank, world, dev, w):
     """N > 1: the same step on the same graph, nodes row-partitioned over the ranks (strong
     scaling).  NCCL all-gather of the propagated rows per hop, all-reduce of the centroid
-    partial sums / counts per Lloyd iteration, dense all-reduce merge of the coarsened graph."""
+    partial sums / counts per Lloyd iteration, key-range exchange merge of the coarsened graph."""
     import torch
     import torch.distributed as dist
     import gdr
+    from gdr import _lib
     from gdr import parallel as par
     dist.init_process_group("nccl", device_id=dev)
-    w = make_workload(args.workload)
     n, F, K, hops, seed = w["n"], w["f"], w["k"], w["hops"], w["seed"]
     pk = peaks()
     part = par.RowPartition(n, world, rank)
@@ -488,7 +1012,11 @@ def run_ours_multi(args, rank, world, dev):
     perm = torch.from_numpy(np.random.RandomState(seed).permutation(n)[:K].astype(np.int64)).to(dev)
     C0 = tgt0[perm].clone()
     nnz = A0.nnz
-    del A0, tgt0
+    parity = None
+    if not args.no_parity:
+        parity = multi_parity(gdr, par, comm, part, ops, dev, w, A0, tgt0, C0, u_sl, v_sl)
+    del A0, tgt0, u_d, v_d
+    torch.cuda.empty_cache()
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -505,12 +1033,7 @@ def run_ours_multi(args, rank, world, dev):
         e[3].record()
         adj_syn, _ = par.dist_graph_compress(comm, part, km.labels_, A_local, ops=ops)
         e[4].record()
-        # keep only scalars: holding km / adj_syn of every step alive fragments the caching allocator
-        # and forces cudaMalloc (a device-wide sync) inside later timed steps
-        import types
-        nnz_syn = int(adj_syn._nnz())
-        return (e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_),
-                types.SimpleNamespace(_nnz=lambda v=nnz_syn: v))
+        return e, types.SimpleNamespace(n_iter_=km.n_iter_, inertia_=km.inertia_), int(adj_syn._nnz())
 
     t_warm = time.perf_counter()
     n_warm = 0
@@ -549,21 +1072,20 @@ def run_ours_multi(args, rank, world, dev):
 
     # ---- roofline leg (per GPU): the E-step tensor-core screen of this rank's row block, timed by the
     #      library's own CUDA-event pairs on its launch stream ----
-    import ctypes
-    from gdr import _lib
     A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)
     _, target_l = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops)
-    tot_ms, n_l = ctypes.c_double(0), ctypes.c_int64(0)
-    _lib.call("gdr_profile_enable", 1)
-    flush.fill_(1)
-    par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target_l)
-    torch.cuda.synchronize()
-    _lib.call("gdr_profile_collect", ctypes.addressof(tot_ms), ctypes.addressof(n_l))
-    _lib.call("gdr_profile_enable", 0)
-    assign_ms = tot_ms.value / max(1, n_l.value)
+    assign_ms, _ = _profile_kernel(
+        _lib, 1, lambda: par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target_l), 1, flush)
     am = torch.tensor([assign_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(am, op=dist.ReduceOp.MAX)
     assign_ms = float(am.item())
+    # per-hop split: the SpMM of this rank's rows alone (library event pairs) beside the whole hop
+    spmm_ms, n_sp = _profile_kernel(
+        _lib, 2, lambda: par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs,
+                                            row_chunks=args.row_chunks), 3, flush)
+    sm = torch.tensor([spmm_ms * n_sp / 3.0 / hops], dtype=torch.float64, device=dev)   # SpMM kernel time per hop
+    dist.all_reduce(sm, op=dist.ReduceOp.MAX)
+    spmm_per_hop = float(sm.item())
 
     # ---- e2e: DistKMeans.fit through the public API from pinned HOST rows (H2D of this rank's block of the
     #      propagated features, D2H of its labels + the centres), max over ranks ----
@@ -579,8 +1101,8 @@ def run_ours_multi(args, rank, world, dev):
         t0e = time.perf_counter()
         x_dev = target_host.to(dev, non_blocking=True)
         km = par.DistKMeans(K, C0_host, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(x_dev)
-        lab_h = km.labels_.cpu()
-        cen_h = km.cluster_centers_.cpu()
+        km.labels_.cpu()
+        km.cluster_centers_.cpu()
         torch.cuda.synchronize()
         tt = torch.tensor([time.perf_counter() - t0e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -607,64 +1129,39 @@ def run_ours_multi(args, rank, world, dev):
             "metric": "kmeans_iters_per_s", "value": iters_per_s, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config {args.workload}: {w['name']}-shaped uniform graph, N={n}, nnz(A_hat)={nnz}, F={F}, "
-                                   f"hops={hops}, K={K}, k-means D={F}, {LLOYD_ITERS} Lloyd iterations tol=0",
-                       "parallelism": f"row-partition x{world} (stage 1: pair slices, all-to-all by owner, all-gather of degrees; "
-                                      f"stage 2: all-gather per hop pipelined over {par.default_row_chunks(world) if args.row_chunks is None else args.row_chunks} row chunks; "
-                                      "stage 3: all-reduce of centroid sums/counts per Lloyd iteration; stage 4: dense n x n all-reduce)",
+            "config": {"workload": workload_string(args.workload, w), "nnz_a_hat": int(nnz),
+                       "parallelism": f"row-partition x{world}: " + par.describe(world, args.row_chunks),
                        "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
             "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / (pk["hbm"] * world),
-                     "bytes_model": ("B_gather" if prop_model == "gather" else "B_min") + " (whole job, incl. the all-gather time)", "ms": float(prop_ms.mean())},
+                     "bytes_model": ("B_gather" if prop_model == "gather" else "B_min") + " (whole job, incl. the all-gather time)",
+                     "ms": float(prop_ms.mean()), "ms_per_hop": float(prop_ms.mean() / hops),
+                     "spmm_kernel_ms_per_hop": spmm_per_hop,
+                     "exposed_gather_ms_per_hop": float(max(0.0, prop_ms.mean() / hops - spmm_per_hop))},
             "stages_ms": {"s1_build_normalize": float(st[:, 0].mean()), "s2_propagate": float(prop_ms.mean()),
                           "s3_kmeans": float(km_ms.mean()), "s3_kmeans_per_iter": float(km_ms.sum() / np.sum(n_iter)),
                           "s4_coarsen": float(st[:, 3].mean())},
-            "roofline": roofline, "cpu_baseline": None, "same_workload_1gpu": one_gpu_reference(args.workload),
+            "roofline": roofline, "parity": parity, "cpu_baseline": None, "same_workload_1gpu": one_gpu_reference(args.workload),
             "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks, "wall_s": t_wall,
-            "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2]._nnz())},
+            "result": {"inertia": recs[-1][1].inertia_, "n_iter": int(n_iter[-1]), "syn_nnz": int(recs[-1][2])},
         }
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
 
 
-CPU_SAMPLE_ROWS = 200_000   # bounded k-means sample of the large workload (all K centres, first rows of X)
-
-
-def cpu_kmeans_rate(w, it_lo, it_hi, rows_cap=None):
-    """k-means iterations/s of the reference's CPU path (sklearn Lloyd, all host threads) on workload w,
-    differenced between two max_iter values so that validation / centring / the final E-step cancel.
-    With rows_cap the fit runs on the first rows_cap rows against all K centres and the rate is scaled by
-    rows_cap / N (the E-step is linear in the rows and dominates: 2*N*K*D flops per iteration)."""
-    from oracle import ref_port as rp
-    from gdr import synth
-    n, K = w["n"], w["k"]
-    X = w["X"]
-    C0 = synth.kmeans_init(X, K, w["seed"])
-    m = n if rows_cap is None else min(n, int(rows_cap))
-    Xs = np.ascontiguousarray(X[:m])
-    if m < n:   # the init rows must lie inside the sample
-        C0 = synth.kmeans_init(Xs, K, w["seed"])
-    rp.kmeans_fit(Xs[:20000], C0[: min(K, 100)], 2)  # warm the thread pools
-    t0 = time.perf_counter()
-    rp.kmeans_fit(Xs, C0, it_lo)
-    t1 = time.perf_counter()
-    rp.kmeans_fit(Xs, C0, it_hi)
-    t2 = time.perf_counter()
-    s_iter = ((t2 - t1) - (t1 - t0)) / float(it_hi - it_lo)
-    rate = (1.0 / s_iter) * (m / n)
-    what = (f"sklearn KMeans(init=C0,n_init=1,tol=0) on "
-            + (f"the full {n}x{X.shape[1]} matrix" if m == n else f"the first {m} of {n} rows (x{X.shape[1]}), rate scaled by {m}/{n}")
-            + f", K={K}: fit({it_hi} it) - fit({it_lo} it)")
-    return rate, what
-
-
-def cpu_baseline(w, args):
-    """Bounded CPU sample on this box's host cores (oracle-side port of the reference)."""
-    from oracle import ref_port as rp
-    big = w["n"] * w["k"] > 1e9
-    rate, what = cpu_kmeans_rate(w, 1, 3, CPU_SAMPLE_ROWS) if big else cpu_kmeans_rate(w, 2, 12)
-    info = rp.host_info()
-    return {"value": rate, "unit": "iters/s", "cores": info["affinity"], "kind": "port", "sample": what, "host": info}
+def run_ours_multi_bipartite(args, rank, world, dev, w):
+    """Configs C / D on N GPUs: users and items each split N ways."""
+    import torch
+    import torch.distributed as dist
+    import gdr
+    from gdr import parallel as par
+    dist.init_process_group("nccl", device_id=dev)
+    line = par.bench_bipartite(args, rank, world, dev, w, dist, peaks(), ClockSampler, workload_string(args.workload, w),
+                               LLOYD_ITERS)
+    if rank == 0:
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -673,13 +1170,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["A", "B", "E"])
+    ap.add_argument("--workload", default=None, choices=["A", "B", "C", "D", "E"])
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
     ap.add_argument("--slabs", type=int, default=None, help="N > 1: column slabs of the pipelined hop (default: automatic)")
-    ap.add_argument("--row-chunks", type=int, default=None, help="N > 1: row chunks of the pipelined hop (default: 4)")
+    ap.add_argument("--row-chunks", type=int, default=None, help="N > 1: row chunks of the pipelined hop (default: automatic)")
     ap.add_argument("--tc-screen", type=int, default=0, help="debug: 0 auto, 1 direct 3xTF32, 2/3 two-level screen (BN 128/256)")
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
+    ap.add_argument("--ref-full-budget", type=float, default=420.0,
+                    help="reference arm, config E: seconds the once-per-run full-size legs may take (0 = skip them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the logit-space and skewed-graph legs")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity record")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no CPU baseline, minimal e2e leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

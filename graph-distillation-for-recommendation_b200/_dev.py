@@ -9,7 +9,14 @@ from . import _lib
 
 
 def ptr(t) -> int:
-    return 0 if t is None else t.data_ptr()
+    """Raw device pointer of a tensor argument.  Every kernel is launched on the CURRENT device's current stream, so a
+    tensor that lives on another GPU is rejected here instead of being dereferenced from the wrong device."""
+    if t is None:
+        return 0
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise ValueError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                         "select it first (torch.cuda.set_device / `with torch.cuda.device(...)`)")
+    return t.data_ptr()
 
 
 def stream() -> int:
@@ -30,6 +37,9 @@ def device_of(device=None) -> torch.device:
         raise ValueError(f"device {d} requested: the distillation core runs on CUDA only")
     if d.index is None:
         d = torch.device("cuda", torch.cuda.current_device())
+    elif d.index != torch.cuda.current_device():
+        raise ValueError(f"device {d} requested but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                         "select it first (torch.cuda.set_device / `with torch.cuda.device(...)`)")
     return d
 
 

@@ -87,6 +87,20 @@ _SIGNATURES = {
     "gdr_inertia_ws_bytes": (i64, [i64, i64]),
     "gdr_inertia": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp]),
     "gdr_add_row_vector": (i32, [i64, i64, vp, i64, vp, f32, vp]),
+    "gdr_comm_unique_id": (i32, [vp]),
+    "gdr_comm_init": (i32, [vp, vp, i32, i32]),
+    "gdr_comm_destroy": (i32, [vp]),
+    "gdr_comm_info": (i32, [vp, vp, vp, vp]),
+    "gdr_allgather_rows": (i32, [vp, vp, i64, i64, vp, vp]),
+    "gdr_allgather_bytes": (i32, [vp, vp, i64, vp, vp]),
+    "gdr_allreduce_centroids": (i32, [vp, vp, i64, vp, i64, vp]),
+    "gdr_allreduce_f64": (i32, [vp, vp, i64, i32, vp]),
+    "gdr_alltoallv": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_kmeans_lloyd_dist": (i32, [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i32, C.c_double, i32, vp, vp, vp, i32, vp,
+                                    i64, vp]),
+    "gdr_coarse_records": (i32, [i64, i64, vp, vp, vp, vp, vp, vp]),
+    "gdr_coarse_merge_ws_bytes": (i64, [i64]),
+    "gdr_coarse_merge": (i32, [i64, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_coarsen": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_scale": (i32, [i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -1,0 +1,244 @@
+// comm.cu — the multi-GPU exchange steps of the path as C-ABI entry points:
+//   gdr_comm_init / gdr_comm_destroy      one NCCL communicator per process (one process per GPU)
+//   gdr_allgather_rows                    stage 2: the propagated row block of every rank -> the full matrix
+//   gdr_allreduce_centroids               stage 3: [K x ld sums | K counts + n_changed] in ONE grouped all-reduce
+//   gdr_allgather_bytes / gdr_alltoallv   stage 1 / 4: degree vectors, edge buckets, (cell, count, sum) runs
+// The reference is single-device, so nothing here restates it; these are the exchanges the row partition needs.
+//
+// NCCL is bound at RUN time (dlopen of the libnccl.so.2 already mapped by the host framework, else the system one):
+// the library itself keeps no link-time dependency on NCCL and single-GPU users never load it.
+#include "common.cuh"
+#include "comm.cuh"
+#include <dlfcn.h>
+#include <mutex>
+#include <string.h>
+#include <vector>
+
+namespace gdr {
+
+static NcclApi g_api;
+static std::once_flag g_api_once;
+static bool g_api_ok = false;
+static char g_api_err[256] = "";
+
+static void load_nccl() {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy the host framework (torch) already mapped
+    if (h) break;
+  }
+  if (!h) {
+    if (const char* p = getenv("GDR_NCCL_LIB")) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+    for (const char* n : names) {
+      if (h) break;
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+  }
+  if (!h) {
+    snprintf(g_api_err, sizeof(g_api_err), "cannot load libnccl.so.2 (%s); set GDR_NCCL_LIB", dlerror());
+    return;
+  }
+#define GDR_SYM(field, name)                                                        \
+  g_api.field = (decltype(g_api.field))dlsym(h, name);                              \
+  if (!g_api.field) {                                                               \
+    snprintf(g_api_err, sizeof(g_api_err), "libnccl lacks %s", name);               \
+    return;                                                                         \
+  }
+  GDR_SYM(GetUniqueId, "ncclGetUniqueId")
+  GDR_SYM(CommInitRank, "ncclCommInitRank")
+  GDR_SYM(CommDestroy, "ncclCommDestroy")
+  GDR_SYM(AllReduce, "ncclAllReduce")
+  GDR_SYM(AllGather, "ncclAllGather")
+  GDR_SYM(Send, "ncclSend")
+  GDR_SYM(Recv, "ncclRecv")
+  GDR_SYM(GroupStart, "ncclGroupStart")
+  GDR_SYM(GroupEnd, "ncclGroupEnd")
+  GDR_SYM(GetErrorString, "ncclGetErrorString")
+  GDR_SYM(GetVersion, "ncclGetVersion")
+#undef GDR_SYM
+  g_api_ok = true;
+}
+
+const NcclApi* nccl_api() {
+  std::call_once(g_api_once, load_nccl);
+  if (!g_api_ok) {
+    set_error("%s", g_api_err);
+    return nullptr;
+  }
+  return &g_api;
+}
+
+#define GDR_NCCL(call)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r__ = (call);                                                                  \
+    if (r__ != ncclSuccess) {                                                                   \
+      ::gdr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, api->GetErrorString(r__));  \
+      return GDR_ECUDA;                                                                         \
+    }                                                                                           \
+  } while (0)
+
+int comm_allreduce_lloyd(gdr_comm* c, float* sums, int64_t n_floats, int32_t* ints, int64_t n_ints, cudaStream_t s) {
+  if (!c || c->world == 1) return GDR_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return GDR_ECUDA;
+  GDR_NCCL(api->GroupStart());
+  if (n_floats > 0) GDR_NCCL(api->AllReduce(sums, sums, (size_t)n_floats, ncclFloat32, ncclSum, c->nccl, s));
+  if (n_ints > 0) GDR_NCCL(api->AllReduce(ints, ints, (size_t)n_ints, ncclInt32, ncclSum, c->nccl, s));
+  GDR_NCCL(api->GroupEnd());
+  count_launch(1);
+  return GDR_OK;
+}
+
+int comm_allreduce_f64(gdr_comm* c, double* buf, int64_t n, int op_max, cudaStream_t s) {
+  if (!c || c->world == 1) return GDR_OK;
+  const NcclApi* api = nccl_api();
+  if (!api) return GDR_ECUDA;
+  GDR_NCCL(api->AllReduce(buf, buf, (size_t)n, ncclFloat64, op_max ? ncclMax : ncclSum, c->nccl, s));
+  count_launch(1);
+  return GDR_OK;
+}
+
+int comm_allgather(gdr_comm* c, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s) {
+  if (!c || c->world == 1) {
+    if (send != recv && bytes_per_rank > 0)
+      GDR_CUDA(cudaMemcpyAsync(recv, send, (size_t)bytes_per_rank, cudaMemcpyDeviceToDevice, s));
+    return GDR_OK;
+  }
+  const NcclApi* api = nccl_api();
+  if (!api) return GDR_ECUDA;
+  GDR_NCCL(api->AllGather(send, recv, (size_t)bytes_per_rank, ncclInt8, c->nccl, s));
+  count_launch(1);
+  return GDR_OK;
+}
+
+}  // namespace gdr
+
+using namespace gdr;
+
+extern "C" {
+
+int gdr_comm_unique_id(void* id128_host) {
+  GDR_CHECK_ARG(id128_host, "comm_unique_id: null output");
+  const NcclApi* api = nccl_api();
+  if (!api) return GDR_ECUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  GDR_NCCL(api->GetUniqueId(&id));
+  memcpy(id128_host, &id, sizeof(id));
+  return GDR_OK;
+}
+
+int gdr_comm_init(gdr_comm_t** comm_out, const void* id128_host, int rank, int world) {
+  GDR_CHECK_ARG(comm_out && world >= 1 && rank >= 0 && rank < world, "comm_init: bad arguments");
+  gdr_comm* c = new gdr_comm();
+  c->rank = rank;
+  c->world = world;
+  c->nccl = nullptr;
+  GDR_CUDA(cudaGetDevice(&c->device));
+  if (world > 1) {
+    const NcclApi* api = nccl_api();
+    if (!api || !id128_host) {
+      delete c;
+      if (api) set_error("comm_init: null unique id");
+      return api ? GDR_EINVAL : GDR_ECUDA;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128_host, sizeof(id));
+    ncclResult_t r = api->CommInitRank(&c->nccl, world, id, rank);
+    if (r != ncclSuccess) {
+      set_error("ncclCommInitRank -> %s", api->GetErrorString(r));
+      delete c;
+      return GDR_ECUDA;
+    }
+  }
+  *comm_out = c;
+  return GDR_OK;
+}
+
+int gdr_comm_destroy(gdr_comm_t* comm) {
+  if (!comm) return GDR_OK;
+  if (comm->nccl) {
+    const NcclApi* api = nccl_api();
+    if (api) api->CommDestroy(comm->nccl);
+  }
+  delete comm;
+  return GDR_OK;
+}
+
+int gdr_comm_info(const gdr_comm_t* comm, int* rank_host, int* world_host, int* nccl_version_host) {
+  GDR_CHECK_ARG(comm, "comm_info: null communicator");
+  if (rank_host) *rank_host = comm->rank;
+  if (world_host) *world_host = comm->world;
+  if (nccl_version_host) {
+    *nccl_version_host = 0;
+    if (comm->world > 1) {
+      const NcclApi* api = nccl_api();
+      if (api) api->GetVersion(nccl_version_host);
+    }
+  }
+  return GDR_OK;
+}
+
+int gdr_allgather_rows(gdr_comm_t* comm, const float* local, int64_t rows_per_rank, int64_t ld, float* full,
+                       gdr_stream_t stream) {
+  GDR_CHECK_ARG(comm && rows_per_rank >= 0 && ld > 0 && (rows_per_rank == 0 || (local && full)),
+                "allgather_rows: bad arguments");
+  return comm_allgather(comm, local, full, rows_per_rank * ld * 4, (cudaStream_t)stream);
+}
+
+int gdr_allgather_bytes(gdr_comm_t* comm, const void* local, int64_t bytes_per_rank, void* full, gdr_stream_t stream) {
+  GDR_CHECK_ARG(comm && bytes_per_rank >= 0 && (bytes_per_rank == 0 || (local && full)), "allgather_bytes: bad arguments");
+  return comm_allgather(comm, local, full, bytes_per_rank, (cudaStream_t)stream);
+}
+
+int gdr_allreduce_centroids(gdr_comm_t* comm, float* sums, int64_t n_floats, int32_t* ints, int64_t n_ints,
+                            gdr_stream_t stream) {
+  GDR_CHECK_ARG(comm && n_floats >= 0 && n_ints >= 0 && (n_floats == 0 || sums) && (n_ints == 0 || ints),
+                "allreduce_centroids: bad arguments");
+  return comm_allreduce_lloyd(comm, sums, n_floats, ints, n_ints, (cudaStream_t)stream);
+}
+
+int gdr_allreduce_f64(gdr_comm_t* comm, double* buf, int64_t n, int op_max, gdr_stream_t stream) {
+  GDR_CHECK_ARG(comm && n >= 0 && (n == 0 || buf), "allreduce_f64: bad arguments");
+  return comm_allreduce_f64(comm, buf, n, op_max, (cudaStream_t)stream);
+}
+
+int gdr_alltoallv(gdr_comm_t* comm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,
+                  void* recv, const int64_t* recv_off_host, const int64_t* recv_cnt_host, int64_t elem_bytes,
+                  gdr_stream_t stream) {
+  GDR_CHECK_ARG(comm && send_off_host && send_cnt_host && recv_off_host && recv_cnt_host && elem_bytes > 0,
+                "alltoallv: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int me = comm->rank;
+  if (comm->world == 1) {
+    if (send_cnt_host[0] > 0)
+      GDR_CUDA(cudaMemcpyAsync((char*)recv + recv_off_host[0] * elem_bytes, (const char*)send + send_off_host[0] * elem_bytes,
+                               (size_t)(send_cnt_host[0] * elem_bytes), cudaMemcpyDeviceToDevice, s));
+    return GDR_OK;
+  }
+  const NcclApi* api = nccl_api();
+  if (!api) return GDR_ECUDA;
+  if (send_cnt_host[me] != recv_cnt_host[me]) {
+    set_error("alltoallv: own block sizes differ");
+    return GDR_EINVAL;
+  }
+  if (send_cnt_host[me] > 0)
+    GDR_CUDA(cudaMemcpyAsync((char*)recv + recv_off_host[me] * elem_bytes, (const char*)send + send_off_host[me] * elem_bytes,
+                             (size_t)(send_cnt_host[me] * elem_bytes), cudaMemcpyDeviceToDevice, s));
+  GDR_NCCL(api->GroupStart());
+  for (int p = 0; p < comm->world; ++p) {
+    if (p == me) continue;
+    if (send_cnt_host[p] > 0)
+      GDR_NCCL(api->Send((const char*)send + send_off_host[p] * elem_bytes, (size_t)(send_cnt_host[p] * elem_bytes), ncclInt8, p,
+                         comm->nccl, s));
+    if (recv_cnt_host[p] > 0)
+      GDR_NCCL(api->Recv((char*)recv + recv_off_host[p] * elem_bytes, (size_t)(recv_cnt_host[p] * elem_bytes), ncclInt8, p,
+                         comm->nccl, s));
+  }
+  GDR_NCCL(api->GroupEnd());
+  count_launch(1);
+  return GDR_OK;
+}
+
+}  // extern "C"

@@ -54,6 +54,18 @@ struct ProfileScope {
 
 constexpr int kSMs = 148;  // B200
 
+// "done once" flags for per-device function attributes (cudaFuncSetAttribute is per device: a second
+// GPU driven from the same process needs its own opt-in).  Usage: static PerDevice<bool> set; if (!set.get()) ...
+template <typename T>
+struct PerDevice {
+  T v[64] = {};
+  T& get() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return v[dev & 63];
+  }
+};
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

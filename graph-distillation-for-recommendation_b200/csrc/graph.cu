@@ -496,6 +496,65 @@ __global__ void __launch_bounds__(256) k_coarsen_scale(int64_t n_src, const int3
   }
 }
 
+// ---- key-range merge of per-rank coarsened graphs (multi-GPU stage 4) ----
+// cell key of every entry of a coarse CSR: (a << bbits) | b
+// 16-byte record per entry: [cell key | (count << 32) | weight-sum bits]
+__global__ void k_coarse_records(int64_t n_src, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 const int32_t* __restrict__ counts, const float* __restrict__ wsum, int bbits,
+                                 uint64_t* __restrict__ rec) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < n_src; r += nw)
+    for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+      rec[2 * (int64_t)j] = ((uint64_t)r << bbits) | (uint64_t)(uint32_t)colidx[j];
+      rec[2 * (int64_t)j + 1] = ((uint64_t)(uint32_t)counts[j] << 32) | (uint64_t)(wsum ? __float_as_uint(wsum[j]) : 0u);
+    }
+}
+
+__global__ void k_split_records(int64_t n, const uint64_t* __restrict__ rec, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ perm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = rec[2 * i];
+    perm[i] = (uint32_t)i;
+  }
+}
+
+// one thread per run of equal cells: integer count sum (exact) and fp32 weight sum in the stable order of the
+// records (= source-rank order of the exchange: deterministic); runs are at most `world` long
+__global__ void k_merge_runs(const int32_t* __restrict__ n_runs_dev, const int32_t* __restrict__ head_index,
+                             const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ perm,
+                             const uint64_t* __restrict__ rec, uint64_t bmask,
+                             int32_t* __restrict__ colidx, int32_t* __restrict__ counts, float* __restrict__ wsum) {
+  int64_t m = *n_runs_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    float s = 0.f;
+    for (int j = head_index[p]; j < head_index[p + 1]; ++j) {
+      const uint64_t v = rec[2 * (int64_t)perm[j] + 1];
+      c += (int)(uint32_t)(v >> 32);
+      s = __fadd_rn(s, __uint_as_float((uint32_t)v));
+    }
+    colidx[p] = (int32_t)(ukeys[p] & bmask);
+    counts[p] = c;
+    if (wsum) wsum[p] = s;
+  }
+}
+
+// rowptr of the coarse rows [a_lo, a_lo + n_rows) from the sorted unique keys
+__global__ void k_rowptr_from_ukeys_range(const int32_t* __restrict__ n_runs_dev, int64_t a_lo, int64_t n_rows, int shift,
+                                          const uint64_t* __restrict__ ukeys, int32_t* __restrict__ rowptr,
+                                          int64_t* __restrict__ nnz_out) {
+  int64_t m = *n_runs_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= m; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = i == 0 ? -1 : (int64_t)(ukeys[i - 1] >> shift) - a_lo;
+    int64_t hi = i == m ? n_rows : (int64_t)(ukeys[i] >> shift) - a_lo;
+    if (hi > n_rows) hi = n_rows;
+    if (lo < -1) lo = -1;
+    for (int64_t r = lo + 1; r <= hi; ++r) rowptr[r] = (int32_t)i;
+    if (i == m) *nnz_out = m;
+  }
+}
+
 // sparse (rowptr, colidx, counts, wsum) -> dense n_src x n_dst (one writer per cell: no atomics)
 __global__ void k_scatter_dense(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr,
                                 const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts,
@@ -908,6 +967,59 @@ int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx,
   GDR_CHECK_ARG(rowptr && colidx && row_out, "csr_to_coo: null pointer");
   k_csr_to_coo<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, row_out,
                                                                        col_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- key-range merge of per-rank coarsened graphs (multi-GPU stage 4) ----------------
+int gdr_coarse_records(int64_t n_src, int64_t n_dst, const int32_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                       const float* wsum, uint64_t* records_out, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_src > 0 && n_dst > 0 && rowptr && colidx && counts && records_out, "coarse_records: bad arguments");
+  k_coarse_records<<<grid_for(n_src * 32), 256, 0, (cudaStream_t)stream>>>(n_src, rowptr, colidx, counts, wsum,
+                                                                          bits_for(n_dst), records_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_coarse_merge_ws_bytes(int64_t m) {
+  m = m > 0 ? m : 1;
+  return ws_need(m, 8) + ws_need(m, 4) + sort_pairs_ws_bytes(m) + runs_ws_bytes(m, false) + 512;
+}
+
+int gdr_coarse_merge(int64_t m, const uint64_t* records, int64_t a_lo, int64_t n_rows, int64_t n_src, int64_t n_dst,
+                     int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum, int64_t* nnz_out_dev, void* ws,
+                     int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(m >= 0 && n_rows >= 0 && n_src > 0 && n_dst > 0 && a_lo >= 0 && rowptr && nnz_out_dev,
+                "coarse_merge: bad arguments");
+  GDR_CHECK_ARG(m < (1ll << 31), "coarse_merge: size exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_rows + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(records && colidx && counts, "coarse_merge: null pointer");
+  if (ws_bytes < gdr_coarse_merge_ws_bytes(m)) {
+    set_error("coarse_merge: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(m);
+  uint32_t* perm = W.take<uint32_t>(m);
+  const int64_t sws_b = sort_pairs_ws_bytes(m);
+  void* sws = W.take<char>(sws_b);
+  RunBuffers R = carve_runs(W, m, false);
+  k_split_records<<<grid_for(m), 256, 0, s>>>(m, records, keys, perm);
+  GDR_LAUNCHED();
+  const int abits = bits_for(n_src), bbits = bits_for(n_dst);
+  int rc = sort_pairs(m, abits + bbits, keys, perm, sws, sws_b, s);   // stable: equal cells keep the exchange order
+  if (rc) return rc;
+  rc = reduce_runs(m, keys, nullptr, R, s);
+  if (rc) return rc;
+  k_merge_runs<<<grid_for(m), 256, 0, s>>>(R.pos + m, R.head_index, R.ukeys, perm, records, (1ull << bbits) - 1, colidx,
+                                           counts, wsum);
+  GDR_LAUNCHED();
+  k_rowptr_from_ukeys_range<<<grid_for(m + 1), 256, 0, s>>>(R.pos + m, a_lo, n_rows, bbits, R.ukeys, rowptr, nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -376,7 +376,8 @@ int launch_assign_simt_rows(int64_t max_rows, int64_t K, int64_t D, const float*
     set_error("re-score kernel: D=%lld exceeds its shared-memory plan", (long long)D);
     return GDR_EUNSUPPORTED;
   }
-  static size_t smem_set = 0;
+  static PerDevice<size_t> smem_set_dev;
+  size_t& smem_set = smem_set_dev.get();
   if (smem > 48 * 1024 && smem > smem_set) {
     GDR_CUDA(cudaFuncSetAttribute(k_refine_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
@@ -517,7 +518,10 @@ __global__ void __launch_bounds__(256) k_average(int64_t K, int D, const float* 
 
 // single block: total shift (fixed order), #empty, first argmax of counts; then the
 // empty clusters take the centre of the largest cluster and their shift is added.
+// sklearn's _average_centers (_k_means_common.pyx:274-295) does this IN PLACE while walking j upwards: an empty
+// cluster j < argmax copies the argmax row BEFORE that row has been scaled (the raw sums), j > argmax the mean.
 __global__ void __launch_bounds__(1024) k_finalize_tail(int64_t K, int D,
+                                                        const float* __restrict__ sums, int64_t lds,
                                                         const int32_t* __restrict__ counts,
                                                         const float* __restrict__ C_old, int64_t ldo,
                                                         float* __restrict__ C_new, int64_t ldn,
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(1024) k_finalize_tail(int64_t K, int D,
       if (counts[k] != 0) continue;
       double sh = 0.0;
       for (int c = l; c < D; c += 32) {
-        float v = C_new[(int64_t)amax * ldn + c];
+        float v = k < amax ? sums[(int64_t)amax * lds + c] : C_new[(int64_t)amax * ldn + c];
         C_new[k * ldn + c] = v;
         if (C_old) {
           double d = (double)v - (double)C_old[k * ldo + c];
@@ -704,6 +708,73 @@ __global__ void __launch_bounds__(256) k_relocate_one(int nparts, const float* _
   }
 }
 
+// ---- distributed relocation (lloyd.cu: relocate_distributed) ----------------------------------
+// candidate record: [dist, rank (int bits), old label (int bits), x[0..D)]
+__global__ void __launch_bounds__(256) k_pick_candidate(int nparts, const float* __restrict__ pv,
+                                                        const int32_t* __restrict__ pi, int D,
+                                                        const float* __restrict__ X, int64_t ldx,
+                                                        const int32_t* __restrict__ labels, float* __restrict__ dist,
+                                                        float* __restrict__ rec, int rank) {
+  __shared__ int s_far;
+  __shared__ float s_val;
+  if (threadIdx.x == 0) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = 0; i < nparts; ++i) {
+      if (pv[i] > bv || (pv[i] == bv && pi[i] < bi)) {
+        bv = pv[i];
+        bi = pi[i];
+      }
+    }
+    s_far = bi;
+    s_val = bv;
+  }
+  __syncthreads();
+  const int far = s_far;
+  const float val = s_val;
+  if (!(val >= 0.f) || far == 0x7fffffff) {   // no row left on this rank
+    if (threadIdx.x == 0) rec[0] = -1.f;
+    return;
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) rec[3 + c] = X[(int64_t)far * ldx + c];
+  if (threadIdx.x == 0) {
+    rec[0] = val;
+    rec[1] = __int_as_float(rank);
+    rec[2] = __int_as_float(labels[far]);
+    dist[far] = -1.f;  // never picked again
+  }
+}
+
+__global__ void k_fill_f32(int64_t n, float* __restrict__ p, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// applies the global choice: the e-th empty cluster receives candidate order[e] (sequentially: a cluster may lose
+// several rows and the fp32 subtraction order is part of the result)
+__global__ void __launch_bounds__(256) k_relocate_apply(int ne, const int32_t* __restrict__ order,
+                                                        const int32_t* __restrict__ empties, const float* __restrict__ allrec,
+                                                        int D, float* __restrict__ sums, int64_t lds,
+                                                        int32_t* __restrict__ counts) {
+  for (int e = 0; e < ne; ++e) {
+    const int j = order[e];
+    if (j < 0) break;
+    const float* r = allrec + (int64_t)j * (D + 3);
+    const int old = __float_as_int(r[2]);
+    const int nw = empties[e];
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      const float x = r[3 + c];
+      sums[(int64_t)old * lds + c] = __fsub_rn(sums[(int64_t)old * lds + c], x);
+      sums[(int64_t)nw * lds + c] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      counts[nw] = 1;
+      counts[old] -= 1;
+    }
+    __syncthreads();
+  }
+}
+
 // second pass of the variance: per-block sums of (x - mean) and (x - mean)^2
 __global__ void __launch_bounds__(256) k_colvar_partial(int64_t N, int D, const float* __restrict__ X, int64_t ldx,
                                                         const double* __restrict__ mean, double* __restrict__ part) {
@@ -786,6 +857,47 @@ __global__ void __launch_bounds__(256) k_colstats_reduce(int D, int nblocks, con
 }  // namespace gdr
 
 using namespace gdr;
+
+namespace gdr {
+
+int64_t relocate_candidates_ws_bytes(int64_t N) { return ws_need(N > 0 ? N : 1, 4) + 2 * ws_need(1024, 4) + 256; }
+
+// this rank's `ne` farthest rows (distance to their own centre, largest first, ties by row order) as records
+int relocate_candidates(int64_t N, int64_t D, const float* X, int64_t ldx, const float* C_old, int64_t ldc,
+                        const int32_t* labels, int ne, int rank, float* rec, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < relocate_candidates_ws_bytes(N)) {
+    set_error("relocate_candidates: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  const int64_t rec_w = D + 3;
+  k_fill_f32<<<(unsigned)std::min<int64_t>(cdiv((int64_t)ne * rec_w, 256), 1024), 256, 0, s>>>((int64_t)ne * rec_w, rec, -1.f);
+  GDR_LAUNCHED();
+  if (N == 0) return GDR_OK;
+  Workspace W(ws, ws_bytes);
+  float* dist = W.take<float>(N);
+  float* pv = W.take<float>(1024);
+  int32_t* pi = W.take<int32_t>(1024);
+  k_row_dist<<<(unsigned)cdiv(N, 8), 256, 0, s>>>(N, (int)D, X, ldx, C_old, ldc, labels, dist, nullptr);
+  GDR_LAUNCHED();
+  const int nparts = (int)std::min<int64_t>(1024, cdiv(N, 256));
+  const int take = (int)std::min<int64_t>(ne, N);
+  for (int e = 0; e < take; ++e) {
+    k_argmax_part<<<nparts, 256, 0, s>>>(N, dist, pv, pi);
+    GDR_LAUNCHED();
+    k_pick_candidate<<<1, 256, 0, s>>>(nparts, pv, pi, (int)D, X, ldx, labels, dist, rec + (int64_t)e * rec_w, rank);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
+}
+
+int relocate_apply(int ne, const int32_t* order_dev, const int32_t* empties_dev, const float* allrec, int64_t D,
+                   float* sums, int64_t lds, int32_t* counts, cudaStream_t s) {
+  k_relocate_apply<<<1, 256, 0, s>>>(ne, order_dev, empties_dev, allrec, (int)D, sums, lds, counts);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+}  // namespace gdr
 
 extern "C" {
 
@@ -1023,7 +1135,7 @@ int gdr_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t lds, co
   k_average<<<(unsigned)cdiv(K, 8), 256, 0, s>>>(K, (int)D, sums, lds, counts, C_old, ldc_old, C_new,
                                                 ldc_new, shift_arr, mean_mode);
   GDR_LAUNCHED();
-  k_finalize_tail<<<1, 1024, 0, s>>>(K, (int)D, counts, C_old, ldc_old, C_new, ldc_new, shift_arr,
+  k_finalize_tail<<<1, 1024, 0, s>>>(K, (int)D, sums, lds, counts, C_old, ldc_old, C_new, ldc_new, shift_arr,
                                      stats_dev, mean_mode);
   GDR_LAUNCHED();
   return GDR_OK;

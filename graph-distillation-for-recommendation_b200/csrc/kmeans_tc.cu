@@ -1313,7 +1313,8 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
                             const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D_eff, int64_t Kp,
                             int nkb, const float* cnorm, float* best, float* second, int32_t* idx, cudaStream_t s) {
   using Cfg = TcCfg<NPASS, BN, SUB>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.get();
   if (!attr_set) {
     GDR_CUDA(cudaFuncSetAttribute(k_assign_tc<NPASS, BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TC_SMEM_LIMIT));
@@ -1336,7 +1337,8 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
 static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c, int64_t N_max, const int32_t* n_rows_dev,
                                  int D_eff, int64_t Kp, int nkb, float* best, float* second, int32_t* idx, int fwd,
                                  cudaStream_t s) {
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.get();
   if (!attr_set) {
     GDR_CUDA(cudaFuncSetAttribute(k_assign_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::total(TC_BAR_KB)));
     attr_set = true;

@@ -349,7 +349,8 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
     set_error("sort_pairs: n=%lld exceeds int32 positions", (long long)n);
     return GDR_ERANGE;
   }
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.get();
   if (!attr_set) {
     GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)rs_scatter_smem(4, RS_MAX_BITS)));

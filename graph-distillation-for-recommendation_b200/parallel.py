@@ -59,6 +59,21 @@ class RowPartition:
         return hi - lo
 
 
+def _wire(t: torch.Tensor) -> torch.Tensor:
+    """The tensor a collective is given for ``t``.  Row-padded matrices (``_dev.new_padded``: width f inside a
+    leading dimension pad4(f)) are non-contiguous views whenever f % 4 != 0, which NCCL and gloo reject; the
+    collective then runs on the padded base (same storage, all ld columns — the padding columns are zeros on every
+    rank, so sums and gathers leave them zero)."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        ld, rows = t.stride(0), t.shape[0]
+        have = t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()
+        if rows * ld <= have:
+            return t.as_strided((rows, ld), (ld, 1))
+    raise ValueError("collective on a non-contiguous tensor that is not a row-padded matrix")
+
+
 class Comm:
     """Thin wrapper over torch.distributed (or a no-op for world size 1)."""
 
@@ -68,10 +83,44 @@ class Comm:
         self.rank = 0 if dist is None else dist.get_rank(group)
         self.backend = None if dist is None else dist.get_backend(group)
 
+    # -- the library's own communicator (gdr_comm_t: NCCL bound inside libgdr_b200) --------------------
+    def lib_handle(self):
+        """gdr_comm_t* of this group, created on first use (collective: every rank must call it at the same
+        point).  Rank 0 draws the NCCL unique id through the C ABI, torch.distributed broadcasts the 128 bytes."""
+        if getattr(self, "_lib_comm", None) is not None:
+            return self._lib_comm
+        import ctypes
+        from . import _lib
+        handle = ctypes.c_void_p()
+        if self.dist is None or self.world == 1:
+            _lib.call("gdr_comm_init", ctypes.addressof(handle), 0, 0, 1)
+        else:
+            if self.backend != "nccl":
+                raise RuntimeError("the in-library communicator needs the nccl backend")
+            idbuf = (ctypes.c_ubyte * 128)()
+            if self.rank == 0:
+                _lib.call("gdr_comm_unique_id", ctypes.addressof(idbuf))
+            t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            self.dist.broadcast(t, src=src, group=self.group)
+            raw = bytes(t.cpu().tolist())
+            idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+            _lib.call("gdr_comm_init", ctypes.addressof(handle), ctypes.addressof(idbuf), self.rank, self.world)
+        self._lib_comm = handle
+        return handle
+
+    def close(self):
+        """Destroys the library communicator (call before torch.distributed.destroy_process_group)."""
+        h = getattr(self, "_lib_comm", None)
+        if h is not None:
+            from . import _lib
+            _lib.call("gdr_comm_destroy", h)
+            self._lib_comm = None
+
     def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
         if self.dist is not None and self.world > 1:
-            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX}
-            self.dist.all_reduce(t, op=ops[op], group=self.group)
+            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}
+            self.dist.all_reduce(_wire(t), op=ops[op], group=self.group)
         return t
 
     def all_gather_rows(self, local: torch.Tensor, out: torch.Tensor, async_op: bool = False):
@@ -81,11 +130,14 @@ class Comm:
         if self.dist is None or self.world == 1:
             out[: local.shape[0]].copy_(local)
             return _Done() if async_op else out
-        if self.backend == "nccl" and out.is_contiguous() and local.is_contiguous():
-            w = self.dist.all_gather_into_tensor(out, local, group=self.group, async_op=async_op)
+        lw, ow = _wire(local), _wire(out)
+        if lw.dim() == 2 and lw.shape[1] != ow.shape[1]:
+            raise ValueError("all_gather_rows: blocks of different leading dimension")
+        if self.backend == "nccl":
+            w = self.dist.all_gather_into_tensor(ow, lw, group=self.group, async_op=async_op)
         else:
-            chunks = list(out.chunk(self.world, dim=0))
-            w = self.dist.all_gather(chunks, local, group=self.group, async_op=async_op)
+            chunks = list(ow.chunk(self.world, dim=0))
+            w = self.dist.all_gather(chunks, lw, group=self.group, async_op=async_op)
         return w if async_op else out
 
 
@@ -305,6 +357,31 @@ class CudaOps:
         s = stats[:2].cpu()
         return float(s[0]), int(s[1])
 
+    def lloyd_native(self, comm, Xc, n_total, C0c, max_iter, tol_abs, verbose=False):
+        """The whole Lloyd loop inside libgdr_b200 (gdr_kmeans_lloyd_dist): graph-replayed iterations with the packed
+        all-reduce inside, one 24-byte status read-back per iteration.  Returns (labels, inertia, centres, n_iter)."""
+        import ctypes
+        n_local, D = Xc.shape
+        K = C0c.shape[0]
+        dev = C0c.device
+        mode = 1 if (self.precision == "tc" or (self.precision == "auto" and D <= 128)) else 0
+        centers = self.new_padded(K, D, dev, zero=True)
+        centers.copy_(C0c)
+        labels = torch.empty(max(n_local, 1), dtype=torch.int32, device=dev)[:n_local]
+        ws = self.workspace(self._lib.query("gdr_kmeans_lloyd_ws_bytes", n_local, K, D, mode), dev)
+        inertia, n_iter, info = ctypes.c_double(0.0), ctypes.c_int32(0), (ctypes.c_int32 * 2)()
+        self._lib.call("gdr_kmeans_lloyd_dist", comm.lib_handle(), n_local, int(n_total), K, D,
+                       self.ptr(Xc) if n_local else 0, Xc.stride(0) if n_local else self._pad4(D), self.ptr(centers),
+                       centers.stride(0), self.ptr(labels) if n_local else 0, int(max_iter), float(tol_abs), mode,
+                       ctypes.addressof(inertia), ctypes.addressof(n_iter), ctypes.addressof(info), int(bool(verbose)),
+                       self.ptr(ws), ws.numel(), self.stream())
+        self.last_info = (bool(info[0]), int(info[1]))
+        return labels, float(inertia.value), centers, int(n_iter.value)
+
+    @staticmethod
+    def _pad4(d):
+        return (int(d) + 3) // 4 * 4
+
     def inertia(self, Xc, C, labels):
         out = torch.zeros(1, dtype=torch.float64, device=C.device)
         if Xc.shape[0] == 0:
@@ -321,38 +398,45 @@ class CudaOps:
     def label_counts(self, labels, n):
         return self._co.label_counts(labels, n)
 
-    def coarsen_dense(self, A_local, labels_src, labels_dst, n):
+    def coarsen_records(self, A_local, labels_src, labels_dst, n, world):
+        """Local edges -> sorted (cell, count, weight sum) records [m, 2] int64 (gdr_coarsen + gdr_coarse_records) and the
+        number of records per owner rank of the key-range partition (coarse row a belongs to rank a // ceil(n / world))."""
         rowptr, colidx, counts, wsum = self._co.coarsen_edges(labels_src, labels_dst, n, n, csr=A_local,
                                                               weights=A_local.vals, drop_diag=True)
-        dev = labels_dst.device
-        dc = torch.empty((n, n), dtype=torch.int32, device=dev)
-        dw = torch.empty((n, n), dtype=torch.float32, device=dev)
-        self._lib.call("gdr_coarse_scatter_dense", n, n, self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum),
-                       self.ptr(dc), self.ptr(dw), self.stream())
-        return dc, dw
-
-    def dense_to_coo(self, dc, dw, sizes):
-        n = dc.shape[0]
-        dev = dc.device
-        cap = int(n) * int(n)
-        rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
-        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
-        # count first so that the outputs are sized by the merged nnz, not n^2
-        m_est = int((dc != 0).sum().item())
-        colidx = torch.empty(max(m_est, 1), dtype=torch.int32, device=dev)
-        counts = torch.empty(max(m_est, 1), dtype=torch.int32, device=dev)
-        wsum = torch.empty(max(m_est, 1), dtype=torch.float32, device=dev)
-        ws = self.workspace(self._lib.query("gdr_dense_to_coarse_ws_bytes", n), dev)
-        self._lib.call("gdr_dense_to_coarse", n, n, self.ptr(dc), self.ptr(dw), self.ptr(rowptr), self.ptr(colidx),
-                       self.ptr(counts), self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
-        m = int(nnz.item())
-        assert m == m_est and m <= cap
-        vals = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        m = int(colidx.numel())
+        rec = torch.empty((m, 2), dtype=torch.int64, device=labels_dst.device)
         if m:
-            self._lib.call("gdr_coarsen_scale", n, self.ptr(rowptr), self.ptr(colidx), self.ptr(wsum), self.ptr(sizes),
-                           self.ptr(sizes), self.ptr(vals), self.stream())
-        S = self._g.CSR(rowptr, colidx[:m], vals[:m], (n, n))
-        return S.to_torch_coo(), counts[:m]
+            self._lib.call("gdr_coarse_records", n, n, self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum),
+                           self.ptr(rec), self.stream())
+        cr = (n + world - 1) // world
+        bounds = torch.tensor([min(n, r * cr) for r in range(world + 1)], dtype=torch.int64, device=rowptr.device)
+        cuts = rowptr[bounds].cpu().tolist()
+        return rec, [int(cuts[r + 1] - cuts[r]) for r in range(world)]
+
+    def coarse_merge(self, rec, a_lo, n_rows, n):
+        """Records received from every rank -> CSR (rowptr, colidx, counts, wsum) of the coarse rows [a_lo, a_lo + n_rows)."""
+        m = int(rec.shape[0])
+        dev = rec.device
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        wsum = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = self.workspace(self._lib.query("gdr_coarse_merge_ws_bytes", m), dev)
+        self._lib.call("gdr_coarse_merge", m, self.ptr(rec) if m else 0, int(a_lo), int(n_rows), n, n, self.ptr(rowptr),
+                       self.ptr(colidx), self.ptr(counts), self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
+        k = int(nnz.item())
+        return rowptr, colidx[:k], counts[:k], wsum[:k]
+
+    def coarse_scale(self, rowptr, colidx, wsum, sizes, a_lo, n_rows):
+        vals = torch.empty_like(wsum)
+        if n_rows > 0 and wsum.numel():
+            self._lib.call("gdr_coarsen_scale", n_rows, self.ptr(rowptr), self.ptr(colidx), self.ptr(wsum),
+                           self.ptr(sizes[a_lo:]), self.ptr(sizes), self.ptr(vals), self.stream())
+        return vals
+
+    def csr_to_coo(self, rowptr, colidx, vals, n):
+        return self._g.CSR(rowptr, colidx, vals, (n, n)).to_torch_coo()
 
 
 # ------------------------------------------------------------------------------------------
@@ -436,6 +520,15 @@ def default_row_chunks(world: int) -> int:
     8 GPUs 8.49 ms (one pass) -> 7.94 ms (4 chunks); 4 GPUs 11.97 -> 11.75 ms; 2 GPUs 19.1 -> 20.8 ms (the all-gather is only 0.8 ms of a
     6.3 ms hop there and the extra launches / concurrent NCCL traffic cost more), hence 4 chunks from 4 ranks up."""
     return 4 if world >= 4 else 1
+
+
+def describe(world: int, row_chunks: Optional[int] = None) -> str:
+    """One-line description of the exchanges, for bench.py's config.parallelism."""
+    rc = default_row_chunks(world) if row_chunks is None else int(row_chunks)
+    return ("stage 1: pair slices, all-to-all by owner, all-gather of degrees; "
+            f"stage 2: all-gather of the propagated rows per hop, pipelined over {rc} row chunk(s); "
+            "stage 3: one packed all-reduce [sums | counts | n_changed] per Lloyd iteration; "
+            "stage 4: key-range all-to-all of the local (cell, count, sum) runs")
 
 
 def dist_propagate(comm: Comm, part: RowPartition, A_local, x_local: torch.Tensor, prop_num: int, alpha: float,
@@ -527,10 +620,13 @@ class DistKMeans:
     """Lloyd k-means on row-partitioned X with replicated centres (init must be an array that
     is identical on every rank)."""
 
-    def __init__(self, n_clusters: int, init, max_iter: int = 300, tol: float = 1e-4, ops=None, comm: Comm = None):
+    def __init__(self, n_clusters: int, init, max_iter: int = 300, tol: float = 1e-4, ops=None, comm: Comm = None,
+                 verbose: bool = False, python_loop: bool = False):
         self.n_clusters, self.init, self.max_iter, self.tol = int(n_clusters), init, int(max_iter), tol
         self.ops = ops or CudaOps()
         self.comm = comm or Comm()
+        self.verbose = verbose
+        self.python_loop = python_loop   # force the host-driven loop (any backend / injected ops); default: in-library loop
 
     def fit(self, X_local: torch.Tensor):
         ops, comm, K = self.ops, self.comm, self.n_clusters
@@ -553,6 +649,15 @@ class DistKMeans:
                              dtype=torch.float32).to(dev)
         if tuple(C0.shape) != (K, D):
             raise ValueError("init has the wrong shape")
+        if hasattr(ops, "lloyd_native") and (comm.world == 1 or comm.backend == "nccl") and not self.python_loop:
+            lab, inertia, cen, n_iter = ops.lloyd_native(comm, Xc, N, ops.centers_like(C0 - mean, dev), self.max_iter,
+                                                         tol_abs, self.verbose)
+            self.labels_ = lab
+            self.cluster_centers_ = (cen + mean).contiguous()
+            self.inertia_ = inertia
+            self.n_iter_ = n_iter
+            self._centers_centered, self._mean = cen, mean
+            return self
         centers = [ops.centers_like(C0 - mean, dev), ops.centers_like(torch.zeros_like(C0), dev)]
         labels = [torch.full((n_local,), -1, dtype=torch.int32, device=dev) for _ in range(2)]
         psums = ops.centers_like(torch.zeros_like(C0), dev)
@@ -631,28 +736,58 @@ class DistKMeans:
 # ------------------------------------------------------------------------------------------
 # stage 4
 # ------------------------------------------------------------------------------------------
-MAX_DENSE_CELLS = 1 << 28   # 2^28 cells = 1 GiB int32 + 1 GiB f32 per rank
+def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None, replicate: bool = True):
+    """graph_compress (clustgdd_agent_transduct.py:234-250) for a row-partitioned A_hat.
 
-
-def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None):
-    """graph_compress (clustgdd_agent_transduct.py:234-250) for a row-partitioned A_hat: returns
-    (adj_syn torch sparse COO n x n replicated on every rank, merged integer cell counts)."""
+    Every rank coarsens its local edges into sorted (cell, count, weight sum) runs; the runs are exchanged by KEY RANGE
+    (coarse row a -> rank a // ceil(n / world), all-to-all) and merged by their owner: integer counts are exact and
+    independent of the rank count, fp32 weight sums are added in source-rank order (deterministic).  O(local nnz) memory
+    on every rank, no n x n array anywhere (config E: n^2 = 10^8 cells).  With ``replicate`` (default) the pieces are
+    all-gathered, and every rank returns the reference's result: (adj_syn torch sparse COO n x n, merged integer cell
+    counts).  Without it: this rank's coarse rows as (a_lo, rowptr, colidx, vals, counts)."""
     ops = ops or CudaOps()
     dev = labels_local.device
-    rows_per = part.rows_per
+    rows_per, world = part.rows_per, part.world
     block = torch.full((rows_per,), -1, dtype=torch.int32, device=dev)
     block[: labels_local.shape[0]] = labels_local.to(torch.int32)
-    gathered = torch.empty(rows_per * part.world, dtype=torch.int32, device=dev)
+    gathered = torch.empty(rows_per * world, dtype=torch.int32, device=dev)
     comm.all_gather_rows(block, gathered)
     # drop the padding of every rank's block
-    pieces = [gathered[r * rows_per: r * rows_per + (part.bounds(r)[1] - part.bounds(r)[0])] for r in range(part.world)]
+    pieces = [gathered[r * rows_per: r * rows_per + (part.bounds(r)[1] - part.bounds(r)[0])] for r in range(world)]
     labels_all = torch.cat(pieces).contiguous()
     nmax = labels_all.max().to(torch.int64).reshape(1)
     n = int(comm.all_reduce(nmax, "max").item()) + 1
-    if n * n > MAX_DENSE_CELLS:
-        raise NotImplementedError(f"dense merge needs n^2 <= {MAX_DENSE_CELLS}; key-range exchange is the next step")
     sizes = ops.label_counts(labels_all, n)
-    dc, dw = ops.coarsen_dense(A_local, labels_local.to(torch.int32).contiguous(), labels_all, n)
-    comm.all_reduce(dc)
-    comm.all_reduce(dw)
-    return ops.dense_to_coo(dc, dw, sizes)
+    rec, send_counts = ops.coarsen_records(A_local, labels_local.to(torch.int32).contiguous(), labels_all, n, world)
+    recv, _ = comm.all_to_all_rows(rec, send_counts)
+    cr = (n + world - 1) // world
+    a_lo = min(n, comm.rank * cr)
+    n_rows = min(n, a_lo + cr) - a_lo
+    rowptr, colidx, counts, wsum = ops.coarse_merge(recv, a_lo, n_rows, n)
+    vals = ops.coarse_scale(rowptr, colidx, wsum, sizes, a_lo, n_rows)
+    if not replicate:
+        return a_lo, rowptr, colidx, vals, counts
+    if world == 1:
+        return ops.csr_to_coo(rowptr, colidx, vals, n), counts
+    # replicate: all-gather the pieces (variable sizes) and the row pointers
+    nnz_mine = torch.tensor([int(colidx.shape[0])], dtype=torch.int64, device=dev)
+    nnz_all = torch.empty(world, dtype=torch.int64, device=dev)
+    comm.all_gather_rows(nnz_mine, nnz_all)
+    nnz_list = [int(v) for v in nnz_all.tolist()]
+    col_all = comm.all_gather_var(colidx, nnz_list)
+    val_all = comm.all_gather_var(vals, nnz_list)
+    cnt_all = comm.all_gather_var(counts, nnz_list)
+    rp_block = torch.zeros(cr + 1, dtype=torch.int32, device=dev)
+    rp_block[: n_rows + 1] = rowptr
+    rp_g = torch.empty(world * (cr + 1), dtype=torch.int32, device=dev)
+    comm.all_gather_rows(rp_block, rp_g)
+    rowptr_all = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    off = 0
+    for r in range(world):
+        lo = min(n, r * cr)
+        rows_r = min(n, lo + cr) - lo
+        if rows_r > 0:
+            rowptr_all[lo: lo + rows_r] = rp_g[r * (cr + 1): r * (cr + 1) + rows_r] + off
+        off += nnz_list[r]
+    rowptr_all[n] = off
+    return ops.csr_to_coo(rowptr_all, col_all, val_all, n), cnt_all

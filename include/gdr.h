@@ -424,6 +424,55 @@ int gdr_softmax_rows(int64_t n, int64_t C, const float* X, int64_t ld, float* ou
 int gdr_class_edge_weight(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                           const float* er, const float* prob, int64_t ldp, int64_t cls, float* w_out,
                           gdr_stream_t stream);
+/* ---- multi-GPU exchange steps (one process per GPU, NCCL over NVLink) -------------------
+ * The reference is single-device (clustgdd_agent_transduct.py:38-129 runs every stage on one `device`), so
+ * these entry points replace nothing in it: they are the exchanges a row partition of the same path needs.
+ * NCCL is bound at run time (dlopen of the already mapped libnccl.so.2, else the system copy / $GDR_NCCL_LIB).
+ * Protocol: rank 0 calls gdr_comm_unique_id, the host framework broadcasts the 128 bytes, every rank calls
+ * gdr_comm_init (collective).  All exchange calls are collective and are enqueued on `stream`. */
+typedef struct gdr_comm gdr_comm_t;
+int gdr_comm_unique_id(void* id128_host);
+int gdr_comm_init(gdr_comm_t** comm_out, const void* id128_host, int rank, int world);
+int gdr_comm_destroy(gdr_comm_t* comm);
+int gdr_comm_info(const gdr_comm_t* comm, int* rank_host, int* world_host, int* nccl_version_host);
+/* stage 2 (clustgdd_agent_transduct.py:59-65 on a row partition): full[r*rows_per_rank + i][:] = rank r's local[i][:];
+ * rows are ld floats wide (padding columns travel with the row), every rank passes the same rows_per_rank. */
+int gdr_allgather_rows(gdr_comm_t* comm, const float* local, int64_t rows_per_rank, int64_t ld, float* full,
+                       gdr_stream_t stream);
+int gdr_allgather_bytes(gdr_comm_t* comm, const void* local, int64_t bytes_per_rank, void* full, gdr_stream_t stream);
+/* stage 3 (sklearn/_k_means_lloyd.pyx:124-152: the per-thread partial sums are reduced there; here per GPU):
+ * sums[n_floats] (f32) and ints[n_ints] (i32: counts, n_changed) summed over the ranks IN PLACE as ONE grouped
+ * NCCL operation; every rank receives bit-identical results. */
+int gdr_allreduce_centroids(gdr_comm_t* comm, float* sums, int64_t n_floats, int32_t* ints, int64_t n_ints,
+                            gdr_stream_t stream);
+int gdr_allreduce_f64(gdr_comm_t* comm, double* buf, int64_t n, int op_max, gdr_stream_t stream);
+/* stage 1 / 4: variable all-to-all of fixed-size elements (edge buckets by owner row, (cell, count, sum) runs by key
+ * range).  Offsets / counts are HOST arrays of `world` entries, in elements of elem_bytes. */
+int gdr_alltoallv(gdr_comm_t* comm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,
+                  void* recv, const int64_t* recv_off_host, const int64_t* recv_cnt_host, int64_t elem_bytes,
+                  gdr_stream_t stream);
+/* stage 4 on a row partition (clustgdd_agent_transduct.py:234-250): every rank coarsens its local edges
+ * (gdr_coarsen), turns the result into 16-byte records [cell key = (a << bits(n_dst)) | b ; (count << 32) | weight-sum
+ * bits] (gdr_coarse_records; uint64[m][2]), exchanges them by key range (coarse row a -> owner rank, gdr_alltoallv) and merges what it
+ * receives: stable sort by cell, integer count sums (exact, independent of the rank count), fp32 weight sums in
+ * source-rank order (deterministic).  Output: the CSR of coarse rows [a_lo, a_lo + n_rows). */
+int     gdr_coarse_records(int64_t n_src, int64_t n_dst, const int32_t* rowptr, const int32_t* colidx,
+                           const int32_t* counts, const float* wsum, uint64_t* records_out, gdr_stream_t stream);
+int64_t gdr_coarse_merge_ws_bytes(int64_t m);
+int     gdr_coarse_merge(int64_t m, const uint64_t* records, int64_t a_lo, int64_t n_rows, int64_t n_src,
+                         int64_t n_dst, int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
+                         int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+/* gdr_kmeans_lloyd on a row partition: Xc_local = this rank's N_local rows (may be 0) of the mean-centred matrix of
+ * N_total rows, centres replicated.  Each iteration all-reduces [K x ld sums | K counts | n_changed] inside the replayed
+ * CUDA graph; the replicated centres stay bit-identical across ranks; empty clusters are relocated from the globally
+ * farthest rows (_k_means_common.pyx:167-211).  Workspace: gdr_kmeans_lloyd_ws_bytes(N_local, ...).  inertia is the
+ * global WCSS.  SYNCHRONISES the stream once per iteration (24-byte status), like gdr_kmeans_lloyd. */
+int gdr_kmeans_lloyd_dist(gdr_comm_t* comm, int64_t N_local, int64_t N_total, int64_t K, int64_t D,
+                          const float* Xc_local, int64_t ldx, float* C_inout, int64_t ldc, int32_t* labels_out,
+                          int max_iter, double tol_abs, int precision_mode, double* inertia_out_host,
+                          int32_t* n_iter_out_host, int32_t* info_out_host, int verbose, void* ws, int64_t ws_bytes,
+                          gdr_stream_t stream);
+
 /* Induced subgraph  adj[np.ix_(idx, idx)]  (utils_graphsaint.py:34-36, utils.py:127-129) as relabelled COO
  * triplets: row i of the result is node idx[i].  Outputs have the capacity of the source nnz; the caller turns
  * them into a CSR with gdr_coo_to_csr.  idx entries must lie in [0, n). */

@@ -151,7 +151,8 @@ void oracle_segment_sum(int64_t N, int64_t K, int64_t D, const float* X, int64_t
 }
 
 /* _average_centers + _center_shift   sklearn/_k_means_common.pyx:274-311
- * alpha = 1.0f / weight ; centers *= alpha ; empty -> centre of the first largest cluster.
+ * alpha = 1.0f / weight ; centers *= alpha ; empty -> row of the first largest cluster, copied IN PLACE while j
+ * walks upwards as sklearn does: an empty j < argmax sees that row before it is scaled (raw sums), j > argmax after.
  * Returns sum_j |new_j - old_j|^2 (accumulated in double). */
 double oracle_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t lds,
                               const int32_t* counts, const float* C_old, int64_t ldo, float* C_new,
@@ -167,7 +168,8 @@ double oracle_kmeans_finalize(int64_t K, int64_t D, const float* sums, int64_t l
   }
   for (int64_t j = 0; j < K; ++j) {
     if (counts[j] <= 0)
-      for (int64_t k = 0; k < D; ++k) C_new[j * ldn + k] = C_new[amax * ldn + k];
+      for (int64_t k = 0; k < D; ++k)
+        C_new[j * ldn + k] = j < amax ? sums[amax * lds + k] : C_new[amax * ldn + k];
   }
   double tot = 0.0;
   for (int64_t j = 0; j < K; ++j)

@@ -99,6 +99,35 @@ def build_condensed_bipartite(train_u, train_i, u2cu, i2ci, num_cu, num_ci) -> s
     return C.tocsr()
 
 
+def build_interaction_matrix(num_users: int, num_items: int, u: np.ndarray, i: np.ndarray) -> sp.csr_matrix:
+    """distill_recsys.py:110-117: COO of ones -> CSR (duplicate lines summed by tocsr)."""
+    vals = np.ones_like(u, dtype=np.float32)
+    return sp.coo_matrix((vals, (u, i)), shape=(num_users, num_items)).tocsr()
+
+
+def lightgcn_propagate(cu: torch.Tensor, ci: torch.Tensor, w: torch.Tensor, u0: torch.Tensor, i0: torch.Tensor,
+                       num_layers: int):
+    """distill_recsys.py:329-353 on torch CPU: index_add_ degrees, edge norm, L simultaneous layers, layer mean."""
+    deg_u = torch.zeros(u0.shape[0]).index_add_(0, cu, w)
+    deg_i = torch.zeros(i0.shape[0]).index_add_(0, ci, w)
+    norm = w / (torch.sqrt(deg_u[cu] + 1e-8) * torch.sqrt(deg_i[ci] + 1e-8))
+    u, it = u0, i0
+    u_layers, i_layers = [u], [it]
+    for _ in range(num_layers):
+        u_msg = torch.zeros_like(u).index_add_(0, cu, it[ci] * norm.unsqueeze(1))
+        i_msg = torch.zeros_like(it).index_add_(0, ci, u[cu] * norm.unsqueeze(1))
+        u, it = u_msg, i_msg
+        u_layers.append(u)
+        i_layers.append(it)
+    return torch.stack(u_layers, dim=0).mean(dim=0), torch.stack(i_layers, dim=0).mean(dim=0)
+
+
+def standard_scale(X: np.ndarray) -> np.ndarray:
+    """distill_recsys.py:172."""
+    from sklearn.preprocessing import StandardScaler
+    return StandardScaler(with_mean=True, with_std=True).fit_transform(X)
+
+
 def er_estimator(adj: torch.Tensor, src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     """utils_clustgdd.py:151-162."""
     degree = adj @ torch.ones(adj.shape[0])

@@ -64,10 +64,30 @@ def _worker(rank, world, port):
         tn = t1.cpu().numpy()
         C0 = synth.kmeans_init(tn, k, seed=13)
         # single step from shared centres (SURVEY §8c protocol 1): labels equal, centres to 1e-5
+        # (rows of `target` are bit-identical to t1's, asserted above, so the labels must be EQUAL, not nearly equal)
         km1 = par.DistKMeans(k, C0, max_iter=1, tol=0, ops=ops, comm=comm).fit(target)
         ref1 = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=1, tol=0).fit(t1)
-        assert (km1.labels_ == ref1.labels_[part.lo:part.hi]).float().mean().item() > 0.9999
+        assert torch.equal(km1.labels_, ref1.labels_[part.lo:part.hi])
         torch.testing.assert_close(km1.cluster_centers_, ref1.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
+        # the host-driven loop (torch.distributed collectives) and the in-library loop (NCCL inside libgdr_b200,
+        # graph-replayed) are the same algorithm: identical fits
+        kmp = par.DistKMeans(k, C0, max_iter=8, tol=0, ops=ops, comm=comm, python_loop=True).fit(target)
+        kml = par.DistKMeans(k, C0, max_iter=8, tol=0, ops=ops, comm=comm).fit(target)
+        assert kmp.n_iter_ == kml.n_iter_ and torch.equal(kmp.labels_, kml.labels_)
+        assert torch.equal(kmp.cluster_centers_, kml.cluster_centers_)
+        # replicated centres bit-identical on every rank
+        cc = kml.cluster_centers_.clone()
+        mx = cc.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        assert torch.equal(cc, mx)
+        # empty clusters: duplicated initial centres -> distributed relocation == single-GPU relocation
+        C0e = C0.copy()
+        C0e[3] = C0e[2]
+        C0e[4] = C0e[2]
+        kme = par.DistKMeans(k, C0e, max_iter=1, tol=0, ops=ops, comm=comm).fit(target)
+        refe = gdr.KMeans(n_clusters=k, init=C0e, n_init=1, max_iter=1, tol=0).fit(t1)
+        torch.testing.assert_close(kme.cluster_centers_, refe.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
+        assert torch.equal(kme.labels_, refe.labels_[part.lo:part.hi])
         # end to end (protocol 2): same iteration count, WCSS within 1e-4, labels nearly all equal
         km = par.DistKMeans(k, C0, max_iter=15, tol=0, ops=ops, comm=comm).fit(target)
         ref = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=15, tol=0).fit(t1)
@@ -86,7 +106,29 @@ def _worker(rank, world, port):
         assert torch.equal(adj_syn._indices(), syn1._indices())
         assert torch.equal(counts, cnt1)
         torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+        # not replicated: this rank's key range of the coarse rows
+        a_lo, rp_p, ci_p, v_p, c_p = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
+                                                             replicate=False)
+        rp1, ci1, cnt1b, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_full, drop_diag=True)
+        nr = rp_p.shape[0] - 1
+        b, e = int(rp1[a_lo]), int(rp1[a_lo + nr])
+        assert torch.equal(rp_p + b, rp1[a_lo:a_lo + nr + 1]) and torch.equal(ci_p, ci1[b:e]) and torch.equal(c_p, cnt1b[b:e])
+        # feature widths that are not a multiple of 4 (row-padded, non-contiguous views in the collectives)
+        for f2 in (7, 47):
+            X2 = synth.clustered_features(n, f2, 20, seed=21 + f2)
+            x2 = torch.from_numpy(X2[part.lo:part.hi].copy()).to(dev)
+            for rc in (1, 3):
+                p2, t2 = par.dist_propagate(comm, part, A_local, x2, 3, 0.8, ops=ops, row_chunks=rc)
+                p2r, t2r = gdr.propagate(A_full, torch.from_numpy(X2).to(dev), 3, 0.8)
+                assert torch.equal(p2, p2r[part.lo:part.hi]) and torch.equal(t2, t2r[part.lo:part.hi])
+            C2 = synth.kmeans_init(X2, 50, seed=3)
+            for py in (False, True):
+                k2 = par.DistKMeans(50, C2, max_iter=1, tol=0, ops=ops, comm=comm, python_loop=py).fit(x2)
+                r2 = gdr.KMeans(n_clusters=50, init=C2, n_init=1, max_iter=1, tol=0).fit(torch.from_numpy(X2).to(dev))
+                assert torch.equal(k2.labels_, r2.labels_[part.lo:part.hi])
+                torch.testing.assert_close(k2.cluster_centers_, r2.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
         torch.cuda.synchronize()
+        comm.close()
     finally:
         dist.destroy_process_group()
 

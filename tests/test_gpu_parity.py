@@ -210,6 +210,18 @@ def test_kmeans_empty_cluster_relocation_golden(gdr, dev):
     assert abs(km.inertia_ - float(g["empty_inertia"])) <= 1e-4 * float(g["empty_inertia"])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_kmeans_empty_clusters_filled_in_place_golden(gdr, dev, precision):
+    """sklearn's own fit on the degenerate case (n_clusters > distinct rows): skipped relocation, in-place
+    _average_centers (an empty cluster below the largest one gets its raw SUM), then a real relocation."""
+    g = golden("kmeans_edge.npz")
+    for it in (1, 2, 5):
+        km = gdr.KMeans(n_clusters=6, init=g["c0"], n_init=1, max_iter=it, tol=0, precision=precision).fit(g["x"])
+        assert km.n_iter_ == int(g[f"it{it}_n_iter"])
+        assert np.array_equal(km.labels_, g[f"it{it}_labels"])
+        np.testing.assert_allclose(km.cluster_centers_, g[f"it{it}_centers"], rtol=1e-5, atol=2e-6)
+
+
 def test_kmeans_errors(gdr, dev):
     x = np.random.RandomState(0).randn(10, 3).astype(np.float32)
     with pytest.raises(ValueError):

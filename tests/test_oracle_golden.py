@@ -134,6 +134,17 @@ def test_kmeans_empty_cluster_relocation(oracle):
     assert abs(res["inertia"] - float(g["empty_inertia"])) <= 1e-4 * float(g["empty_inertia"])
 
 
+def test_kmeans_empty_clusters_filled_in_place(oracle):
+    """More clusters than distinct rows: relocation is skipped (all distances zero) and sklearn's in-place
+    _average_centers gives an empty cluster BELOW the largest one that cluster's raw sum, one above it the mean."""
+    g = golden("kmeans_edge.npz")
+    for it in (1, 2, 5):
+        res = oracle.kmeans_fit(g["x"], g["c0"], max_iter=it, tol=0)
+        assert res["n_iter"] == int(g[f"it{it}_n_iter"])
+        assert np.array_equal(res["labels"], g[f"it{it}_labels"])
+        np.testing.assert_allclose(res["centers"], g[f"it{it}_centers"], rtol=1e-5, atol=2e-6)
+
+
 def test_standard_scaler(oracle):
     g = golden("standard_scaler.npz")
     np.testing.assert_allclose(oracle.standard_scale(g["x"]), g["out"], rtol=1e-6, atol=1e-6)

@@ -3,7 +3,7 @@
 The product has no CPU kernels, so the compute backend is replaced by ``OracleOps`` — the
 oracle behind the same small interface as ``CudaOps`` — and what is under test is the
 multi-rank host logic: partition bounds, padded all-gathers, packed all-reduces, the
-replicated finalise / convergence decisions, the dense merge of stage 4 and the
+replicated finalise / convergence decisions, the key-range exchange merge of stage 4 and the
 distributed empty-cluster relocation.  Results are compared with the single-process oracle.
 """
 import os
@@ -174,22 +174,58 @@ class OracleOps:
     def label_counts(self, labels, n):
         return torch.bincount(labels.long(), minlength=n).to(torch.int32)
 
-    def coarsen_dense(self, A, labels_src, labels_dst, n):
+    @staticmethod
+    def _bits(n):
+        b = 1
+        while (1 << b) < n:
+            b += 1
+        return b
+
+    def coarsen_records(self, A, labels_src, labels_dst, n, world):
         rows = np.repeat(np.arange(A.shape[0]), np.diff(A.rowptr.numpy()))
         rp, ci, cnt, wsum = self.o.coarsen_counts(rows, A.colidx.numpy(), labels_src.numpy(), labels_dst.numpy(), n, n,
                                                   w=A.vals.numpy(), drop_diag=True)
-        dc = np.zeros((n, n), np.int32)
-        dw = np.zeros((n, n), np.float32)
-        rr = np.repeat(np.arange(n), np.diff(rp))
-        dc[rr, ci] = cnt
-        dw[rr, ci] = wsum
-        return torch.from_numpy(dc), torch.from_numpy(dw)
+        a = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+        key = (a << self._bits(n)) | ci.astype(np.int64)
+        wbits = wsum.astype(np.float32).view(np.uint32).astype(np.int64)
+        rec = np.stack([key, (cnt.astype(np.int64) << 32) | wbits], axis=1)
+        cr = (n + world - 1) // world
+        cuts = [int(rp[min(n, r * cr)]) for r in range(world + 1)]
+        return torch.from_numpy(rec), [cuts[r + 1] - cuts[r] for r in range(world)]
 
-    def dense_to_coo(self, dc, dw, sizes):
-        idx = torch.nonzero(dc).t()
-        s = sizes.to(torch.float32)
-        vals = dw[idx[0], idx[1]] * (1.0 / s[idx[0]]) * (1.0 / s[idx[1]])
-        return torch.sparse_coo_tensor(idx, vals, dc.shape), dc[idx[0], idx[1]]
+    def coarse_merge(self, rec, a_lo, n_rows, n):
+        rec = rec.numpy()
+        bb = self._bits(n)
+        order = np.argsort(rec[:, 0], kind="stable")
+        key, val = rec[order, 0], rec[order, 1]
+        head = np.ones(key.shape[0], bool)
+        head[1:] = key[1:] != key[:-1]
+        starts = np.flatnonzero(head)
+        cnt = np.add.reduceat(val >> 32, starts).astype(np.int32) if key.size else np.zeros(0, np.int32)
+        w = (val & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+        wsum = np.zeros(starts.shape[0], np.float32)
+        ends = np.append(starts[1:], key.shape[0])
+        for p, (b, e) in enumerate(zip(starts, ends)):          # fp32, source-rank order (what the kernel does)
+            acc = np.float32(0)
+            for j in range(b, e):
+                acc = np.float32(acc + w[j])
+            wsum[p] = acc
+        ukey = key[starts]
+        a = (ukey >> bb) - a_lo
+        rp = np.zeros(n_rows + 1, np.int64)
+        np.add.at(rp, a + 1, 1)
+        return (torch.from_numpy(np.cumsum(rp).astype(np.int32)), torch.from_numpy((ukey & ((1 << bb) - 1)).astype(np.int32)),
+                torch.from_numpy(cnt), torch.from_numpy(wsum))
+
+    def coarse_scale(self, rowptr, colidx, wsum, sizes, a_lo, n_rows):
+        s = sizes.numpy().astype(np.float32)
+        a = np.repeat(np.arange(n_rows), np.diff(rowptr.numpy())) + a_lo
+        ia, ib = np.float32(1.0) / s[a], np.float32(1.0) / s[colidx.numpy()]
+        return torch.from_numpy(((wsum.numpy() * ia) * ib).astype(np.float32))
+
+    def csr_to_coo(self, rowptr, colidx, vals, n):
+        rows = torch.repeat_interleave(torch.arange(n), (rowptr[1:] - rowptr[:-1]).long())
+        return torch.sparse_coo_tensor(torch.stack([rows, colidx.long()]), vals, (n, n))
 
 
 def _free_port():
@@ -262,6 +298,26 @@ def _worker(rank, world, port, case):
             mx = cc.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             assert torch.equal(cc, mx)
+        elif case == "wire":
+            # row-padded views (width 7 inside a leading dimension of 8: what _dev.new_padded returns for f % 4 != 0)
+            # are non-contiguous; the collectives run on the padded base and leave the padding column zero
+            buf = torch.zeros((5, 8))
+            v = buf[:, :7]
+            v[:] = float(rank + 1)
+            assert not v.is_contiguous()
+            comm.all_reduce(v)
+            assert torch.equal(v, torch.full((5, 7), 3.0)) and float(buf[:, 7].abs().max()) == 0.0
+            loc = torch.zeros((3, 8))[:, :7]
+            loc[:] = float(rank + 10)
+            out_b = torch.zeros((6, 8))
+            out = out_b[:, :7]
+            comm.all_gather_rows(loc, out)
+            assert torch.equal(out[:3], torch.full((3, 7), 10.0)) and torch.equal(out[3:], torch.full((3, 7), 11.0))
+            assert float(out_b[:, 7].abs().max()) == 0.0
+            h = comm.all_gather_rows(loc, out, async_op=True)
+            h.wait()
+            with pytest.raises(ValueError):
+                comm.all_reduce(torch.zeros((4, 6)).t())
         elif case == "coarsen":
             labels = np.random.RandomState(6).randint(0, 17, n).astype(np.int32)
             labels[labels == 11] = 10      # an empty cluster
@@ -272,13 +328,23 @@ def _worker(rank, world, port, case):
             np.testing.assert_allclose(got[fin], S[fin], rtol=1e-5, atol=1e-8)
             rows = np.repeat(np.arange(n), np.diff(rpo))
             _, _, cnt_ref, _ = o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)
-            assert np.array_equal(np.sort(counts.numpy()), np.sort(cnt_ref))
-            assert int(counts.sum()) == int(cnt_ref.sum())
+            assert np.array_equal(counts.numpy(), cnt_ref)          # integer cell counts, CSR order, independent of the rank count
+            ad = adj_syn.coalesce()
+            assert ad._nnz() == cnt_ref.shape[0]
+            # this rank's own key range, not replicated
+            a_lo, rp_p, ci_p, v_p, c_p = par.dist_graph_compress(comm, part, torch.from_numpy(labels[lo:hi].copy()), A_local,
+                                                                 ops=ops, replicate=False)
+            rp_ref, ci_ref, _, _ = o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)
+            nr = rp_p.shape[0] - 1
+            assert np.array_equal(rp_p.numpy() + rp_ref[a_lo], rp_ref[a_lo:a_lo + nr + 1])
+            assert np.array_equal(ci_p.numpy(), ci_ref[rp_ref[a_lo]:rp_ref[a_lo + nr]])
+            assert np.array_equal(c_p.numpy(), cnt_ref[rp_ref[a_lo]:rp_ref[a_lo + nr]])
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "propagate_rows", "kmeans", "kmeans_empty", "coarsen"])
+@pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "propagate_rows", "kmeans", "kmeans_empty", "coarsen",
+                                  "wire"])
 def test_world2_gloo(case, oracle):
     mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
 
@@ -323,3 +389,10 @@ def test_world1_drivers_without_process_group(oracle, slabs, row_chunks):
         send = torch.arange(12).reshape(6, 2)
         out, counts = comm.all_to_all_rows(send, [6])
         assert torch.equal(out, send) and counts == [6]
+        labels = np.random.RandomState(6).randint(0, 17, n).astype(np.int32)
+        adj_syn, cnt = par.dist_graph_compress(comm, part, torch.from_numpy(labels), A, ops=ops)
+        S = o.graph_compress_dense(labels.astype(np.int64), rpo, cio, vo, 17)
+        fin = np.isfinite(S)
+        np.testing.assert_allclose(adj_syn.to_dense().numpy()[fin], S[fin], rtol=1e-5, atol=1e-8)
+        rows = np.repeat(np.arange(n), np.diff(rpo))
+        assert np.array_equal(cnt.numpy(), o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)[2])
