@@ -95,6 +95,9 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, int
 int64_t sort_pairs_ws_bytes(int64_t n);
 int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
                cudaStream_t s);
+// same sort; the result is reported where the last pass left it (no copy back): *keys_sorted / *vals_sorted
+int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
+                  uint64_t** keys_sorted, uint32_t** vals_sorted, cudaStream_t s);
 
 // SpMM launcher shared by stage 2 and the k-means M-step (vals == nullptr -> 1.0,
 // colidx32 gathers rows of X).

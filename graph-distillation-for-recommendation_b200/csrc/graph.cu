@@ -187,24 +187,27 @@ __global__ void k_pack_coo(int64_t nnz, int64_t n_rows, int64_t n_cols, const in
     if (symmetrize) {
       keys[2 * e] = ((uint64_t)r << cbits) | (uint64_t)c;
       keys[2 * e + 1] = ((uint64_t)c << cbits) | (uint64_t)r;
-      payload[2 * e] = __float_as_uint(v);
-      payload[2 * e + 1] = __float_as_uint(v);
+      if (payload) {
+        payload[2 * e] = __float_as_uint(v);
+        payload[2 * e + 1] = __float_as_uint(v);
+      }
     } else {
       keys[e] = ((uint64_t)r << cbits) | (uint64_t)c;
-      payload[e] = __float_as_uint(v);
+      if (payload) payload[e] = __float_as_uint(v);
     }
   }
 }
 
 __global__ void k_emit_csr_entries(const int32_t* __restrict__ n_runs_dev,
                                    const uint64_t* __restrict__ ukeys, const float* __restrict__ run_sum,
+                                   const int32_t* __restrict__ run_len,
                                    uint64_t cmask, int binarize, int32_t* __restrict__ colidx,
                                    float* __restrict__ vals) {
   int64_t m = *n_runs_dev;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m;
        p += (int64_t)gridDim.x * blockDim.x) {
     colidx[p] = (int32_t)(ukeys[p] & cmask);
-    vals[p] = binarize ? 1.0f : run_sum[p];
+    vals[p] = binarize ? 1.0f : (run_sum ? run_sum[p] : (float)run_len[p]);
   }
 }
 
@@ -667,15 +670,20 @@ int gdr_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz_in, const int64_t
   void* sws = W.take<char>(sws_b);
   RunBuffers R = carve_runs(W, n, true);
   int cbits = bits_for(n_cols), rbits = bits_for(n_rows);
+  // values travel through the sort only when they are needed: binarised output is all ones and unit input values
+  // sum to the run length (exact in fp32: the sequential sum of ones equals the count up to 2^24)
+  const bool carry = val != nullptr && !binarize;
   k_pack_coo<<<grid_for(nnz_in), 256, 0, s>>>(nnz_in, n_rows, n_cols, row, col, val, symmetrize, cbits,
-                                              keys, payload, status_dev);
+                                              keys, carry ? payload : nullptr, status_dev);
   GDR_LAUNCHED();
-  int rc = sort_pairs(n, rbits + cbits, keys, payload, sws, sws_b, s);
+  uint64_t* skeys = keys;
+  uint32_t* spay = carry ? payload : nullptr;
+  int rc = sort_pairs_ex(n, rbits + cbits, keys, spay, sws, sws_b, &skeys, carry ? &spay : nullptr, s);
   if (rc) return rc;
-  rc = reduce_runs(n, keys, payload, R, s);
+  rc = reduce_runs(n, skeys, spay, R, s);
   if (rc) return rc;
-  k_emit_csr_entries<<<grid_for(n), 256, 0, s>>>(R.pos + n, R.ukeys, R.run_sum, (1ull << cbits) - 1,
-                                                 binarize, colidx, vals);
+  k_emit_csr_entries<<<grid_for(n), 256, 0, s>>>(R.pos + n, R.ukeys, carry ? R.run_sum : nullptr, R.run_len,
+                                                 (1ull << cbits) - 1, binarize, colidx, vals);
   GDR_LAUNCHED();
   k_rowptr_from_ukeys<<<grid_for(n + 1), 256, 0, s>>>(R.pos + n, n_rows, cbits, ~0ull, R.ukeys, rowptr,
                                                       nnz_out_dev);

@@ -46,6 +46,7 @@ constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
 // from the measured rounding residuals |x - tf32(x)|, |c - tf32(c)| (see k_split_tf32 / k_tc_select1).
 static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
 int g_tc_ablate = 0;   // experiment: 1 no epilogue math, 2 no tcgen05.ld either, 3 no MMAs, 4 one K-block of MMAs only
+int g_tc_gate = 2;      // gdr_debug_set("tc_gate", v): first-level epilogue gate — 0 off (exact running top-2 over all columns), 1 gate on the running best, 2 (default) also seeded with the previous label's score
 int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles, 4 two-level on CTA pairs (cta_group::2, 256 x 256)
 
 // ---------------------------------------------------------------------------------
@@ -236,10 +237,12 @@ __global__ void __launch_bounds__(256) k_split_tf32(int64_t rows, int64_t rows_p
 
 // cmax = max_j |c_j| over the real centres, |c_j| per centre (0 on padding); also resets the list lengths
 __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, const float* __restrict__ cnorm,
-                                                       float* __restrict__ cnorm_sqrt, float* __restrict__ cmax,
+                                                       const float* __restrict__ cdnorm /*nullable*/,
+                                                       float* __restrict__ cnorm_sqrt, float* __restrict__ cmax /*[2]*/,
                                                        int32_t* __restrict__ amb_count, int32_t* __restrict__ count1) {
   __shared__ float s_m[1024];
-  float m = 0.f;
+  __shared__ float s_d[1024];
+  float m = 0.f, md = 0.f;
   if (threadIdx.x == 0) {
     if (amb_count) amb_count[0] = 0;
     if (count1) count1[0] = 0;
@@ -247,15 +250,23 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
   for (int64_t j = threadIdx.x; j < Kp; j += 1024) {
     const float c2 = j < K ? cnorm[j] : 0.f;
     m = fmaxf(m, c2);
+    if (cdnorm && j < K) md = fmaxf(md, cdnorm[j]);
     cnorm_sqrt[j] = sqrtf(c2);
   }
   s_m[threadIdx.x] = m;
+  s_d[threadIdx.x] = md;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
-    if (threadIdx.x < o) s_m[threadIdx.x] = fmaxf(s_m[threadIdx.x], s_m[threadIdx.x + o]);
+    if (threadIdx.x < o) {
+      s_m[threadIdx.x] = fmaxf(s_m[threadIdx.x], s_m[threadIdx.x + o]);
+      s_d[threadIdx.x] = fmaxf(s_d[threadIdx.x], s_d[threadIdx.x + o]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) cmax[0] = sqrtf(s_m[0]);
+  if (threadIdx.x == 0) {
+    cmax[0] = sqrtf(s_m[0]);
+    cmax[1] = s_d[0];
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -274,6 +285,20 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 __device__ long long g_tc_probe[4];   // ablation runs: MMA-thread cycles / nanoseconds / MMAs issued of CTA 0
+
+// First-level epilogue gate.  k_tc_select1 only needs to know (a) the best score of a row and (b) whether ANY other
+// centre comes within tol(i, best) of it, and tol(i, j) <= tolmax_i = the same expression with max_j |c_j|, max_j |dc_j|.
+// So the running top-2 has to look only at chunks that hold a score within tolmax_i of a lower bound of the row's
+// final best: the running best, and — from the second Lloyd iteration on — the score of the row's PREVIOUS label
+// against the new centres (k_tc_seed), which is already the final best for the rows that keep their label.  A warp
+// (32 rows) then takes the per-element path for a few percent of the 8-column chunks instead of ~a third.
+struct TcGate {
+  const float* xnorm;    // |x_i|           (nullptr: gate off, exact running top-2 over all columns)
+  const float* xdnorm;   // |x_i - tf32(x_i)|
+  const float* cscal;    // [0] = max_j |c_j|, [1] = max_j (|c_j - tf32(c_j)|)
+  const float* seed;     // upper bound of the row's final best (negated score), +inf when unknown; nullable
+  float band;
+};
 
 template <int NPASS, int BN, int SUB>
 struct TcCfg {
@@ -301,7 +326,8 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
             int64_t N_host, const int32_t* __restrict__ n_rows_dev /*nullable: row count on the device*/,
             int D /*contraction width incl. the 3 augmented columns for NPASS 1*/, int n_col_tiles, int nkb,
             const float* __restrict__ cnorm /*NPASS 3: |c_j|^2*/,
-            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate) {
+            float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate,
+            TcGate gate) {
   using Cfg = TcCfg<NPASS, BN, SUB>;
   static_assert(Cfg::kTmemCols <= 512 && (NPASS == 1 || SUB == 1) && (SUB == 1 || SUB == 2), "tile plan");
   const int S = Cfg::stages(nkb);
@@ -508,6 +534,17 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
       // both variants share the min-tracking code and the merge below
       float best = INFINITY, second = INFINITY;
       int bidx = 0;
+      // gate (NPASS 1): limt = (lower bound of the final best, as a negated score) + tolmax_i; a chunk whose smallest
+      // negated score is not below limt for any lane cannot hold the row's best nor anything within tol of it
+      float tolmax = 0.f, limt = INFINITY;
+      const bool gated = NPASS == 1 && chunk_skip && gate.xnorm != nullptr;
+      if (gated) {
+        const float xn = row < N ? gate.xnorm[row] : 0.f, xd = row < N ? gate.xdnorm[row] : 0.f;
+        const float cm = gate.cscal[0], cdm = gate.cscal[1];
+        tolmax = 1.001f * (2.02f * (xd * cm + xn * (cdm + 3.0517578125e-05f * cm) + 1.52587890625e-05f * cm * cm) +
+                           gate.band * xn * cm + 9.5367431640625e-07f * (xn * cm + cm * cm));
+        if (gate.seed != nullptr && row < N) limt = gate.seed[row] + tolmax;
+      }
       for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
         const uint32_t a = g & 1, aph = (g >> 1) & 1;
         mbar_wait(&t_full[a], aph);
@@ -538,7 +575,8 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
                                 fmaxf(__uint_as_float(v[c][u0 + 2]), __uint_as_float(v[c][u0 + 3])));
                 m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[c][u0 + 4]), __uint_as_float(v[c][u0 + 5])),
                                    fmaxf(__uint_as_float(v[c][u0 + 6]), __uint_as_float(v[c][u0 + 7]))));
-                if (!chunk_skip || __any_sync(0xffffffffu, -m < second)) {     // scores are stored negated: d = -score
+                // scores are stored negated: d = -score
+                if (!chunk_skip || __any_sync(0xffffffffu, -m < (gated ? limt : second))) {
 #pragma unroll
                   for (int u = u0; u < u0 + 8; ++u) {
                     const float d = -__uint_as_float(v[c][u]);
@@ -546,6 +584,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
                     bidx = d < best ? jbase + u : bidx;
                     best = fminf(best, d);
                   }
+                  if (gated) limt = fminf(limt, best + tolmax);
                 }
               }
             } else {
@@ -1020,8 +1059,9 @@ __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __re
     const int l = idx[i];
     const float b = best[i], s2 = second[i], xn = xnorm[i], cr = cnorm_sqrt[l];
     const float E = xdnorm[i] * cr + xn * (cdnorm[l] + 3.0517578125e-05f * cr);
+    // s2 = +inf: the gated epilogue met no other centre within tolmax_i >= tol of the best -> decided
     const float tol = 2.02f * (E + 1.52587890625e-05f * cnorm[l]) + band * xn * cmax[0] +
-                      4.76837158e-07f * fmaxf(fabsf(b), fabsf(s2));
+                      4.76837158e-07f * fmaxf(fabsf(b), s2 == INFINITY ? 0.f : fabsf(s2));
     const bool ambiguous = !(s2 - b > tol);   // also catches NaN / inf - inf
     if (ambiguous) {
       list1[atomicAdd(count1, 1)] = (int32_t)i;
@@ -1034,6 +1074,38 @@ __global__ void __launch_bounds__(256) k_tc_select1(int64_t N, const float* __re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
     if (lane_id() == 0 && changed) atomicAdd(n_changed, changed);
+  }
+}
+
+// Seed of the first-level gate: the score of row i against the NEW centre of its previous label, evaluated on the
+// same augmented TF32 operands the GEMM multiplies (fp32 FMA chain instead of the TMEM accumulation: the two agree to
+// ~(D + 4) 2^-23 |x||c|, covered by the 2^-18 slack).  seed_i >= the row's final best negated score.
+__global__ void __launch_bounds__(256) k_tc_seed(int64_t N, int64_t K, int Dp1, const float* __restrict__ x1,
+                                                 const float* __restrict__ c1, const int32_t* __restrict__ hint,
+                                                 const float* __restrict__ xnorm, const float* __restrict__ cscal,
+                                                 float* __restrict__ seed) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= N) return;
+  const int j = hint[r];
+  if (j < 0 || j >= K) {
+    if (lane_id() == 0) seed[r] = INFINITY;
+    return;
+  }
+  const float4* a = reinterpret_cast<const float4*>(x1 + r * Dp1);
+  const float4* b = reinterpret_cast<const float4*>(c1 + (int64_t)j * Dp1);
+  float acc = 0.f;
+  for (int c = lane_id(); c < (Dp1 >> 2); c += 32) {
+    const float4 p = __ldg(a + c), q = __ldg(b + c);
+    acc = fmaf(p.x, q.x, acc);
+    acc = fmaf(p.y, q.y, acc);
+    acc = fmaf(p.z, q.z, acc);
+    acc = fmaf(p.w, q.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane_id() == 0) {
+    const float xn = xnorm[r], cm = cscal[0];
+    seed[r] = -acc + 3.814697265625e-06f * (xn * cm + cm * cm);
   }
 }
 
@@ -1311,7 +1383,8 @@ int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
 template <int NPASS, int BN, int SUB>
 static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, const CUtensorMap& m_chi,
                             const CUtensorMap& m_clo, int64_t N_max, const int32_t* n_rows_dev, int D_eff, int64_t Kp,
-                            int nkb, const float* cnorm, float* best, float* second, int32_t* idx, cudaStream_t s) {
+                            int nkb, const float* cnorm, float* best, float* second, int32_t* idx, cudaStream_t s,
+                            TcGate gate = TcGate{nullptr, nullptr, nullptr, nullptr, 0.f}) {
   using Cfg = TcCfg<NPASS, BN, SUB>;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.get();
@@ -1329,7 +1402,7 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
   const int64_t tiles = cdiv(N_max, TC_BM * SUB);
   const int grid = (int)(tiles < sms ? tiles : sms);
   k_assign_tc<NPASS, BN, SUB><<<grid, TC_THREADS, Cfg::total(nkb), s>>>(m_xhi, m_xlo, m_chi, m_clo, N_max, n_rows_dev, D_eff,
-                                                                  (int)(Kp / BN), nkb, cnorm, best, second, idx, g_tc_ablate);
+                                                                  (int)(Kp / BN), nkb, cnorm, best, second, idx, g_tc_ablate, gate);
   GDR_LAUNCHED();
   return GDR_OK;
 }
@@ -1372,7 +1445,7 @@ static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c,
 int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_t ldx, const void* xsplit,
                          const float* C, int64_t ldc, int32_t* labels, const int32_t* labels_prev,
                          int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev, void* ws,
-                         int64_t ws_bytes, cudaStream_t s) {
+                         int64_t ws_bytes, cudaStream_t s, const int32_t* labels_hint) {
   if (D > TC_MAX_KB * TC_BK) {
     set_error("kmeans_assign(tc): D=%lld > %d is not supported by the tensor-core path", (long long)D,
               TC_MAX_KB * TC_BK);
@@ -1394,7 +1467,7 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   float* cnorm = W.take<float>(Kp);
   float* cnorm_sqrt = W.take<float>(Kp);
   float* cdnorm = W.take<float>(Kp);
-  float* cmax = W.take<float>(1);
+  float* cmax = W.take<float>(2);   // [max |c|, max |c - tf32(c)|]
   float* best = W.take<float>(N);
   float* second = W.take<float>(N);
   int32_t* idx = W.take<int32_t>(N);
@@ -1417,7 +1490,7 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
                                                            two_level ? c1 : nullptr, Dp1, 2, cdnorm);
   GDR_LAUNCHED();
   int rc;
-  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, cnorm_sqrt, cmax, amb_count, count1);
+  k_cnorm_finish<<<1, 1024, 0, s>>>(K, Kp, cnorm, two_level ? cdnorm : nullptr, cnorm_sqrt, cmax, amb_count, count1);
   GDR_LAUNCHED();
 
   CUtensorMap m_xhi, m_xlo, m_chi, m_clo;
@@ -1454,8 +1527,21 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
         return rc;
     } else {
       if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
+      TcGate gate{nullptr, nullptr, nullptr, nullptr, TC_BAND};
+      if (g_tc_gate) {
+        gate.xnorm = xs.norm;
+        gate.xdnorm = xs.dnorm;
+        gate.cscal = cmax;
+        const int32_t* hint = labels_hint ? labels_hint : labels_prev;
+        if (hint && g_tc_gate >= 2) {
+          float* seed = g_norm;   // free until k_tc_gather fills it after the first level
+          k_tc_seed<<<(unsigned)cdiv(N * 32, 256), 256, 0, s>>>(N, K, Dp1, xs.x1, c1, hint, xs.norm, cmax, seed);
+          GDR_LAUNCHED();
+          gate.seed = seed;
+        }
+      }
       if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
-                                         idx, s)))
+                                         idx, s, gate)))
         return rc;
     }
     if (g_tc_ablate) return GDR_OK;   // timing experiment: first-level kernel only
@@ -1497,7 +1583,7 @@ int kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_t ld
   int rc = kmeans_tc_prepare(N, D, X, ldx, xsplit, s);
   if (rc) return rc;
   return kmeans_assign_tc_run(N, K, D, X, ldx, xsplit, C, ldc, labels, labels_prev, n_changed_dev, best_out,
-                              nullptr, ws, kmeans_assign_tc_ws_bytes(N, K, D), s);
+                              nullptr, ws, kmeans_assign_tc_ws_bytes(N, K, D), s, nullptr);
 }
 
 }  // namespace gdr
@@ -1591,7 +1677,7 @@ int gdr_kmeans_assign_tc(int64_t N, int64_t K, int64_t D, const float* X, int64_
     return GDR_EWORKSPACE;
   }
   return gdr::kmeans_assign_tc_run(N, K, D, X, ldx, xsplit, C, ldc, labels, labels_prev, n_changed_dev, best_out,
-                                   n_refined_dev, ws, ws_bytes, (cudaStream_t)stream);
+                                   n_refined_dev, ws, ws_bytes, (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

@@ -339,6 +339,16 @@ int64_t sort_pairs_ws_bytes(int64_t n) {
 
 int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
                cudaStream_t s) {
+  return sort_pairs_ex(n, key_bits, keys, vals, ws, ws_bytes, nullptr, nullptr, s);
+}
+
+// keys_sorted / vals_sorted != nullptr: the caller accepts the result wherever the last pass left it (the input
+// arrays or their twins inside the workspace) and the copy back after an odd number of passes (n * 12 bytes
+// read + written) is skipped.
+int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
+                  uint64_t** keys_sorted, uint32_t** vals_sorted, cudaStream_t s) {
+  if (keys_sorted) *keys_sorted = keys;
+  if (vals_sorted) *vals_sorted = vals;
   if (n <= 1 || key_bits <= 0) return GDR_OK;
   if (ws_bytes < sort_pairs_ws_bytes(n)) {
     set_error("sort_pairs: workspace %lld < %lld", (long long)ws_bytes,
@@ -390,8 +400,14 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
     uint32_t* tv = vin; vin = vout; vout = tv;
   }
   if (kin != keys) {
-    GDR_CUDA(cudaMemcpyAsync(keys, kin, n * 8, cudaMemcpyDeviceToDevice, s));
-    if (vals) GDR_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (keys_sorted) {
+      *keys_sorted = kin;
+      if (vals_sorted) *vals_sorted = vin;
+      else if (vals) GDR_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      GDR_CUDA(cudaMemcpyAsync(keys, kin, n * 8, cudaMemcpyDeviceToDevice, s));
+      if (vals) GDR_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, s));
+    }
   }
   return GDR_OK;
 }

@@ -153,3 +153,67 @@ def test_tc_full_size_labels_equal_exact_kernel(gdr, cfg_name):
     torch.cuda.synchronize()
     assert torch.equal(lab_tc, lab_32)
     assert 0 < int(n_ref.item()) < n // 100 and 0 < lvl2.value < n // 5     # both refinement levels were exercised
+
+
+@pytest.fixture
+def gate_mode():
+    """First-level epilogue gate (gdr_debug_set "tc_gate": 0 off, 1 running best, 2 + previous-label seed)."""
+    from gdr import _lib
+    yield lambda v: _lib.call("gdr_debug_set", b"tc_gate", int(v))
+    _lib.call("gdr_debug_set", b"tc_gate", 2)
+
+
+@pytest.mark.parametrize("N,K,D,kind", [(100000, 4096, 100, "zscore"), (80000, 5000, 47, "clustered"), (90001, 4100, 128, "zscore")])
+def test_tc_gate_modes_take_identical_decisions(gdr, oracle, gate_mode, screen_mode, N, K, D, kind):
+    """The gated first-level epilogue (chunks are looked at only when they hold a score within tolmax_i of a lower
+    bound of the row's best) must hand EXACTLY the same rows to level 2 and produce the same labels as the ungated
+    running top-2 — with good hints (the true labels), useless hints (all zero) and no hints."""
+    import ctypes
+    from gdr import synth, _lib
+    from gdr._dev import padded_rows
+    from gdr.kmeans import TcOperand
+    X = synth.clustered_features(N, D, max(2, K // 3), seed=N + K) if kind == "clustered" else synth.features(N, D, seed=N + K)
+    X -= X.mean(axis=0)
+    C = synth.kmeans_init(X, K, seed=1)
+    Xd, Cd = padded_rows(torch.from_numpy(X).to(DEV)), padded_rows(torch.from_numpy(C).to(DEV))
+    op = TcOperand(Xd)
+    screen_mode(3)          # two-level screen with 128 x 256 tiles whatever N
+
+    def run(gate, prev):
+        gate_mode(gate)
+        labels = torch.full((N,), -7, dtype=torch.int32, device=DEV)
+        nch = torch.zeros(1, dtype=torch.int32, device=DEV)
+        n_ref = torch.zeros(1, dtype=torch.int32, device=DEV)
+        gdr.assign_labels(Xd, Cd, labels, labels_prev=prev, n_changed=None if prev is None else nch, tc_operand=op,
+                          n_refined=n_ref)
+        lvl2 = ctypes.c_int64(-1)
+        _lib.call("gdr_debug_get", b"tc_level2_rows", ctypes.addressof(lvl2))
+        return labels, int(lvl2.value), int(n_ref.item()), int(nch.item())
+
+    lab0, l2_0, ref_0, _ = run(0, None)
+    ok, _, n_bad = oracle.labels_match(np_(lab0), X, C, band=1e-6)
+    assert ok, n_bad
+    truth = lab0.clone()
+    zeros = torch.zeros(N, dtype=torch.int32, device=DEV)
+    shuffled = truth[torch.randperm(N, device=DEV)]
+    for gate in (1, 2):
+        for prev in (None, truth, zeros, shuffled):
+            lab, l2, ref, nch = run(gate, prev)
+            assert torch.equal(lab, lab0), (gate, "labels differ")
+            assert (l2, ref) == (l2_0, ref_0), (gate, l2, l2_0, ref, ref_0)
+            if prev is not None:
+                assert nch == int((prev != lab0).sum().item())
+
+
+def test_tc_gate_full_fit_equals_ungated(gdr, gate_mode):
+    from gdr import synth
+    N, K, D = 120000, 4500, 100
+    X = synth.features(N, D, seed=21)
+    C0 = synth.kmeans_init(X, K, seed=5)
+    gate_mode(0)
+    a = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=6, tol=0, precision="tc").fit(X)
+    gate_mode(2)
+    b = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=6, tol=0, precision="tc").fit(X)
+    assert np.array_equal(a.labels_, b.labels_)
+    np.testing.assert_array_equal(a.cluster_centers_, b.cluster_centers_)
+    assert a.inertia_ == b.inertia_ and a.n_iter_ == b.n_iter_
