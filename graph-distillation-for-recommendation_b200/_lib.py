@@ -101,6 +101,9 @@ _SIGNATURES = {
     "gdr_coarse_records": (i32, [i64, i64, vp, vp, vp, vp, vp, vp]),
     "gdr_coarse_merge_ws_bytes": (i64, [i64]),
     "gdr_coarse_merge": (i32, [i64, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_bipartite_norm_block": (i32, [i64, i64, vp, vp, vp, vp, vp, f32, vp, vp]),
+    "gdr_column_moments": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp]),
+    "gdr_standardize_apply": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp]),
     "gdr_coarsen_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_coarsen": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_scale": (i32, [i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -875,6 +875,21 @@ int gdr_bipartite_normalize(int64_t n_u, int64_t n_i, int64_t nnz, const int32_t
 // Rankformer GCN edge weights (Rankformer/code/rec.py:118-124): degrees = row / column sums of the
 // interaction counts clamped to >= 1;  out = w / du^a / di^b  and, for the transposed matrix,
 // t_out = w / du^b / di^a  (written in transposed order through t_perm).
+// LightGCN edge norm of a ROW BLOCK of the weight matrix (or of its transpose): norm = w / (sqrt(d_row + eps) *
+// sqrt(d_col + eps)) with the block's own row degrees and the all-gathered degrees of the other side
+// (distill_recsys.py:329-335 on a row partition; same arithmetic as gdr_bipartite_normalize)
+int gdr_bipartite_norm_block(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx, const float* w,
+                             const float* deg_rows, const float* deg_cols, float eps, float* norm_out,
+                             gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0 && nnz >= 0, "bipartite_norm_block: negative size");
+  if (n_rows == 0 || nnz == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && colidx && w && deg_rows && deg_cols && norm_out, "bipartite_norm_block: null pointer");
+  k_bip_norm<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, w, deg_rows,
+                                                                               deg_cols, eps, norm_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
 int gdr_bipartite_pow_normalize(int64_t n_u, int64_t n_i, int64_t nnz, const int32_t* rowptr,
                                 const int32_t* colidx, const float* w, const int32_t* t_rowptr,
                                 const int32_t* t_perm, float a, float b, float* out, float* t_out,

@@ -1009,6 +1009,43 @@ int gdr_standard_scale(int64_t N, int64_t D, const float* X, int64_t ldx, float*
 }
 
 // Xc = X - mean (fp32 subtract, padding columns zeroed) — sklearn/_kmeans.py:1489
+// second pass of StandardScaler on a row block: out[0..D) = sum (x - mean), out[D..2D) = sum (x - mean)^2 (fp64), so that
+// the blocks of a row partition can be all-reduced (distill_recsys.py:172 on row-partitioned embeddings)
+int gdr_column_moments(int64_t N, int64_t D, const float* X, int64_t ldx, const double* mean64, double* sums_out,
+                       void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && D > 0 && mean64 && sums_out, "column_moments: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N == 0) {
+    GDR_CUDA(cudaMemsetAsync(sums_out, 0, 2 * D * 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(X && ldx >= D, "column_moments: null X");
+  if (ws_bytes < gdr_center_columns_ws_bytes(N, D)) {
+    set_error("column_moments: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  const int nb = (int)cdiv(N, CC_ROWS_PER_BLOCK);
+  double* part = (double*)ws;
+  k_colvar_partial<<<nb, dim3(32, 8), 0, s>>>(N, (int)D, X, ldx, mean64, part);
+  GDR_LAUNCHED();
+  k_colstats_reduce<<<(unsigned)cdiv(D, 256), 256, 0, s>>>((int)D, nb, part, sums_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// out = fp32((x - mean) / scale) with given fp32 column parameters (StandardScaler.transform)
+int gdr_standardize_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean32, const float* scale32,
+                          float* out, int64_t ldo, gdr_stream_t stream) {
+  GDR_CHECK_ARG(N >= 0 && D > 0 && mean32 && scale32, "standardize_apply: bad arguments");
+  if (N == 0) return GDR_OK;
+  GDR_CHECK_ARG(X && out && ldx >= D && ldo >= D, "standardize_apply: null pointer");
+  const int64_t total = N * D;
+  k_standardize<<<(unsigned)std::min<int64_t>(cdiv(total, 256), kSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      N, (int)D, X, ldx, mean32, scale32, out, ldo);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
 int gdr_center_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean, float* Xc,
                      int64_t ldxc, gdr_stream_t stream) {
   GDR_CHECK_ARG(N >= 0 && D > 0 && mean && ldx >= D && ldxc >= D, "center_apply: bad arguments");

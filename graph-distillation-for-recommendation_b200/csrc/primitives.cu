@@ -207,63 +207,79 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
   for (int d = threadIdx.x; d < bins; d += RS_THREADS) table[(int64_t)d * nblocks + blockIdx.x] = hist[d];
 }
 
-// Scatter pass.  Every key gets its rank inside the tile (warp match + warp-private counters: no atomics, so the
-// sort is stable); the tile is then REORDERED IN SHARED MEMORY into digit order and written out with consecutive
-// threads on consecutive addresses of each digit's run.  Writing straight from registers sends every 8-byte key
-// to its own 32-byte sector (the runs of one tile in one bin are short), which cost 4.5 ms per pass at 124 M
-// keys = 0.66 TB/s; staged, a run of r keys is r * 8 contiguous bytes.
-template <int RS_ROUNDS>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in,
-                                                           const uint32_t* __restrict__ vals_in,
-                                                           uint64_t* __restrict__ keys_out,
-                                                           uint32_t* __restrict__ vals_out, int64_t n,
-                                                           int shift, int bits,
-                                                           const int32_t* __restrict__ table_scanned,
-                                                           int nblocks) {
+// Scatter pass.  Every key gets its rank inside the tile (warp match + warp-private counters, so the sort is
+// stable); the tile is then REORDERED IN SHARED MEMORY into digit order and written out with consecutive threads on
+// consecutive addresses of each digit's run.  Writing straight from registers sends every 8-byte key to its own
+// 32-byte sector (the runs of one tile in one bin are short), which cost 4.5 ms per pass at 124 M keys = 0.66 TB/s;
+// staged, a run of r keys is r * 8 contiguous bytes.
+//
+// The ranking is written for latency, not instruction count (ncu, round 2: 60 % of the stall samples sat on the
+// consumer of MATCH.ANY, one round at a time, at 25 % occupancy):
+//   phase A  all ROUNDS match.any are issued back to back (independent);
+//   phase B  the lowest lane of every peer group adds the group size to the warp's counter of that digit with a
+//            shared-memory ATOMIC that returns the old value — no load / store / __syncwarp chain between rounds, the
+//            atomics of one warp reach the shared-memory pipe in program order, so the returned bases are the
+//            in-order prefix;
+//   phase C  the bases are broadcast with shuffles.
+// FULL = the tile holds TILE keys (no bounds checks on the hot path); the last, partial tile runs the <.., false> variant.
+template <int RS_ROUNDS, bool HAS_VALS, bool FULL>
+__global__ void __launch_bounds__(RS_THREADS, HAS_VALS ? 2 : 3)
+k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+             uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+             const int32_t* __restrict__ table_scanned, int nblocks, int block0) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   constexpr int TILE = RS_THREADS * RS_ROUNDS;
   const int bins = 1 << bits;
   const uint32_t dmask = (uint32_t)bins - 1u;
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_raw);                 // [TILE]
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);          // [TILE]
-  int* cnt = reinterpret_cast<int*>(s_vals + TILE);                       // [RS_WARPS][bins] -> offsets inside the tile
-  int* tile_off = cnt + RS_WARPS * bins;                                  // [bins] first tile position of digit d
-  int* gbase = tile_off + bins;                                           // [bins] global position of that first key
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_raw);                                    // [TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);                             // [TILE] (HAS_VALS)
+  int* cnt = reinterpret_cast<int*>(s_vals + (HAS_VALS ? TILE : 0));                         // [RS_WARPS][bins + 1]
+  int* tile_off = cnt + RS_WARPS * (bins + 1);                                               // [bins] first tile position of digit d
+  int* delta = tile_off + bins;                                                              // [bins] global position - tile position
   __shared__ int s_wsum[RS_WARPS];
-  for (int i = threadIdx.x; i < RS_WARPS * bins; i += RS_THREADS) cnt[i] = 0;
+  const int cstride = bins + 1;                       // + 1: the sentinel digit of padding lanes (partial tile)
+  for (int i = threadIdx.x; i < RS_WARPS * cstride; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int* mycnt = cnt + w * bins;
-  const int64_t tile0 = (int64_t)blockIdx.x * TILE;
-  const int tile_n = (int)min((int64_t)TILE, n - tile0);
-  const int64_t base = tile0 + (int64_t)w * (RS_ROUNDS * 32);
+  int* mycnt = cnt + w * cstride;
+  const int blk = block0 + blockIdx.x;
+  const int64_t tile0 = (int64_t)blk * TILE;
+  const int tile_n = FULL ? TILE : (int)min((int64_t)TILE, n - tile0);
+  const int64_t base = tile0 + (int64_t)w * (RS_ROUNDS * 32) + lane;
   uint64_t k[RS_ROUNDS];
-  uint32_t v[RS_ROUNDS];
-  int rank[RS_ROUNDS];
+  uint32_t v[HAS_VALS ? RS_ROUNDS : 1];
+  unsigned pr[RS_ROUNDS];                             // peers mask, then the rank inside the warp's keys of that digit
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
-    int64_t idx = base + r * 32 + lane;
-    bool valid = idx < n;
-    k[r] = valid ? keys_in[idx] : 0ull;
-    v[r] = (valid && vals_in) ? vals_in[idx] : 0u;
+    const bool valid = FULL || base + r * 32 < n;
+    k[r] = valid ? keys_in[base + r * 32] : 0ull;
+    if (HAS_VALS) v[r] = valid ? vals_in[base + r * 32] : 0u;
   }
+  // phase A
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
-    int64_t idx = base + r * 32 + lane;
-    bool valid = idx < n;
-    int d = valid ? (int)((uint32_t)(k[r] >> shift) & dmask) : bins;  // sentinel digit for padding lanes
-    unsigned peers = __match_any_sync(0xffffffffu, d);
-    int before = __popc(peers & lt_mask);
-    int leader = __ffs(peers) - 1;
-    int basecnt = 0;
-    if (valid && lane == leader) {
-      basecnt = mycnt[d];
-      mycnt[d] = basecnt + __popc(peers);
-    }
-    basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
-    rank[r] = basecnt + before;
-    __syncwarp();
+    const bool valid = FULL || base + r * 32 < n;
+    const int d = valid ? (int)((uint32_t)(k[r] >> shift) & dmask) : bins;
+    pr[r] = __match_any_sync(0xffffffffu, d);
+  }
+  // phase B: group leader (lowest lane) reserves the group's slots; the round's state is packed into one register:
+  // [base of the group << 10 | leader lane << 5 | peers before me]
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const bool valid = FULL || base + r * 32 < n;
+    const int d = valid ? (int)((uint32_t)(k[r] >> shift) & dmask) : bins;
+    const unsigned peers = pr[r];
+    const unsigned before = __popc(peers & lt_mask);
+    unsigned b = 0;
+    if (before == 0u) b = (unsigned)atomicAdd(&mycnt[d], __popc(peers));
+    pr[r] = (b << 10) | ((unsigned)(__ffs(peers) - 1) << 5) | before;
+  }
+  // phase C
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const unsigned b = __shfl_sync(0xffffffffu, pr[r] >> 10, (int)((pr[r] >> 5) & 31u));
+    pr[r] = b + (pr[r] & 31u);
   }
   __syncthreads();
   // per digit: counts of the warps -> exclusive offsets; tile-wide exclusive scan of the digit totals
@@ -274,8 +290,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
     int run = 0;
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) {
-      int t = cnt[ww * bins + d];
-      cnt[ww * bins + d] = run;
+      int t = cnt[ww * cstride + d];
+      cnt[ww * cstride + d] = run;
       run += t;
     }
     tile_off[d] = run;          // digit total for now
@@ -296,34 +312,61 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __res
   for (int d = d0; d < d1; ++d) {
     const int t = tile_off[d];
     tile_off[d] = run;
-    gbase[d] = table_scanned[(int64_t)d * nblocks + blockIdx.x];
+    delta[d] = table_scanned[(int64_t)d * nblocks + blk] - run;
     run += t;
   }
   __syncthreads();
   // stage the tile in digit order
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
-    int64_t idx = base + r * 32 + lane;
-    if (idx < n) {
-      int d = (int)((uint32_t)(k[r] >> shift) & dmask);
-      int p = tile_off[d] + mycnt[d] + rank[r];
+    if (FULL || base + r * 32 < n) {
+      const int d = (int)((uint32_t)(k[r] >> shift) & dmask);
+      const int p = tile_off[d] + mycnt[d] + (int)pr[r];
       s_keys[p] = k[r];
-      s_vals[p] = v[r];
+      if (HAS_VALS) s_vals[p] = v[r];
     }
   }
   __syncthreads();
   // consecutive threads -> consecutive positions of a digit's run
+#pragma unroll 4
   for (int t = threadIdx.x; t < tile_n; t += RS_THREADS) {
     const uint64_t kk = s_keys[t];
     const int d = (int)((uint32_t)(kk >> shift) & dmask);
-    const int64_t pos = (int64_t)gbase[d] + (t - tile_off[d]);
+    const int64_t pos = (int64_t)(delta[d] + t);
     keys_out[pos] = kk;
-    if (vals_out) vals_out[pos] = s_vals[t];
+    if (HAS_VALS) vals_out[pos] = s_vals[t];
   }
 }
 
-static inline size_t rs_scatter_smem(int rounds, int bits) {
-  return (size_t)RS_THREADS * rounds * 12 + (size_t)(RS_WARPS + 2) * (1 << bits) * 4;
+static inline size_t rs_scatter_smem(int rounds, int bits, bool has_vals) {
+  return (size_t)RS_THREADS * rounds * (has_vals ? 12 : 8) + (size_t)RS_WARPS * ((1 << bits) + 1) * 4 + (size_t)2 * (1 << bits) * 4;
+}
+
+template <int ROUNDS, bool HAS_VALS>
+static int launch_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, int64_t n, int shift,
+                             int bits, const int32_t* table, int64_t nb, cudaStream_t s) {
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.get();
+  const int smem_max = (int)rs_scatter_smem(ROUNDS, RS_MAX_BITS, HAS_VALS);
+  if (!attr_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    attr_set = true;
+  }
+  const size_t smem = rs_scatter_smem(ROUNDS, bits, HAS_VALS);
+  const int64_t tile = (int64_t)RS_THREADS * ROUNDS;
+  const int64_t full = n / tile;
+  if (full > 0) {
+    k_rs_scatter<ROUNDS, HAS_VALS, true><<<(unsigned)full, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits, table,
+                                                                               (int)nb, 0);
+    GDR_LAUNCHED();
+  }
+  if (full < nb) {
+    k_rs_scatter<ROUNDS, HAS_VALS, false><<<(unsigned)(nb - full), RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits,
+                                                                                       table, (int)nb, (int)full);
+    GDR_LAUNCHED();
+  }
+  return GDR_OK;
 }
 // digit width: wide digits save passes, but a tile of T keys leaves runs of T / 2^bits keys per digit, and a run
 // is what one coalesced write covers: at most 9 bits for the 4096-key tiles of large sorts (runs of >= 8 keys =
@@ -359,15 +402,6 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
     set_error("sort_pairs: n=%lld exceeds int32 positions", (long long)n);
     return GDR_ERANGE;
   }
-  static PerDevice<bool> attr_set_dev;
-  bool& attr_set = attr_set_dev.get();
-  if (!attr_set) {
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)rs_scatter_smem(4, RS_MAX_BITS)));
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)rs_scatter_smem(16, RS_MAX_BITS)));
-    attr_set = true;
-  }
   const int rounds = rs_rounds(n);
   int64_t nb = cdiv(n, RS_THREADS * rounds);
   const int passes = rs_passes(key_bits, rs_max_bits(n));
@@ -383,7 +417,7 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
   uint32_t* vin = vals;
   uint64_t* kout = kalt;
   uint32_t* vout = vals ? valt : nullptr;
-  const size_t hist_smem = (size_t)bins * 4, scat_smem = rs_scatter_smem(rounds, bits);
+  const size_t hist_smem = (size_t)bins * 4;
   for (int p = 0; p < passes; ++p) {
     int shift = bits * p;
     if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
@@ -392,10 +426,12 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
     int rc = exclusive_scan_i32(table, table, tbl, sws, scan_ws_bytes(tbl), s);
     if (rc) return rc;
     if (rounds == 16)
-      k_rs_scatter<16><<<(unsigned)nb, RS_THREADS, scat_smem, s>>>(kin, vin, kout, vout, n, shift, bits, table, (int)nb);
+      rc = vals ? launch_rs_scatter<16, true>(kin, vin, kout, vout, n, shift, bits, table, nb, s)
+                : launch_rs_scatter<16, false>(kin, vin, kout, vout, n, shift, bits, table, nb, s);
     else
-      k_rs_scatter<4><<<(unsigned)nb, RS_THREADS, scat_smem, s>>>(kin, vin, kout, vout, n, shift, bits, table, (int)nb);
-    GDR_LAUNCHED();
+      rc = vals ? launch_rs_scatter<4, true>(kin, vin, kout, vout, n, shift, bits, table, nb, s)
+                : launch_rs_scatter<4, false>(kin, vin, kout, vout, n, shift, bits, table, nb, s);
+    if (rc) return rc;
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

@@ -252,6 +252,39 @@ class CudaOps:
         m = int(nnz_out.item())
         return self._g.CSR(rowptr_out, colidx[:m], vals[:m], A_blk.shape)
 
+    # -- bipartite (distill_recsys) --
+    def build_block_csr_weighted(self, rows_local, cols, n_local, n_cols):
+        """CSR of a row block with duplicate (row, col) lines SUMMED (distill_recsys.py:110-117), global column ids."""
+        return self._g.coo_to_csr(rows_local, cols, None, (n_local, n_cols), symmetrize=False, binarize=False,
+                                  device=rows_local.device)
+
+    def row_sums(self, A):
+        deg = torch.empty(A.shape[0], dtype=torch.float32, device=A.device)
+        if A.shape[0]:
+            self._lib.call("gdr_row_sums_f32", A.shape[0], self.ptr(A.rowptr), self.ptr(A.vals), self.ptr(deg), self.stream())
+        return deg
+
+    def bip_norm_block(self, A, deg_rows, deg_cols, eps):
+        norm = torch.empty_like(A.vals)
+        self._lib.call("gdr_bipartite_norm_block", A.shape[0], A.nnz, self.ptr(A.rowptr), self.ptr(A.colidx), self.ptr(A.vals),
+                       self.ptr(deg_rows), self.ptr(deg_cols), float(eps), self.ptr(norm), self.stream())
+        return self._g.CSR(A.rowptr, A.colidx, norm, A.shape)
+
+    def column_moments(self, X, mean64):
+        N, D = X.shape
+        out = torch.zeros(2 * D, dtype=torch.float64, device=X.device)
+        ws = self.workspace(self._lib.query("gdr_center_columns_ws_bytes", max(N, 1), D), X.device)
+        self._lib.call("gdr_column_moments", N, D, self.ptr(X) if N else 0, X.stride(0) if N else D, self.ptr(mean64), self.ptr(out),
+                       self.ptr(ws), ws.numel(), self.stream())
+        return out
+
+    def standardize_apply(self, X, mean32, scale32):
+        N, D = X.shape
+        out = self.new_padded(N, D, X.device)
+        self._lib.call("gdr_standardize_apply", N, D, self.ptr(X) if N else 0, X.stride(0) if N else D, self.ptr(mean32),
+                       self.ptr(scale32), self.ptr(out) if N else 0, out.stride(0) if N else D, self.stream())
+        return out
+
     # -- stage 2 --
     def empty_rows(self, rows, f, like):
         return self.new_padded(rows, f, like.device, zero=True)
@@ -398,23 +431,30 @@ class CudaOps:
     def label_counts(self, labels, n):
         return self._co.label_counts(labels, n)
 
-    def coarsen_records(self, A_local, labels_src, labels_dst, n, world):
+    def coarsen_records(self, A_local, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
         """Local edges -> sorted (cell, count, weight sum) records [m, 2] int64 (gdr_coarsen + gdr_coarse_records) and the
-        number of records per owner rank of the key-range partition (coarse row a belongs to rank a // ceil(n / world))."""
-        rowptr, colidx, counts, wsum = self._co.coarsen_edges(labels_src, labels_dst, n, n, csr=A_local,
-                                                              weights=A_local.vals, drop_diag=True)
+        number of records per owner rank of the key-range partition (coarse row a belongs to rank a // ceil(n / world)).
+        Edges: the CSR ``A_local`` (graph_compress: weights summed, diagonal dropped) or the COO lines ``src`` / ``dst``
+        (build_condensed_bipartite: plain line counts)."""
+        n_dst = n if n_dst is None else n_dst
+        if A_local is not None:
+            rowptr, colidx, counts, wsum = self._co.coarsen_edges(labels_src, labels_dst, n, n_dst, csr=A_local,
+                                                                  weights=A_local.vals, drop_diag=True)
+        else:
+            rowptr, colidx, counts, wsum = self._co.coarsen_edges(labels_src, labels_dst, n, n_dst, src=src, dst=dst)
         m = int(colidx.numel())
         rec = torch.empty((m, 2), dtype=torch.int64, device=labels_dst.device)
         if m:
-            self._lib.call("gdr_coarse_records", n, n, self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum),
+            self._lib.call("gdr_coarse_records", n, n_dst, self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum),
                            self.ptr(rec), self.stream())
         cr = (n + world - 1) // world
         bounds = torch.tensor([min(n, r * cr) for r in range(world + 1)], dtype=torch.int64, device=rowptr.device)
         cuts = rowptr[bounds].cpu().tolist()
         return rec, [int(cuts[r + 1] - cuts[r]) for r in range(world)]
 
-    def coarse_merge(self, rec, a_lo, n_rows, n):
+    def coarse_merge(self, rec, a_lo, n_rows, n, n_dst=None):
         """Records received from every rank -> CSR (rowptr, colidx, counts, wsum) of the coarse rows [a_lo, a_lo + n_rows)."""
+        n_dst = n if n_dst is None else n_dst
         m = int(rec.shape[0])
         dev = rec.device
         rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
@@ -423,7 +463,7 @@ class CudaOps:
         wsum = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
         nnz = torch.zeros(1, dtype=torch.int64, device=dev)
         ws = self.workspace(self._lib.query("gdr_coarse_merge_ws_bytes", m), dev)
-        self._lib.call("gdr_coarse_merge", m, self.ptr(rec) if m else 0, int(a_lo), int(n_rows), n, n, self.ptr(rowptr),
+        self._lib.call("gdr_coarse_merge", m, self.ptr(rec) if m else 0, int(a_lo), int(n_rows), n, n_dst, self.ptr(rowptr),
                        self.ptr(colidx), self.ptr(counts), self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
         k = int(nnz.item())
         return rowptr, colidx[:k], counts[:k], wsum[:k]
@@ -769,7 +809,15 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
         return a_lo, rowptr, colidx, vals, counts
     if world == 1:
         return ops.csr_to_coo(rowptr, colidx, vals, n), counts
-    # replicate: all-gather the pieces (variable sizes) and the row pointers
+    rowptr_all, col_all, val_all, cnt_all = _replicate_coarse_rows(comm, n, rowptr, colidx, vals, counts)
+    return ops.csr_to_coo(rowptr_all, col_all, val_all, n), cnt_all
+
+
+def _replicate_coarse_rows(comm: Comm, n: int, rowptr, colidx, vals, counts):
+    """All-gather of the key-range pieces (variable sizes) and their row pointers: every rank ends with the whole CSR."""
+    world, dev = comm.world, rowptr.device
+    cr = (n + world - 1) // world
+    n_rows = int(rowptr.shape[0]) - 1
     nnz_mine = torch.tensor([int(colidx.shape[0])], dtype=torch.int64, device=dev)
     nnz_all = torch.empty(world, dtype=torch.int64, device=dev)
     comm.all_gather_rows(nnz_mine, nnz_all)
@@ -790,4 +838,125 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
             rowptr_all[lo: lo + rows_r] = rp_g[r * (cr + 1): r * (cr + 1) + rows_r] + off
         off += nnz_list[r]
     rowptr_all[n] = off
-    return ops.csr_to_coo(rowptr_all, col_all, val_all, n), cnt_all
+    return rowptr_all, col_all, val_all, cnt_all
+
+
+# ------------------------------------------------------------------------------------------
+# distill_recsys on a row partition: users and items each split over the ranks
+# ------------------------------------------------------------------------------------------
+def _block_sizes(part: RowPartition):
+    return [part.bounds(r)[1] - part.bounds(r)[0] for r in range(part.world)]
+
+
+def dist_build_interaction(comm: Comm, part_u: RowPartition, part_i: RowPartition, u_slice: torch.Tensor,
+                           i_slice: torch.Tensor, ops=None):
+    """build_interaction_matrix (distill_recsys.py:110-117) from a SLICE of the interaction lines per rank.  Returns
+    (R_local, RT_local): the rows of R (users x items) of this rank's users and the rows of R^T of this rank's items,
+    duplicate lines summed, global column ids — two all-to-alls of the lines, bucketed by the owner of u and of i."""
+    ops = ops or CudaOps()
+    nu, ni = part_u.n, part_i.n
+    u = u_slice.to(torch.int64)
+    i = i_slice.to(torch.int64)
+    if u.numel() and (int(u.min()) < 0 or int(u.max()) >= nu or int(i.min()) < 0 or int(i.max()) >= ni):
+        raise ValueError("row/col index exceeds matrix dimensions")
+    e_u, c_u = ops.bucket_by_owner(u, i, part_u.rows_per, part_u.world)
+    recv_u, _ = comm.all_to_all_rows(e_u, c_u)
+    R_local = ops.build_block_csr_weighted(recv_u[:, 0] - part_u.lo, recv_u[:, 1], part_u.n_local, ni)
+    e_i, c_i = ops.bucket_by_owner(i, u, part_i.rows_per, part_i.world)
+    recv_i, _ = comm.all_to_all_rows(e_i, c_i)
+    RT_local = ops.build_block_csr_weighted(recv_i[:, 0] - part_i.lo, recv_i[:, 1], part_i.n_local, nu)
+    return R_local, RT_local
+
+
+def dist_bipartite_normalize(comm: Comm, part_u: RowPartition, part_i: RowPartition, R_local, RT_local, ops=None,
+                             eps: float = 1e-8):
+    """LightGCN edge norm (distill_recsys.py:329-335) for both row blocks: own row degrees, all-gather of the degree vector
+    of the other side.  Same fp32 chains as the single-device build: values bit-identical.
+    Returns (A_local [users x items], AT_local [items x users], deg_u_local, deg_i_local)."""
+    ops = ops or CudaOps()
+    deg_u_l, deg_i_l = ops.row_sums(R_local), ops.row_sums(RT_local)
+    deg_u = comm.all_gather_var(deg_u_l, _block_sizes(part_u))
+    deg_i = comm.all_gather_var(deg_i_l, _block_sizes(part_i))
+    return (ops.bip_norm_block(R_local, deg_u_l, deg_i, eps), ops.bip_norm_block(RT_local, deg_i_l, deg_u, eps),
+            deg_u_l, deg_i_l)
+
+
+def dist_lightgcn_propagate(comm: Comm, part_u: RowPartition, part_i: RowPartition, A_local, AT_local,
+                            u0_local: torch.Tensor, i0_local: torch.Tensor, num_layers: int, ops=None):
+    """Forward of LightGCNCondensed.propagate (distill_recsys.py:337-353) on row-partitioned embeddings: per layer an
+    all-gather of the item rows and of the user rows, then the two CSR SpMMs on the local rows (u <- A i, i <- A^T u,
+    simultaneous update), output = mean over the L + 1 layers.  Row-wise independent: bit-identical to one device."""
+    ops = ops or CudaOps()
+    u, it = ops.prep_rows(u0_local), ops.prep_rows(i0_local)
+    d = u.shape[1]
+    u_acc, i_acc = ops.scale(u, 1.0), ops.scale(it, 1.0)
+    ru, ri = part_u.rows_per, part_i.rows_per
+    u_full, i_full = ops.empty_rows(ru * part_u.world, d, u), ops.empty_rows(ri * part_i.world, d, it)
+    u_blk, i_blk = ops.empty_rows(ru, d, u), ops.empty_rows(ri, d, it)
+    for _ in range(int(num_layers)):
+        u_blk[: u.shape[0]].copy_(u)
+        i_blk[: it.shape[0]].copy_(it)
+        comm.all_gather_rows(u_blk, u_full)
+        comm.all_gather_rows(i_blk, i_full)
+        u_next = ops.spmm(A_local, i_full, 1.0, u_acc, 1.0)
+        i_next = ops.spmm(AT_local, u_full, 1.0, i_acc, 1.0)
+        u, it = u_next, i_next
+    inv = 1.0 / float(num_layers + 1)
+    return ops.scale(u_acc, inv), ops.scale(i_acc, inv)
+
+
+def dist_standard_scale(comm: Comm, x_local: torch.Tensor, ops=None):
+    """StandardScaler().fit_transform (distill_recsys.py:172) on row-partitioned X: fp64 column sums and second moments
+    about the mean are all-reduced (two passes, as sklearn's), result fp32((x - fp32(mean)) / fp32(scale))."""
+    ops = ops or CudaOps()
+    X = ops.prep_rows(x_local)
+    n_local, D = X.shape
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=X.device)
+    comm.all_reduce(cnt)
+    N = int(cnt.item())
+    s1 = ops.column_sums(X)
+    comm.all_reduce(s1)
+    mean64 = (s1[:D] / N).contiguous()
+    s2 = ops.column_moments(X, mean64)
+    comm.all_reduce(s2)
+    var = s2[D:] / N
+    eps = 2.220446049250313e-16                                   # sklearn _is_constant_feature
+    bound = N * eps * var + (N * mean64 * eps) ** 2
+    scale = torch.where(var <= bound, torch.ones_like(var), var.sqrt())
+    return ops.standardize_apply(X, mean64.to(torch.float32).contiguous(), scale.to(torch.float32).contiguous())
+
+
+def dist_build_condensed_bipartite(comm: Comm, part_u: RowPartition, part_i: RowPartition, u_slice: torch.Tensor,
+                                   i_slice: torch.Tensor, u2cu_local: torch.Tensor, i2ci_local: torch.Tensor, num_cu: int,
+                                   num_ci: int, ops=None, replicate: bool = True):
+    """build_condensed_bipartite (distill_recsys.py:184-201): C[cu, ci] = number of train LINES (u, i) with
+    u2cu[u] = cu, i2ci[i] = ci, duplicates counted.  The cluster maps (row-partitioned k-means labels) are all-gathered,
+    every rank counts its slice of the lines, the (cell, count) runs are exchanged by key range and merged: integer
+    counts, independent of the rank count.  Returns (rowptr, colidx, counts f32) of the whole num_cu x num_ci CSR
+    (``replicate``) or (a_lo, rowptr, colidx, counts f32) of this rank's range of cu rows."""
+    ops = ops or CudaOps()
+    dev = u_slice.device
+    world = comm.world
+
+    def gather_map(part, local):
+        block = torch.full((part.rows_per,), -1, dtype=torch.int32, device=dev)
+        block[: local.shape[0]] = local.to(torch.int32)
+        full = torch.empty(part.rows_per * world, dtype=torch.int32, device=dev)
+        comm.all_gather_rows(block, full)
+        return full            # padded layout index == global id (equal contiguous blocks)
+
+    mu, mi = gather_map(part_u, u2cu_local), gather_map(part_i, i2ci_local)
+    rec, send_counts = ops.coarsen_records(None, mu, mi, int(num_cu), world, n_dst=int(num_ci),
+                                           src=u_slice.to(torch.int64), dst=i_slice.to(torch.int64))
+    recv, _ = comm.all_to_all_rows(rec, send_counts)
+    cr = (int(num_cu) + world - 1) // world
+    a_lo = min(int(num_cu), comm.rank * cr)
+    n_rows = min(int(num_cu), a_lo + cr) - a_lo
+    rowptr, colidx, counts, _ = ops.coarse_merge(recv, a_lo, n_rows, int(num_cu), n_dst=int(num_ci))
+    vals = counts.to(torch.float32)
+    if not replicate:
+        return a_lo, rowptr, colidx, vals
+    if world == 1:
+        return rowptr, colidx, vals
+    rowptr_all, col_all, val_all, _ = _replicate_coarse_rows(comm, int(num_cu), rowptr, colidx, vals, counts)
+    return rowptr_all, col_all, val_all

@@ -464,6 +464,19 @@ int64_t gdr_coarse_merge_ws_bytes(int64_t m);
 int     gdr_coarse_merge(int64_t m, const uint64_t* records, int64_t a_lo, int64_t n_rows, int64_t n_src,
                          int64_t n_dst, int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
                          int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+/* distill_recsys on a row partition (users and items each split over the ranks):
+ *   gdr_bipartite_norm_block   distill_recsys.py:329-335 for a row block of R (or of R^T): own row degrees
+ *                              (gdr_row_sums_f32) + the all-gathered degrees of the other side
+ *   gdr_column_moments         second pass of StandardScaler (distill_recsys.py:172) on a row block: fp64
+ *                              [sum (x - mean) | sum (x - mean)^2], to be all-reduced (first pass: gdr_column_sums)
+ *   gdr_standardize_apply      fp32((x - mean) / scale) with the reduced column parameters */
+int gdr_bipartite_norm_block(int64_t n_rows, int64_t nnz, const int32_t* rowptr, const int32_t* colidx, const float* w,
+                             const float* deg_rows, const float* deg_cols, float eps, float* norm_out,
+                             gdr_stream_t stream);
+int gdr_column_moments(int64_t N, int64_t D, const float* X, int64_t ldx, const double* mean64, double* sums_out,
+                       void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int gdr_standardize_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean32, const float* scale32,
+                          float* out, int64_t ldo, gdr_stream_t stream);
 /* gdr_kmeans_lloyd on a row partition: Xc_local = this rank's N_local rows (may be 0) of the mean-centred matrix of
  * N_total rows, centres replicated.  Each iteration all-reduces [K x ld sums | K counts | n_changed] inside the replayed
  * CUDA graph; the replicated centres stay bit-identical across ranks; empty clusters are relocated from the globally

@@ -73,6 +73,55 @@ def exact_band_check(labels, rows, Xc, Cc, band=1e-6):
     return n_band, n_bad
 
 
+def single_step_protocol(gdr, dev, oracle, X, C0, sample=None):
+    """SURVEY 8c protocol 1 against scikit-learn's own E-step (sklearn/cluster/_kmeans.py:761 _labels_inertia, the routine
+    behind KMeans.fit) on SHARED mean-centred inputs:
+      labels     ours == sklearn's, except rows inside the 1e-6 relative margin band (either of the two nearest accepted,
+                 checked in exact fp64); ours additionally against the exact fp64 argmin (all rows, or ``sample`` rows)
+      M-step     per-cluster sums / counts on our labels bit-identical to the sequential fp32 oracle
+      C_{t+1}    KMeans(max_iter=1) centres within 1e-5 of sklearn's for every cluster whose membership is identical,
+                 WCSS within 1e-4
+    Returns our first-step labels."""
+    import os
+    from sklearn.cluster import KMeans as SkKMeans
+    from sklearn.cluster._kmeans import _labels_inertia_threadpool_limit
+    from gdr._dev import padded_rows
+    n, K = X.shape[0], C0.shape[0]
+    mean = X.mean(axis=0)
+    Xc, C0c = np.ascontiguousarray(X - mean), np.ascontiguousarray(C0 - mean)
+    Xd, Cd = padded_rows(torch.from_numpy(Xc).to(dev)), padded_rows(torch.from_numpy(C0c).to(dev))
+    lab_d = torch.empty(n, dtype=torch.int32, device=dev)
+    gdr.assign_labels(Xd, Cd, lab_d, tc_operand=gdr.kmeans.TcOperand(Xd) if X.shape[1] <= 128 else None)
+    lab = np_(lab_d)
+    rows = np.arange(n) if sample is None else np.sort(np.random.RandomState(1).choice(n, sample, replace=False))
+    _, n_bad = exact_band_check(lab, rows, Xc, C0c)
+    assert n_bad == 0, f"{n_bad} rows outside the 1e-6 band disagree with the exact fp64 argmin"
+    sk_lab = _labels_inertia_threadpool_limit(Xc, np.ones(n, dtype=np.float32), C0c, n_threads=len(os.sched_getaffinity(0)),
+                                              return_inertia=False)
+    diff = np.flatnonzero(lab != sk_lab)
+    assert diff.size <= max(8, int(2e-4 * n)), f"{diff.size} rows differ from sklearn's E-step"
+    if diff.size:
+        _, bad_ours = exact_band_check(lab, diff, Xc, C0c)
+        _, bad_sk = exact_band_check(sk_lab, diff, Xc, C0c)
+        assert bad_ours == 0, f"{bad_ours} of {diff.size} differing rows: our label is outside the band"
+        assert bad_sk == 0      # (sklearn's fp32 GEMM is itself only exact inside the band)
+    sums, counts = gdr.segment_sum(Xd, lab_d, K)
+    s_ref, c_ref = oracle.segment_sum(Xc, lab, K)
+    assert np.array_equal(np_(counts), c_ref) and np.array_equal(np_(sums), s_ref)
+    del Xd, lab_d, sums
+    km1 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(X)
+    sk1 = SkKMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0, algorithm="lloyd").fit(X)
+    same = np.ones(K, dtype=bool)
+    same[lab[diff]] = False
+    same[sk_lab[diff]] = False
+    same &= c_ref > 0
+    assert same.sum() >= K - 4 * max(1, diff.size) - (c_ref == 0).sum()
+    np.testing.assert_allclose(km1.cluster_centers_[same], sk1.cluster_centers_[same], rtol=1e-5, atol=1e-5)
+    assert abs(km1.inertia_ - sk1.inertia_) <= 1e-4 * sk1.inertia_
+    assert (km1.labels_ != sk1.labels_).mean() <= 1e-3
+    return lab
+
+
 # ---------------------------------------------------------------------------------------------- config B
 @pytest.fixture(scope="module")
 def cfg_b(gdr, dev):
@@ -121,27 +170,7 @@ def test_config_b_stage3_equals_sklearn(gdr, dev, oracle, cfg_b, space):
     else:
         X = synth.clustered_features(n, cfg_b["d_logit"], cfg_b["d_logit"], seed=77)
     C0 = synth.kmeans_init(X, K, seed=1235)
-    # protocol 1: ONE Lloyd step from shared centres — labels exact outside the band, centres 1e-5, counts exact
-    km1 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(X)
-    sk1 = SkKMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0, algorithm="lloyd").fit(X)
-    mean = X.mean(axis=0)
-    diff = np.flatnonzero(km1.labels_ != sk1.labels_)
-    if diff.size:
-        n_band, n_bad = exact_band_check(km1.labels_, diff, X - mean, sk1.cluster_centers_ - mean)
-        assert n_bad == 0, f"{n_bad} of {diff.size} differing rows lie outside the 1e-6 band"
-    np.testing.assert_allclose(km1.cluster_centers_, sk1.cluster_centers_, rtol=1e-5, atol=1e-5)
-    # the E-step alone from C0 against the exact fp64 argmin on every row
-    from gdr._dev import padded_rows
-    Xc = X - mean
-    Xd, Cd = padded_rows(torch.from_numpy(Xc).to(dev)), padded_rows(torch.from_numpy(C0 - mean).to(dev))
-    lab = torch.empty(n, dtype=torch.int32, device=dev)
-    gdr.assign_labels(Xd, Cd, lab, tc_operand=gdr.kmeans.TcOperand(Xd))
-    n_band, n_bad = exact_band_check(np_(lab), np.arange(n), Xc, C0 - mean)
-    assert n_bad == 0
-    # M-step on those labels: bit-identical to the sequential oracle
-    sums, counts = gdr.segment_sum(Xd, lab, K)
-    s_ref, c_ref = oracle.segment_sum(Xc, np_(lab), K)
-    assert np.array_equal(np_(counts), c_ref) and np.array_equal(np_(sums), s_ref)
+    single_step_protocol(gdr, dev, oracle, X, C0)
     # protocol 2: end to end, 20 iterations tol = 0 — same iteration count, WCSS within 1e-4
     km = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=20, tol=0).fit(X)
     sk = SkKMeans(n_clusters=K, init=C0, n_init=1, max_iter=20, tol=0, algorithm="lloyd").fit(X)
@@ -242,36 +271,17 @@ def test_config_e_one_hop_equals_oracle_on_sampled_rows(gdr, dev, oracle, cfg_e)
 
 
 def test_config_e_estep_equals_exact_argmin_and_sklearn(gdr, dev, oracle, cfg_e):
-    """K = 10 000 (10 240 padded) centres x 2.45 M rows through the two-level tcgen05 screen: (i) one E-step from C0
-    against the exact fp64 argmin on 60 000 sampled rows, (ii) KMeans(max_iter=1) against sklearn's labels on all rows."""
-    from sklearn.cluster import KMeans as SkKMeans
+    """K = 10 000 (10 240 padded) centres x 2.45 M rows through the two-level tcgen05 screen: one E-step from shared
+    centres against sklearn's own E-step on ALL rows and against the exact fp64 argmin on 60 000 sampled rows, the
+    M-step against the sequential oracle, and KMeans(max_iter=1) against sklearn's fit (single_step_protocol)."""
     from gdr import synth
-    from gdr._dev import padded_rows
     n, K, f = cfg_e["n"], cfg_e["k"], cfg_e["f"]
     target = cfg_e.get("target")
     if target is None:
         target = gdr.propagate(cfg_e["An"], torch.from_numpy(synth.features(n, f, seed=1338)).to(dev), 2, 0.8)[1]
     X = np.ascontiguousarray(np_(target))
     C0 = synth.kmeans_init(X, K, seed=1238)
-    mean = X.mean(axis=0)
-    Xc = X - mean
-    Xd, Cd = padded_rows(torch.from_numpy(Xc).to(dev)), padded_rows(torch.from_numpy(C0 - mean).to(dev))
-    lab = torch.empty(n, dtype=torch.int32, device=dev)
-    gdr.assign_labels(Xd, Cd, lab, tc_operand=gdr.kmeans.TcOperand(Xd))
-    rows = np.sort(np.random.RandomState(1).choice(n, 60_000, replace=False))
-    n_band, n_bad = exact_band_check(np_(lab), rows, Xc, C0 - mean)
-    assert n_bad == 0, f"{n_bad} sampled rows outside the 1e-6 band disagree with the exact argmin"
-    del Xd, lab
-    km1 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(X)
-    sk1 = SkKMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0, algorithm="lloyd").fit(X)
-    np.testing.assert_allclose(km1.cluster_centers_, sk1.cluster_centers_, rtol=1e-5, atol=1e-5)
-    diff = np.flatnonzero(km1.labels_ != sk1.labels_)
-    assert diff.size <= 1e-4 * n
-    if diff.size:
-        n_band, n_bad = exact_band_check(km1.labels_, diff, Xc, sk1.cluster_centers_ - mean)
-        assert n_bad == 0, f"{n_bad} of {diff.size} differing rows lie outside the 1e-6 band"
-    assert abs(km1.inertia_ - sk1.inertia_) <= 1e-4 * sk1.inertia_
-    cfg_e["labels"] = km1.labels_
+    cfg_e["labels"] = single_step_protocol(gdr, dev, oracle, X, C0, sample=60_000)
 
 
 def test_config_e_stage4_counts_equal_scipy(gdr, dev, cfg_e):
@@ -327,15 +337,8 @@ def test_bipartite_config_equals_oracle(gdr, dev, oracle, name, idx):
         got = np_(gdr.standard_scale(torch.from_numpy(emb).to(dev)))
         np.testing.assert_allclose(got, Xs, rtol=1e-6, atol=1e-6)
         C0 = synth.kmeans_init(got, K, seed)
-        km = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(got)
-        sk = SkKMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0, algorithm="lloyd").fit(got)
-        np.testing.assert_allclose(km.cluster_centers_, sk.cluster_centers_, rtol=1e-5, atol=1e-5)
-        diff = np.flatnonzero(km.labels_ != sk.labels_)
-        if diff.size:
-            mean = got.mean(axis=0)
-            _, n_bad = exact_band_check(km.labels_, diff, got - mean, sk.cluster_centers_ - mean)
-            assert n_bad == 0
-        maps.append((km.labels_.astype(np.int64), K))
+        lab = single_step_protocol(gdr, dev, oracle, got, C0)
+        maps.append((lab.astype(np.int64), K))
     # a10: condensed bipartite counts (distill_recsys.py:184-201), duplicates included: sum C = #lines
     (u2cu, ncu), (i2ci, nci) = maps
     C = gdr.build_condensed_bipartite(u, i, u2cu, i2ci, ncu, nci, device=dev)

@@ -82,6 +82,28 @@ class OracleOps:
         assert np.array_equal(np.bincount(r_all, minlength=nl), np.diff(rowptr_out.numpy()))
         return CpuCSR(rowptr_out, torch.from_numpy(c_all.astype(np.int32)), torch.from_numpy(out), A.shape)
 
+    # -- bipartite --
+    def build_block_csr_weighted(self, rows_local, cols, n_local, n_cols):
+        rp, ci, va = self.o.coo_to_csr(rows_local.numpy(), cols.numpy(), None, (n_local, n_cols), symmetrize=False, binarize=False)
+        return CpuCSR(torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va), (n_local, n_cols))
+
+    def row_sums(self, A):
+        return torch.from_numpy(self.o.row_degree_f32(A.rowptr.numpy(), A.vals.numpy()))
+
+    def bip_norm_block(self, A, deg_rows, deg_cols, eps):
+        rows = np.repeat(np.arange(A.shape[0], dtype=np.int64), np.diff(A.rowptr.numpy()))
+        e = np.float32(eps)
+        w = A.vals.numpy()
+        norm = w / (np.sqrt(deg_rows.numpy()[rows] + e) * np.sqrt(deg_cols.numpy()[A.colidx.numpy()] + e))
+        return CpuCSR(A.rowptr, A.colidx, torch.from_numpy(norm.astype(np.float32)), A.shape)
+
+    def column_moments(self, X, mean64):
+        d = X.numpy().astype(np.float64) - mean64.numpy()[None, :]
+        return torch.from_numpy(np.concatenate([d.sum(0), (d * d).sum(0)]))
+
+    def standardize_apply(self, X, mean32, scale32):
+        return torch.from_numpy(((X.numpy() - mean32.numpy()) / scale32.numpy()).astype(np.float32))
+
     def prep_rows(self, x):
         return x.to(torch.float32).contiguous()
 
@@ -181,21 +203,26 @@ class OracleOps:
             b += 1
         return b
 
-    def coarsen_records(self, A, labels_src, labels_dst, n, world):
-        rows = np.repeat(np.arange(A.shape[0]), np.diff(A.rowptr.numpy()))
-        rp, ci, cnt, wsum = self.o.coarsen_counts(rows, A.colidx.numpy(), labels_src.numpy(), labels_dst.numpy(), n, n,
-                                                  w=A.vals.numpy(), drop_diag=True)
+    def coarsen_records(self, A, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
+        n_dst = n if n_dst is None else n_dst
+        if A is not None:
+            rows = np.repeat(np.arange(A.shape[0]), np.diff(A.rowptr.numpy()))
+            rp, ci, cnt, wsum = self.o.coarsen_counts(rows, A.colidx.numpy(), labels_src.numpy(), labels_dst.numpy(), n, n_dst,
+                                                      w=A.vals.numpy(), drop_diag=True)
+        else:
+            rp, ci, cnt, _ = self.o.coarsen_counts(src.numpy(), dst.numpy(), labels_src.numpy(), labels_dst.numpy(), n, n_dst)
+            wsum = np.zeros(cnt.shape[0], np.float32)
         a = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
-        key = (a << self._bits(n)) | ci.astype(np.int64)
+        key = (a << self._bits(n_dst)) | ci.astype(np.int64)
         wbits = wsum.astype(np.float32).view(np.uint32).astype(np.int64)
         rec = np.stack([key, (cnt.astype(np.int64) << 32) | wbits], axis=1)
         cr = (n + world - 1) // world
         cuts = [int(rp[min(n, r * cr)]) for r in range(world + 1)]
         return torch.from_numpy(rec), [cuts[r + 1] - cuts[r] for r in range(world)]
 
-    def coarse_merge(self, rec, a_lo, n_rows, n):
+    def coarse_merge(self, rec, a_lo, n_rows, n, n_dst=None):
         rec = rec.numpy()
-        bb = self._bits(n)
+        bb = self._bits(n if n_dst is None else n_dst)
         order = np.argsort(rec[:, 0], kind="stable")
         key, val = rec[order, 0], rec[order, 1]
         head = np.ones(key.shape[0], bool)
@@ -298,6 +325,41 @@ def _worker(rank, world, port, case):
             mx = cc.clone()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             assert torch.equal(cc, mx)
+        elif case == "bipartite":
+            # distill_recsys on a row partition: users and items each split over the ranks
+            nu, ni, d, L = 301, 207, 8, 2
+            uu, ii = synth.bipartite_interactions(nu, ni, 4000, seed=9)
+            rs = np.random.RandomState(10)
+            u0 = (0.1 * rs.standard_normal((nu, d))).astype(np.float32)
+            i0 = (0.1 * rs.standard_normal((ni, d))).astype(np.float32)
+            pu, pi = par.RowPartition(nu, world, rank), par.RowPartition(ni, world, rank)
+            per = (uu.shape[0] + world - 1) // world
+            sl = slice(rank * per, min(uu.shape[0], (rank + 1) * per))
+            u_sl, i_sl = torch.from_numpy(uu[sl].copy()), torch.from_numpy(ii[sl].copy())
+            R_l, RT_l = par.dist_build_interaction(comm, pu, pi, u_sl, i_sl, ops=ops)
+            rp, ci, w = o.coo_to_csr(uu, ii, None, (nu, ni))
+            b, e = int(rp[pu.lo]), int(rp[pu.hi])
+            assert np.array_equal(R_l.rowptr.numpy(), rp[pu.lo:pu.hi + 1] - rp[pu.lo])
+            assert np.array_equal(R_l.colidx.numpy(), ci[b:e]) and np.array_equal(R_l.vals.numpy(), w[b:e])
+            A_l, AT_l, du_l, di_l = par.dist_bipartite_normalize(comm, pu, pi, R_l, RT_l, ops=ops)
+            norm, du, di = o.bipartite_normalize(rp, ci, w, nu, ni)
+            assert np.array_equal(du_l.numpy(), du[pu.lo:pu.hi]) and np.array_equal(di_l.numpy(), di[pi.lo:pi.hi])
+            assert np.array_equal(A_l.vals.numpy(), norm[b:e])
+            uo, io = par.dist_lightgcn_propagate(comm, pu, pi, A_l, AT_l, torch.from_numpy(u0[pu.lo:pu.hi].copy()),
+                                                 torch.from_numpy(i0[pi.lo:pi.hi].copy()), L, ops=ops)
+            ur, ir = o.lightgcn_propagate(rp, ci, w, u0, i0, L)
+            np.testing.assert_allclose(uo.numpy(), ur[pu.lo:pu.hi], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(io.numpy(), ir[pi.lo:pi.hi], rtol=1e-6, atol=1e-7)
+            xs = par.dist_standard_scale(comm, torch.from_numpy(u0[pu.lo:pu.hi].copy()), ops=ops)
+            np.testing.assert_allclose(xs.numpy(), o.standard_scale(u0)[pu.lo:pu.hi], rtol=1e-6, atol=1e-6)
+            ncu, nci = 31, 21
+            u2cu = rs.randint(0, ncu, nu).astype(np.int32)
+            i2ci = rs.randint(0, nci, ni).astype(np.int32)
+            rpc, cic, vc = par.dist_build_condensed_bipartite(comm, pu, pi, u_sl, i_sl, torch.from_numpy(u2cu[pu.lo:pu.hi].copy()),
+                                                              torch.from_numpy(i2ci[pi.lo:pi.hi].copy()), ncu, nci, ops=ops)
+            rp_r, ci_r, cnt_r, _ = o.coarsen_counts(uu, ii, u2cu, i2ci, ncu, nci)
+            assert np.array_equal(rpc.numpy(), rp_r) and np.array_equal(cic.numpy(), ci_r)
+            assert np.array_equal(vc.numpy(), cnt_r.astype(np.float32)) and int(vc.sum()) == uu.shape[0]
         elif case == "wire":
             # row-padded views (width 7 inside a leading dimension of 8: what _dev.new_padded returns for f % 4 != 0)
             # are non-contiguous; the collectives run on the padded base and leave the padding column zero
@@ -344,7 +406,7 @@ def _worker(rank, world, port, case):
 
 
 @pytest.mark.parametrize("case", ["build", "propagate", "propagate_slabs", "propagate_rows", "kmeans", "kmeans_empty", "coarsen",
-                                  "wire"])
+                                  "wire", "bipartite"])
 def test_world2_gloo(case, oracle):
     mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
 
