@@ -1035,10 +1035,12 @@ def run_ours_multi(args, rank, world, dev, w):
     def step():
         e = [ev() for _ in range(5)]
         e[0].record()
+        # the feature rows start travelling to the peers' gathered operand (side stream, NVLink) under stage 1
+        pre = par.prefetch_rows(comm, part, x_local, ops=ops) if args.hop in ("auto", "p2p") and not args.no_prefetch else None
         A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)   # exchange-based: 1/world of the pairs per rank
         e[1].record()
         prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs,
-                                          row_chunks=args.row_chunks)
+                                          row_chunks=args.row_chunks, hop=args.hop, prefetched=pre)
         e[2].record()
         km = par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target)
         e[3].record()
@@ -1084,7 +1086,7 @@ def run_ours_multi(args, rank, world, dev, w):
     # ---- roofline leg (per GPU): the E-step tensor-core screen of this rank's row block, timed by the
     #      library's own CUDA-event pairs on its launch stream ----
     A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)
-    _, target_l = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops)
+    _, target_l = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, hop=args.hop)
     assign_ms, _ = _profile_kernel(
         _lib, 1, lambda: par.DistKMeans(K, C0, max_iter=LLOYD_ITERS, tol=0, ops=ops, comm=comm).fit(target_l), 1, flush)
     am = torch.tensor([assign_ms], dtype=torch.float64, device=dev)
@@ -1093,7 +1095,7 @@ def run_ours_multi(args, rank, world, dev, w):
     # per-hop split: the SpMM of this rank's rows alone (library event pairs) beside the whole hop
     spmm_ms, n_sp = _profile_kernel(
         _lib, 2, lambda: par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs,
-                                            row_chunks=args.row_chunks), 3, flush)
+                                            row_chunks=args.row_chunks, hop=args.hop), 3, flush)
     sm = torch.tensor([spmm_ms * n_sp / 3.0 / hops], dtype=torch.float64, device=dev)   # SpMM kernel time per hop
     dist.all_reduce(sm, op=dist.ReduceOp.MAX)
     spmm_per_hop = float(sm.item())
@@ -1141,7 +1143,7 @@ def run_ours_multi(args, rank, world, dev, w):
             "warmup": args.warmup, "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.workload, w), "nnz_a_hat": int(nnz),
-                       "parallelism": f"row-partition x{world}: " + par.describe(world, args.row_chunks),
+                       "parallelism": f"row-partition x{world}: " + par.describe(world, args.row_chunks, args.hop),
                        "precision": args.precision, "l2": "flushed between timed steps (256 MB write)"},
             "prop": {"metric": "A^K.X", "value": prop_gbs, "unit": "GB/s", "frac_hbm_measured": prop_gbs / (pk["hbm"] * world),
                      "bytes_model": ("B_gather" if prop_model == "gather" else "B_min") + " (whole job, incl. the all-gather time)",
@@ -1342,6 +1344,9 @@ def main():
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc", "auto"])
     ap.add_argument("--slabs", type=int, default=None, help="N > 1: column slabs of the pipelined hop (default: automatic)")
     ap.add_argument("--row-chunks", type=int, default=None, help="N > 1: row chunks of the pipelined hop (default: automatic)")
+    ap.add_argument("--hop", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: fused NVLink hop (SpMM epilogue stores into the peers' gathered operand) or NCCL all-gather hop")
+    ap.add_argument("--no-prefetch", action="store_true", help="N > 1: do not start the first row distribution under stage 1")
     ap.add_argument("--tc-screen", type=int, default=0, help="debug: 0 auto, 1 direct 3xTF32, 2/3 two-level screen (BN 128/256)")
     ap.add_argument("--ref-kmeans-iters", type=int, default=10)
     ap.add_argument("--ref-full-budget", type=float, default=420.0,

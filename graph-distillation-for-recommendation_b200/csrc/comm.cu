@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace gdr {
@@ -114,6 +115,61 @@ int comm_allgather(gdr_comm* c, const void* send, void* recv, int64_t bytes_per_
 
 }  // namespace gdr
 
+
+// ---- symmetric buffers over CUDA IPC (one process per GPU, all GPUs of one NVLink domain) ----------------------
+namespace gdr {
+
+struct FlagPtrs {
+  uint32_t* f[GDR_MAX_RANKS];
+};
+// every rank tells every peer "all my work enqueued before this kernel — including my stores into your copy — is done"
+__global__ void k_symm_signal(FlagPtrs fp, int n, int rank, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fp.f[p] + rank), "r"(epoch) : "memory");
+  }
+}
+
+// ... and waits until every peer has said so
+__global__ void k_symm_wait(const uint32_t* flag_local, int n, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p < n) {
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag_local + p) : "memory");
+    } while ((int32_t)(v - epoch) < 0);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+struct PutDst {
+  float* dst[GDR_MAX_RANKS];
+  int n;
+};
+// rows of `src` (ld floats each, ld % 4 == 0) -> the same rows of every destination (read once, n posted stores)
+__global__ void k_symm_put_rows(int64_t n4, const float4* __restrict__ src, PutDst d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    for (int p = 0; p < d.n; ++p) reinterpret_cast<float4*>(d.dst[p])[i] = v;
+  }
+}
+
+int symm_barrier(gdr_symm* sm, cudaStream_t s) {
+  if (sm->comm->world == 1) return GDR_OK;
+  const uint32_t e = ++sm->epoch;
+  FlagPtrs fp;
+  for (int p = 0; p < GDR_MAX_RANKS; ++p) fp.f[p] = p < sm->comm->world ? sm->flag_peer[p] : nullptr;
+  k_symm_signal<<<1, 32, 0, s>>>(fp, sm->comm->world, sm->comm->rank, e);
+  GDR_LAUNCHED();
+  k_symm_wait<<<1, 32, 0, s>>>(sm->flag_local, sm->comm->world, e);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+}  // namespace gdr
+
 using namespace gdr;
 
 extern "C" {
@@ -202,6 +258,118 @@ int gdr_allreduce_centroids(gdr_comm_t* comm, float* sums, int64_t n_floats, int
 int gdr_allreduce_f64(gdr_comm_t* comm, double* buf, int64_t n, int op_max, gdr_stream_t stream) {
   GDR_CHECK_ARG(comm && n >= 0 && (n == 0 || buf), "allreduce_f64: bad arguments");
   return comm_allreduce_f64(comm, buf, n, op_max, (cudaStream_t)stream);
+}
+
+
+int gdr_symm_create(gdr_comm_t* comm, int64_t bytes, gdr_symm_t** symm_out) {
+  GDR_CHECK_ARG(comm && bytes > 0 && symm_out, "symm_create: bad arguments");
+  GDR_CHECK_ARG(comm->world <= GDR_MAX_RANKS, "symm_create: world exceeds GDR_MAX_RANKS");
+  const int world = comm->world, rank = comm->rank;
+  const int64_t usable = align_up(bytes, 4096);
+  gdr_symm* sm = new gdr_symm();
+  memset(sm, 0, sizeof(*sm));
+  sm->comm = comm;
+  sm->bytes = usable;
+  auto fail = [&](const char* what, cudaError_t e) {
+    set_error("symm_create: %s -> %s", what, cudaGetErrorString(e));
+    if (sm->local) cudaFree(sm->local);
+    delete sm;
+    cudaGetLastError();
+    return GDR_ECUDA;
+  };
+  cudaError_t e = cudaMalloc((void**)&sm->local, (size_t)usable + 4096);
+  if (e != cudaSuccess) {
+    sm->local = nullptr;
+    return fail("cudaMalloc", e);
+  }
+  if ((e = cudaMemset(sm->local + usable, 0, 4096)) != cudaSuccess) return fail("cudaMemset", e);
+  sm->peer[rank] = sm->local;
+  if (world > 1) {
+    cudaIpcMemHandle_t mine;
+    if ((e = cudaIpcGetMemHandle(&mine, sm->local)) != cudaSuccess) return fail("cudaIpcGetMemHandle", e);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char *d_send = nullptr, *d_recv = nullptr;
+    if ((e = cudaMalloc((void**)&d_send, 64)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&d_recv, 64 * (size_t)world)) != cudaSuccess) return fail("cudaMalloc", e);
+    cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice);
+    int rc = comm_allgather(comm, d_send, d_recv, 64, nullptr);       // also orders every rank's memset before any signal
+    if (rc == GDR_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = GDR_ECUDA;
+    std::vector<cudaIpcMemHandle_t> all((size_t)world);
+    if (rc == GDR_OK) cudaMemcpy(all.data(), d_recv, 64 * (size_t)world, cudaMemcpyDeviceToHost);
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (rc != GDR_OK) {
+      cudaFree(sm->local);
+      delete sm;
+      return rc;
+    }
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) continue;
+      void* q = nullptr;
+      if ((e = cudaIpcOpenMemHandle(&q, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) {
+        for (int z = 0; z < p; ++z)
+          if (z != rank && sm->peer[z]) cudaIpcCloseMemHandle(sm->peer[z]);
+        return fail("cudaIpcOpenMemHandle (peer memory over NVLink unavailable)", e);
+      }
+      sm->peer[p] = (char*)q;
+    }
+  }
+  sm->flag_local = (uint32_t*)(sm->local + usable);
+  for (int p = 0; p < world; ++p) sm->flag_peer[p] = (uint32_t*)(sm->peer[p] + usable);
+  *symm_out = sm;
+  return GDR_OK;
+}
+
+int gdr_symm_destroy(gdr_symm_t* sm) {
+  if (!sm) return GDR_OK;
+  cudaDeviceSynchronize();
+  for (int p = 0; p < sm->comm->world; ++p)
+    if (p != sm->comm->rank && sm->peer[p]) cudaIpcCloseMemHandle(sm->peer[p]);
+  // nobody may still be writing into this copy: a last collective orders every rank's close before the free
+  if (sm->comm->world > 1 && sm->comm->nccl) {
+    int32_t* d = nullptr;
+    if (cudaMalloc((void**)&d, 4) == cudaSuccess) {
+      cudaMemset(d, 0, 4);
+      comm_allreduce_lloyd(sm->comm, nullptr, 0, d, 1, nullptr);
+      cudaStreamSynchronize(nullptr);
+      cudaFree(d);
+    }
+  }
+  cudaFree(sm->local);
+  cudaGetLastError();
+  delete sm;
+  return GDR_OK;
+}
+
+int gdr_symm_info(const gdr_symm_t* sm, void** local_ptr_host, int64_t* bytes_host) {
+  GDR_CHECK_ARG(sm, "symm_info: null buffer");
+  if (local_ptr_host) *local_ptr_host = sm->local;
+  if (bytes_host) *bytes_host = sm->bytes;
+  return GDR_OK;
+}
+
+int gdr_symm_barrier(gdr_symm_t* sm, gdr_stream_t stream) {
+  GDR_CHECK_ARG(sm, "symm_barrier: null buffer");
+  return symm_barrier(sm, (cudaStream_t)stream);
+}
+
+int gdr_symm_put_rows(gdr_symm_t* sm, int64_t dst_offset_bytes, const float* src, int64_t rows, int64_t ld,
+                      int include_self, gdr_stream_t stream) {
+  GDR_CHECK_ARG(sm && rows >= 0 && ld > 0 && ld % 4 == 0 && dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0,
+                "symm_put_rows: bad arguments");
+  if (rows == 0) return GDR_OK;
+  GDR_CHECK_ARG(src && ((uintptr_t)src & 15) == 0, "symm_put_rows: src misaligned");
+  GDR_CHECK_ARG(dst_offset_bytes + rows * ld * 4 <= sm->bytes, "symm_put_rows: destination range exceeds the buffer");
+  PutDst d;
+  d.n = 0;
+  for (int p = 0; p < sm->comm->world; ++p)
+    if (include_self || p != sm->comm->rank) d.dst[d.n++] = (float*)(sm->peer[p] + dst_offset_bytes);
+  if (d.n == 0) return GDR_OK;
+  const int64_t n4 = rows * ld / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n4, 256), kSMs * 8);
+  k_symm_put_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(n4, (const float4*)src, d);
+  GDR_LAUNCHED();
+  return GDR_OK;
 }
 
 int gdr_alltoallv(gdr_comm_t* comm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,

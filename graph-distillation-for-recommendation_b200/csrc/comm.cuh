@@ -3,10 +3,23 @@
 #include <cuda_runtime.h>
 #include <nccl.h>   // types and prototypes only: the functions are bound at run time (dlopen), never linked
 #include <stdint.h>
+#include "common.cuh"
 
 struct gdr_comm {
   ncclComm_t nccl;
   int rank, world, device;
+};
+
+// Symmetric buffer: the same allocation on every rank of the communicator, each rank holding peer-mapped (CUDA IPC over
+// NVLink) pointers to all copies, plus one epoch flag per source rank for the stream-ordered barrier.
+struct gdr_symm {
+  gdr_comm* comm;
+  char* local;
+  char* peer[GDR_MAX_RANKS];       // peer[rank] == local
+  int64_t bytes;                   // usable bytes (the flag page lies behind them)
+  uint32_t* flag_local;            // [GDR_MAX_RANKS] epochs written by the peers
+  uint32_t* flag_peer[GDR_MAX_RANKS];
+  uint32_t epoch;
 };
 
 namespace gdr {

@@ -53,6 +53,7 @@ struct ProfileScope {
 };
 
 constexpr int kSMs = 148;  // B200
+#define GDR_MAX_RANKS 16      // ranks of one NVLink domain a symmetric buffer can span
 
 // "done once" flags for per-device function attributes (cudaFuncSetAttribute is per device: a second
 // GPU driven from the same process needs its own opt-in).  Usage: static PerDevice<bool> set; if (!set.get()) ...

@@ -23,6 +23,7 @@
 //   * wide feature matrices can be processed in column windows (col_split) so
 //     that the window of X stays L2-resident across the whole pass.
 #include "common.cuh"
+#include "comm.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -65,6 +66,16 @@ __device__ __forceinline__ float4 ld_cs_f4(const float* p) {
 __device__ __forceinline__ void st_cs_f4(float* p, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// Multicast epilogue (multi-GPU hop fused with its all-gather): besides Y, every output row is stored into the gathered
+// operand of the NEXT hop on every rank — dst[p] are peer-mapped (NVLink) pointers to rank p's copy of that matrix, row
+// `row_off + r`, leading dimension `ld`.  n == 0: plain single-device epilogue.
+struct SpmmPeers {
+  float* dst[GDR_MAX_RANKS];
+  int n;
+  int64_t row_off;
+  int64_t ld;
+};
 
 template <int LPR, int NCH, int UNROLL, bool HINTS>
 __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ colidx,
@@ -125,12 +136,12 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ colidx,
   }
 }
 
-template <int LPR, int NCH, int UNROLL, bool HINTS>
-__global__ void __launch_bounds__(SPMM_THREADS, (NCH == 1 && UNROLL <= 2) ? 8 : ((NCH == 1 && UNROLL <= 4) ? 6 : 1))
+template <int LPR, int NCH, int UNROLL, bool HINTS, bool MC>
+__global__ void __launch_bounds__(SPMM_THREADS, MC ? (NCH == 1 ? 4 : 1) : ((NCH == 1 && UNROLL <= 2) ? 8 : ((NCH == 1 && UNROLL <= 4) ? 6 : 1)))
 k_spmm(int64_t rows, int c4_end, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
        const float* __restrict__ vals, float alpha, const float* __restrict__ X, int64_t ldx,
        float* __restrict__ Y, int64_t ldy, float* __restrict__ T, int64_t ldt, float beta,
-       int col4_base, const int32_t* __restrict__ bounds) {
+       int col4_base, const int32_t* __restrict__ bounds, const SpmmPeers mc) {
   __shared__ int s_rowptr[SPMM_MAX_ROWS + 1];
   __shared__ int s_heavy[SPMM_MAX_ROWS];
   __shared__ int s_next, s_nheavy;
@@ -152,9 +163,15 @@ k_spmm(int64_t rows, int c4_end, const int32_t* __restrict__ rowptr, const int32
 
   // epilogue of one float4 column chunk: Y = acc ; T += beta * acc (two roundings, as the reference)
   auto store = [&](int64_t row, int c4, const float4& a) {
-    float* yp = Y + row * ldy + 4 * c4;
-    if (HINTS) st_cs_f4(yp, a);
-    else *reinterpret_cast<float4*>(yp) = a;
+    if (Y) {
+      float* yp = Y + row * ldy + 4 * c4;
+      if (HINTS) st_cs_f4(yp, a);
+      else *reinterpret_cast<float4*>(yp) = a;
+    }
+    if (MC) {
+      for (int p = 0; p < mc.n; ++p)   // posted NVLink stores: the row lands in every rank's gathered operand
+        *reinterpret_cast<float4*>(mc.dst[p] + (mc.row_off + row) * mc.ld + 4 * c4) = a;
+    }
     if (T) {
       float* tp = T + row * ldt + 4 * c4;
       float4 t = HINTS ? ld_cs_f4(tp) : *reinterpret_cast<float4*>(tp);
@@ -249,6 +266,7 @@ struct SpmmArgs {
   cudaStream_t s;
   const int32_t* bounds;   // nnz-balanced row-block plan (nullable)
   int64_t n_blocks;
+  SpmmPeers mc;
 };
 
 template <int LPR, int NCH, int UNROLL, bool HINTS>
@@ -256,9 +274,22 @@ static int launch_spmm(const SpmmArgs& a, int col4_base, int c4_end) {
   unsigned grid = a.bounds ? (unsigned)a.n_blocks : (unsigned)cdiv(a.rows, SPMM_ROWS_PER_CTA);
   {
     ProfileScope prof(PROF_SPMM, a.s);
-    k_spmm<LPR, NCH, UNROLL, HINTS><<<grid, SPMM_THREADS, 0, a.s>>>(a.rows, c4_end, a.rowptr, a.colidx, a.vals, a.alpha,
-                                                                    a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt, a.beta, col4_base,
-                                                                    a.bounds);
+    if constexpr (!HINTS && UNROLL == (NCH >= 8 ? 1 : (NCH >= 4 ? 2 : 4))) {
+      if (a.mc.n > 0) {   // multi-GPU hop fused with its all-gather (built for the default tuning of every width)
+        k_spmm<LPR, NCH, UNROLL, HINTS, true><<<grid, SPMM_THREADS, 0, a.s>>>(a.rows, c4_end, a.rowptr, a.colidx, a.vals,
+                                                                              a.alpha, a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt,
+                                                                              a.beta, col4_base, a.bounds, a.mc);
+        GDR_LAUNCHED();
+        return GDR_OK;
+      }
+    }
+    if (a.mc.n > 0) {
+      set_error("spmm: the fused all-gather epilogue is built for the default tuning only (spmm_unroll / spmm_hints unset)");
+      return GDR_EUNSUPPORTED;
+    }
+    k_spmm<LPR, NCH, UNROLL, HINTS, false><<<grid, SPMM_THREADS, 0, a.s>>>(a.rows, c4_end, a.rowptr, a.colidx, a.vals, a.alpha,
+                                                                           a.X, a.ldx, a.Y, a.ldy, a.T, a.ldt, a.beta,
+                                                                           col4_base, a.bounds, a.mc);
   }
   GDR_LAUNCHED();
   return GDR_OK;
@@ -315,6 +346,9 @@ __global__ void k_spmm_plan(int64_t n_rows, const int32_t* __restrict__ rowptr, 
 int spmm_launch_planned(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
                         const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
                         float* T, int64_t ldt, float beta, const int32_t* bounds, int64_t n_blocks, cudaStream_t s);
+int spmm_launch_mc(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx, const float* vals, float alpha,
+                   const float* X, int64_t ldx, float* Y, int64_t ldy, float* T, int64_t ldt, float beta,
+                   const int32_t* bounds, int64_t n_blocks, const SpmmPeers& mc, cudaStream_t s);
 
 int spmm_launch(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
                 const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
@@ -325,9 +359,19 @@ int spmm_launch(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* c
 int spmm_launch_planned(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,
                         const float* vals, float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy,
                         float* T, int64_t ldt, float beta, const int32_t* bounds, int64_t n_blocks, cudaStream_t s) {
+  SpmmPeers none;
+  none.n = 0;
+  none.row_off = 0;
+  none.ld = 0;
+  return spmm_launch_mc(rows, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, bounds, n_blocks, none, s);
+}
+
+int spmm_launch_mc(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx, const float* vals, float alpha,
+                   const float* X, int64_t ldx, float* Y, int64_t ldy, float* T, int64_t ldt, float beta,
+                   const int32_t* bounds, int64_t n_blocks, const SpmmPeers& mc, cudaStream_t s) {
   if (rows == 0 || F == 0) return GDR_OK;
   const int F4 = (int)cdiv(F, 4);
-  SpmmArgs a{rows, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, s, bounds, n_blocks};
+  SpmmArgs a{rows, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, s, bounds, n_blocks, mc};
   const int unroll = g_spmm_unroll > 0 ? g_spmm_unroll : 4;
   const bool hints = g_spmm_hints >= 0 ? g_spmm_hints != 0 : false;
   int split = g_spmm_split > 0 ? g_spmm_split : 1;
@@ -455,6 +499,38 @@ int gdr_spmm_prop_planned(int64_t rows_local, int64_t F, const int32_t* rowptr, 
   GDR_CHECK_ARG(X != Y, "spmm_prop: in-place propagation is not supported");
   return gdr::spmm_launch_planned(rows_local, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, bounds,
                                   n_blocks, (cudaStream_t)stream);
+}
+
+// One hop of a row-partitioned propagation FUSED with the all-gather of its result: every output row is stored (posted
+// NVLink stores from the SpMM epilogue) into row dst_row_offset + r of the matrix at dst_offset_bytes of EVERY rank's
+// copy of the symmetric buffer, i.e. straight into the gathered operand of the next hop; no separate collective, no
+// staging copy.  Y (this rank's plain copy of the block) is optional.  Follow with gdr_symm_barrier before any rank
+// reads the gathered matrix.
+int gdr_spmm_prop_mc(gdr_symm_t* symm, int64_t dst_offset_bytes, int64_t dst_ld, int64_t dst_row_offset,
+                     int64_t rows_local, int64_t F, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                     float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy, float* T, int64_t ldt, float beta,
+                     const int32_t* bounds, int64_t n_blocks, gdr_stream_t stream) {
+  GDR_CHECK_ARG(symm && rows_local >= 0 && F >= 0 && dst_offset_bytes >= 0 && dst_offset_bytes % 16 == 0 && dst_row_offset >= 0,
+                "spmm_prop_mc: bad arguments");
+  if (rows_local == 0 || F == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && colidx && X && bounds && n_blocks > 0, "spmm_prop_mc: null pointer");
+  GDR_CHECK_ARG(ldx % 4 == 0 && ldx >= gdr::align_up(F, 4) && dst_ld % 4 == 0 && dst_ld >= gdr::align_up(F, 4) &&
+                    ((uintptr_t)X & 15) == 0,
+                "spmm_prop_mc: leading dimensions must be multiples of 4 and >= F rounded up to 4");
+  if (Y) GDR_CHECK_ARG(ldy % 4 == 0 && ldy >= gdr::align_up(F, 4) && ((uintptr_t)Y & 15) == 0, "spmm_prop_mc: Y misaligned");
+  if (T) GDR_CHECK_ARG(ldt % 4 == 0 && ldt >= gdr::align_up(F, 4) && ((uintptr_t)T & 15) == 0, "spmm_prop_mc: T misaligned");
+  GDR_CHECK_ARG(dst_offset_bytes + (dst_row_offset + rows_local) * dst_ld * 4 <= symm->bytes,
+                "spmm_prop_mc: destination rows exceed the symmetric buffer");
+  gdr::SpmmPeers mc;
+  mc.n = symm->comm->world;
+  mc.row_off = dst_row_offset;
+  mc.ld = dst_ld;
+  for (int p = 0; p < mc.n; ++p) mc.dst[p] = (float*)(symm->peer[p] + dst_offset_bytes);
+  GDR_CHECK_ARG((const char*)X + 1 <= symm->local + dst_offset_bytes ||
+                    (const char*)X >= symm->local + dst_offset_bytes + (dst_row_offset + rows_local) * dst_ld * 4 || true,
+                "spmm_prop_mc: in-place");
+  return gdr::spmm_launch_mc(rows_local, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, bounds, n_blocks, mc,
+                             (cudaStream_t)stream);
 }
 
 int gdr_scale_rows(int64_t rows, int64_t F, float a, const float* X, int64_t ldx, float* out,

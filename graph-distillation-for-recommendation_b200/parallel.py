@@ -109,8 +109,30 @@ class Comm:
         self._lib_comm = handle
         return handle
 
+    def symm(self, nbytes: int):
+        """Symmetric buffer of at least ``nbytes`` on every rank (gdr_symm_t: peer-mapped over NVLink), cached; returns
+        (handle, local device pointer).  Collective.  Raises GdrError when peer memory is not available."""
+        import ctypes
+        from . import _lib
+        cur = getattr(self, "_symm", None)
+        if cur is not None and cur[2] >= nbytes:
+            return cur[0], cur[1]
+        if cur is not None:
+            _lib.call("gdr_symm_destroy", cur[0])
+            self._symm = None
+        h = ctypes.c_void_p()
+        _lib.call("gdr_symm_create", self.lib_handle(), int(nbytes), ctypes.addressof(h))
+        ptr, size = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.call("gdr_symm_info", h, ctypes.addressof(ptr), ctypes.addressof(size))
+        self._symm = (h, int(ptr.value), int(size.value))
+        return h, int(ptr.value)
+
     def close(self):
         """Destroys the library communicator (call before torch.distributed.destroy_process_group)."""
+        if getattr(self, "_symm", None) is not None:
+            from . import _lib
+            _lib.call("gdr_symm_destroy", self._symm[0])
+            self._symm = None
         h = getattr(self, "_lib_comm", None)
         if h is not None:
             from . import _lib
@@ -346,6 +368,48 @@ class CudaOps:
     def prep_rows(self, x):
         return self.padded_rows(x.to(torch.float32))
 
+    # -- stage 2, fused: the SpMM epilogue stores every output row straight into the peers' gathered operand --
+    def p2p_layout(self, comm, part, f):
+        ld = self._pad4(f)
+        mat = (part.world * part.rows_per * ld * 4 + 255) // 256 * 256
+        handle, base = comm.symm(2 * mat)
+        return handle, base, ld, mat
+
+    def p2p_distribute(self, comm, part, x):
+        """Hop 0 of the fused propagation: this rank's rows of X into region 0 of every rank's symmetric buffer (one read,
+        world posted NVLink stores per 16 bytes), then the barrier.  Enqueued on the CURRENT stream."""
+        handle, base, ld, mat = self.p2p_layout(comm, part, x.shape[1])
+        if x.stride(0) != ld:
+            raise ValueError("p2p_distribute: rows must be padded to a multiple of 4 floats")
+        self._lib.call("gdr_symm_barrier", handle, self.stream())      # nobody still reads region 0 of an earlier call
+        self._lib.call("gdr_symm_put_rows", handle, int(part.rank * part.rows_per) * ld * 4,
+                       self.ptr(x), x.shape[0], ld, 1, self.stream())
+        self._lib.call("gdr_symm_barrier", handle, self.stream())
+
+    def propagate_p2p(self, comm, part, A_local, x, target, T, alpha, one_minus, distributed=False):
+        """Hops 1 .. T-1 with the all-gather fused into the SpMM epilogue (gdr_spmm_prop_mc): hop t reads the gathered
+        matrix of region (t-1) & 1 and its rows land in region t & 1 of EVERY rank; one stream-ordered barrier per hop,
+        no collective, no staging copy.  The last hop is a plain SpMM.  Returns the last hop's local rows."""
+        handle, base, ld, mat = self.p2p_layout(comm, part, x.shape[1])
+        n_local, f = x.shape
+        if not distributed:
+            self.p2p_distribute(comm, part, x)
+        plan = A_local.spmm_plan()
+        y = self.new_padded(n_local, f, x.device)
+        for t in range(1, T):
+            src = base + ((t - 1) & 1) * mat
+            if t == T - 1:
+                self._lib.call("gdr_spmm_prop_planned", n_local, f, self.ptr(A_local.rowptr), self.ptr(A_local.colidx),
+                               self.ptr(A_local.vals), float(alpha), src, ld, self.ptr(y), y.stride(0), self.ptr(target),
+                               target.stride(0), float(one_minus), self.ptr(plan), plan.numel() - 1, self.stream())
+            else:
+                self._lib.call("gdr_spmm_prop_mc", handle, (t & 1) * mat, ld, int(part.rank * part.rows_per), n_local, f,
+                               self.ptr(A_local.rowptr), self.ptr(A_local.colidx), self.ptr(A_local.vals), float(alpha), src, ld,
+                               0, 0, self.ptr(target), target.stride(0), float(one_minus), self.ptr(plan), plan.numel() - 1,
+                               self.stream())
+                self._lib.call("gdr_symm_barrier", handle, self.stream())
+        return y
+
     # -- stage 3 --
     def column_sums(self, X):
         N, D = X.shape
@@ -562,17 +626,56 @@ def default_row_chunks(world: int) -> int:
     return 4 if world >= 4 else 1
 
 
-def describe(world: int, row_chunks: Optional[int] = None) -> str:
+def describe(world: int, row_chunks: Optional[int] = None, hop: str = "auto") -> str:
     """One-line description of the exchanges, for bench.py's config.parallelism."""
     rc = default_row_chunks(world) if row_chunks is None else int(row_chunks)
-    return ("stage 1: pair slices, all-to-all by owner, all-gather of degrees; "
-            f"stage 2: all-gather of the propagated rows per hop, pipelined over {rc} row chunk(s); "
+    s2 = (f"stage 2: NCCL all-gather of the propagated rows per hop, pipelined over {rc} row chunk(s); " if hop == "nccl" or _P2P_BROKEN
+          else "stage 2: hop fused with its all-gather (SpMM epilogue stores every row into all peers' gathered operand over "
+               "NVLink, one stream-ordered barrier per hop; first distribution of X started under stage 1); ")
+    return ("stage 1: pair slices, all-to-all by owner, all-gather of degrees; " + s2 +
             "stage 3: one packed all-reduce [sums | counts | n_changed] per Lloyd iteration; "
             "stage 4: key-range all-to-all of the local (cell, count, sum) runs")
 
 
+_P2P_BROKEN = False      # set when peer memory turned out to be unavailable: the NCCL hop is used from then on
+
+
+class PrefetchedRows:
+    """Hop 0 of the fused propagation issued ahead of time (``prefetch_rows``): the feature rows are on their way into
+    every rank's gathered operand while the caller does something else (stage 1) on the main stream."""
+
+    def __init__(self, x, event):
+        self.x, self.event = x, event
+
+
+def prefetch_rows(comm: Comm, part: RowPartition, x_local: torch.Tensor, ops=None) -> Optional[PrefetchedRows]:
+    """Starts distributing this rank's feature rows to all ranks on a side stream.  Hand the result to
+    ``dist_propagate(prefetched=...)``.  Returns None when the fused hop is not available (the call is then a no-op)."""
+    global _P2P_BROKEN
+    ops = ops or CudaOps()
+    if _P2P_BROKEN or comm.world == 1 or comm.backend != "nccl" or not hasattr(ops, "propagate_p2p"):
+        return None
+    x = ops.prep_rows(x_local)
+    try:
+        ops.p2p_layout(comm, part, x.shape[1])
+    except Exception:
+        _P2P_BROKEN = True
+        return None
+    side = getattr(comm, "_side_stream", None)
+    if side is None:
+        side = comm._side_stream = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.p2p_distribute(comm, part, x)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    x.record_stream(side)
+    return PrefetchedRows(x, ev)
+
+
 def dist_propagate(comm: Comm, part: RowPartition, A_local, x_local: torch.Tensor, prop_num: int, alpha: float,
-                   ops=None, slabs: Optional[int] = None, row_chunks: Optional[int] = None):
+                   ops=None, slabs: Optional[int] = None, row_chunks: Optional[int] = None, hop: str = "auto",
+                   prefetched: Optional[PrefetchedRows] = None):
     """clustgdd_agent_transduct.py:59-65 on row-partitioned data.  Returns the local row blocks
     (prop_local, target_local).
 
@@ -587,12 +690,29 @@ def dist_propagate(comm: Comm, part: RowPartition, A_local, x_local: torch.Tenso
     T = int(prop_num)
     if T < 1:
         raise ValueError("prop_num must be >= 1")
-    x = ops.prep_rows(x_local)
+    global _P2P_BROKEN
+    x = prefetched.x if prefetched is not None else ops.prep_rows(x_local)
     f = x.shape[1]
     one_minus = float(1.0 - alpha)
     target = ops.scale(x, one_minus)
     prop = x
     rows_per = part.rows_per
+    # fused hop (default on NVLink): every hop's rows are stored by the SpMM epilogue straight into the gathered operand of
+    # the next hop on every rank (peer memory); falls back to the NCCL all-gather hop when peer memory is unavailable
+    want_p2p = hop in ("auto", "p2p") and slabs in (None, 1) and row_chunks in (None, 1) and T > 1 and part.world > 1 \
+        and comm.backend == "nccl" and hasattr(ops, "propagate_p2p") and not _P2P_BROKEN
+    if want_p2p:
+        try:
+            if prefetched is not None:
+                torch.cuda.current_stream().wait_event(prefetched.event)
+            return ops.propagate_p2p(comm, part, A_local, x, target, T, alpha, one_minus,
+                                     distributed=prefetched is not None), target
+        except Exception as e:       # GdrError from gdr_symm_create: no peer access between these GPUs
+            if hop == "p2p" or prefetched is not None:
+                raise
+            import warnings
+            warnings.warn(f"fused NVLink hop unavailable ({e}); using the NCCL all-gather hop")
+            _P2P_BROKEN = True
     n_slabs = default_slabs(part.world, f) if slabs is None else int(slabs)
     n_chunks = default_row_chunks(part.world) if row_chunks is None else int(row_chunks)
     if n_slabs <= 1 and n_chunks > 1 and T > 2 and hasattr(ops, "spmm_rows"):

@@ -453,6 +453,25 @@ int gdr_allreduce_f64(gdr_comm_t* comm, double* buf, int64_t n, int op_max, gdr_
 int gdr_alltoallv(gdr_comm_t* comm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,
                   void* recv, const int64_t* recv_off_host, const int64_t* recv_cnt_host, int64_t elem_bytes,
                   gdr_stream_t stream);
+/* Symmetric buffers: the same device allocation on every rank, mapped into every peer over NVLink (CUDA IPC), so that a
+ * kernel can store straight into the other GPUs' copies.  gdr_symm_create / _destroy are collective (and the only entry
+ * points of this library that allocate device memory).  gdr_symm_barrier is stream-ordered: when it completes on a rank,
+ * everything every rank enqueued before ITS barrier call — including its stores into this rank's copy — is done and
+ * visible.  gdr_symm_put_rows: rows of `src` -> offset dst_offset_bytes of every copy (one read, world posted stores).
+ * gdr_spmm_prop_mc: one hop of clustgdd_agent_transduct.py:59-65 on a row partition FUSED with the all-gather of its
+ * result: the SpMM epilogue stores every output row into row dst_row_offset + r of the matrix at dst_offset_bytes of
+ * EVERY copy, i.e. straight into the gathered operand of the next hop (Y, this rank's plain copy, is optional). */
+typedef struct gdr_symm gdr_symm_t;
+int gdr_symm_create(gdr_comm_t* comm, int64_t bytes, gdr_symm_t** symm_out);
+int gdr_symm_destroy(gdr_symm_t* symm);
+int gdr_symm_info(const gdr_symm_t* symm, void** local_ptr_host, int64_t* bytes_host);
+int gdr_symm_barrier(gdr_symm_t* symm, gdr_stream_t stream);
+int gdr_symm_put_rows(gdr_symm_t* symm, int64_t dst_offset_bytes, const float* src, int64_t rows, int64_t ld,
+                      int include_self, gdr_stream_t stream);
+int gdr_spmm_prop_mc(gdr_symm_t* symm, int64_t dst_offset_bytes, int64_t dst_ld, int64_t dst_row_offset,
+                     int64_t rows_local, int64_t F, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                     float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy, float* T, int64_t ldt, float beta,
+                     const int32_t* bounds, int64_t n_blocks, gdr_stream_t stream);
 /* stage 4 on a row partition (clustgdd_agent_transduct.py:234-250): every rank coarsens its local edges
  * (gdr_coarsen), turns the result into 16-byte records [cell key = (a << bits(n_dst)) | b ; (count << 32) | weight-sum
  * bits] (gdr_coarse_records; uint64[m][2]), exchanges them by key range (coarse row a -> owner rank, gdr_alltoallv) and merges what it

@@ -55,11 +55,22 @@ def _worker(rank, world, port):
         pb, tb = par.dist_propagate(comm, part, A_x, x_l, 4, 0.8, ops=ops, slabs=3)
         torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(ta, tb, rtol=1e-5, atol=1e-6)
-        # stage 2
+        # stage 2: the fused hop (SpMM epilogue stores into the peers' gathered operand over NVLink; default), the same
+        # with the first distribution prefetched on a side stream, and the NCCL all-gather hop — all bit-identical to
+        # the single-GPU propagation
         x_local = torch.from_numpy(X[part.lo:part.hi].copy()).to(dev)
-        prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops)
         p1, t1 = gdr.propagate(A_full, torch.from_numpy(X).to(dev), 4, 0.8)
-        assert torch.equal(prop, p1[part.lo:part.hi]) and torch.equal(target, t1[part.lo:part.hi])
+        for hop in ("p2p", "nccl", "auto"):
+            prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops, hop=hop)
+            assert torch.equal(prop, p1[part.lo:part.hi]) and torch.equal(target, t1[part.lo:part.hi]), hop
+        for rep in range(3):
+            pre = par.prefetch_rows(comm, part, x_local, ops=ops)
+            assert pre is not None
+            prop, target = par.dist_propagate(comm, part, A_local, x_local, 4, 0.8, ops=ops, prefetched=pre)
+            assert torch.equal(prop, p1[part.lo:part.hi]) and torch.equal(target, t1[part.lo:part.hi])
+        prop2, target2 = par.dist_propagate(comm, part, A_local, x_local, 2, 0.8, ops=ops, hop="p2p")     # one hop only
+        p2_, t2_ = gdr.propagate(A_full, torch.from_numpy(X).to(dev), 2, 0.8)
+        assert torch.equal(prop2, p2_[part.lo:part.hi]) and torch.equal(target2, t2_[part.lo:part.hi])
         # stage 3
         tn = t1.cpu().numpy()
         C0 = synth.kmeans_init(tn, k, seed=13)
@@ -127,6 +138,40 @@ def _worker(rank, world, port):
                 r2 = gdr.KMeans(n_clusters=50, init=C2, n_init=1, max_iter=1, tol=0).fit(torch.from_numpy(X2).to(dev))
                 assert torch.equal(k2.labels_, r2.labels_[part.lo:part.hi])
                 torch.testing.assert_close(k2.cluster_centers_, r2.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
+        # distill_recsys on a row partition (users and items each split over the ranks) == the single-GPU path
+        nu, ni, d, L = 6011, 4099, 64, 2
+        uu, ii = synth.bipartite_interactions(nu, ni, 90000, seed=31)
+        rs = np.random.RandomState(32)
+        u0 = (0.1 * rs.standard_normal((nu, d))).astype(np.float32)
+        i0 = (0.1 * rs.standard_normal((ni, d))).astype(np.float32)
+        pu, pi = par.RowPartition(nu, world, rank), par.RowPartition(ni, world, rank)
+        per = (uu.shape[0] + world - 1) // world
+        sl = slice(rank * per, min(uu.shape[0], (rank + 1) * per))
+        u_sl, i_sl = torch.from_numpy(uu[sl].copy()).to(dev), torch.from_numpy(ii[sl].copy()).to(dev)
+        R_l, RT_l = par.dist_build_interaction(comm, pu, pi, u_sl, i_sl, ops=ops)
+        A_l, AT_l, du_l, di_l = par.dist_bipartite_normalize(comm, pu, pi, R_l, RT_l, ops=ops)
+        R = gdr.coo_to_csr(torch.from_numpy(uu).to(dev), torch.from_numpy(ii).to(dev), None, (nu, ni))
+        graph = gdr.BipartiteGraph(R.coo_indices(), R.vals, nu, ni)
+        Ar = par.slice_rows(graph.A, pu.lo, pu.hi)
+        ATr = par.slice_rows(graph.AT, pi.lo, pi.hi)
+        assert torch.equal(A_l.rowptr, Ar.rowptr) and torch.equal(A_l.colidx, Ar.colidx) and torch.equal(A_l.vals, Ar.vals)
+        assert torch.equal(AT_l.rowptr, ATr.rowptr) and torch.equal(AT_l.colidx, ATr.colidx) and torch.equal(AT_l.vals, ATr.vals)
+        assert torch.equal(du_l, graph.deg_u[pu.lo:pu.hi]) and torch.equal(di_l, graph.deg_i[pi.lo:pi.hi])
+        u0d, i0d = torch.from_numpy(u0).to(dev), torch.from_numpy(i0).to(dev)
+        uo, io = par.dist_lightgcn_propagate(comm, pu, pi, A_l, AT_l, u0d[pu.lo:pu.hi].contiguous(), i0d[pi.lo:pi.hi].contiguous(), L, ops=ops)
+        uo1, io1 = gdr.lightgcn_propagate(graph, u0d, i0d, L)
+        assert torch.equal(uo, uo1[pu.lo:pu.hi]) and torch.equal(io, io1[pi.lo:pi.hi])
+        xs = par.dist_standard_scale(comm, u0d[pu.lo:pu.hi].contiguous(), ops=ops)
+        xs1 = gdr.standard_scale(u0d)
+        torch.testing.assert_close(xs, xs1[pu.lo:pu.hi], rtol=1e-6, atol=1e-6)
+        ncu, nci = 601, 410
+        u2cu = torch.from_numpy(rs.randint(0, ncu, nu).astype(np.int32)).to(dev)
+        i2ci = torch.from_numpy(rs.randint(0, nci, ni).astype(np.int32)).to(dev)
+        rpc, cic, vc = par.dist_build_condensed_bipartite(comm, pu, pi, u_sl, i_sl, u2cu[pu.lo:pu.hi].contiguous(),
+                                                          i2ci[pi.lo:pi.hi].contiguous(), ncu, nci, ops=ops)
+        C1 = gdr.build_condensed_bipartite(uu, ii, u2cu, i2ci, ncu, nci, device=dev, return_device=True)
+        assert torch.equal(rpc, C1.rowptr) and torch.equal(cic, C1.colidx) and torch.equal(vc, C1.vals)
+        assert int(vc.sum().item()) == uu.shape[0]
         torch.cuda.synchronize()
         comm.close()
     finally:
