@@ -78,6 +78,7 @@ _SIGNATURES = {
     "gdr_kmeans_lloyd": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i32, C.c_double, i32, vp, vp, vp, i32, vp, i64, vp]),
     "gdr_kmeans_plusplus_ws_bytes": (i64, [i64, i64, i64, i32]),
     "gdr_kmeans_plusplus": (i32, [i64, i64, i64, vp, i64, i64, vp, i32, vp, i64, vp, vp, i64, vp]),
+    "gdr_minibatch_update": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, i64, vp, vp]),
     "gdr_segment_sum_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_segment_sum": (i32, [i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
     "gdr_label_histogram": (i32, [i64, i64, vp, vp, vp, vp]),
@@ -110,6 +111,14 @@ _SIGNATURES = {
     "gdr_bipartite_norm_block": (i32, [i64, i64, vp, vp, vp, vp, vp, f32, vp, vp]),
     "gdr_column_moments": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp]),
     "gdr_standardize_apply": (i32, [i64, i64, vp, i64, vp, vp, vp, i64, vp]),
+    "gdr_dense_gram_ws_bytes": (i64, [i64, i64, i64]),
+    "gdr_dense_gram": (i32, [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+    "gdr_dense_chol": (i32, [i64, vp, i64, vp, i64, vp, C.c_double, vp]),
+    "gdr_dense_trsm_rows": (i32, [i64, i64, vp, i64, vp, i64, vp]),
+    "gdr_dense_gemm_small": (i32, [i64, i64, i64, C.c_double, vp, i64, vp, i64, C.c_double, vp, i64, vp, i64, vp, vp]),
+    "gdr_sym_eig_jacobi_ws_bytes": (i64, [i64]),
+    "gdr_sym_eig_jacobi": (i32, [i64, vp, vp, vp, vp, i32, C.c_double, vp, vp, i64, vp]),
+    "gdr_dense_gather_cols": (i32, [i64, i64, vp, vp, vp, vp]),
     "gdr_coarsen_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_coarsen": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_scale": (i32, [i64, vp, vp, vp, vp, vp, vp, vp]),

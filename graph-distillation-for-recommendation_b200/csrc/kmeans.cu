@@ -708,6 +708,64 @@ __global__ void __launch_bounds__(256) k_relocate_one(int nparts, const float* _
   }
 }
 
+// ---- MiniBatchKMeans centre update (sklearn/cluster/_k_means_minibatch.pyx:56-110 update_center_dense) --------
+// one warp per cluster, lanes over the feature columns; the batch is walked IN ORDER so that every centre element
+// is the same fp32 chain as sklearn's:  acc = old * weight ; acc += x (members in batch order) ; weight += count ;
+// acc *= 1 / weight.  A cluster without members in the batch copies its old centre.
+__global__ void __launch_bounds__(256) k_minibatch_update(int64_t B, int64_t K, int D, const float* __restrict__ Xb,
+                                                          int64_t ldx, const int32_t* __restrict__ labels,
+                                                          const float* __restrict__ C_old, int64_t ldo,
+                                                          float* __restrict__ C_new, int64_t ldn,
+                                                          float* __restrict__ weight_sums) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= K) return;
+  const int lane = lane_id();
+  constexpr int MAXC = 8;                       // D <= 256 per pass
+  for (int c0 = 0; c0 < D; c0 += 32 * MAXC) {
+    float acc[MAXC];
+    const float w = weight_sums[c];
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      const int col = c0 + q * 32 + lane;
+      acc[q] = col < D ? __fmul_rn(C_old[c * ldo + col], w) : 0.f;
+    }
+    int cnt = 0;
+    for (int64_t s0 = 0; s0 < B; s0 += 32) {
+      const int64_t s = s0 + lane;
+      const unsigned hit = __ballot_sync(0xffffffffu, s < B && labels[s] == (int32_t)c);
+      unsigned m = hit;
+      while (m) {                               // members of this 32-sample window, ascending
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float* x = Xb + (s0 + j) * ldx;
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+          const int col = c0 + q * 32 + lane;
+          if (col < D) acc[q] = __fadd_rn(acc[q], x[col]);
+        }
+      }
+      cnt += __popc(hit);
+    }
+    if (cnt > 0) {
+      const float wn = __fadd_rn(w, (float)cnt);     // wsum accumulates 1.0f per member: exact
+      const float alpha = __fdiv_rn(1.0f, wn);
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        const int col = c0 + q * 32 + lane;
+        if (col < D) C_new[c * ldn + col] = __fmul_rn(acc[q], alpha);
+      }
+      __syncwarp();
+      if (lane == 0 && c0 + 32 * MAXC >= D) weight_sums[c] = wn;
+    } else {
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        const int col = c0 + q * 32 + lane;
+        if (col < D) C_new[c * ldn + col] = C_old[c * ldo + col];
+      }
+    }
+  }
+}
+
 // ---- distributed relocation (lloyd.cu: relocate_distributed) ----------------------------------
 // candidate record: [dist, rank (int bits), old label (int bits), x[0..D)]
 __global__ void __launch_bounds__(256) k_pick_candidate(int nparts, const float* __restrict__ pv,
@@ -1250,6 +1308,18 @@ int gdr_kmeans_relocate(int64_t N, int64_t K, int64_t D, const float* X, int64_t
                                      empties[e], dist);
     GDR_LAUNCHED();
   }
+  return GDR_OK;
+}
+
+int gdr_minibatch_update(int64_t B, int64_t K, int64_t D, const float* Xb, int64_t ldx, const int32_t* labels,
+                         const float* C_old, int64_t ldc_old, float* C_new, int64_t ldc_new, float* weight_sums,
+                         gdr_stream_t stream) {
+  GDR_CHECK_ARG(B >= 0 && K > 0 && D > 0 && C_old && C_new && weight_sums && (B == 0 || (Xb && labels)),
+                "minibatch_update: bad arguments");
+  GDR_CHECK_ARG(C_old != C_new, "minibatch_update: in-place update is not supported");
+  k_minibatch_update<<<(unsigned)cdiv(K * 32, 256), 256, 0, (cudaStream_t)stream>>>(B, K, (int)D, Xb, ldx, labels, C_old,
+                                                                                   ldc_old, C_new, ldc_new, weight_sums);
+  GDR_LAUNCHED();
   return GDR_OK;
 }
 

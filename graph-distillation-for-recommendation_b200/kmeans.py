@@ -372,13 +372,19 @@ class KMeans:
 
 
 class MiniBatchKMeans(KMeans):
-    """Entry point for the reference's ``MiniBatchKMeans(n_clusters, random_state, batch_size)``
-    call sites (clustgdd_agent_transduct.py:103, clustgdd_agent_induct.py:132,
-    distill_recsys.py:174-176).  The reference switches to mini-batches only because full Lloyd
-    is slow on the host; on the B200 the full-batch Lloyd run is the fast path and gives a lower
-    WCSS, so this class accepts the mini-batch keywords and runs full Lloyd (SURVEY §8f item 2:
-    the mini-batch RNG stream cannot be reproduced, parity is judged on WCSS).  ``batch_size``,
-    ``init_size``, ``max_no_improvement`` and ``reassignment_ratio`` are accepted and ignored."""
+    """scikit-learn's MiniBatchKMeans on the GPU — the estimator behind ``MiniBatchKMeans(n_clusters, random_state,
+    batch_size)`` at clustgdd_agent_transduct.py:102-103, clustgdd_agent_induct.py:131-132 and
+    distill_recsys.py:173-176.
+
+    Control flow and arithmetic follow sklearn/cluster/_kmeans.py:2056-2224 (``fit``), :1566-1685 (``_mini_batch_step``),
+    :1974-2053 (EWA early stopping, random reassignment) and _k_means_minibatch.pyx:56-110 (centre update):
+    no mean-centring, validation subset + ``init_size`` subset for the initialisation, ``max_iter * N // batch`` steps of
+    [sample a batch with replacement -> E-step on the batch -> per-centre running mean -> reassignment of starved
+    centres], stop on ``max_no_improvement`` steps without a better smoothed inertia (or ``tol``), final E-step over all
+    rows.  The random numbers come from numpy's RandomState on the host in the order sklearn draws them (``randint`` for
+    the subsets, the k-means++ draws, ``choice(p=...)`` as cumsum + searchsorted per step, ``choice(replace=False)`` for the
+    reassignments); every distance, assignment and update runs in libgdr_b200.  The E-step labels are exact up to the
+    1e-6 margin band, so a trajectory can part from sklearn's at a near-tie: parity is judged on WCSS."""
 
     def __init__(self, n_clusters=8, *, init="k-means++", max_iter=100, batch_size=1024, verbose=0,
                  compute_labels=True, random_state=None, tol=0.0, max_no_improvement=10, init_size=None,
@@ -387,6 +393,173 @@ class MiniBatchKMeans(KMeans):
                          random_state=random_state, precision=precision, device=device)
         self.batch_size, self.compute_labels, self.max_no_improvement = batch_size, compute_labels, max_no_improvement
         self.init_size, self.reassignment_ratio = init_size, reassignment_ratio
+
+    # -- E-step + inertia of a row block against given centres (sklearn _labels_inertia) --
+    @staticmethod
+    def _labels_inertia(Xp: torch.Tensor, C: torch.Tensor, labels: torch.Tensor, mode: int = 0, tc=None):
+        assign_labels(Xp, C, labels, precision_mode=0, tc_operand=tc if mode == 1 else None)
+        out = torch.zeros(1, dtype=torch.float64, device=Xp.device)
+        ws = workspace(_lib.query("gdr_inertia_ws_bytes", Xp.shape[0], Xp.shape[1]), Xp.device)
+        _lib.call("gdr_inertia", Xp.shape[0], Xp.shape[1], ptr(Xp), Xp.stride(0), ptr(C), C.stride(0), ptr(labels), ptr(out),
+                  ptr(ws), ws.numel(), stream())
+        return out
+
+    def _mb_init(self, Xp: torch.Tensor, rs, init_size: int) -> torch.Tensor:
+        """_init_centroids (sklearn/_kmeans.py:985-1060) on an ``init_size`` random subset."""
+        N, D = Xp.shape
+        K = int(self.n_clusters)
+        Xi = Xp
+        if init_size is not None and init_size < N:
+            idx = torch.from_numpy(rs.randint(0, N, init_size).astype(np.int64)).to(Xp.device)
+            Xi = padded_rows(Xp[idx].contiguous())
+        C0 = new_padded(K, D, Xp.device, zero=True)
+        if isinstance(self.init, str):
+            if self.init == "k-means++":
+                from .kmeans_init import kmeans_plusplus_device
+                C0.copy_(kmeans_plusplus_device(Xi, K, rs))
+            elif self.init == "random":
+                n_i = Xi.shape[0]
+                seeds = rs.choice(n_i, size=K, replace=False, p=np.ones(n_i, dtype=np.float32) / np.float32(n_i))
+                C0.copy_(Xi[torch.from_numpy(np.asarray(seeds, dtype=np.int64)).to(Xp.device)])
+            else:
+                raise ValueError(f"init should be 'k-means++', 'random' or an array, got {self.init!r}")
+        else:
+            arr = self.init if isinstance(self.init, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(np.asarray(self.init), dtype=np.float32))
+            if tuple(arr.shape) != (K, D):
+                raise ValueError(f"The shape of the initial centers {tuple(arr.shape)} does not match "
+                                 f"the number of clusters {K} / features {D}.")
+            C0.copy_(arr.to(device=Xp.device, dtype=torch.float32))
+        return C0
+
+    def fit(self, X, y=None, sample_weight=None):
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is not supported (the reference never passes it)")
+        Xd = self._to_device(X)
+        N, D = Xd.shape
+        K = int(self.n_clusters)
+        if K <= 0:
+            raise ValueError("n_clusters must be > 0")
+        if N < K:
+            raise ValueError(f"n_samples={N} should be >= n_clusters={K}.")
+        if self.reassignment_ratio < 0:
+            raise ValueError(f"reassignment_ratio should be >= 0, got {self.reassignment_ratio} instead.")
+        dev = Xd.device
+        rs = _check_random_state(self.random_state)
+        Xp = padded_rows(Xd.contiguous())
+        batch = min(int(self.batch_size), N)
+        init_size = self.init_size
+        if init_size is None:
+            init_size = 3 * batch
+            if init_size < K:
+                init_size = 3 * K
+        elif init_size < K:
+            init_size = 3 * K
+        init_size = min(int(init_size), N)
+        init_is_array = not isinstance(self.init, str)
+        n_init = self.n_init
+        if n_init == "auto":
+            n_init = 1 if (init_is_array or self.init == "k-means++") else 3
+        if init_is_array:
+            n_init = 1
+        tol_abs = 0.0
+        if self.tol > 0:       # _tolerance (:285-293): mean of the column variances * tol
+            var_mean = torch.zeros(1, dtype=torch.float64, device=dev)
+            mean = torch.empty(D, dtype=torch.float32, device=dev)
+            scratch = new_padded(N, D, dev)
+            ws = workspace(_lib.query("gdr_center_columns_ws_bytes", N, D), dev)
+            _lib.call("gdr_center_columns", N, D, ptr(Xp), Xp.stride(0), ptr(mean), ptr(var_mean), ptr(scratch), scratch.stride(0),
+                      ptr(ws), ws.numel(), stream())
+            tol_abs = float(var_mean.item()) * float(self.tol)
+            del scratch
+
+        # validation set for the initialisation (:2110-2112)
+        valid_idx = torch.from_numpy(rs.randint(0, N, init_size).astype(np.int64)).to(dev)
+        X_valid = padded_rows(Xp[valid_idx].contiguous())
+        lab_valid = torch.empty(X_valid.shape[0], dtype=torch.int32, device=dev)
+        best_inertia, centers = None, None
+        for _ in range(int(n_init)):
+            cand = self._mb_init(Xp, rs, init_size)
+            inertia = float(self._labels_inertia(X_valid, cand, lab_valid).item())
+            if best_inertia is None or inertia < best_inertia:
+                centers, best_inertia = cand, inertia
+        centers_new = new_padded(K, D, dev, zero=True)
+        counts = torch.zeros(K, dtype=torch.float32, device=dev)
+        ewa, ewa_min, no_improvement, n_since = None, None, 0, 0
+        n_steps = (int(self.max_iter) * N) // batch
+        # RandomState.choice(n, size, p=w / w.sum(), replace=True): cdf = p.cumsum(); cdf /= cdf[-1];
+        # cdf.searchsorted(random_sample(size), side="right") — the same table, built once
+        w32 = np.ones(N, dtype=np.float32)
+        cdf = (w32 / np.sum(w32)).astype(np.float64).cumsum()
+        cdf /= cdf[-1]
+        labels_b = torch.empty(batch, dtype=torch.int32, device=dev)
+        host = torch.empty(2, dtype=torch.float64).pin_memory()
+        step, any_zero = -1, True          # counts start at zero: the first step always reassigns
+        for step in range(n_steps):
+            idx = torch.from_numpy(cdf.searchsorted(rs.random_sample(batch), side="right").astype(np.int64)).to(dev, non_blocking=True)
+            Xb = padded_rows(Xp[idx].contiguous())
+            # _random_reassign (:2039-2053): every 10 * n_clusters samples, or as soon as a centre has no weight
+            n_since += batch
+            inertia_dev = self._labels_inertia(Xb, centers, labels_b)
+            _lib.call("gdr_minibatch_update", batch, K, D, ptr(Xb), Xb.stride(0), ptr(labels_b), ptr(centers), centers.stride(0),
+                      ptr(centers_new), centers_new.stride(0), ptr(counts), stream())
+            # the reassignment decision looks at the counts BEFORE this step's update in sklearn (the flag is an argument
+            # of _mini_batch_step), so it is taken from the previous step's read-back
+            reassign = any_zero or n_since >= 10 * K
+            if reassign:
+                n_since = 0
+                if self.reassignment_ratio > 0:
+                    to_re = counts < float(self.reassignment_ratio) * counts.max()
+                    n_re = int(to_re.sum().item())
+                    if n_re > 0.5 * batch:
+                        keep = torch.argsort(counts)[int(0.5 * batch):]
+                        to_re[keep] = False
+                        n_re = int(to_re.sum().item())
+                    if n_re:
+                        picks = torch.from_numpy(np.asarray(rs.choice(batch, replace=False, size=n_re), dtype=np.int64)).to(dev)
+                        centers_new[to_re] = Xb[picks]
+                    if n_re and n_re < K:
+                        counts[to_re] = counts[~to_re].min()
+            host[0:1].copy_(inertia_dev, non_blocking=True)
+            host[1:2].copy_((counts == 0).any().to(torch.float64).reshape(1), non_blocking=True)
+            csd = float(((centers_new - centers) ** 2).sum().item()) if tol_abs > 0 else 0.0
+            centers, centers_new = centers_new, centers
+            torch.cuda.current_stream().synchronize()
+            any_zero = bool(host[1] > 0)
+            # _mini_batch_convergence (:1974-2037)
+            b_inertia = float(host[0]) / batch
+            if step == 0:
+                continue
+            if ewa is None:
+                ewa = b_inertia
+            else:
+                alpha = min(batch * 2.0 / (N + 1), 1.0)
+                ewa = ewa * (1 - alpha) + b_inertia * alpha
+            if self.verbose:
+                print(f"Minibatch step {step + 1}/{n_steps}: mean batch inertia: {b_inertia}, ewa inertia: {ewa}")
+            if tol_abs > 0.0 and csd <= tol_abs:
+                break
+            if ewa_min is None or ewa < ewa_min:
+                no_improvement, ewa_min = 0, ewa
+            else:
+                no_improvement += 1
+            if self.max_no_improvement is not None and no_improvement >= self.max_no_improvement:
+                break
+        self.n_steps_ = step + 1
+        self.n_iter_ = int(np.ceil(((step + 1) * batch) / N))
+        self._centers_dev = centers
+        self.n_features_in_ = D
+        self.cluster_centers_ = self._out(centers.contiguous() if pad4(D) == D else centers.clone().contiguous())
+        if self.compute_labels:
+            labels = torch.empty(N, dtype=torch.int32, device=dev)
+            mode = self._mode(D)
+            tc = TcOperand(Xp) if mode == 1 else None
+            self.inertia_ = float(self._labels_inertia(Xp, centers, labels, mode=mode, tc=tc).item())
+            self._labels_dev = labels
+            self.labels_ = self._out(labels)
+        else:
+            self.inertia_ = (ewa if ewa is not None else 0.0) * N
+        return self
 
 
 def standard_scale(X: torch.Tensor) -> torch.Tensor:
@@ -409,9 +582,9 @@ def kmeans_cluster(X, n_clusters: int, seed: int, minibatch: bool = True, batch_
                    init="k-means++", device=None, precision: str = "auto"):
     """distill_recsys.py:158-181 — returns (labels int64[N], centers f32[K, D]) as numpy.
 
-    z-scores the columns, then clusters.  The reference switches to MiniBatchKMeans above
-    20 000 rows only because full Lloyd is slow on the host; on the B200 the full Lloyd run
-    is the fast path, so ``minibatch`` is accepted and ignored (documented in DESIGN.md)."""
+    z-scores the columns, then clusters: MiniBatchKMeans(n_clusters, random_state=seed, batch_size, n_init="auto") when
+    ``minibatch`` and more than 20 000 rows, else KMeans(n_clusters, random_state=seed, n_init="auto") — the reference's
+    rule (:173-178).  ``init`` (an array, or "random") is an extension for parity runs with pinned centres."""
     if n_clusters <= 0:
         raise ValueError("n_clusters must be > 0")
     Xn = np.asarray(X)
@@ -420,6 +593,10 @@ def kmeans_cluster(X, n_clusters: int, seed: int, minibatch: bool = True, batch_
     dev = device_of(device)
     Xd = torch.from_numpy(np.ascontiguousarray(Xn, dtype=np.float32)).to(dev)
     Xs = standard_scale(Xd)
-    km = KMeans(n_clusters=n_clusters, random_state=seed, n_init="auto", init=init, precision=precision)
+    if minibatch and Xn.shape[0] > 20000:
+        km = MiniBatchKMeans(n_clusters=n_clusters, random_state=seed, batch_size=batch_size, n_init="auto", init=init,
+                             precision=precision)
+    else:
+        km = KMeans(n_clusters=n_clusters, random_state=seed, n_init="auto", init=init, precision=precision)
     labels = km.fit_predict(Xs)
     return labels.cpu().numpy().astype(np.int64), km.cluster_centers_.cpu().numpy().astype(np.float32)

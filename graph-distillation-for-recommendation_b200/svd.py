@@ -3,36 +3,69 @@
 ``compute_svd_embeddings(R, dim, seed)`` of distill_recsys.py:124-155 — the step right before the k-means
 stage of distill_recsys — returns ``(U sqrt(S), V sqrt(S))`` of the ``dim`` leading singular triplets.  The
 reference calls scipy's ``svds`` (ARPACK, fp64, host).  Here the factorisation is a **block Krylov
-Rayleigh-Ritz** whose sparse products R·Q and Rᵀ·Q run on the stage-2 CSR SpMM kernel (R and Rᵀ as device CSR),
-i.e. the hot operation is the same HBM-bound gather kernel as the propagation; the small dense steps
-(orthogonalisation of the N x b blocks, the (q·b)² Ritz problem) use torch's fp64 / fp32 linear algebra.
+Rayleigh-Ritz** on the device:
+
+  * the sparse products R·Q and Rᵀ·Q run on the stage-2 CSR SpMM kernel (R and Rᵀ as device CSR) — the hot
+    operation is the same HBM-bound gather kernel as the propagation;
+  * every dense step is a hand-written fp64 kernel of csrc/svd.cu (no cuSOLVER / cuBLAS): CholeskyQR2 of the tall
+    blocks (``gdr_dense_gram`` -> ``gdr_dense_chol`` -> ``gdr_dense_trsm_rows``), block Gram-Schmidt against the earlier
+    blocks (``gdr_dense_gram`` + ``gdr_dense_gemm_small``), the (q·b)² Ritz problem by parallel cyclic Jacobi on the
+    Gram matrix of R·Q (``gdr_sym_eig_jacobi``) and the Ritz vectors (``gdr_dense_gemm_small``).
+
+The Krylov space lives on the SMALLER side of R and never exceeds it (blocks stop when the space is exhausted or a
+block loses rank), so small matrices are factorised exactly instead of on noise.
 
 Parity with the reference is defined on what it determines uniquely: the singular values (relative 1e-4) and
 the singular vectors of well separated values up to sign; the tail of a slowly decaying spectrum is only
-determined as a subspace (the downstream k-means is invariant to rotations inside it only approximately —
-the reference itself depends on ARPACK's starting vector there).
+determined as a subspace (the reference itself depends on ARPACK's starting vector there).
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Tuple, Union
 
 import numpy as np
 import scipy.sparse as sp
 import torch
 
-from ._dev import device_of
+from . import _lib
+from ._dev import device_of, ptr, stream, workspace
 from .graph import CSR
 from .propagation import spmm
 
 
-def _orth_against(Y: torch.Tensor, basis: list) -> torch.Tensor:
-    """Two passes of block Gram-Schmidt against the previous blocks, then a thin QR (fp64: the Krylov basis loses
-    orthogonality quickly in fp32)."""
+def _gram(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """AᵀB for fp64 row-major (possibly column-sliced) tall matrices."""
+    N, p, r = A.shape[0], A.shape[1], B.shape[1]
+    C = torch.empty((p, r), dtype=torch.float64, device=A.device)
+    ws = workspace(_lib.query("gdr_dense_gram_ws_bytes", N, p, r), A.device)
+    _lib.call("gdr_dense_gram", N, p, r, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), r, ptr(ws), ws.numel(), stream())
+    return C
+
+
+def _cholqr2(Y: torch.Tensor) -> bool:
+    """In-place orthonormalisation of the columns of the fp64 block Y [N, b] (CholeskyQR, twice).  False when the block
+    has lost rank (a pivot of the Gram matrix is below 1e-13 of its largest diagonal entry)."""
+    N, b = Y.shape
+    info = torch.zeros(1, dtype=torch.int32, device=Y.device)
+    L = torch.empty((b, b), dtype=torch.float64, device=Y.device)
     for _ in range(2):
-        for Q in basis:
-            Y = Y - Q @ (Q.T @ Y)
-    Qn, _ = torch.linalg.qr(Y)
-    return Qn
+        S = _gram(Y, Y)
+        _lib.call("gdr_dense_chol", b, ptr(S), b, ptr(L), b, ptr(info), 1e-13, stream())
+        if int(info.item()):
+            return False
+        _lib.call("gdr_dense_trsm_rows", N, b, ptr(Y), Y.stride(0), ptr(L), b, stream())
+    return True
+
+
+def _project_out(Z: torch.Tensor, Q: torch.Tensor):
+    """Z <- Z - Q (Qᵀ Z), twice (block Gram-Schmidt with re-orthogonalisation), Q [N, m] orthonormal."""
+    N, b = Z.shape
+    m = Q.shape[1]
+    for _ in range(2):
+        P = _gram(Q, Z)
+        _lib.call("gdr_dense_gemm_small", N, m, b, -1.0, ptr(Q), Q.stride(0), ptr(P), b, 1.0, ptr(Z), Z.stride(0), 0, 0, 0,
+                  stream())
 
 
 def truncated_svd(R: CSR, k: int, seed: int = 42, block: int = None, n_blocks: int = None
@@ -41,27 +74,57 @@ def truncated_svd(R: CSR, k: int, seed: int = 42, block: int = None, n_blocks: i
     n_rows, n_cols = R.shape
     dev = R.device
     Rt, _ = R.transpose()
-    b = int(block or (k + 8))
+    # Krylov space on the smaller side: A maps it to the larger one
+    if n_cols <= n_rows:
+        A, At, ns = R, Rt, n_cols
+    else:
+        A, At, ns = Rt, R, n_rows
+    k = int(min(k, ns))
+    b = int(min(block or (k + 8), ns, 128))
     q = int(n_blocks or max(6, min(14, 600 // b)))
+    q = max(1, min(q, ns // b))                                  # q b <= ns: the space cannot be larger than the side
     gen = torch.Generator(device="cpu").manual_seed(int(seed))
-    G = torch.randn((n_cols, b), generator=gen, dtype=torch.float32).to(dev)
-    # Krylov blocks of R^T R on the column side:  V_0 = orth(G), V_{j+1} = orth(R^T (R V_j)) against all previous
-    basis = []
-    V = _orth_against(G.double(), basis)
-    basis.append(V)
-    for _ in range(1, q):
-        Y = spmm(R, V.to(torch.float32).contiguous())                   # [n_rows, b]  sparse x dense on the CSR kernel
-        Z = spmm(Rt, Y.contiguous())                                    # [n_cols, b]
-        V = _orth_against(Z.double(), basis)
-        basis.append(V)
-    Q = torch.cat(basis, dim=1)                                         # [n_cols, q b], orthonormal
-    B = spmm(R, Q.to(torch.float32).contiguous()).double()              # [n_rows, q b] = R Q
-    # Rayleigh-Ritz: SVD of B through its Gram matrix would square the condition number; QR + small SVD instead
-    Qb, Rb = torch.linalg.qr(B)
-    Us, S, Vh = torch.linalg.svd(Rb)
-    U = (Qb @ Us[:, :k]).to(torch.float32)
-    Vk = (Q @ Vh.T[:, :k]).to(torch.float32)
-    return U, S[:k].to(torch.float32), Vk
+    G = torch.randn((ns, b), generator=gen, dtype=torch.float32).to(dev)
+    Q = torch.zeros((ns, q * b), dtype=torch.float64, device=dev)
+    V = Q[:, :b]
+    V.copy_(G)
+    if not _cholqr2(V):
+        raise ValueError("truncated_svd: the random start block is rank deficient")
+    m = b
+    for j in range(1, q):
+        Vp = Q[:, (j - 1) * b: j * b]
+        Y = spmm(A, Vp.to(torch.float32).contiguous())           # [n_other, b]  sparse x dense on the CSR kernel
+        Z = spmm(At, Y.contiguous())                             # [ns, b]
+        Vn = Q[:, j * b: (j + 1) * b]
+        Vn.copy_(Z)
+        _project_out(Vn, Q[:, :m])
+        if not _cholqr2(Vn):                                     # Krylov space exhausted: keep the blocks so far
+            break
+        m += b
+    Qm = Q[:, :m]
+    B = spmm(A, Qm.to(torch.float32).contiguous()).double()      # [n_other, m] = A Q
+    # Rayleigh-Ritz on the Gram matrix of B (fp64; the leading Ritz values lose nothing to the squared condition number)
+    T = _gram(B, B).contiguous()
+    W = torch.empty((m, m), dtype=torch.float64, device=dev)
+    evals = torch.empty(m, dtype=torch.float64, device=dev)
+    order = torch.empty(m, dtype=torch.int32, device=dev)
+    sweeps = ctypes.c_int32(0)
+    ws = workspace(_lib.query("gdr_sym_eig_jacobi_ws_bytes", m), dev)
+    _lib.call("gdr_sym_eig_jacobi", m, ptr(T), ptr(W), ptr(evals), ptr(order), 30, 1e-14, ctypes.addressof(sweeps), ptr(ws),
+              ws.numel(), stream())
+    kk = min(k, m)
+    Wk = torch.empty((m, kk), dtype=torch.float64, device=dev)
+    _lib.call("gdr_dense_gather_cols", m, kk, ptr(W), ptr(order), ptr(Wk), stream())
+    S = evals[:kk].clamp_min(0).sqrt()
+    inv_s = torch.where(S > 0, 1.0 / S, torch.zeros_like(S)).contiguous()
+    n_other = B.shape[0]
+    Vs = torch.empty((ns, kk), dtype=torch.float32, device=dev)          # small-side vectors  Q W
+    Uo = torch.empty((n_other, kk), dtype=torch.float32, device=dev)     # other-side vectors  B W / sigma
+    _lib.call("gdr_dense_gemm_small", ns, m, kk, 1.0, ptr(Qm), Qm.stride(0), ptr(Wk), kk, 0.0, 0, 0, ptr(Vs), kk, 0, stream())
+    _lib.call("gdr_dense_gemm_small", n_other, m, kk, 1.0, ptr(B), B.stride(0), ptr(Wk), kk, 0.0, 0, 0, ptr(Uo), kk, ptr(inv_s),
+              stream())
+    S32 = S.to(torch.float32)
+    return (Uo, S32, Vs) if n_cols <= n_rows else (Vs, S32, Uo)
 
 
 def compute_svd_embeddings(R: Union[sp.spmatrix, CSR], dim: int, seed: int = 42, device=None

@@ -278,6 +278,14 @@ int     gdr_kmeans_assign_tc(int64_t N, int64_t K, int64_t D,
                              int32_t* n_changed_dev, float* best_out, int32_t* n_refined_dev,
                              void* ws, int64_t ws_bytes, gdr_stream_t stream);
 
+/* MiniBatchKMeans centre update for one batch (sklearn/cluster/_k_means_minibatch.pyx:56-110, behind
+ * clustgdd_agent_transduct.py:103, clustgdd_agent_induct.py:132, distill_recsys.py:174-176):
+ * C_new[c] = (C_old[c] * weight_sums[c] + sum of the batch rows labelled c, in batch order) / (weight_sums[c] + count),
+ * weight_sums[c] += count; a cluster without members in the batch keeps its old centre.  Same fp32 chain as sklearn. */
+int gdr_minibatch_update(int64_t B, int64_t K, int64_t D, const float* Xb, int64_t ldx, const int32_t* labels,
+                         const float* C_old, int64_t ldc_old, float* C_new, int64_t ldc_new, float* weight_sums,
+                         gdr_stream_t stream);
+
 /* One complete Lloyd run from given (already mean-centred) initial centres — the loop of
  * _kmeans_single_lloyd (sklearn/_kmeans.py:630-758) behind KMeans(...).fit()
  * (clustgdd_agent_transduct.py:105, distill_recsys.py:178).  C_inout holds the initial
@@ -506,6 +514,32 @@ int gdr_kmeans_lloyd_dist(gdr_comm_t* comm, int64_t N_local, int64_t N_total, in
                           int max_iter, double tol_abs, int precision_mode, double* inertia_out_host,
                           int32_t* n_iter_out_host, int32_t* info_out_host, int verbose, void* ws, int64_t ws_bytes,
                           gdr_stream_t stream);
+
+/* ---- dense fp64 steps of the truncated SVD embeddings (distill_recsys.py:124-155 compute_svd_embeddings; the reference
+ * calls scipy's ARPACK svds on the host).  The block Krylov Rayleigh-Ritz of svd.py runs its sparse products on
+ * gdr_spmm_prop and everything else here — hand-written, no cuSOLVER / cuBLAS, fixed-order reductions:
+ *   gdr_dense_gram        C[p x r] = A^T B, A [N x p], B [N x r] tall-skinny (Gram matrices, projections Q^T Z)
+ *   gdr_dense_chol        lower Cholesky factor of an n x n SPD matrix, n <= 128; info_dev[0] = 0 or 1 + failing pivot
+ *   gdr_dense_trsm_rows   Y <- Y L^-T (CholeskyQR: Y becomes orthonormal)
+ *   gdr_dense_gemm_small  Z <- (beta Z + alpha A P) * colscale, A [N x m] tall, P [m x r] small; fp64 and/or fp32 output
+ *   gdr_sym_eig_jacobi    eigen-decomposition of an n x n symmetric matrix by parallel cyclic Jacobi (A is destroyed;
+ *                         evals descending, order[k] = column of W holding the k-th eigenvector); SYNCHRONISES per sweep
+ *   gdr_dense_gather_cols Wk[:, k] = W[:, order[k]], k < kcols */
+int64_t gdr_dense_gram_ws_bytes(int64_t N, int64_t p, int64_t r);
+int     gdr_dense_gram(int64_t N, int64_t p, int64_t r, const double* A, int64_t lda, const double* B, int64_t ldb,
+                       double* C, int64_t ldc, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int     gdr_dense_chol(int64_t n, const double* S, int64_t lds, double* L, int64_t ldl, int32_t* info_dev, double rel_tol,
+                       gdr_stream_t stream);
+int     gdr_dense_trsm_rows(int64_t N, int64_t n, double* Y, int64_t ldy, const double* L, int64_t ldl,
+                            gdr_stream_t stream);
+int     gdr_dense_gemm_small(int64_t N, int64_t m, int64_t r, double alpha, const double* A, int64_t lda, const double* P,
+                             int64_t ldp, double beta, double* Z, int64_t ldz, float* Zf, int64_t ldzf,
+                             const double* colscale, gdr_stream_t stream);
+int64_t gdr_sym_eig_jacobi_ws_bytes(int64_t n);
+int     gdr_sym_eig_jacobi(int64_t n, double* A, double* W, double* evals, int32_t* order, int max_sweeps, double tol,
+                           int32_t* sweeps_out_host, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int     gdr_dense_gather_cols(int64_t n, int64_t kcols, const double* W, const int32_t* order, double* Wk,
+                              gdr_stream_t stream);
 
 /* Induced subgraph  adj[np.ix_(idx, idx)]  (utils_graphsaint.py:34-36, utils.py:127-129) as relabelled COO
  * triplets: row i of the result is node idx[i].  Outputs have the capacity of the source nnz; the caller turns

@@ -117,12 +117,27 @@ def test_rankformer_gcn_forward():
         np.testing.assert_allclose(out, np.concatenate([zu, zi]), rtol=2e-5, atol=1e-6)
 
 
-def test_minibatch_kmeans_entry_point():
+def test_minibatch_kmeans_follows_sklearn():
+    """MiniBatchKMeans (clustgdd_agent_transduct.py:103, distill_recsys.py:174-176): sklearn's algorithm with sklearn's
+    random stream — same subsets, same batches, same reassignment draws.  A near-tie in an E-step can part the two
+    trajectories, so the contract is WCSS; on well separated data the fits coincide."""
     import gdr
     from gdr import synth
-    X = synth.clustered_features(30000, 40, 50, seed=2)
-    mb = gdr.MiniBatchKMeans(n_clusters=100, random_state=0, batch_size=1000).fit(X)   # transduct :103
-    assert mb.labels_.shape == (30000,) and mb.cluster_centers_.shape == (100, 40)
     from sklearn.cluster import MiniBatchKMeans as SkMB
-    sk = SkMB(n_clusters=100, random_state=0, batch_size=1000, n_init=1).fit(X)
-    assert mb.inertia_ <= sk.inertia_ * 1.02        # full Lloyd is at least as good as the mini-batch fit
+    X = synth.clustered_features(30000, 40, 50, seed=2)
+    for kw in (dict(n_clusters=100, random_state=0, batch_size=1000),
+               dict(n_clusters=50, random_state=3, batch_size=2048, init="random", n_init=1),
+               dict(n_clusters=64, random_state=1, batch_size=512, max_iter=5, max_no_improvement=None)):
+        mb = gdr.MiniBatchKMeans(**kw).fit(X)
+        sk = SkMB(**kw).fit(X)
+        assert mb.labels_.shape == (30000,) and mb.cluster_centers_.shape == (kw["n_clusters"], 40)
+        assert mb.labels_.dtype == np.int32 and mb.n_steps_ >= 1
+        assert abs(mb.inertia_ - sk.inertia_) <= 0.05 * sk.inertia_, (kw, mb.inertia_, sk.inertia_, mb.n_steps_, sk.n_steps_)
+        # the inertia reported is the WCSS of the returned labels against the returned centres
+        d = ((X - mb.cluster_centers_[mb.labels_]) ** 2).sum()
+        assert abs(d - mb.inertia_) <= 1e-4 * mb.inertia_
+    # distill_recsys.kmeans_cluster switches to mini-batches above 20 000 rows (distill_recsys.py:173-176)
+    labels, centers = gdr.kmeans_cluster(X, 100, seed=0, minibatch=True, batch_size=2048)
+    assert labels.dtype == np.int64 and centers.shape == (100, 40) and len(np.unique(labels)) > 50
+    with pytest.raises(ValueError):
+        gdr.MiniBatchKMeans(n_clusters=10, reassignment_ratio=-1.0).fit(X)
