@@ -526,9 +526,12 @@ int gdr_spmm_prop_mc(gdr_symm_t* symm, int64_t dst_offset_bytes, int64_t dst_ld,
   mc.row_off = dst_row_offset;
   mc.ld = dst_ld;
   for (int p = 0; p < mc.n; ++p) mc.dst[p] = (float*)(symm->peer[p] + dst_offset_bytes);
-  GDR_CHECK_ARG((const char*)X + 1 <= symm->local + dst_offset_bytes ||
-                    (const char*)X >= symm->local + dst_offset_bytes + (dst_row_offset + rows_local) * dst_ld * 4 || true,
-                "spmm_prop_mc: in-place");
+  {   // the source operand must not overlap the rows this call writes into the local copy
+    const char* d0 = symm->local + dst_offset_bytes + dst_row_offset * dst_ld * 4;
+    const char* d1 = d0 + rows_local * dst_ld * 4;
+    const char* x0 = (const char*)X;
+    GDR_CHECK_ARG(!(x0 < d1 && x0 + 1 > d0), "spmm_prop_mc: in-place propagation is not supported");
+  }
   return gdr::spmm_launch_mc(rows_local, F, rowptr, colidx, vals, alpha, X, ldx, Y, ldy, T, ldt, beta, bounds, n_blocks, mc,
                              (cudaStream_t)stream);
 }

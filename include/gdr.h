@@ -70,7 +70,7 @@ int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
  * "sparsify_batch" (cap on the classes per batch of gdr_sparsify_classes), "tc_screen" (1 direct 3xTF32; two-level screen with 2: 256x128 CTA tiles, 3: 128x256 CTA tiles [default for large
  * inputs], 4: CTA pairs with 2-SM TMA, 5: CTA pairs with forwarded 1-SM TMA), "tc_ablate" (role ablations of the
  * first-level kernel for tools/estep_probe.py / tools/mma_rate_probe.py; results are garbage while it is set);
- * "tc_gate" (first-level epilogue gate of the two-level screen: 0 off, 1 on the running best, 2 [default] also seeded
+ * "tc_gate" (first-level epilogue gate of the two-level screen: 0 off, 1 [default] on the running best, 2 also seeded
  * with the previous label's score; every setting produces the same labels);
  * value 0 / -1 = automatic. */
 int gdr_debug_set(const char* key, int value);

@@ -160,7 +160,7 @@ def gate_mode():
     """First-level epilogue gate (gdr_debug_set "tc_gate": 0 off, 1 running best, 2 + previous-label seed)."""
     from gdr import _lib
     yield lambda v: _lib.call("gdr_debug_set", b"tc_gate", int(v))
-    _lib.call("gdr_debug_set", b"tc_gate", 2)
+    _lib.call("gdr_debug_set", b"tc_gate", 1)
 
 
 @pytest.mark.parametrize("N,K,D,kind", [(100000, 4096, 100, "zscore"), (80000, 5000, 47, "clustered"), (90001, 4100, 128, "zscore")])

@@ -58,5 +58,5 @@ for D in (cfg["f"], cfg["d_logit"]):
             t = timed(lambda: assign_labels(X, C, out, labels_prev=truth, n_changed=nch, tc_operand=op, ws=ws))
             print(f"D={D} gate {gate} level-1 kernel only, ablate {ab}: {t*1e3:.0f} us", flush=True)
         _lib.call("gdr_debug_set", b"tc_ablate", 0)
-    _lib.call("gdr_debug_set", b"tc_gate", 2)
+    _lib.call("gdr_debug_set", b"tc_gate", 1)
     del X, C, op, ws
