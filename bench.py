@@ -947,8 +947,9 @@ def multi_parity(gdr, par, comm, part, ops, dev, w, A_ref, tgt_ref, C0, u_sl, v_
     block of each stage against the same rows of the single-GPU path run on this very GPU.
       adj_block_equal   rows of A_hat built by the all-to-all exchange == rows of the one-GPU build (rowptr/colidx/vals)
       prop_rows_equal   distributed hops == one-GPU hops on this rank's rows (bit-exact: same fp32 chains)
-      labels_equal      ONE Lloyd step from shared centres on bit-identical rows: labels torch.equal to the one-GPU labels
-      centres_close     centres after that step within 1e-5 (the all-reduce order changes the last bits)
+      labels_equal      the E-step from shared centres on bit-identical rows: labels torch.equal to the one-GPU labels
+      centres_close     centres after ONE Lloyd step within 1e-5 (the all-reduce order changes the last bits; the labels
+                        of the E-step that follows may then differ on a few near-tie rows: labels_differ_after_update)
       counts_equal      integer cell counts of the coarsened graph == one-GPU counts (same labels in)"""
     import torch
     import torch.distributed as dist
@@ -963,12 +964,18 @@ def multi_parity(gdr, par, comm, part, ops, dev, w, A_ref, tgt_ref, C0, u_sl, v_
     _, t_l = par.dist_propagate(comm, part, A_blk, x_local, hops + 1, ALPHA, ops=ops)
     out["prop_rows_equal"] = bool(torch.equal(t_l, tgt_ref[lo:hi]))
     out["prop_rows_max_rel_err"] = float(((t_l - tgt_ref[lo:hi]).abs().max() / tgt_ref.abs().max()).item())
-    km1 = par.DistKMeans(K, C0, max_iter=1, tol=0, ops=ops, comm=comm).fit(tgt_ref[lo:hi].contiguous())
+    # the E-step from the SHARED centres (max_iter = 0: no update, labels of C0) must agree bit for bit; after one update
+    # the centres differ in their last bits (all-reduce order), so only their closeness is part of the contract
+    x_blk = tgt_ref[lo:hi].contiguous()
+    km0 = par.DistKMeans(K, C0, max_iter=0, tol=0, ops=ops, comm=comm).fit(x_blk)
+    ref0 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=0, tol=0).fit(tgt_ref)
+    out["labels_equal"] = bool(torch.equal(km0.labels_, ref0.labels_[lo:hi]))
+    out["labels_differ"] = int((km0.labels_ != ref0.labels_[lo:hi]).sum().item())
+    km1 = par.DistKMeans(K, C0, max_iter=1, tol=0, ops=ops, comm=comm).fit(x_blk)
     ref1 = gdr.KMeans(n_clusters=K, init=C0, n_init=1, max_iter=1, tol=0).fit(tgt_ref)
-    out["labels_equal"] = bool(torch.equal(km1.labels_, ref1.labels_[lo:hi]))
-    out["labels_differ"] = int((km1.labels_ != ref1.labels_[lo:hi]).sum().item())
     cdiff = (km1.cluster_centers_ - ref1.cluster_centers_).abs().max() / ref1.cluster_centers_.abs().max()
     out["centres_close"] = bool(cdiff.item() <= 1e-5)
+    out["labels_differ_after_update"] = int((km1.labels_ != ref1.labels_[lo:hi]).sum().item())
     labels = ref1.labels_
     adj_syn, counts = par.dist_graph_compress(comm, part, labels[lo:hi].contiguous(), A_blk, ops=ops)
     kk = int(labels.max()) + 1
@@ -981,12 +988,12 @@ def multi_parity(gdr, par, comm, part, ops, dev, w, A_ref, tgt_ref, C0, u_sl, v_
     flags = [k for k, v in out.items() if isinstance(v, bool)]
     t = torch.tensor([1 if out[k] else 0 for k in flags], dtype=torch.int32, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    d = torch.tensor([out["labels_differ"]], dtype=torch.int64, device=dev)
+    d = torch.tensor([out["labels_differ"], out["labels_differ_after_update"]], dtype=torch.int64, device=dev)
     dist.all_reduce(d)
     e = torch.tensor([out["prop_rows_max_rel_err"]], dtype=torch.float64, device=dev)
     dist.all_reduce(e, op=dist.ReduceOp.MAX)
     res = {k: bool(v) for k, v in zip(flags, t.tolist())}
-    res["labels_differ"] = int(d.item())
+    res["labels_differ"], res["labels_differ_after_update"] = int(d[0].item()), int(d[1].item())
     res["prop_rows_max_rel_err"] = float(e.item())
     must = ["adj_block_equal", "labels_equal", "centres_close", "counts_equal", "coarse_values_close"]
     res["status"] = "ok" if all(res[k] for k in must) and res["prop_rows_max_rel_err"] <= 1e-5 else "MISMATCH"
@@ -1234,9 +1241,11 @@ def run_ours_multi_bipartite(args, rank, world, dev, w):
         }
         lab_ok, cen_ok, maps1 = True, True, []
         for Xs, part, K, c0 in ((Xs_full[0], pu, ku, C0[0]), (Xs_full[1], pi, ki, C0[1])):
+            km0 = par.DistKMeans(K, c0, max_iter=0, tol=0, ops=ops, comm=comm).fit(Xs[part.lo:part.hi].contiguous())
+            ref0 = gdr.KMeans(n_clusters=K, init=c0, n_init=1, max_iter=0, tol=0).fit(Xs)
+            lab_ok &= bool(torch.equal(km0.labels_, ref0.labels_[part.lo:part.hi]))
             km1 = par.DistKMeans(K, c0, max_iter=1, tol=0, ops=ops, comm=comm).fit(Xs[part.lo:part.hi].contiguous())
             ref1 = gdr.KMeans(n_clusters=K, init=c0, n_init=1, max_iter=1, tol=0).fit(Xs)
-            lab_ok &= bool(torch.equal(km1.labels_, ref1.labels_[part.lo:part.hi]))
             cen_ok &= bool(((km1.cluster_centers_ - ref1.cluster_centers_).abs().max() / ref1.cluster_centers_.abs().max()).item() <= 1e-5)
             maps1.append(ref1.labels_)
         flags["labels_equal"], flags["centres_close"] = lab_ok, cen_ok

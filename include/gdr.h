@@ -72,6 +72,7 @@ int gdr_profile_collect(double* total_ms_host, int64_t* launches_host);
  * first-level kernel for tools/estep_probe.py / tools/mma_rate_probe.py; results are garbage while it is set);
  * "tc_gate" (first-level epilogue gate of the two-level screen: 0 off, 1 [default] on the running best, 2 also seeded
  * with the previous label's score; every setting produces the same labels);
+ * "rs_match" (radix-sort ranking: 0 [default] per-bit warp ballots, 1 MATCH.ANY);
  * value 0 / -1 = automatic. */
 int gdr_debug_set(const char* key, int value);
 /* Debug read-back (synchronises the device).  keys: "tc_level2_rows" = rows the last two-level

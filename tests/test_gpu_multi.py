@@ -76,9 +76,14 @@ def _worker(rank, world, port):
         C0 = synth.kmeans_init(tn, k, seed=13)
         # single step from shared centres (SURVEY §8c protocol 1): labels equal, centres to 1e-5
         # (rows of `target` are bit-identical to t1's, asserted above, so the labels must be EQUAL, not nearly equal)
+        # max_iter = 0 is the E-step from the shared centres alone; after one update the centres differ in their last bits
+        # (all-reduce order), so the labels of the E-step that follows may differ on near-tie rows
+        km0 = par.DistKMeans(k, C0, max_iter=0, tol=0, ops=ops, comm=comm).fit(target)
+        ref0 = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=0, tol=0).fit(t1)
+        assert km0.n_iter_ == 0 and torch.equal(km0.labels_, ref0.labels_[part.lo:part.hi])
         km1 = par.DistKMeans(k, C0, max_iter=1, tol=0, ops=ops, comm=comm).fit(target)
         ref1 = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=1, tol=0).fit(t1)
-        assert torch.equal(km1.labels_, ref1.labels_[part.lo:part.hi])
+        assert (km1.labels_ != ref1.labels_[part.lo:part.hi]).sum().item() <= 3
         torch.testing.assert_close(km1.cluster_centers_, ref1.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
         # the host-driven loop (torch.distributed collectives) and the in-library loop (NCCL inside libgdr_b200,
         # graph-replayed) are the same algorithm: identical fits
@@ -98,7 +103,7 @@ def _worker(rank, world, port):
         kme = par.DistKMeans(k, C0e, max_iter=1, tol=0, ops=ops, comm=comm).fit(target)
         refe = gdr.KMeans(n_clusters=k, init=C0e, n_init=1, max_iter=1, tol=0).fit(t1)
         torch.testing.assert_close(kme.cluster_centers_, refe.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
-        assert torch.equal(kme.labels_, refe.labels_[part.lo:part.hi])
+        assert (kme.labels_ != refe.labels_[part.lo:part.hi]).sum().item() <= 3
         # end to end (protocol 2): same iteration count, WCSS within 1e-4, labels nearly all equal
         km = par.DistKMeans(k, C0, max_iter=15, tol=0, ops=ops, comm=comm).fit(target)
         ref = gdr.KMeans(n_clusters=k, init=C0, n_init=1, max_iter=15, tol=0).fit(t1)
@@ -134,9 +139,12 @@ def _worker(rank, world, port):
                 assert torch.equal(p2, p2r[part.lo:part.hi]) and torch.equal(t2, t2r[part.lo:part.hi])
             C2 = synth.kmeans_init(X2, 50, seed=3)
             for py in (False, True):
+                k0 = par.DistKMeans(50, C2, max_iter=0, tol=0, ops=ops, comm=comm, python_loop=py).fit(x2)
+                r0 = gdr.KMeans(n_clusters=50, init=C2, n_init=1, max_iter=0, tol=0).fit(torch.from_numpy(X2).to(dev))
+                assert torch.equal(k0.labels_, r0.labels_[part.lo:part.hi])
                 k2 = par.DistKMeans(50, C2, max_iter=1, tol=0, ops=ops, comm=comm, python_loop=py).fit(x2)
                 r2 = gdr.KMeans(n_clusters=50, init=C2, n_init=1, max_iter=1, tol=0).fit(torch.from_numpy(X2).to(dev))
-                assert torch.equal(k2.labels_, r2.labels_[part.lo:part.hi])
+                assert (k2.labels_ != r2.labels_[part.lo:part.hi]).sum().item() <= 3
                 torch.testing.assert_close(k2.cluster_centers_, r2.cluster_centers_.contiguous(), rtol=1e-5, atol=1e-5)
         # distill_recsys on a row partition (users and items each split over the ranks) == the single-GPU path
         nu, ni, d, L = 6011, 4099, 64, 2

@@ -13,7 +13,11 @@ n = cfg["n"]
 u, v = synth.uniform_graph(n, cfg["pairs"], 1238)
 dev = torch.device("cuda:0")
 u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
-for r in range(reps):
+from gdr import _lib
+for mode in ((0, 1) if reps > 1 else (0,)):
+  _lib.call("gdr_debug_set", b"rs_match", mode)
+  print("rs_match", mode)
+  for r in range(reps):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     A = gdr.coo_to_csr(u_d, v_d, None, (n, n), symmetrize=True, binarize=True)
@@ -21,12 +25,15 @@ for r in range(reps):
     An = gdr.sym_normalize(A, 2)
     e2.record()
     torch.cuda.synchronize()
-    print(f"rep {r}: coo_to_csr {e0.elapsed_time(e1):.3f} ms, sym_normalize {e1.elapsed_time(e2):.3f} ms, nnz {An.nnz}")
+    print(f"  rep {r}: coo_to_csr {e0.elapsed_time(e1):.3f} ms, sym_normalize {e1.elapsed_time(e2):.3f} ms, nnz {An.nnz}")
 lab = torch.from_numpy(np.random.RandomState(0).randint(0, cfg["k"], n).astype(np.int32)).to(dev)
-for r in range(reps):
+for mode in ((0, 1) if reps > 1 else (0,)):
+  _lib.call("gdr_debug_set", b"rs_match", mode)
+  for r in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gdr.graph_compress(lab, An, [])
     e1.record()
     torch.cuda.synchronize()
-    print(f"rep {r}: graph_compress {e0.elapsed_time(e1):.3f} ms")
+    print(f"  rs_match {mode} rep {r}: graph_compress {e0.elapsed_time(e1):.3f} ms")
+_lib.call("gdr_debug_set", b"rs_match", 0)
