@@ -212,6 +212,85 @@ __global__ void k_emit_csr_entries(const int32_t* __restrict__ n_runs_dev,
 }
 
 // ----------------------------------------------------------------------------
+// sorted unique keys -> binarised CSR in two passes over the keys (the keys-only build of stage 1):
+// count the heads of every 2048-key tile, scan the tile counts, then emit (colidx, 1.0) per head and fill rowptr on the
+// fly.  Replaces head flags + scan + head index + run reduce + emit + rowptr (six passes) when no values are carried.
+// ----------------------------------------------------------------------------
+constexpr int UQ_THREADS = 256;
+constexpr int UQ_ITEMS = 8;
+constexpr int UQ_TILE = UQ_THREADS * UQ_ITEMS;
+
+__global__ void __launch_bounds__(UQ_THREADS) k_unique_count(int64_t n, const uint64_t* __restrict__ keys,
+                                                             int32_t* __restrict__ tile_count) {
+  __shared__ int s_w[UQ_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * UQ_TILE;
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < UQ_ITEMS; ++q) {
+    const int64_t i = base + q * UQ_THREADS + threadIdx.x;
+    if (i < n) c += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane_id() == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < UQ_THREADS / 32; ++w) t += s_w[w];
+    tile_count[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(UQ_THREADS) k_unique_emit_csr(int64_t n, int64_t n_rows, int cbits,
+                                                                const uint64_t* __restrict__ keys,
+                                                                const int32_t* __restrict__ tile_off /*[tiles + 1]*/,
+                                                                int32_t* __restrict__ rowptr, int32_t* __restrict__ colidx,
+                                                                float* __restrict__ vals, int64_t* __restrict__ nnz_out) {
+  __shared__ int s_w[UQ_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * UQ_TILE;
+  const uint64_t cmask = (1ull << cbits) - 1ull;
+  int run = tile_off[blockIdx.x];
+  const int w = threadIdx.x >> 5;
+  // items are taken round by round (q * UQ_THREADS + thread): positions inside a round are consecutive over the threads
+  for (int q = 0; q < UQ_ITEMS; ++q) {
+    const int64_t i = base + q * UQ_THREADS + threadIdx.x;
+    uint64_t k = 0, kp = 0;
+    bool head = false;
+    if (i < n) {
+      k = keys[i];
+      kp = i > 0 ? keys[i - 1] : 0;
+      head = i == 0 || k != kp;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (lane_id() == 0) s_w[w] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < UQ_THREADS / 32; ++ww) {
+      const int c = s_w[ww];
+      woff += ww < w ? c : 0;
+      tot += c;
+    }
+    if (head) {
+      const int pos = run + woff + __popc(bal & ((1u << lane_id()) - 1u));
+      colidx[pos] = (int32_t)(k & cmask);
+      vals[pos] = 1.0f;
+      // rows (previous row, this row] start at this entry
+      const int64_t r = (int64_t)(k >> cbits), rp = i == 0 ? -1 : (int64_t)(kp >> cbits);
+      for (int64_t rr = rp + 1; rr <= r; ++rr) rowptr[rr] = pos;
+    }
+    if (i == n - 1) {   // rows after the last key, and the total
+      const int total = run + tot;
+      for (int64_t rr = (int64_t)(k >> cbits) + 1; rr <= n_rows; ++rr) rowptr[rr] = total;
+      *nnz_out = total;
+    }
+    run += tot;
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------
 // CSR transpose
 // ----------------------------------------------------------------------------
 __global__ void k_pack_transpose(int64_t n_rows, const int32_t* __restrict__ rowptr,
@@ -680,6 +759,19 @@ int gdr_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz_in, const int64_t
   uint32_t* spay = carry ? payload : nullptr;
   int rc = sort_pairs_ex(n, rbits + cbits, keys, spay, sws, sws_b, &skeys, carry ? &spay : nullptr, s);
   if (rc) return rc;
+  if (binarize) {
+    // keys only, all values 1: count heads per tile, scan, emit CSR — two passes over the sorted keys
+    const int64_t tiles = cdiv(n, UQ_TILE);
+    int32_t* tile_cnt = R.pos;            // run scratch reused: [tiles + 1] ints, scan workspace behind it
+    k_unique_count<<<(unsigned)tiles, UQ_THREADS, 0, s>>>(n, skeys, tile_cnt);
+    GDR_LAUNCHED();
+    rc = exclusive_scan_i32(tile_cnt, tile_cnt, tiles, R.scan_ws, R.scan_ws_b, s);
+    if (rc) return rc;
+    k_unique_emit_csr<<<(unsigned)tiles, UQ_THREADS, 0, s>>>(n, n_rows, cbits, skeys, tile_cnt, rowptr, colidx, vals,
+                                                            nnz_out_dev);
+    GDR_LAUNCHED();
+    return GDR_OK;
+  }
   rc = reduce_runs(n, skeys, spay, R, s);
   if (rc) return rc;
   k_emit_csr_entries<<<grid_for(n), 256, 0, s>>>(R.pos + n, R.ukeys, carry ? R.run_sum : nullptr, R.run_len,

@@ -223,22 +223,25 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restri
 //            in-order prefix;
 //   phase C  the bases are broadcast with shuffles.
 // FULL = the tile holds TILE keys (no bounds checks on the hot path); the last, partial tile runs the <.., false> variant.
-template <int RS_ROUNDS, bool HAS_VALS, bool FULL>
+// BITS = digit width, a compile-time constant (the per-bit ballot loop and the per-digit scans unroll exactly; with a
+// run-time width the compiler emitted all RS_MAX_BITS + 1 predicated votes: 96 instructions per key instead of 27).
+template <int RS_ROUNDS, bool HAS_VALS, bool FULL, int BITS>
 __global__ void __launch_bounds__(RS_THREADS, HAS_VALS ? 2 : 3)
 k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-             uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+             uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
              const int32_t* __restrict__ table_scanned, int nblocks, int block0, int use_match) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
   constexpr int TILE = RS_THREADS * RS_ROUNDS;
-  const int bins = 1 << bits;
-  const uint32_t dmask = (uint32_t)bins - 1u;
+  constexpr int bits = BITS;
+  constexpr int bins = 1 << BITS;
+  constexpr uint32_t dmask = (uint32_t)bins - 1u;
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_raw);                                    // [TILE]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);                             // [TILE] (HAS_VALS)
   int* cnt = reinterpret_cast<int*>(s_vals + (HAS_VALS ? TILE : 0));                         // [RS_WARPS][bins + 1]
   int* tile_off = cnt + RS_WARPS * (bins + 1);                                               // [bins] first tile position of digit d
   int* delta = tile_off + bins;                                                              // [bins] global position - tile position
   __shared__ int s_wsum[RS_WARPS];
-  const int cstride = bins + 1;                       // + 1: the sentinel digit of padding lanes (partial tile)
+  constexpr int cstride = bins + 1;                   // + 1: the sentinel digit of padding lanes (partial tile)
   for (int i = threadIdx.x; i < RS_WARPS * cstride; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -269,12 +272,10 @@ k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ 
       peers = __match_any_sync(0xffffffffu, d);
     } else {
 #pragma unroll
-      for (int b = 0; b < RS_MAX_BITS + 1; ++b) {
-        if (b < bits + (FULL ? 0 : 1)) {
-          const bool bit = (d >> b) & 1u;
-          const unsigned bal = __ballot_sync(0xffffffffu, bit);
-          peers &= bit ? bal : ~bal;
-        }
+      for (int b = 0; b < BITS + (FULL ? 0 : 1); ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
       }
     }
     pr[r] = peers;
@@ -299,19 +300,23 @@ k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ 
   }
   __syncthreads();
   // per digit: counts of the warps -> exclusive offsets; tile-wide exclusive scan of the digit totals
-  const int per = (bins + RS_THREADS - 1) / RS_THREADS;      // digits owned by this thread (contiguous)
+  constexpr int per = (bins + RS_THREADS - 1) / RS_THREADS;      // digits owned by this thread (contiguous)
   const int d0 = threadIdx.x * per, d1 = min(bins, d0 + per);
   int mine = 0;
-  for (int d = d0; d < d1; ++d) {
-    int run = 0;
 #pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) {
-      int t = cnt[ww * cstride + d];
-      cnt[ww * cstride + d] = run;
-      run += t;
+  for (int q = 0; q < per; ++q) {
+    const int d = d0 + q;
+    if (d < d1) {
+      int run = 0;
+#pragma unroll
+      for (int ww = 0; ww < RS_WARPS; ++ww) {
+        int t = cnt[ww * cstride + d];
+        cnt[ww * cstride + d] = run;
+        run += t;
+      }
+      tile_off[d] = run;          // digit total for now
+      mine += run;
     }
-    tile_off[d] = run;          // digit total for now
-    mine += run;
   }
   int incl = mine;
 #pragma unroll
@@ -358,31 +363,45 @@ static inline size_t rs_scatter_smem(int rounds, int bits, bool has_vals) {
   return (size_t)RS_THREADS * rounds * (has_vals ? 12 : 8) + (size_t)RS_WARPS * ((1 << bits) + 1) * 4 + (size_t)2 * (1 << bits) * 4;
 }
 
-template <int ROUNDS, bool HAS_VALS>
-static int launch_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, int64_t n, int shift,
-                             int bits, const int32_t* table, int64_t nb, cudaStream_t s) {
+template <int ROUNDS, bool HAS_VALS, int BITS>
+static int launch_rs_scatter_b(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, int64_t n, int shift,
+                               const int32_t* table, int64_t nb, cudaStream_t s) {
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.get();
-  const int smem_max = (int)rs_scatter_smem(ROUNDS, RS_MAX_BITS, HAS_VALS);
+  const int smem = (int)rs_scatter_smem(ROUNDS, BITS, HAS_VALS);
   if (!attr_set) {
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, true, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GDR_CUDA(cudaFuncSetAttribute(k_rs_scatter<ROUNDS, HAS_VALS, false, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const size_t smem = rs_scatter_smem(ROUNDS, bits, HAS_VALS);
   const int64_t tile = (int64_t)RS_THREADS * ROUNDS;
   const int64_t full = n / tile;
   if (full > 0) {
-    k_rs_scatter<ROUNDS, HAS_VALS, true><<<(unsigned)full, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits, table,
-                                                                               (int)nb, 0, g_rs_match);
+    k_rs_scatter<ROUNDS, HAS_VALS, true, BITS><<<(unsigned)full, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, table,
+                                                                                     (int)nb, 0, g_rs_match);
     GDR_LAUNCHED();
   }
   if (full < nb) {
-    k_rs_scatter<ROUNDS, HAS_VALS, false><<<(unsigned)(nb - full), RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, bits,
-                                                                                       table, (int)nb, (int)full, g_rs_match);
+    k_rs_scatter<ROUNDS, HAS_VALS, false, BITS><<<(unsigned)(nb - full), RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift,
+                                                                                             table, (int)nb, (int)full,
+                                                                                             g_rs_match);
     GDR_LAUNCHED();
   }
   return GDR_OK;
+}
+
+template <int ROUNDS, bool HAS_VALS>
+static int launch_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout, int64_t n, int shift,
+                             int bits, const int32_t* table, int64_t nb, cudaStream_t s) {
+  switch (bits) {
+    case 7: return launch_rs_scatter_b<ROUNDS, HAS_VALS, 7>(kin, vin, kout, vout, n, shift, table, nb, s);
+    case 8: return launch_rs_scatter_b<ROUNDS, HAS_VALS, 8>(kin, vin, kout, vout, n, shift, table, nb, s);
+    case 9: return launch_rs_scatter_b<ROUNDS, HAS_VALS, 9>(kin, vin, kout, vout, n, shift, table, nb, s);
+    case 10: return launch_rs_scatter_b<ROUNDS, HAS_VALS, 10>(kin, vin, kout, vout, n, shift, table, nb, s);
+    case 11: return launch_rs_scatter_b<ROUNDS, HAS_VALS, 11>(kin, vin, kout, vout, n, shift, table, nb, s);
+  }
+  set_error("sort_pairs: digit width %d is not one of the built widths (7..11)", bits);
+  return GDR_EUNSUPPORTED;
 }
 // digit width: wide digits save passes, but a tile of T keys leaves runs of T / 2^bits keys per digit, and a run
 // is what one coalesced write covers: at most 9 bits for the 4096-key tiles of large sorts (runs of >= 8 keys =
@@ -421,7 +440,10 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
   const int rounds = rs_rounds(n);
   int64_t nb = cdiv(n, RS_THREADS * rounds);
   const int passes = rs_passes(key_bits, rs_max_bits(n));
-  const int bits = rs_digit_bits(key_bits, rs_max_bits(n));
+  // the scatter kernel is built for digit widths 7..11; a narrower plan runs as 7 bits (its digits then overlap the
+  // next pass's, which sorts those bits again: still a stable LSD sort; keys are < 2^key_bits, the bits above are zero)
+  const int bits = std::max(7, rs_digit_bits(key_bits, rs_max_bits(n)));
+  const int step = rs_digit_bits(key_bits, rs_max_bits(n));
   const int bins = 1 << bits;
   int64_t tbl = (int64_t)bins * nb;
   Workspace W(ws, ws_bytes);
@@ -435,7 +457,7 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
   uint32_t* vout = vals ? valt : nullptr;
   const size_t hist_smem = (size_t)bins * 4;
   for (int p = 0; p < passes; ++p) {
-    int shift = bits * p;
+    int shift = step * p;
     if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
     else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
     GDR_LAUNCHED();

@@ -34,6 +34,9 @@ from .graph import CSR
 from .propagation import spmm
 
 
+EXACT_SIDE = 768     # smaller side up to which the factorisation is the exact Gram eigen-problem (no Krylov space)
+
+
 def _gram(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     """AᵀB for fp64 row-major (possibly column-sliced) tall matrices."""
     N, p, r = A.shape[0], A.shape[1], B.shape[1]
@@ -80,28 +83,34 @@ def truncated_svd(R: CSR, k: int, seed: int = 42, block: int = None, n_blocks: i
     else:
         A, At, ns = Rt, R, n_rows
     k = int(min(k, ns))
-    b = int(min(block or (k + 8), ns, 128))
-    q = int(n_blocks or max(6, min(14, 600 // b)))
-    q = max(1, min(q, ns // b))                                  # q b <= ns: the space cannot be larger than the side
-    gen = torch.Generator(device="cpu").manual_seed(int(seed))
-    G = torch.randn((ns, b), generator=gen, dtype=torch.float32).to(dev)
-    Q = torch.zeros((ns, q * b), dtype=torch.float64, device=dev)
-    V = Q[:, :b]
-    V.copy_(G)
-    if not _cholqr2(V):
-        raise ValueError("truncated_svd: the random start block is rank deficient")
-    m = b
-    for j in range(1, q):
-        Vp = Q[:, (j - 1) * b: j * b]
-        Y = spmm(A, Vp.to(torch.float32).contiguous())           # [n_other, b]  sparse x dense on the CSR kernel
-        Z = spmm(At, Y.contiguous())                             # [ns, b]
-        Vn = Q[:, j * b: (j + 1) * b]
-        Vn.copy_(Z)
-        _project_out(Vn, Q[:, :m])
-        if not _cholqr2(Vn):                                     # Krylov space exhausted: keep the blocks so far
-            break
-        m += b
-    Qm = Q[:, :m]
+    if ns <= EXACT_SIDE and block is None and n_blocks is None:
+        # the whole space of the smaller side: Q = I, the Ritz problem below is the exact Gram eigen-problem of A
+        # (a Krylov space clamped to a few dimensions short of ns interlaces the spectrum instead of matching it)
+        m = ns
+        Qm = torch.eye(ns, dtype=torch.float64, device=dev)
+    else:
+        b = int(min(block or (k + 8), ns, 128))
+        q = int(n_blocks or max(6, min(14, 600 // b)))
+        q = max(1, min(q, ns // b))                              # q b <= ns: the space cannot be larger than the side
+        gen = torch.Generator(device="cpu").manual_seed(int(seed))
+        G = torch.randn((ns, b), generator=gen, dtype=torch.float32).to(dev)
+        Q = torch.zeros((ns, q * b), dtype=torch.float64, device=dev)
+        V = Q[:, :b]
+        V.copy_(G)
+        if not _cholqr2(V):
+            raise ValueError("truncated_svd: the random start block is rank deficient")
+        m = b
+        for j in range(1, q):
+            Vp = Q[:, (j - 1) * b: j * b]
+            Y = spmm(A, Vp.to(torch.float32).contiguous())       # [n_other, b]  sparse x dense on the CSR kernel
+            Z = spmm(At, Y.contiguous())                         # [ns, b]
+            Vn = Q[:, j * b: (j + 1) * b]
+            Vn.copy_(Z)
+            _project_out(Vn, Q[:, :m])
+            if not _cholqr2(Vn):                                 # Krylov space exhausted: keep the blocks so far
+                break
+            m += b
+        Qm = Q[:, :m]
     B = spmm(A, Qm.to(torch.float32).contiguous()).double()      # [n_other, m] = A Q
     # Rayleigh-Ritz on the Gram matrix of B (fp64; the leading Ritz values lose nothing to the squared condition number)
     T = _gram(B, B).contiguous()
