@@ -100,6 +100,11 @@ int sort_pairs(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws
 int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
                   uint64_t** keys_sorted, uint32_t** vals_sorted, cudaStream_t s);
 
+// one stable pass on the digit [shift, shift + bits), bits in 7..11 (a stable partition); result in the workspace twins
+int sort_pairs_digit(int64_t n, int shift, int bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
+                     uint64_t** keys_sorted, uint32_t** vals_sorted, int64_t* starts_dev, cudaStream_t s,
+                     uint64_t* keys_dst = nullptr, uint32_t* vals_dst = nullptr);
+
 // SpMM launcher shared by stage 2 and the k-means M-step (vals == nullptr -> 1.0,
 // colidx32 gathers rows of X).
 int spmm_launch(int64_t rows, int64_t F, const int32_t* rowptr, const int32_t* colidx,

@@ -578,6 +578,47 @@ __global__ void __launch_bounds__(256) k_coarsen_scale(int64_t n_src, const int3
   }
 }
 
+// ---- multi-GPU stage 4, routing form: every edge becomes a (cell key, weight) pair tagged with the OWNER of its coarse
+// row in the top byte of the key; one stable partition pass groups the pairs by owner (dropped diagonal pairs go to bucket
+// 127), the owners sort + reduce what they receive.  One sort per edge instead of two (local coarsening + merge), and the
+// in-cell order of the weights is the global CSR order, so the sums are bit-identical to the single-device result.
+constexpr int ROUTE_SHIFT = 56;
+constexpr int ROUTE_DROP = 127;
+__global__ void k_pack_route_coo(int64_t E, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                 const float* __restrict__ w, const int32_t* __restrict__ lab_s,
+                                 const int32_t* __restrict__ lab_d, int bbits, int drop_diag, int cr, int world,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = (uint32_t)lab_s[src[e]], b = (uint32_t)lab_d[dst[e]];
+    const uint64_t owner = (drop_diag && a == b) ? (uint64_t)ROUTE_DROP : (uint64_t)min((int)(a / (uint32_t)cr), world - 1);
+    keys[e] = (owner << ROUTE_SHIFT) | ((uint64_t)a << bbits) | (uint64_t)b;
+    if (payload) payload[e] = __float_as_uint(w[e]);
+  }
+}
+
+__global__ void k_pack_route_csr(int64_t n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 const float* __restrict__ w, const int32_t* __restrict__ lab_s,
+                                 const int32_t* __restrict__ lab_d, int bbits, int drop_diag, int cr, int world,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < n_rows; r += nw) {
+    const uint32_t a = (uint32_t)lab_s[r];
+    const uint64_t own = (uint64_t)min((int)(a / (uint32_t)cr), world - 1);
+    for (int j = rowptr[r] + lane_id(); j < rowptr[r + 1]; j += 32) {
+      const uint32_t b = (uint32_t)lab_d[colidx[j]];
+      const uint64_t owner = (drop_diag && a == b) ? (uint64_t)ROUTE_DROP : own;
+      keys[j] = (owner << ROUTE_SHIFT) | ((uint64_t)a << bbits) | (uint64_t)b;
+      if (payload) payload[j] = __float_as_uint(w[j]);
+    }
+  }
+}
+
+__global__ void k_mask_keys(int64_t n, const uint64_t* __restrict__ in, uint64_t mask, uint64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] & mask;
+}
+
 // ---- key-range merge of per-rank coarsened graphs (multi-GPU stage 4) ----
 // cell key of every entry of a coarse CSR: (a << bbits) | b
 // 16-byte record per entry: [cell key | (count << 32) | weight-sum bits]
@@ -1082,6 +1123,97 @@ int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx,
   GDR_CHECK_ARG(rowptr && colidx && row_out, "csr_to_coo: null pointer");
   k_csr_to_coo<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, row_out,
                                                                        col_out);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- routing form of the multi-GPU stage 4 ----------------
+int64_t gdr_coarsen_route_ws_bytes(int64_t E) {
+  if (E <= 0) return 256;
+  return ws_need(E, 8) + ws_need(E, 4) + sort_pairs_ws_bytes(E) + 512;
+}
+
+int gdr_coarsen_route(int64_t E, const int64_t* src, const int64_t* dst, int64_t n_rows, const int32_t* csr_rowptr,
+                      const int32_t* csr_colidx, const float* w, const int32_t* labels_src, const int32_t* labels_dst,
+                      int64_t n_src, int64_t n_dst, int drop_diag, int world, uint64_t* keys_out, float* w_out,
+                      int64_t* owner_starts_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(E >= 0 && n_src > 0 && n_dst > 0 && world >= 1 && world < ROUTE_DROP && owner_starts_dev,
+                "coarsen_route: bad arguments");
+  GDR_CHECK_ARG(E < (1ll << 31) && bits_for(n_src) + bits_for(n_dst) <= ROUTE_SHIFT, "coarsen_route: size out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (E == 0) {
+    GDR_CUDA(cudaMemsetAsync(owner_starts_dev, 0, 129 * 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(labels_src && labels_dst && keys_out && (!w || w_out), "coarsen_route: null pointer");
+  GDR_CHECK_ARG((src && dst) || (csr_rowptr && csr_colidx && n_rows > 0), "coarsen_route: need COO or CSR edges");
+  if (ws_bytes < gdr_coarsen_route_ws_bytes(E)) {
+    set_error("coarsen_route: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(E);
+  uint32_t* payload = W.take<uint32_t>(E);
+  const int64_t sws_b = sort_pairs_ws_bytes(E);
+  void* sws = W.take<char>(sws_b);
+  const int bbits = bits_for(n_dst);
+  const int cr = (int)cdiv(n_src, world);
+  uint32_t* pl = w ? payload : nullptr;
+  if (src)
+    k_pack_route_coo<<<grid_for(E), 256, 0, s>>>(E, src, dst, w, labels_src, labels_dst, bbits, drop_diag, cr, world, keys, pl);
+  else
+    k_pack_route_csr<<<grid_for(n_rows * 32), 256, 0, s>>>(n_rows, csr_rowptr, csr_colidx, w, labels_src, labels_dst, bbits,
+                                                           drop_diag, cr, world, keys, pl);
+  GDR_LAUNCHED();
+  uint64_t* ks = nullptr;
+  uint32_t* vs = nullptr;
+  return sort_pairs_digit(E, ROUTE_SHIFT, 7, keys, pl, sws, sws_b, &ks, pl ? &vs : nullptr, owner_starts_dev, s, keys_out,
+                          (uint32_t*)w_out);
+}
+
+int64_t gdr_coarse_merge_edges_ws_bytes(int64_t m) {
+  m = m > 0 ? m : 1;
+  return ws_need(m, 8) + ws_need(m, 4) + sort_pairs_ws_bytes(m) + runs_ws_bytes(m, true) + 512;
+}
+
+int gdr_coarse_merge_edges(int64_t m, const uint64_t* keys_in, const float* w_in, int64_t a_lo, int64_t n_rows, int64_t n_src,
+                           int64_t n_dst, int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum,
+                           int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(m >= 0 && n_rows >= 0 && n_src > 0 && n_dst > 0 && a_lo >= 0 && rowptr && nnz_out_dev,
+                "coarse_merge_edges: bad arguments");
+  GDR_CHECK_ARG(m < (1ll << 31), "coarse_merge_edges: size exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_rows + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(keys_in && colidx && counts && (!wsum || w_in), "coarse_merge_edges: null pointer");
+  if (ws_bytes < gdr_coarse_merge_edges_ws_bytes(m)) {
+    set_error("coarse_merge_edges: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(m);
+  uint32_t* payload = W.take<uint32_t>(m);
+  const int64_t sws_b = sort_pairs_ws_bytes(m);
+  void* sws = W.take<char>(sws_b);
+  RunBuffers R = carve_runs(W, m, true);
+  const int abits = bits_for(n_src), bbits = bits_for(n_dst);
+  k_mask_keys<<<grid_for(m), 256, 0, s>>>(m, keys_in, (1ull << ROUTE_SHIFT) - 1ull, keys);
+  GDR_LAUNCHED();
+  uint32_t* pl = wsum ? payload : nullptr;
+  if (pl) GDR_CUDA(cudaMemcpyAsync(payload, w_in, m * 4, cudaMemcpyDeviceToDevice, s));
+  uint64_t* skeys = keys;
+  uint32_t* spay = pl;
+  int rc = sort_pairs_ex(m, abits + bbits, keys, pl, sws, sws_b, &skeys, pl ? &spay : nullptr, s);
+  if (rc) return rc;
+  rc = reduce_runs(m, skeys, spay, R, s);
+  if (rc) return rc;
+  k_emit_coarse<<<grid_for(m), 256, 0, s>>>(R.pos + m, R.ukeys, R.run_len, pl ? R.run_sum : nullptr, (1ull << bbits) - 1, ~0ull,
+                                            colidx, counts, wsum);
+  GDR_LAUNCHED();
+  k_rowptr_from_ukeys_range<<<grid_for(m + 1), 256, 0, s>>>(R.pos + m, a_lo, n_rows, bbits, R.ukeys, rowptr, nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
 }

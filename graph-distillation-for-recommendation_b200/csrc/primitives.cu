@@ -406,7 +406,11 @@ static int launch_rs_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t*
 // digit width: wide digits save passes, but a tile of T keys leaves runs of T / 2^bits keys per digit, and a run
 // is what one coalesced write covers: at most 9 bits for the 4096-key tiles of large sorts (runs of >= 8 keys =
 // two full 32-byte sectors), up to 11 for small ones (the whole output stays in L2)
-static inline int rs_max_bits(int64_t n) { return n >= (1ll << 21) ? 9 : RS_MAX_BITS; }
+int g_rs_max_bits = 0;   // gdr_debug_set("rs_max_bits", 9 | 10 | 11): digit width cap of large sorts (experiment)
+static inline int rs_max_bits(int64_t n) {
+  if (n < (1ll << 21)) return RS_MAX_BITS;
+  return (g_rs_max_bits >= 7 && g_rs_max_bits <= RS_MAX_BITS) ? g_rs_max_bits : 9;
+}
 
 int64_t sort_pairs_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
@@ -483,6 +487,67 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
       if (vals) GDR_CUDA(cudaMemcpyAsync(vals, vin, n * 4, cudaMemcpyDeviceToDevice, s));
     }
   }
+  return GDR_OK;
+}
+
+// first position of every digit value in the output of a pass: starts[d] = table_scanned[d * nblocks], starts[bins] = n
+__global__ void k_digit_starts(int bins, int nblocks, int64_t n, const int32_t* __restrict__ table_scanned,
+                               int64_t* __restrict__ starts) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < bins) starts[d] = table_scanned[(int64_t)d * nblocks];
+  if (d == bins) starts[d] = n;
+}
+
+// ONE stable pass on the `bits`-wide digit at `shift` (bits in 7..11): a stable partition into 2^bits buckets.
+// The result is left in the twin arrays of the workspace (*keys_sorted / *vals_sorted); starts_dev (nullable,
+// int64[2^bits + 1]) receives the first position of every bucket.
+int sort_pairs_digit(int64_t n, int shift, int bits, uint64_t* keys, uint32_t* vals, void* ws, int64_t ws_bytes,
+                     uint64_t** keys_sorted, uint32_t** vals_sorted, int64_t* starts_dev, cudaStream_t s,
+                     uint64_t* keys_dst, uint32_t* vals_dst) {
+  if (bits < 7 || bits > RS_MAX_BITS || !keys_sorted || (vals && !vals_sorted)) {
+    set_error("sort_pairs_digit: bad arguments");
+    return GDR_EINVAL;
+  }
+  if (ws_bytes < sort_pairs_ws_bytes(n) || n >= (1ll << 31)) {
+    set_error("sort_pairs_digit: workspace too small or n out of range");
+    return GDR_EWORKSPACE;
+  }
+  const int bins = 1 << bits;
+  if (n == 0) {
+    *keys_sorted = keys;
+    if (vals_sorted) *vals_sorted = vals;
+    if (starts_dev) GDR_CUDA(cudaMemsetAsync(starts_dev, 0, (bins + 1) * 8, s));
+    return GDR_OK;
+  }
+  const int rounds = rs_rounds(n);
+  const int64_t nb = cdiv(n, RS_THREADS * rounds);
+  const int64_t tbl = (int64_t)bins * nb;
+  Workspace W(ws, ws_bytes);
+  uint64_t* kalt = W.take<uint64_t>(n);
+  uint32_t* valt = W.take<uint32_t>(n);
+  if (keys_dst) kalt = keys_dst;      // explicit destination instead of the workspace twins
+  if (vals_dst) valt = vals_dst;
+  int32_t* table = W.take<int32_t>((int64_t)RS_MAX_BINS * nb + 1);
+  void* sws = W.take<char>(scan_ws_bytes((int64_t)RS_MAX_BINS * nb));
+  const size_t hist_smem = (size_t)bins * 4;
+  if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(keys, n, shift, bits, table, (int)nb);
+  else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(keys, n, shift, bits, table, (int)nb);
+  GDR_LAUNCHED();
+  int rc = exclusive_scan_i32(table, table, tbl, sws, scan_ws_bytes(tbl), s);
+  if (rc) return rc;
+  if (rounds == 16)
+    rc = vals ? launch_rs_scatter<16, true>(keys, vals, kalt, valt, n, shift, bits, table, nb, s)
+              : launch_rs_scatter<16, false>(keys, vals, kalt, nullptr, n, shift, bits, table, nb, s);
+  else
+    rc = vals ? launch_rs_scatter<4, true>(keys, vals, kalt, valt, n, shift, bits, table, nb, s)
+              : launch_rs_scatter<4, false>(keys, vals, kalt, nullptr, n, shift, bits, table, nb, s);
+  if (rc) return rc;
+  if (starts_dev) {
+    k_digit_starts<<<(unsigned)cdiv(bins + 1, 256), 256, 0, s>>>(bins, (int)nb, n, table, starts_dev);
+    GDR_LAUNCHED();
+  }
+  *keys_sorted = kalt;
+  if (vals_sorted) *vals_sorted = vals ? valt : nullptr;
   return GDR_OK;
 }
 

@@ -44,6 +44,7 @@ extern int g_lloyd_graph;         // lloyd.cu
 extern int g_tc_screen;           // kmeans_tc.cu
 extern int g_tc_gate;             // kmeans_tc.cu
 extern int g_rs_match;            // primitives.cu
+extern int g_rs_max_bits;         // primitives.cu
 extern int g_tc_ablate;
 }  // namespace gdr
 extern "C" int g_sparsify_batch_cap;   // sparsify.cu
@@ -443,6 +444,7 @@ int gdr_debug_set(const char* key, int value) {
   else if (!strcmp(key, "tc_ablate")) gdr::g_tc_ablate = value;
   else if (!strcmp(key, "tc_gate")) gdr::g_tc_gate = value;
   else if (!strcmp(key, "rs_match")) gdr::g_rs_match = value;
+  else if (!strcmp(key, "rs_max_bits")) gdr::g_rs_max_bits = value;
   else if (!strcmp(key, "sparsify_batch")) g_sparsify_batch_cap = value;
   else {
     gdr::set_error("debug_set: unknown key %s", key);

@@ -163,20 +163,24 @@ class Comm:
         return w if async_op else out
 
 
-    def all_to_all_rows(self, send: torch.Tensor, send_counts) -> Tuple[torch.Tensor, list]:
+    def all_to_all_rows(self, send: torch.Tensor, send_counts, recv_counts=None) -> Tuple[torch.Tensor, list]:
         """Variable all-to-all along dim 0: ``send`` holds the rows for rank 0, 1, ... back to back
-        (``send_counts[r]`` rows each).  Returns (received rows in source-rank order, recv_counts)."""
+        (``send_counts[r]`` rows each).  Returns (received rows in source-rank order, recv_counts); ``recv_counts`` of an
+        earlier exchange with the same counts can be passed in to skip the count exchange."""
         if self.dist is None or self.world == 1:
-            return send, [int(send.shape[0])]
-        sc = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=send.device)
-        rc = torch.empty_like(sc)
-        if self.backend == "nccl":
-            self.dist.all_to_all_single(rc, sc, group=self.group)
-        else:   # gloo has no all_to_all: gather the whole count matrix
-            mat = [torch.empty_like(sc) for _ in range(self.world)]
-            self.dist.all_gather(mat, sc, group=self.group)
-            rc = torch.stack([m[self.rank] for m in mat])
-        recv_counts = [int(c) for c in rc.tolist()]
+            n0 = int(send_counts[0])
+            return send[:n0], [n0]
+        if recv_counts is None:
+            sc = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=send.device)
+            rc = torch.empty_like(sc)
+            if self.backend == "nccl":
+                self.dist.all_to_all_single(rc, sc, group=self.group)
+            else:   # gloo has no all_to_all: gather the whole count matrix
+                mat = [torch.empty_like(sc) for _ in range(self.world)]
+                self.dist.all_gather(mat, sc, group=self.group)
+                rc = torch.stack([m[self.rank] for m in mat])
+            recv_counts = [int(c) for c in rc.tolist()]
+        send = send[: int(sum(int(c) for c in send_counts))]
         out = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         if self.backend == "nccl":
             self.dist.all_to_all_single(out, send, recv_counts, [int(c) for c in send_counts], group=self.group)
@@ -494,6 +498,47 @@ class CudaOps:
     # -- stage 4 --
     def label_counts(self, labels, n):
         return self._co.label_counts(labels, n)
+
+    def coarsen_route(self, A_local, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
+        """Local edges -> (cell key | owner << 56, weight) pairs grouped by the owner rank of the coarse row (one stable
+        partition pass, gdr_coarsen_route).  Returns (keys int64 [E], weights f32 [E] | None, pairs per owner); pairs of
+        dropped diagonal cells sit behind the last owner's and are not sent."""
+        n_dst = n if n_dst is None else n_dst
+        dev = labels_dst.device
+        if A_local is not None:
+            E, w = A_local.nnz, A_local.vals
+            args = (0, 0, A_local.shape[0], self.ptr(A_local.rowptr), self.ptr(A_local.colidx))
+            drop = 1
+        else:
+            E, w = int(src.numel()), None
+            args = (self.ptr(src), self.ptr(dst), 0, 0, 0)
+            drop = 0
+        keys = torch.empty(max(E, 1), dtype=torch.int64, device=dev)
+        w_out = torch.empty(max(E, 1), dtype=torch.float32, device=dev) if w is not None else None
+        starts = torch.zeros(129, dtype=torch.int64, device=dev)
+        ws = self.workspace(self._lib.query("gdr_coarsen_route_ws_bytes", E), dev)
+        self._lib.call("gdr_coarsen_route", E, *args, self.ptr(w), self.ptr(labels_src), self.ptr(labels_dst), int(n), int(n_dst),
+                       drop, int(world), self.ptr(keys), self.ptr(w_out), self.ptr(starts), self.ptr(ws), ws.numel(), self.stream())
+        st = starts.cpu().tolist()
+        return keys, w_out, [int(st[r + 1] - st[r]) for r in range(world)]
+
+    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None):
+        """Pairs received from every rank (source-rank order = global CSR order) -> CSR (rowptr, colidx, counts, wsum) of
+        the coarse rows [a_lo, a_lo + n_rows): stable sort by cell, run lengths, fp32 sums in that order."""
+        n_dst = n if n_dst is None else n_dst
+        m = int(keys.shape[0])
+        dev = keys.device
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        wsum = torch.empty(max(m, 1), dtype=torch.float32, device=dev) if w is not None else None
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = self.workspace(self._lib.query("gdr_coarse_merge_edges_ws_bytes", m), dev)
+        self._lib.call("gdr_coarse_merge_edges", m, self.ptr(keys) if m else 0, self.ptr(w) if (m and w is not None) else 0,
+                       int(a_lo), int(n_rows), int(n), int(n_dst), self.ptr(rowptr), self.ptr(colidx), self.ptr(counts),
+                       self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
+        k = int(nnz.item())
+        return rowptr, colidx[:k], counts[:k], (None if wsum is None else wsum[:k])
 
     def coarsen_records(self, A_local, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
         """Local edges -> sorted (cell, count, weight sum) records [m, 2] int64 (gdr_coarsen + gdr_coarse_records) and the
@@ -896,12 +941,15 @@ class DistKMeans:
 # ------------------------------------------------------------------------------------------
 # stage 4
 # ------------------------------------------------------------------------------------------
-def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None, replicate: bool = True):
+def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None, replicate: bool = True,
+                        merge: str = "route"):
     """graph_compress (clustgdd_agent_transduct.py:234-250) for a row-partitioned A_hat.
 
-    Every rank coarsens its local edges into sorted (cell, count, weight sum) runs; the runs are exchanged by KEY RANGE
-    (coarse row a -> rank a // ceil(n / world), all-to-all) and merged by their owner: integer counts are exact and
-    independent of the rank count, fp32 weight sums are added in source-rank order (deterministic).  O(local nnz) memory
+    ``merge="route"`` (default): every local edge is sent once, as a (cell key, weight) pair, to the owner of its coarse
+    row (a -> rank a // ceil(n / world); one stable partition pass + all-to-all); the owner sorts and reduces what it
+    receives.  The exchange order is the global CSR order, so counts AND weight sums are bit-identical to the single-device
+    result.  ``merge="records"``: every rank coarsens its local edges first and the (cell, count, sum) runs are exchanged and
+    merged (sums added in source-rank order: deterministic, 1e-5 from the single-device sums).  O(local nnz) memory
     on every rank, no n x n array anywhere (config E: n^2 = 10^8 cells).  With ``replicate`` (default) the pieces are
     all-gathered, and every rank returns the reference's result: (adj_syn torch sparse COO n x n, merged integer cell
     counts).  Without it: this rank's coarse rows as (a_lo, rowptr, colidx, vals, counts)."""
@@ -918,12 +966,21 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
     nmax = labels_all.max().to(torch.int64).reshape(1)
     n = int(comm.all_reduce(nmax, "max").item()) + 1
     sizes = ops.label_counts(labels_all, n)
-    rec, send_counts = ops.coarsen_records(A_local, labels_local.to(torch.int32).contiguous(), labels_all, n, world)
-    recv, _ = comm.all_to_all_rows(rec, send_counts)
     cr = (n + world - 1) // world
     a_lo = min(n, comm.rank * cr)
     n_rows = min(n, a_lo + cr) - a_lo
-    rowptr, colidx, counts, wsum = ops.coarse_merge(recv, a_lo, n_rows, n)
+    lab_l = labels_local.to(torch.int32).contiguous()
+    if merge == "route" and hasattr(ops, "coarsen_route"):
+        # every edge goes to the owner of its coarse row once; the owner sorts + reduces (one sort per edge, sums in CSR order)
+        keys, w, send_counts = ops.coarsen_route(A_local, lab_l, labels_all, n, world)
+        recv_k, rc = comm.all_to_all_rows(keys, send_counts)
+        recv_w, _ = comm.all_to_all_rows(w, send_counts, recv_counts=rc)
+        rowptr, colidx, counts, wsum = ops.coarse_merge_edges(recv_k, recv_w, a_lo, n_rows, n)
+    else:
+        # local coarsening first, then (cell, count, sum) records by key range: less traffic when cells repeat a lot locally
+        rec, send_counts = ops.coarsen_records(A_local, lab_l, labels_all, n, world)
+        recv, _ = comm.all_to_all_rows(rec, send_counts)
+        rowptr, colidx, counts, wsum = ops.coarse_merge(recv, a_lo, n_rows, n)
     vals = ops.coarse_scale(rowptr, colidx, wsum, sizes, a_lo, n_rows)
     if not replicate:
         return a_lo, rowptr, colidx, vals, counts
@@ -1066,13 +1123,19 @@ def dist_build_condensed_bipartite(comm: Comm, part_u: RowPartition, part_i: Row
         return full            # padded layout index == global id (equal contiguous blocks)
 
     mu, mi = gather_map(part_u, u2cu_local), gather_map(part_i, i2ci_local)
-    rec, send_counts = ops.coarsen_records(None, mu, mi, int(num_cu), world, n_dst=int(num_ci),
-                                           src=u_slice.to(torch.int64), dst=i_slice.to(torch.int64))
-    recv, _ = comm.all_to_all_rows(rec, send_counts)
     cr = (int(num_cu) + world - 1) // world
     a_lo = min(int(num_cu), comm.rank * cr)
     n_rows = min(int(num_cu), a_lo + cr) - a_lo
-    rowptr, colidx, counts, _ = ops.coarse_merge(recv, a_lo, n_rows, int(num_cu), n_dst=int(num_ci))
+    if hasattr(ops, "coarsen_route"):
+        keys, _, send_counts = ops.coarsen_route(None, mu, mi, int(num_cu), world, n_dst=int(num_ci),
+                                                 src=u_slice.to(torch.int64).contiguous(), dst=i_slice.to(torch.int64).contiguous())
+        recv_k, _ = comm.all_to_all_rows(keys, send_counts)
+        rowptr, colidx, counts, _ = ops.coarse_merge_edges(recv_k, None, a_lo, n_rows, int(num_cu), n_dst=int(num_ci))
+    else:
+        rec, send_counts = ops.coarsen_records(None, mu, mi, int(num_cu), world, n_dst=int(num_ci),
+                                               src=u_slice.to(torch.int64), dst=i_slice.to(torch.int64))
+        recv, _ = comm.all_to_all_rows(rec, send_counts)
+        rowptr, colidx, counts, _ = ops.coarse_merge(recv, a_lo, n_rows, int(num_cu), n_dst=int(num_ci))
     vals = counts.to(torch.float32)
     if not replicate:
         return a_lo, rowptr, colidx, vals

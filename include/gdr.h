@@ -505,6 +505,21 @@ int gdr_column_moments(int64_t N, int64_t D, const float* X, int64_t ldx, const 
                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
 int gdr_standardize_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean32, const float* scale32,
                           float* out, int64_t ldo, gdr_stream_t stream);
+/* stage 4 on a row partition, routing form (default): gdr_coarsen_route turns every local edge into a (cell key, weight)
+ * pair tagged with the owner rank of its coarse row (top byte of the key; dropped diagonal pairs: bucket 127) and groups
+ * the pairs by owner with ONE stable partition pass — keys_out / w_out sorted by owner, owner_starts_dev[0..128] the
+ * first pair of every owner.  After the all-to-all the owner runs gdr_coarse_merge_edges: sort + integer run lengths +
+ * fp32 sums in the exchange order, which is the global CSR order — counts AND sums are bit-identical to the
+ * single-device gdr_coarsen.  Output: CSR of the coarse rows [a_lo, a_lo + n_rows). */
+int64_t gdr_coarsen_route_ws_bytes(int64_t E);
+int     gdr_coarsen_route(int64_t E, const int64_t* src, const int64_t* dst, int64_t n_rows, const int32_t* csr_rowptr,
+                          const int32_t* csr_colidx, const float* w, const int32_t* labels_src, const int32_t* labels_dst,
+                          int64_t n_src, int64_t n_dst, int drop_diag, int world, uint64_t* keys_out, float* w_out,
+                          int64_t* owner_starts_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int64_t gdr_coarse_merge_edges_ws_bytes(int64_t m);
+int     gdr_coarse_merge_edges(int64_t m, const uint64_t* keys_in, const float* w_in, int64_t a_lo, int64_t n_rows,
+                               int64_t n_src, int64_t n_dst, int32_t* rowptr, int32_t* colidx, int32_t* counts,
+                               float* wsum, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
 /* gdr_kmeans_lloyd on a row partition: Xc_local = this rank's N_local rows (may be 0) of the mean-centred matrix of
  * N_total rows, centres replicated.  Each iteration all-reduces [K x ld sums | K counts | n_changed] inside the replayed
  * CUDA graph; the replicated centres stay bit-identical across ranks; empty clusters are relocated from the globally

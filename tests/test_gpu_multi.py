@@ -115,13 +115,17 @@ def _worker(rank, world, port):
         assert abs(km.inertia_ - ref.inertia_) <= 1e-4 * ref.inertia_
         # stage 4 (use the single-GPU labels so that the integer result is comparable bit for bit)
         labels = ref.labels_
-        adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops)
         _, syn1 = gdr.graph_compress(labels, A_full, [])
         kk = int(labels.max()) + 1
         _, _, cnt1, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_full, drop_diag=True)
-        assert torch.equal(adj_syn._indices(), syn1._indices())
-        assert torch.equal(counts, cnt1)
-        torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+        for merge in ("records", "route"):
+            adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
+                                                      merge=merge)
+            assert torch.equal(adj_syn._indices(), syn1._indices())
+            assert torch.equal(counts, cnt1)
+            torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+        # routing form: the exchange order is the global CSR order -> the weight sums are the single-GPU sums, bit for bit
+        assert torch.equal(adj_syn._values(), syn1._values())
         # not replicated: this rank's key range of the coarse rows
         a_lo, rp_p, ci_p, v_p, c_p = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
                                                              replicate=False)

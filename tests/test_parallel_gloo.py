@@ -203,6 +203,50 @@ class OracleOps:
             b += 1
         return b
 
+    def coarsen_route(self, A, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
+        n_dst = n if n_dst is None else n_dst
+        ls, ld = labels_src.numpy().astype(np.int64), labels_dst.numpy().astype(np.int64)
+        if A is not None:
+            rows = np.repeat(np.arange(A.shape[0]), np.diff(A.rowptr.numpy()))
+            a, b, w, drop = ls[rows], ld[A.colidx.numpy().astype(np.int64)], A.vals.numpy(), True
+        else:
+            a, b, w, drop = ls[src.numpy()], ld[dst.numpy()], None, False
+        cr = (n + world - 1) // world
+        owner = np.minimum(a // cr, world - 1)
+        if drop:
+            owner = np.where(a == b, 127, owner)
+        key = (owner << 56) | (a << self._bits(n_dst)) | b
+        order = np.argsort(owner, kind="stable")
+        counts = [int((owner == r).sum()) for r in range(world)]
+        return (torch.from_numpy(key[order]), None if w is None else torch.from_numpy(w[order].astype(np.float32)), counts)
+
+    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None):
+        n_dst = n if n_dst is None else n_dst
+        bb = self._bits(n_dst)
+        key = keys.numpy() & ((1 << 56) - 1)
+        order = np.argsort(key, kind="stable")
+        key = key[order]
+        head = np.ones(key.shape[0], bool)
+        head[1:] = key[1:] != key[:-1]
+        starts = np.flatnonzero(head)
+        ends = np.append(starts[1:], key.shape[0])
+        cnt = (ends - starts).astype(np.int32)
+        wsum = None
+        if w is not None:
+            ww = w.numpy()[order]
+            wsum = np.zeros(starts.shape[0], np.float32)
+            for p, (b0, e0) in enumerate(zip(starts, ends)):      # fp32, exchange order (what the kernel does)
+                acc = np.float32(0)
+                for j in range(b0, e0):
+                    acc = np.float32(acc + ww[j])
+                wsum[p] = acc
+        ukey = key[starts]
+        a = (ukey >> bb) - a_lo
+        rp = np.zeros(n_rows + 1, np.int64)
+        np.add.at(rp, a + 1, 1)
+        return (torch.from_numpy(np.cumsum(rp).astype(np.int32)), torch.from_numpy((ukey & ((1 << bb) - 1)).astype(np.int32)),
+                torch.from_numpy(cnt), None if wsum is None else torch.from_numpy(wsum))
+
     def coarsen_records(self, A, labels_src, labels_dst, n, world, n_dst=None, src=None, dst=None):
         n_dst = n if n_dst is None else n_dst
         if A is not None:
@@ -383,11 +427,13 @@ def _worker(rank, world, port, case):
         elif case == "coarsen":
             labels = np.random.RandomState(6).randint(0, 17, n).astype(np.int32)
             labels[labels == 11] = 10      # an empty cluster
-            adj_syn, counts = par.dist_graph_compress(comm, part, torch.from_numpy(labels[lo:hi].copy()), A_local, ops=ops)
             S = o.graph_compress_dense(labels.astype(np.int64), rpo, cio, vo, int(labels.max()) + 1)
-            got = adj_syn.to_dense().numpy()
             fin = np.isfinite(S)
-            np.testing.assert_allclose(got[fin], S[fin], rtol=1e-5, atol=1e-8)
+            for merge in ("records", "route"):
+                adj_syn, counts = par.dist_graph_compress(comm, part, torch.from_numpy(labels[lo:hi].copy()), A_local, ops=ops,
+                                                          merge=merge)
+                got = adj_syn.to_dense().numpy()
+                np.testing.assert_allclose(got[fin], S[fin], rtol=1e-5, atol=1e-8)
             rows = np.repeat(np.arange(n), np.diff(rpo))
             _, _, cnt_ref, _ = o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)
             assert np.array_equal(counts.numpy(), cnt_ref)          # integer cell counts, CSR order, independent of the rank count

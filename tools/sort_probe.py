@@ -14,9 +14,9 @@ u, v = synth.uniform_graph(n, cfg["pairs"], 1238)
 dev = torch.device("cuda:0")
 u_d, v_d = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
 from gdr import _lib
-for mode in ((0, 1) if reps > 1 else (0,)):
-  _lib.call("gdr_debug_set", b"rs_match", mode)
-  print("rs_match", mode)
+for mode in ((9, 10, 11) if reps > 1 else (9,)):
+  _lib.call("gdr_debug_set", b"rs_max_bits", mode)
+  print("rs_max_bits", mode)
   for r in range(reps):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
@@ -27,13 +27,13 @@ for mode in ((0, 1) if reps > 1 else (0,)):
     torch.cuda.synchronize()
     print(f"  rep {r}: coo_to_csr {e0.elapsed_time(e1):.3f} ms, sym_normalize {e1.elapsed_time(e2):.3f} ms, nnz {An.nnz}")
 lab = torch.from_numpy(np.random.RandomState(0).randint(0, cfg["k"], n).astype(np.int32)).to(dev)
-for mode in ((0, 1) if reps > 1 else (0,)):
-  _lib.call("gdr_debug_set", b"rs_match", mode)
+for mode in ((9, 10, 11) if reps > 1 else (9,)):
+  _lib.call("gdr_debug_set", b"rs_max_bits", mode)
   for r in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gdr.graph_compress(lab, An, [])
     e1.record()
     torch.cuda.synchronize()
-    print(f"  rs_match {mode} rep {r}: graph_compress {e0.elapsed_time(e1):.3f} ms")
-_lib.call("gdr_debug_set", b"rs_match", 0)
+    print(f"  rs_max_bits {mode} rep {r}: graph_compress {e0.elapsed_time(e1):.3f} ms")
+_lib.call("gdr_debug_set", b"rs_max_bits", 0)
