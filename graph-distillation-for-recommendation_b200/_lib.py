@@ -119,6 +119,10 @@ _SIGNATURES = {
     "gdr_sym_eig_jacobi_ws_bytes": (i64, [i64]),
     "gdr_sym_eig_jacobi": (i32, [i64, vp, vp, vp, vp, i32, C.c_double, vp, vp, i64, vp]),
     "gdr_dense_gather_cols": (i32, [i64, i64, vp, vp, vp, vp]),
+    "gdr_edges_route_ws_bytes": (i64, [i64, i32]),
+    "gdr_edges_route": (i32, [i64, vp, vp, i64, i64, i32, i64, i32, vp, vp, vp, vp, i64, vp]),
+    "gdr_csr_from_keys_ws_bytes": (i64, [i64]),
+    "gdr_csr_from_keys": (i32, [i64, vp, i64, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_route_ws_bytes": (i64, [i64]),
     "gdr_coarsen_route": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp]),
     "gdr_coarse_merge_edges_ws_bytes": (i64, [i64]),

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(UQ_THREADS) k_unique_emit_csr(int64_t n, int64
                                                                 const uint64_t* __restrict__ keys,
                                                                 const int32_t* __restrict__ tile_off /*[tiles + 1]*/,
                                                                 int32_t* __restrict__ rowptr, int32_t* __restrict__ colidx,
-                                                                float* __restrict__ vals, int64_t* __restrict__ nnz_out) {
+                                                                float* __restrict__ vals, int64_t* __restrict__ nnz_out,
+                                                                int32_t* __restrict__ head_pos /*nullable: sorted index of every head*/) {
   __shared__ int s_w[UQ_THREADS / 32];
   const int64_t base = (int64_t)blockIdx.x * UQ_TILE;
   const uint64_t cmask = (1ull << cbits) - 1ull;
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(UQ_THREADS) k_unique_emit_csr(int64_t n, int64
     if (head) {
       const int pos = run + woff + __popc(bal & ((1u << lane_id()) - 1u));
       colidx[pos] = (int32_t)(k & cmask);
-      vals[pos] = 1.0f;
+      if (head_pos) head_pos[pos] = (int32_t)i;
+      else vals[pos] = 1.0f;
       // rows (previous row, this row] start at this entry
       const int64_t r = (int64_t)(k >> cbits), rp = i == 0 ? -1 : (int64_t)(kp >> cbits);
       for (int64_t rr = rp + 1; rr <= r; ++rr) rowptr[rr] = pos;
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(UQ_THREADS) k_unique_emit_csr(int64_t n, int64
       const int total = run + tot;
       for (int64_t rr = (int64_t)(k >> cbits) + 1; rr <= n_rows; ++rr) rowptr[rr] = total;
       *nnz_out = total;
+      if (head_pos) head_pos[total] = (int32_t)n;
     }
     run += tot;
     __syncthreads();
@@ -619,6 +622,47 @@ __global__ void k_mask_keys(int64_t n, const uint64_t* __restrict__ in, uint64_t
     out[i] = in[i] & mask;
 }
 
+// vals[p] = multiplicity of the p-th unique key (duplicate COO lines summed: unit values, exact in fp32 up to 2^24)
+__global__ void k_run_length_vals(const int64_t* __restrict__ nnz_dev, const int32_t* __restrict__ head_pos,
+                                  float* __restrict__ vals) {
+  const int64_t m = *nnz_dev;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x)
+    vals[p] = (float)(head_pos[p + 1] - head_pos[p]);
+}
+
+// ---- multi-GPU stage 1, routing form: every (row, col) pair [and its mirror] becomes a key tagged with the owner rank of
+// its row in the top byte; one stable partition pass groups the keys by owner.  status bit 0: index out of range,
+// bit 1: the pair (0, 0) is present (the reference's `if mx[0, 0] == 0` rule needs to know).
+__global__ void k_pack_edge_route(int64_t E, int64_t n_rows, int64_t n_cols, const int64_t* __restrict__ row,
+                                  const int64_t* __restrict__ col, int symmetrize, int cbits, int64_t rows_per, int world,
+                                  uint64_t* __restrict__ keys, int32_t* __restrict__ status) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = row[e], c = col[e];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) {
+      atomicOr(status, 1);
+      r = 0;
+      c = 0;
+    } else if (r == 0 && c == 0) {
+      atomicOr(status, 2);
+    }
+    const uint64_t o1 = (uint64_t)min((int64_t)(world - 1), r / rows_per);
+    if (symmetrize) {
+      const uint64_t o2 = (uint64_t)min((int64_t)(world - 1), c / rows_per);
+      keys[2 * e] = (o1 << ROUTE_SHIFT) | ((uint64_t)r << cbits) | (uint64_t)c;
+      keys[2 * e + 1] = (o2 << ROUTE_SHIFT) | ((uint64_t)c << cbits) | (uint64_t)r;
+    } else {
+      keys[e] = (o1 << ROUTE_SHIFT) | ((uint64_t)r << cbits) | (uint64_t)c;
+    }
+  }
+}
+
+// received keys -> keys of the local row block: owner byte cleared, row made local
+__global__ void k_localise_keys(int64_t n, const uint64_t* __restrict__ in, uint64_t mask, uint64_t row_lo_shifted,
+                                uint64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (in[i] & mask) - row_lo_shifted;
+}
+
 // ---- key-range merge of per-rank coarsened graphs (multi-GPU stage 4) ----
 // cell key of every entry of a coarse CSR: (a << bbits) | b
 // 16-byte record per entry: [cell key | (count << 32) | weight-sum bits]
@@ -809,7 +853,7 @@ int gdr_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz_in, const int64_t
     rc = exclusive_scan_i32(tile_cnt, tile_cnt, tiles, R.scan_ws, R.scan_ws_b, s);
     if (rc) return rc;
     k_unique_emit_csr<<<(unsigned)tiles, UQ_THREADS, 0, s>>>(n, n_rows, cbits, skeys, tile_cnt, rowptr, colidx, vals,
-                                                            nnz_out_dev);
+                                                            nnz_out_dev, nullptr);
     GDR_LAUNCHED();
     return GDR_OK;
   }
@@ -1124,6 +1168,94 @@ int gdr_csr_to_coo(int64_t n_rows, const int32_t* rowptr, const int32_t* colidx,
   k_csr_to_coo<<<grid_for(n_rows * 32), 256, 0, (cudaStream_t)stream>>>(n_rows, rowptr, colidx, row_out,
                                                                        col_out);
   GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- routing form of the multi-GPU stage 1 ----------------
+int64_t gdr_edges_route_ws_bytes(int64_t E, int symmetrize) {
+  const int64_t n = E * (symmetrize ? 2 : 1);
+  if (n <= 0) return 256;
+  return ws_need(n, 8) + sort_pairs_ws_bytes(n) + 512;
+}
+
+int gdr_edges_route(int64_t E, const int64_t* row, const int64_t* col, int64_t n_rows, int64_t n_cols, int symmetrize,
+                    int64_t rows_per, int world, uint64_t* keys_out, int64_t* owner_starts_dev, int32_t* status_dev, void* ws,
+                    int64_t ws_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(E >= 0 && n_rows > 0 && n_cols > 0 && rows_per > 0 && world >= 1 && world < ROUTE_DROP && owner_starts_dev &&
+                    status_dev,
+                "edges_route: bad arguments");
+  GDR_CHECK_ARG(!symmetrize || n_rows == n_cols, "edges_route: symmetrize needs a square matrix");
+  const int64_t n = E * (symmetrize ? 2 : 1);
+  GDR_CHECK_ARG(n < (1ll << 31) && bits_for(n_rows) + bits_for(n_cols) <= ROUTE_SHIFT, "edges_route: size out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  GDR_CUDA(cudaMemsetAsync(status_dev, 0, 4, s));
+  if (n == 0) {
+    GDR_CUDA(cudaMemsetAsync(owner_starts_dev, 0, 129 * 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(row && col && keys_out, "edges_route: null pointer");
+  if (ws_bytes < gdr_edges_route_ws_bytes(E, symmetrize)) {
+    set_error("edges_route: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(n);
+  const int64_t sws_b = sort_pairs_ws_bytes(n);
+  void* sws = W.take<char>(sws_b);
+  k_pack_edge_route<<<grid_for(E), 256, 0, s>>>(E, n_rows, n_cols, row, col, symmetrize, bits_for(n_cols), rows_per, world, keys,
+                                                status_dev);
+  GDR_LAUNCHED();
+  uint64_t* ks = nullptr;
+  return sort_pairs_digit(n, ROUTE_SHIFT, 7, keys, nullptr, sws, sws_b, &ks, nullptr, owner_starts_dev, s, keys_out, nullptr);
+}
+
+int64_t gdr_csr_from_keys_ws_bytes(int64_t m) {
+  m = m > 0 ? m : 1;
+  return ws_need(m, 8) + sort_pairs_ws_bytes(m) + runs_ws_bytes(m, false) + 512;
+}
+
+// keys received from every rank -> CSR of the local rows [row_lo, row_lo + n_rows_local), columns global.
+// binarize = 1: all values 1 (utils_graphsaint.py:20-22); 0: value = number of equal pairs (distill_recsys.py:110-117).
+int gdr_csr_from_keys(int64_t m, const uint64_t* keys_in, int64_t row_lo, int64_t n_rows_local, int64_t n_cols, int binarize,
+                      int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes,
+                      gdr_stream_t stream) {
+  GDR_CHECK_ARG(m >= 0 && row_lo >= 0 && n_rows_local >= 0 && n_cols > 0 && rowptr && nnz_out_dev, "csr_from_keys: bad arguments");
+  GDR_CHECK_ARG(m < (1ll << 31), "csr_from_keys: size exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0 || n_rows_local == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_rows_local + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(keys_in && colidx && vals, "csr_from_keys: null pointer");
+  if (ws_bytes < gdr_csr_from_keys_ws_bytes(m)) {
+    set_error("csr_from_keys: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(m);
+  const int64_t sws_b = sort_pairs_ws_bytes(m);
+  void* sws = W.take<char>(sws_b);
+  RunBuffers R = carve_runs(W, m, false);
+  const int cbits = bits_for(n_cols), rbits = bits_for(n_rows_local);
+  k_localise_keys<<<grid_for(m), 256, 0, s>>>(m, keys_in, (1ull << ROUTE_SHIFT) - 1ull, (uint64_t)row_lo << cbits, keys);
+  GDR_LAUNCHED();
+  uint64_t* skeys = keys;
+  int rc = sort_pairs_ex(m, rbits + cbits, keys, nullptr, sws, sws_b, &skeys, nullptr, s);
+  if (rc) return rc;
+  const int64_t tiles = cdiv(m, UQ_TILE);
+  int32_t* tile_cnt = R.pos;
+  k_unique_count<<<(unsigned)tiles, UQ_THREADS, 0, s>>>(m, skeys, tile_cnt);
+  GDR_LAUNCHED();
+  rc = exclusive_scan_i32(tile_cnt, tile_cnt, tiles, R.scan_ws, R.scan_ws_b, s);
+  if (rc) return rc;
+  k_unique_emit_csr<<<(unsigned)tiles, UQ_THREADS, 0, s>>>(m, n_rows_local, cbits, skeys, tile_cnt, rowptr, colidx, vals,
+                                                          nnz_out_dev, binarize ? nullptr : R.head_index);
+  GDR_LAUNCHED();
+  if (!binarize) {
+    k_run_length_vals<<<grid_for(m), 256, 0, s>>>(nnz_out_dev, R.head_index, vals);
+    GDR_LAUNCHED();
+  }
   return GDR_OK;
 }
 

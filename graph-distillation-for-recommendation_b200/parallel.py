@@ -232,6 +232,35 @@ class CudaOps:
         self._tc = None
 
     # -- stage 1 --
+    def edges_route(self, row, col, n_rows, n_cols, rows_per, world, symmetrize):
+        """This rank's (row, col) pairs [and their mirrors] -> keys (row << bits(n_cols)) | col tagged with the owner of the
+        row, grouped by owner with one stable partition pass (gdr_edges_route).  Returns (keys int64, keys per owner,
+        status: bit 0 = index out of range, bit 1 = the pair (0, 0) occurs)."""
+        E = int(row.numel())
+        dev = row.device
+        m = E * (2 if symmetrize else 1)
+        keys = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+        meta = torch.zeros(130, dtype=torch.int64, device=dev)        # [owner starts 0..128 | status]
+        ws = self.workspace(self._lib.query("gdr_edges_route_ws_bytes", E, int(symmetrize)), dev)
+        self._lib.call("gdr_edges_route", E, self.ptr(row), self.ptr(col), int(n_rows), int(n_cols), int(symmetrize), int(rows_per),
+                       int(world), self.ptr(keys), self.ptr(meta), self.ptr(meta[129:]), self.ptr(ws), ws.numel(), self.stream())
+        h = meta.cpu().tolist()
+        return keys, [int(h[r + 1] - h[r]) for r in range(world)], int(h[129]) & 0xFFFFFFFF
+
+    def csr_from_keys(self, keys, row_lo, n_local, n_cols, binarize):
+        """Keys received from every rank -> CSR of the local row block (gdr_csr_from_keys: keys-only sort + two-pass emit)."""
+        m = int(keys.shape[0])
+        dev = keys.device
+        rowptr = torch.empty(n_local + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = self.workspace(self._lib.query("gdr_csr_from_keys_ws_bytes", m), dev)
+        self._lib.call("gdr_csr_from_keys", m, self.ptr(keys) if m else 0, int(row_lo), int(n_local), int(n_cols), int(binarize),
+                       self.ptr(rowptr), self.ptr(colidx), self.ptr(vals), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
+        k = int(nnz.item())
+        return self._g.CSR(rowptr, colidx[:k], vals[:k], (n_local, n_cols))
+
     def bucket_by_owner(self, src, dst, rows_per, world):
         """Edges (src, dst) reordered so that the edges of owner 0, 1, ... (owner = src // rows_per) are
         contiguous; returns ([E, 2] int64 rows, per-owner counts).  Stable radix sort on the owner id."""
@@ -618,23 +647,40 @@ def dist_build_adjacency(comm: Comm, part: RowPartition, u_slice: torch.Tensor, 
     vector — normalises them (deep_robust_utils.py:180-207).  Returns the local rows of A_hat with global
     column ids; the block is bit-identical to the same rows of the single-device build."""
     ops = ops or CudaOps()
-    src = torch.cat([u_slice, v_slice]).to(torch.int64)
-    dst = torch.cat([v_slice, u_slice]).to(torch.int64)
-    if src.numel() and (int(src.min()) < 0 or int(src.max()) >= n):
-        raise ValueError("row/col index exceeds matrix dimensions")
-    # reference rule `if mx[0, 0] == 0: mx = mx + I`: a global decision
-    if self_loop_mode == 2:
-        has00 = ((src == 0) & (dst == 0)).any().to(torch.int64).reshape(1)
-        add_identity = int(comm.all_reduce(has00, "max").item()) == 0
-    else:
-        add_identity = bool(self_loop_mode)
-    edges, counts = ops.bucket_by_owner(src, dst, part.rows_per, part.world)
-    recv, _ = comm.all_to_all_rows(edges, counts)
     sizes = [part.bounds(r)[1] - part.bounds(r)[0] for r in range(part.world)]
-    if part.n_local == 0:   # a rank past the end of a short matrix still joins the collectives
-        comm.all_gather_var(torch.zeros(0, dtype=torch.float64, device=src.device), sizes)
-        return None
-    A_blk = ops.build_block_csr(recv[:, 0] - part.lo, recv[:, 1], part.n_local, n)
+    if hasattr(ops, "edges_route"):
+        # routing form: pack + one partition pass in the library, 8-byte keys over the wire, keys-only sort at the owner
+        keys, counts, status = ops.edges_route(u_slice.to(torch.int64).contiguous(), v_slice.to(torch.int64).contiguous(), n, n,
+                                               part.rows_per, part.world, True)
+        if status & 1:
+            raise ValueError("row/col index exceeds matrix dimensions")
+        if self_loop_mode == 2:    # reference rule `if mx[0, 0] == 0: mx = mx + I`: a global decision
+            has00 = torch.tensor([1 if status & 2 else 0], dtype=torch.int64, device=u_slice.device)
+            add_identity = int(comm.all_reduce(has00, "max").item()) == 0
+        else:
+            add_identity = bool(self_loop_mode)
+        recv, _ = comm.all_to_all_rows(keys, counts)
+        if part.n_local == 0:   # a rank past the end of a short matrix still joins the collectives
+            comm.all_gather_var(torch.zeros(0, dtype=torch.float64, device=u_slice.device), sizes)
+            return None
+        A_blk = ops.csr_from_keys(recv, part.lo, part.n_local, n, True)
+    else:
+        src = torch.cat([u_slice, v_slice]).to(torch.int64)
+        dst = torch.cat([v_slice, u_slice]).to(torch.int64)
+        if src.numel() and (int(src.min()) < 0 or int(src.max()) >= n):
+            raise ValueError("row/col index exceeds matrix dimensions")
+        # reference rule `if mx[0, 0] == 0: mx = mx + I`: a global decision
+        if self_loop_mode == 2:
+            has00 = ((src == 0) & (dst == 0)).any().to(torch.int64).reshape(1)
+            add_identity = int(comm.all_reduce(has00, "max").item()) == 0
+        else:
+            add_identity = bool(self_loop_mode)
+        edges, counts = ops.bucket_by_owner(src, dst, part.rows_per, part.world)
+        recv, _ = comm.all_to_all_rows(edges, counts)
+        if part.n_local == 0:   # a rank past the end of a short matrix still joins the collectives
+            comm.all_gather_var(torch.zeros(0, dtype=torch.float64, device=src.device), sizes)
+            return None
+        A_blk = ops.build_block_csr(recv[:, 0] - part.lo, recv[:, 1], part.n_local, n)
     deg_local, rowptr_out = ops.block_degrees(A_blk, part.lo, add_identity)
     deg = comm.all_gather_var(deg_local, sizes)
     return ops.block_fill(A_blk, part.lo, add_identity, deg, rowptr_out)
@@ -1036,6 +1082,14 @@ def dist_build_interaction(comm: Comm, part_u: RowPartition, part_i: RowPartitio
     i = i_slice.to(torch.int64)
     if u.numel() and (int(u.min()) < 0 or int(u.max()) >= nu or int(i.min()) < 0 or int(i.max()) >= ni):
         raise ValueError("row/col index exceeds matrix dimensions")
+    if hasattr(ops, "edges_route"):
+        ku, cu, st_u = ops.edges_route(u.contiguous(), i.contiguous(), nu, ni, part_u.rows_per, part_u.world, False)
+        recv_u, _ = comm.all_to_all_rows(ku, cu)
+        R_local = ops.csr_from_keys(recv_u, part_u.lo, part_u.n_local, ni, False)
+        ki, ci, _ = ops.edges_route(i.contiguous(), u.contiguous(), ni, nu, part_i.rows_per, part_i.world, False)
+        recv_i, _ = comm.all_to_all_rows(ki, ci)
+        RT_local = ops.csr_from_keys(recv_i, part_i.lo, part_i.n_local, nu, False)
+        return R_local, RT_local
     e_u, c_u = ops.bucket_by_owner(u, i, part_u.rows_per, part_u.world)
     recv_u, _ = comm.all_to_all_rows(e_u, c_u)
     R_local = ops.build_block_csr_weighted(recv_u[:, 0] - part_u.lo, recv_u[:, 1], part_u.n_local, ni)

@@ -505,6 +505,20 @@ int gdr_column_moments(int64_t N, int64_t D, const float* X, int64_t ldx, const 
                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
 int gdr_standardize_apply(int64_t N, int64_t D, const float* X, int64_t ldx, const float* mean32, const float* scale32,
                           float* out, int64_t ldo, gdr_stream_t stream);
+/* stage 1 on a row partition, routing form (utils.py:66-67, utils_graphsaint.py:20-22, distill_recsys.py:110-117 from a
+ * SLICE of the pair list per rank): gdr_edges_route packs every pair (and its mirror when symmetrize) into a key
+ * (row << bits(n_cols)) | col tagged with the owner rank of the row (row / rows_per) in the top byte and groups the keys by
+ * owner with one stable partition pass; owner_starts_dev[0..128] = first key of every owner; status bit 0 = index out of
+ * range, bit 1 = the pair (0, 0) occurs (deep_robust_utils.py:199).  After the all-to-all gdr_csr_from_keys sorts the keys
+ * a rank received and emits the CSR of its row block (binarised, or with the multiplicity of every pair as value). */
+int64_t gdr_edges_route_ws_bytes(int64_t E, int symmetrize);
+int     gdr_edges_route(int64_t E, const int64_t* row, const int64_t* col, int64_t n_rows, int64_t n_cols, int symmetrize,
+                        int64_t rows_per, int world, uint64_t* keys_out, int64_t* owner_starts_dev, int32_t* status_dev,
+                        void* ws, int64_t ws_bytes, gdr_stream_t stream);
+int64_t gdr_csr_from_keys_ws_bytes(int64_t m);
+int     gdr_csr_from_keys(int64_t m, const uint64_t* keys_in, int64_t row_lo, int64_t n_rows_local, int64_t n_cols,
+                          int binarize, int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out_dev, void* ws,
+                          int64_t ws_bytes, gdr_stream_t stream);
 /* stage 4 on a row partition, routing form (default): gdr_coarsen_route turns every local edge into a (cell key, weight)
  * pair tagged with the owner rank of its coarse row (top byte of the key; dropped diagonal pairs: bucket 127) and groups
  * the pairs by owner with ONE stable partition pass — keys_out / w_out sorted by owner, owner_starts_dev[0..128] the

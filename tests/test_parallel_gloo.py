@@ -33,6 +33,31 @@ class OracleOps:
         self.o = o
 
     # -- stage 1 (block build): numpy restatement of the block kernels, tests only --
+    def edges_route(self, row, col, n_rows, n_cols, rows_per, world, symmetrize):
+        r, c = row.numpy().astype(np.int64), col.numpy().astype(np.int64)
+        status = 0
+        if r.size and (r.min() < 0 or r.max() >= n_rows or c.min() < 0 or c.max() >= n_cols):
+            status |= 1
+        if ((r == 0) & (c == 0)).any():
+            status |= 2
+        cb = self._bits(n_cols)
+        if symmetrize:
+            rr = np.stack([r, c], axis=1).reshape(-1)          # interleaved: pair, mirror, pair, mirror ...
+            cc = np.stack([c, r], axis=1).reshape(-1)
+        else:
+            rr, cc = r, c
+        owner = np.minimum(rr // rows_per, world - 1)
+        key = (owner << 56) | (rr << cb) | cc
+        order = np.argsort(owner, kind="stable")
+        return torch.from_numpy(key[order]), [int((owner == w).sum()) for w in range(world)], status
+
+    def csr_from_keys(self, keys, row_lo, n_local, n_cols, binarize):
+        cb = self._bits(n_cols)
+        key = keys.numpy() & ((1 << 56) - 1)
+        rows, cols = (key >> cb) - row_lo, key & ((1 << cb) - 1)
+        rp, ci, va = self.o.coo_to_csr(rows, cols, None, (n_local, n_cols), symmetrize=False, binarize=bool(binarize))
+        return CpuCSR(torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va), (n_local, n_cols))
+
     def bucket_by_owner(self, src, dst, rows_per, world):
         owner = (src // rows_per).numpy()
         order = np.argsort(owner, kind="stable")
