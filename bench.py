@@ -1043,8 +1043,12 @@ def run_ours_multi(args, rank, world, dev, w):
         e = [ev() for _ in range(5)]
         e[0].record()
         # the feature rows start travelling to the peers' gathered operand (side stream, NVLink) under stage 1
-        pre = par.prefetch_rows(comm, part, x_local, ops=ops) if args.hop in ("auto", "p2p") and not args.no_prefetch else None
-        A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops)   # exchange-based: 1/world of the pairs per rank
+        # (started right after stage 1's own all-to-all so that the two do not share the links)
+        box = []
+        hook = (lambda: box.append(par.prefetch_rows(comm, part, x_local, ops=ops))) \
+            if args.hop in ("auto", "p2p") and not args.no_prefetch else None
+        A_local = par.dist_build_adjacency(comm, part, u_sl, v_sl, n, ops=ops, after_exchange=hook)   # 1/world of the pairs per rank
+        pre = box[0] if box else None
         e[1].record()
         prop, target = par.dist_propagate(comm, part, A_local, x_local, hops + 1, ALPHA, ops=ops, slabs=args.slabs,
                                           row_chunks=args.row_chunks, hop=args.hop, prefetched=pre)
@@ -1114,7 +1118,7 @@ def run_ours_multi(args, rank, world, dev, w):
     del target_l, A_local
     C0_host = C0.cpu()
     e2e_t = []
-    for i in range(max(3, min(args.steps, 5))):
+    for i in range(max(4, min(args.steps, 8))):
         flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
@@ -1127,6 +1131,7 @@ def run_ours_multi(args, rank, world, dev, w):
         tt = torch.tensor([time.perf_counter() - t0e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_t.append((float(tt.item()), km.n_iter_))
+    e2e_reps_ms = [round(t * 1e3, 3) for t, _ in e2e_t]
     e2e_t = e2e_t[1:]
     e2e_val = float(sum(k for _, k in e2e_t) / sum(t for t, _ in e2e_t))
 
@@ -1140,7 +1145,7 @@ def run_ours_multi(args, rank, world, dev, w):
                     "traffic": None, "peak_source": pk["src"] + " bf16 sustained", "launch_ms": assign_ms,
                     "note": "useful flops 2*(N/world)*K*D per E-step over the slowest rank's screen time; fp32 inputs run as TF32"}
         e2e = {"value": e2e_val, "unit": "iters/s", "h2d_bytes_per_step": n * F * 4 + world * K * F * 4,
-               "d2h_bytes_per_step": n * 4 + world * K * F * 4}
+               "d2h_bytes_per_step": n * 4 + world * K * F * 4, "reps_ms": e2e_reps_ms}
         prop_model = "gather" if n * F * 4 > 96e6 else "min"   # SURVEY §8(d) headline rule
         b_prop = hops * spmm_bytes(nnz, n, n, F, model=prop_model) + 2 * n * F * 4
         prop_gbs = float(b_prop / (prop_ms.mean() / 1e3) / 1e9)

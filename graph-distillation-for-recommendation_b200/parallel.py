@@ -204,6 +204,24 @@ class Comm:
         """Concatenation of every rank's 1-D ``local`` (``counts[r]`` elements from rank r)."""
         if self.dist is None or self.world == 1:
             return local
+        if self.backend == "nccl" and local.is_cuda:
+            # straight into place: one grouped send / recv set inside the library (gdr_alltoallv with the same block for
+            # every peer), no padding to the largest piece and no concatenation pass
+            import ctypes
+            from . import _lib
+            w = self.world
+            arr = ctypes.c_int64 * w
+            offs, tot = [], 0
+            for c in counts:
+                offs.append(tot)
+                tot += int(c)
+            out = torch.empty(tot, dtype=local.dtype, device=local.device)
+            src = local.contiguous()
+            so, sc = arr(*([0] * w)), arr(*([int(src.shape[0])] * w))
+            ro, rc = arr(*offs), arr(*[int(c) for c in counts])
+            _lib.call("gdr_alltoallv", self.lib_handle(), src.data_ptr(), ctypes.addressof(so), ctypes.addressof(sc), out.data_ptr(),
+                      ctypes.addressof(ro), ctypes.addressof(rc), src.element_size(), torch.cuda.current_stream().cuda_stream)
+            return out
         m = max(int(c) for c in counts)
         block = torch.zeros(m, dtype=local.dtype, device=local.device)
         block[: local.shape[0]] = local
@@ -639,13 +657,15 @@ def build_local_adjacency(u, v, n: int, part: RowPartition, device):
 
 
 def dist_build_adjacency(comm: Comm, part: RowPartition, u_slice: torch.Tensor, v_slice: torch.Tensor, n: int, ops=None,
-                         self_loop_mode: int = 2):
+                         self_loop_mode: int = 2, after_exchange=None):
     """Stage 1 on a row partition: every rank holds a SLICE of the undirected pair list
     (utils_graphsaint.py:18-22 symmetrises it: adj + adj.T, values clipped to 1).  Each rank emits both
     directions of its pairs, buckets them by the owner of the source row, exchanges the buckets
     (all-to-all), builds the binarised CSR of its own rows, and — after an all-gather of the degree
     vector — normalises them (deep_robust_utils.py:180-207).  Returns the local rows of A_hat with global
-    column ids; the block is bit-identical to the same rows of the single-device build."""
+    column ids; the block is bit-identical to the same rows of the single-device build.
+    ``after_exchange``: called once the all-to-all of the keys has been enqueued — the place to start work that wants
+    the NVLink fabric for itself (``prefetch_rows``) while the local sort / CSR emit runs."""
     ops = ops or CudaOps()
     sizes = [part.bounds(r)[1] - part.bounds(r)[0] for r in range(part.world)]
     if hasattr(ops, "edges_route"):
@@ -660,6 +680,8 @@ def dist_build_adjacency(comm: Comm, part: RowPartition, u_slice: torch.Tensor, 
         else:
             add_identity = bool(self_loop_mode)
         recv, _ = comm.all_to_all_rows(keys, counts)
+        if after_exchange is not None:
+            after_exchange()
         if part.n_local == 0:   # a rank past the end of a short matrix still joins the collectives
             comm.all_gather_var(torch.zeros(0, dtype=torch.float64, device=u_slice.device), sizes)
             return None
