@@ -102,6 +102,7 @@ _SIGNATURES = {
     "gdr_symm_info": (i32, [vp, vp, vp]),
     "gdr_symm_barrier": (i32, [vp, vp]),
     "gdr_symm_put_rows": (i32, [vp, i64, vp, i64, i64, i32, vp]),
+    "gdr_symm_scatterv": (i32, [vp, vp, vp, vp, vp, i64, vp]),
     "gdr_spmm_prop_mc": (i32, [vp, i64, i64, i64, i64, i64, vp, vp, vp, f32, vp, i64, vp, i64, vp, i64, f32, vp, i64, vp]),
     "gdr_kmeans_lloyd_dist": (i32, [vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i32, C.c_double, i32, vp, vp, vp, i32, vp,
                                     i64, vp]),

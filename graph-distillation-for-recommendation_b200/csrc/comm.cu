@@ -156,6 +156,46 @@ __global__ void k_symm_put_rows(int64_t n4, const float4* __restrict__ src, PutD
   }
 }
 
+// Variable scatter into the peers' copies: segment p = n_words[p] 4-byte words from src[p] to dst[p] (a peer-mapped
+// address, 4-byte aligned).  Per segment: scalar head up to the first 16-byte boundary of the DESTINATION, 16-byte posted
+// stores for the body (the source side is read as one 16-byte or four 4-byte loads), scalar tail.  Block b starts with
+// segment (first + b) % n so that the ranks do not all pour into the same peer at the same time.
+struct ScatterSegs {
+  const uint32_t* src[GDR_MAX_RANKS];
+  uint32_t* dst[GDR_MAX_RANKS];
+  int64_t n_words[GDR_MAX_RANKS];
+  int n, first;
+};
+__global__ void __launch_bounds__(256) k_symm_scatterv(ScatterSegs sg) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int j = 0; j < sg.n; ++j) {
+    const int p = (sg.first + (int)(blockIdx.x % (unsigned)sg.n) + j) % sg.n;
+    const uint32_t* __restrict__ s = sg.src[p];
+    uint32_t* __restrict__ d = sg.dst[p];
+    const int64_t n = sg.n_words[p];
+    if (n <= 0) continue;
+    const int64_t h0 = (int64_t)(((16 - ((uintptr_t)d & 15)) & 15) >> 2), head = h0 < n ? h0 : n;
+    const int64_t body = (n - head) >> 2, tail0 = head + (body << 2);
+    if (tid < head) d[tid] = __ldg(s + tid);
+    if (tid < n - tail0) d[tail0 + tid] = __ldg(s + tail0 + tid);
+    const uint32_t* sb = s + head;
+    uint4* db = reinterpret_cast<uint4*>(d + head);
+    if (((uintptr_t)sb & 15) == 0) {
+      const uint4* sv = reinterpret_cast<const uint4*>(sb);
+      for (int64_t i = tid; i < body; i += nth) db[i] = __ldg(sv + i);
+    } else if (((uintptr_t)sb & 7) == 0) {
+      const uint2* sv = reinterpret_cast<const uint2*>(sb);
+      for (int64_t i = tid; i < body; i += nth) {
+        const uint2 a = __ldg(sv + 2 * i), b = __ldg(sv + 2 * i + 1);
+        db[i] = make_uint4(a.x, a.y, b.x, b.y);
+      }
+    } else {
+      for (int64_t i = tid; i < body; i += nth)
+        db[i] = make_uint4(__ldg(sb + 4 * i), __ldg(sb + 4 * i + 1), __ldg(sb + 4 * i + 2), __ldg(sb + 4 * i + 3));
+    }
+  }
+}
+
 int symm_barrier(gdr_symm* sm, cudaStream_t s) {
   if (sm->comm->world == 1) return GDR_OK;
   const uint32_t e = ++sm->epoch;
@@ -368,6 +408,33 @@ int gdr_symm_put_rows(gdr_symm_t* sm, int64_t dst_offset_bytes, const float* src
   const int64_t n4 = rows * ld / 4;
   const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n4, 256), kSMs * 8);
   k_symm_put_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(n4, (const float4*)src, d);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int gdr_symm_scatterv(gdr_symm_t* sm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,
+                      const int64_t* dst_off_bytes_host, int64_t elem_bytes, gdr_stream_t stream) {
+  GDR_CHECK_ARG(sm && send_off_host && send_cnt_host && dst_off_bytes_host && elem_bytes > 0 && elem_bytes % 4 == 0,
+                "symm_scatterv: bad arguments (elements are multiples of 4 bytes)");
+  const int world = sm->comm->world;
+  ScatterSegs sg;
+  sg.n = world;
+  sg.first = (sm->comm->rank + 1) % world;
+  int64_t total = 0;
+  for (int p = 0; p < world; ++p) {
+    const int64_t cnt = send_cnt_host[p];
+    GDR_CHECK_ARG(cnt >= 0 && send_off_host[p] >= 0 && dst_off_bytes_host[p] >= 0 && dst_off_bytes_host[p] % 4 == 0,
+                  "symm_scatterv: bad segment");
+    GDR_CHECK_ARG(dst_off_bytes_host[p] + cnt * elem_bytes <= sm->bytes, "symm_scatterv: destination range exceeds the buffer");
+    sg.src[p] = reinterpret_cast<const uint32_t*>((const char*)send + send_off_host[p] * elem_bytes);
+    sg.dst[p] = reinterpret_cast<uint32_t*>(sm->peer[p] + dst_off_bytes_host[p]);
+    sg.n_words[p] = cnt * (elem_bytes / 4);
+    total += sg.n_words[p];
+  }
+  if (total == 0) return GDR_OK;
+  GDR_CHECK_ARG(send && ((uintptr_t)send & 3) == 0, "symm_scatterv: send misaligned");
+  const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(total / 4 + 1, 256), 1), kSMs * 8);
+  k_symm_scatterv<<<grid, 256, 0, (cudaStream_t)stream>>>(sg);
   GDR_LAUNCHED();
   return GDR_OK;
 }

@@ -127,6 +127,67 @@ class Comm:
         self._symm = (h, int(ptr.value), int(size.value))
         return h, int(ptr.value)
 
+    def count_matrix(self, send_counts, device):
+        """cnt[src][dst] = rows rank src sends to rank dst, on every rank (one small all-gather + read-back)."""
+        sc = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=device)
+        mat = torch.empty(self.world * self.world, dtype=torch.int64, device=device)
+        self.all_gather_rows(sc, mat)
+        return mat.view(self.world, self.world).tolist()
+
+    def symm_ok(self) -> bool:
+        """True when exchanges can go through peer memory (NCCL process group on CUDA, peer access not found broken)."""
+        return self.dist is not None and self.world > 1 and self.backend == "nccl" and not _P2P_BROKEN \
+            and getattr(self, "use_symm_exchange", True)
+
+    def symm_exchange(self, arrays, cnt_mat):
+        """Variable all-to-all of several arrays with the SAME row split, through the symmetric buffer (gdr_symm_scatterv:
+        one kernel of posted NVLink stores per array, two stream-ordered barriers in all; no NCCL).  ``arrays[a]`` holds
+        the rows for rank 0, 1, ... back to back; ``cnt_mat[src][dst]`` = rows rank src sends to rank dst (known to every
+        rank).  Returns the received rows (source-rank order) as VIEWS of the symmetric buffer — valid until the next
+        exchange or fused propagation on this communicator; clone what has to live longer."""
+        return self._symm_exchange(arrays, cnt_mat, gather=False)
+
+    def all_gather_symm(self, arrays, counts):
+        """Concatenation over the ranks of every rank's 1-D block (``counts[r]`` rows from rank r), same transport."""
+        w = self.world
+        return self._symm_exchange(arrays, [[int(counts[s])] * w for s in range(w)], gather=True)
+
+    def _symm_exchange(self, arrays, cnt_mat, gather):
+        import ctypes
+        from . import _lib
+        w, me = self.world, self.rank
+        tot = [sum(int(cnt_mat[s][d]) for s in range(w)) for d in range(w)]
+        recv_off = [sum(int(cnt_mat[s][p]) for s in range(me)) for p in range(w)]       # my rows' place on rank p
+        srcs, rowb, regions, need = [], [], [], 0
+        for a in arrays:
+            a = a.contiguous()
+            eb = a.element_size() * int(np.prod(a.shape[1:], dtype=np.int64))
+            if eb % 4:
+                raise ValueError("symm_exchange: rows must be multiples of 4 bytes")
+            srcs.append(a)
+            rowb.append(eb)
+            regions.append(need)
+            need += (max(tot) * eb + 255) // 256 * 256
+        cur = getattr(self, "_symm", None)
+        h, base = self.symm(max(need, 256, cur[2] if cur is not None else 0))
+        st = torch.cuda.current_stream().cuda_stream
+        arr = ctypes.c_int64 * w
+        so, tot_s = [], 0
+        for p in range(w):
+            so.append(0 if gather else tot_s)
+            tot_s += int(cnt_mat[me][p])
+        sc = arr(*[int(cnt_mat[me][p]) for p in range(w)])
+        _lib.call("gdr_symm_barrier", h, st)              # every rank is done with what lay in the buffer
+        for a, eb, reg in zip(srcs, rowb, regions):
+            do = arr(*[reg + recv_off[p] * eb for p in range(w)])
+            _lib.call("gdr_symm_scatterv", h, a.data_ptr() if a.numel() else 0, ctypes.addressof(arr(*so)), ctypes.addressof(sc),
+                      ctypes.addressof(do), eb, st)
+        _lib.call("gdr_symm_barrier", h, st)
+        out = []
+        for a, eb, reg in zip(srcs, rowb, regions):
+            out.append(_device_view(base + reg, (tot[me],) + tuple(a.shape[1:]), a.dtype, a.device))
+        return out
+
     def close(self):
         """Destroys the library communicator (call before torch.distributed.destroy_process_group)."""
         if getattr(self, "_symm", None) is not None:
@@ -228,6 +289,22 @@ class Comm:
         out = torch.empty(m * self.world, dtype=local.dtype, device=local.device)
         self.all_gather_rows(block, out)
         return torch.cat([out[r * m: r * m + int(counts[r])] for r in range(self.world)])
+
+
+class _DevWindow:
+    """A window of a device allocation owned by the library, described by the CUDA array interface."""
+    _TYPESTR = {torch.int64: "<i8", torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1"}
+
+    def __init__(self, ptr, shape, dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": self._TYPESTR[dtype],
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def _device_view(ptr: int, shape, dtype, device) -> torch.Tensor:
+    """Tensor aliasing ``shape`` elements of ``dtype`` at device address ``ptr`` (no copy, no ownership)."""
+    if int(np.prod(shape)) == 0:
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
+    return torch.as_tensor(_DevWindow(ptr, shape, dtype), device=device)
 
 
 class _Done:
@@ -679,7 +756,11 @@ def dist_build_adjacency(comm: Comm, part: RowPartition, u_slice: torch.Tensor, 
             add_identity = int(comm.all_reduce(has00, "max").item()) == 0
         else:
             add_identity = bool(self_loop_mode)
-        recv, _ = comm.all_to_all_rows(keys, counts)
+        if comm.symm_ok() and keys.is_cuda:
+            # posted NVLink stores into the owners' symmetric buffers; copied out because the prefetch of X reuses the buffer
+            recv = comm.symm_exchange([keys], comm.count_matrix(counts, keys.device))[0].clone()
+        else:
+            recv, _ = comm.all_to_all_rows(keys, counts)
         if after_exchange is not None:
             after_exchange()
         if part.n_local == 0:   # a rank past the end of a short matrix still joins the collectives
@@ -1010,7 +1091,7 @@ class DistKMeans:
 # stage 4
 # ------------------------------------------------------------------------------------------
 def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tensor, A_local, ops=None, replicate: bool = True,
-                        merge: str = "route"):
+                        merge: str = "route", timing: Optional[dict] = None):
     """graph_compress (clustgdd_agent_transduct.py:234-250) for a row-partitioned A_hat.
 
     ``merge="route"`` (default): every local edge is sent once, as a (cell key, weight) pair, to the owner of its coarse
@@ -1020,10 +1101,21 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
     merged (sums added in source-rank order: deterministic, 1e-5 from the single-device sums).  O(local nnz) memory
     on every rank, no n x n array anywhere (config E: n^2 = 10^8 cells).  With ``replicate`` (default) the pieces are
     all-gathered, and every rank returns the reference's result: (adj_syn torch sparse COO n x n, merged integer cell
-    counts).  Without it: this rank's coarse rows as (a_lo, rowptr, colidx, vals, counts)."""
+    counts).  Without it: this rank's coarse rows as (a_lo, rowptr, colidx, vals, counts).  ``timing``: a dict that receives
+    the wall-clock milliseconds of every section (synchronising; tools/stage4_probe.py)."""
+    import time as _time
     ops = ops or CudaOps()
     dev = labels_local.device
     rows_per, world = part.rows_per, part.world
+    _t = [_time.perf_counter()]
+
+    def mark(name):
+        if timing is not None:
+            if labels_local.is_cuda:
+                torch.cuda.synchronize()
+            now = _time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
     block = torch.full((rows_per,), -1, dtype=torch.int32, device=dev)
     block[: labels_local.shape[0]] = labels_local.to(torch.int32)
     gathered = torch.empty(rows_per * world, dtype=torch.int32, device=dev)
@@ -1034,6 +1126,7 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
     nmax = labels_all.max().to(torch.int64).reshape(1)
     n = int(comm.all_reduce(nmax, "max").item()) + 1
     sizes = ops.label_counts(labels_all, n)
+    mark("labels_allgather_sizes")
     cr = (n + world - 1) // world
     a_lo = min(n, comm.rank * cr)
     n_rows = min(n, a_lo + cr) - a_lo
@@ -1041,21 +1134,31 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
     if merge == "route" and hasattr(ops, "coarsen_route"):
         # every edge goes to the owner of its coarse row once; the owner sorts + reduces (one sort per edge, sums in CSR order)
         keys, w, send_counts = ops.coarsen_route(A_local, lab_l, labels_all, n, world)
-        recv_k, rc = comm.all_to_all_rows(keys, send_counts)
-        recv_w, _ = comm.all_to_all_rows(w, send_counts, recv_counts=rc)
+        mark("route")
+        if comm.symm_ok() and keys.is_cuda:
+            recv_k, recv_w = comm.symm_exchange([keys, w], comm.count_matrix(send_counts, keys.device))
+        else:
+            recv_k, rc = comm.all_to_all_rows(keys, send_counts)
+            recv_w, _ = comm.all_to_all_rows(w, send_counts, recv_counts=rc)
+        mark("all_to_all")
         rowptr, colidx, counts, wsum = ops.coarse_merge_edges(recv_k, recv_w, a_lo, n_rows, n)
+        mark("merge_edges")
     else:
         # local coarsening first, then (cell, count, sum) records by key range: less traffic when cells repeat a lot locally
         rec, send_counts = ops.coarsen_records(A_local, lab_l, labels_all, n, world)
         recv, _ = comm.all_to_all_rows(rec, send_counts)
         rowptr, colidx, counts, wsum = ops.coarse_merge(recv, a_lo, n_rows, n)
     vals = ops.coarse_scale(rowptr, colidx, wsum, sizes, a_lo, n_rows)
+    mark("scale")
     if not replicate:
         return a_lo, rowptr, colidx, vals, counts
     if world == 1:
         return ops.csr_to_coo(rowptr, colidx, vals, n), counts
     rowptr_all, col_all, val_all, cnt_all = _replicate_coarse_rows(comm, n, rowptr, colidx, vals, counts)
-    return ops.csr_to_coo(rowptr_all, col_all, val_all, n), cnt_all
+    mark("replicate")
+    out = ops.csr_to_coo(rowptr_all, col_all, val_all, n), cnt_all
+    mark("to_coo")
+    return out
 
 
 def _replicate_coarse_rows(comm: Comm, n: int, rowptr, colidx, vals, counts):
@@ -1067,9 +1170,13 @@ def _replicate_coarse_rows(comm: Comm, n: int, rowptr, colidx, vals, counts):
     nnz_all = torch.empty(world, dtype=torch.int64, device=dev)
     comm.all_gather_rows(nnz_mine, nnz_all)
     nnz_list = [int(v) for v in nnz_all.tolist()]
-    col_all = comm.all_gather_var(colidx, nnz_list)
-    val_all = comm.all_gather_var(vals, nnz_list)
-    cnt_all = comm.all_gather_var(counts, nnz_list)
+    if comm.symm_ok() and colidx.is_cuda:
+        # the three pieces stored straight into every rank's symmetric buffer (posted NVLink stores), then copied out of it
+        col_all, val_all, cnt_all = (t.clone() for t in comm.all_gather_symm([colidx, vals, counts], nnz_list))
+    else:
+        col_all = comm.all_gather_var(colidx, nnz_list)
+        val_all = comm.all_gather_var(vals, nnz_list)
+        cnt_all = comm.all_gather_var(counts, nnz_list)
     rp_block = torch.zeros(cr + 1, dtype=torch.int32, device=dev)
     rp_block[: n_rows + 1] = rowptr
     rp_g = torch.empty(world * (cr + 1), dtype=torch.int32, device=dev)

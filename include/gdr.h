@@ -467,6 +467,9 @@ int gdr_alltoallv(gdr_comm_t* comm, const void* send, const int64_t* send_off_ho
  * points of this library that allocate device memory).  gdr_symm_barrier is stream-ordered: when it completes on a rank,
  * everything every rank enqueued before ITS barrier call — including its stores into this rank's copy — is done and
  * visible.  gdr_symm_put_rows: rows of `src` -> offset dst_offset_bytes of every copy (one read, world posted stores).
+ * gdr_symm_scatterv: the variable all-to-all / all-gather of stages 1 and 4 without NCCL — block p of `send`
+ * (send_cnt_host[p] elements of elem_bytes at element send_off_host[p]) is stored at BYTE offset dst_off_bytes_host[p]
+ * of rank p's copy (its own included), one kernel, 16-byte posted NVLink stores; bracket it with gdr_symm_barrier.
  * gdr_spmm_prop_mc: one hop of clustgdd_agent_transduct.py:59-65 on a row partition FUSED with the all-gather of its
  * result: the SpMM epilogue stores every output row into row dst_row_offset + r of the matrix at dst_offset_bytes of
  * EVERY copy, i.e. straight into the gathered operand of the next hop (Y, this rank's plain copy, is optional). */
@@ -477,6 +480,8 @@ int gdr_symm_info(const gdr_symm_t* symm, void** local_ptr_host, int64_t* bytes_
 int gdr_symm_barrier(gdr_symm_t* symm, gdr_stream_t stream);
 int gdr_symm_put_rows(gdr_symm_t* symm, int64_t dst_offset_bytes, const float* src, int64_t rows, int64_t ld,
                       int include_self, gdr_stream_t stream);
+int gdr_symm_scatterv(gdr_symm_t* symm, const void* send, const int64_t* send_off_host, const int64_t* send_cnt_host,
+                      const int64_t* dst_off_bytes_host, int64_t elem_bytes, gdr_stream_t stream);
 int gdr_spmm_prop_mc(gdr_symm_t* symm, int64_t dst_offset_bytes, int64_t dst_ld, int64_t dst_row_offset,
                      int64_t rows_local, int64_t F, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                      float alpha, const float* X, int64_t ldx, float* Y, int64_t ldy, float* T, int64_t ldt, float beta,

@@ -118,12 +118,16 @@ def _worker(rank, world, port):
         _, syn1 = gdr.graph_compress(labels, A_full, [])
         kk = int(labels.max()) + 1
         _, _, cnt1, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_full, drop_diag=True)
-        for merge in ("records", "route"):
+        # transports: NCCL send/recv (symm False) and posted stores through the symmetric buffer (gdr_symm_scatterv)
+        for merge, symm in (("records", True), ("route", False), ("route", True)):
+            comm.use_symm_exchange = symm
             adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
                                                       merge=merge)
             assert torch.equal(adj_syn._indices(), syn1._indices())
             assert torch.equal(counts, cnt1)
             torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+            if merge == "route":
+                assert torch.equal(adj_syn._values(), syn1._values())
         # routing form: the exchange order is the global CSR order -> the weight sums are the single-GPU sums, bit for bit
         assert torch.equal(adj_syn._values(), syn1._values())
         # not replicated: this rank's key range of the coarse rows
