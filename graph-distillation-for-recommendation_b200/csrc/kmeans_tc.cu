@@ -47,7 +47,7 @@ constexpr float TC_BAND = 3.0517578125e-05f;      // 2^-15
 static const int32_t* g_last_count1 = nullptr;   // device counter of the last two-level run (debug read-back)
 int g_tc_ablate = 0;   // experiment: 1 no epilogue math, 2 no tcgen05.ld either, 3 no MMAs, 4 one K-block of MMAs only
 int g_tc_gate = 1;      // gdr_debug_set("tc_gate", v): first-level epilogue gate — 0 off (exact running top-2 over all columns), 1 (default) gate on the running best, 2 also seeded with the previous label's score (measured at config E: the seed pass costs 0.9 ms and returns 0.1)
-int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles, 4 two-level on CTA pairs (cta_group::2, 256 x 256)
+int g_tc_screen = 0;    // gdr_debug_set("tc_screen", v): 0 auto, 1 direct 3xTF32, 2 two-level with 256-row x 128-centre CTA tiles, 3 two-level with 128 x 256 tiles, 4 two-level on CTA pairs (cta_group::2, 256 x 256), 6 two-level with the row tile in tensor memory (A operand from TMEM, 128 x 192 tiles)
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(1024) k_cnorm_finish(int64_t K, int64_t Kp, co
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 __device__ long long g_tc_probe[4];   // ablation runs: MMA-thread cycles / nanoseconds / MMAs issued of CTA 0
+// k_assign_tc_ts with tc_ablate bit 16, CTA 0, cycles: [0] MMA warp total, [1] its waits for a centre stage, [2] for an
+// accumulator, [3] for the A operand, [4] issue + commits; [5] producer total, [6] its waits for a free stage;
+// [7] epilogue warp 2 total, [8] its waits for an accumulator, [9] tcgen05.ld + arithmetic, [10] arrive, [11] A store
+__device__ long long g_ts_probe[16];
 
 // First-level epilogue gate.  k_tc_select1 only needs to know (a) the best score of a row and (b) whether ANY other
 // centre comes within tol(i, best) of it, and tol(i, j) <= tolmax_i = the same expression with max_j |c_j|, max_j |dc_j|.
@@ -299,6 +303,39 @@ struct TcGate {
   const float* seed;     // upper bound of the row's final best (negated score), +inf when unknown; nullable
   float band;
 };
+
+// First-level epilogue step: running (max, second max, argmax) over one 32-column chunk of scores (kept negated).  A row's
+// running top-2 changes only ~2 ln(K) times, so most chunks hold nothing below any lane's bound: the four 8-column maxima
+// are formed as independent trees, ONE warp vote on their maximum dismisses the whole chunk, and only otherwise do the
+// 8-column votes and the per-element path run (in column order with the running bounds: the result does not depend on
+// the filtering).  The per-warp dependency chain of a dismissed chunk is one tree + one vote instead of four.
+__device__ __forceinline__ void epi_chunk32(const uint32_t (&v)[32], int jbase, bool chunk_skip, bool gated, float tolmax,
+                                            float& limt, float& best, float& second, int& bidx) {
+  float m8[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int u0 = 8 * q;
+    const float m = fmaxf(fmaxf(__uint_as_float(v[u0]), __uint_as_float(v[u0 + 1])),
+                          fmaxf(__uint_as_float(v[u0 + 2]), __uint_as_float(v[u0 + 3])));
+    m8[q] = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[u0 + 4]), __uint_as_float(v[u0 + 5])),
+                           fmaxf(__uint_as_float(v[u0 + 6]), __uint_as_float(v[u0 + 7]))));
+  }
+  const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  if (chunk_skip && !__any_sync(0xffffffffu, -m32 < (gated ? limt : second))) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!chunk_skip || __any_sync(0xffffffffu, -m8[q] < (gated ? limt : second))) {
+#pragma unroll
+      for (int u = 8 * q; u < 8 * q + 8; ++u) {
+        const float d = -__uint_as_float(v[u]);
+        second = fminf(second, fmaxf(d, best));
+        bidx = d < best ? jbase + u : bidx;
+        best = fminf(best, d);
+      }
+      if (gated) limt = fminf(limt, best + tolmax);
+    }
+  }
+}
 
 template <int NPASS, int BN, int SUB>
 struct TcCfg {
@@ -567,26 +604,7 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
           for (int c = 0; c < 2; ++c) {
             const int jbase = ct * BN + col0 + c * 32;
             if (NPASS == 1) {
-              // chunks of 8 columns: a row's running top-2 changes only ~2 ln(K) times, so most chunks hold nothing
-              // below any lane's `second` — one max-tree + one warp vote skips them (K = 10^4: ~80 % of the chunks)
-#pragma unroll
-              for (int u0 = 0; u0 < 32; u0 += 8) {
-                float m = fmaxf(fmaxf(__uint_as_float(v[c][u0]), __uint_as_float(v[c][u0 + 1])),
-                                fmaxf(__uint_as_float(v[c][u0 + 2]), __uint_as_float(v[c][u0 + 3])));
-                m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[c][u0 + 4]), __uint_as_float(v[c][u0 + 5])),
-                                   fmaxf(__uint_as_float(v[c][u0 + 6]), __uint_as_float(v[c][u0 + 7]))));
-                // scores are stored negated: d = -score
-                if (!chunk_skip || __any_sync(0xffffffffu, -m < (gated ? limt : second))) {
-#pragma unroll
-                  for (int u = u0; u < u0 + 8; ++u) {
-                    const float d = -__uint_as_float(v[c][u]);
-                    second = fminf(second, fmaxf(d, best));
-                    bidx = d < best ? jbase + u : bidx;
-                    best = fminf(best, d);
-                  }
-                  if (gated) limt = fminf(limt, best + tolmax);
-                }
-              }
+              epi_chunk32(v[c], jbase, chunk_skip, gated, tolmax, limt, best, second, bidx);
             } else {
               const float4* cn4 = reinterpret_cast<const float4*>(cnorm + jbase);
 #pragma unroll
@@ -642,6 +660,338 @@ k_assign_tc(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// first level with the row tile in TENSOR MEMORY (tcgen05.mma with the A operand from TMEM)
+// ---------------------------------------------------------------------------------
+// A 128 x BN x 8 TF32 MMA whose operands both come from shared memory reads 4 KB (A) + BN * 32 B (B) of it; the tensor
+// pipe's operand port moves ~64 B per cycle, so at BN = 256 the MMA takes ~171 cycles instead of the 128 the B operand
+// alone needs (tools/mma_issue_probe.py), while the TMA writes of the centre stream compete for the same shared memory.
+// The row tile is the same for all Kp / BN column tiles: it is copied ONCE per row tile into tensor memory (lane = row,
+// one column per TF32 element — the layout of an accumulator) and every MMA reads A from there.  TMEM plan (512
+// columns): two BN-column accumulators + ceil8(D + 4) columns of A  ->  BN = 192 for D + 4 <= 128, BN = 128 up to 256.
+// Roles as in k_assign_tc (warp 0 TMA, warp 1 MMA, warps 2-9 epilogue); in addition the epilogue warps move the next
+// row tile shared -> registers -> TMEM (tcgen05.st) as soon as the LAST accumulator of the current row tile is
+// complete (its commit covers every MMA that read the old A), before they drain that accumulator.
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN>
+struct TsCfg {
+  static constexpr int kStageBytes = BN * TC_BK * 4;
+  static constexpr int kACol = 2 * BN;                        // first TMEM column of the A operand
+  static constexpr int kMaxK8 = (512 - kACol) / 8;            // K = 8 steps the A operand has room for
+  static constexpr int kTail = 512 /*barriers*/ + 1536 /*epilogue merge buffer*/;
+  static constexpr int kStages = (TC_SMEM_LIMIT - 1024 - kTail) / kStageBytes;   // the whole shared memory is the centre ring
+  __host__ __device__ static constexpr int c_stage(int s) { return s * kStageBytes; }
+  __host__ __device__ static constexpr int bars() { return c_stage(kStages); }
+  __host__ __device__ static constexpr int total() { return bars() + kTail + 1024; }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_assign_tc_ts(const float* __restrict__ x1 /*[N][ldx1] augmented TF32 rows*/, int ldx1,
+               const __grid_constant__ CUtensorMap map_c, int64_t N_host, const int32_t* __restrict__ n_rows_dev,
+               int D /*contraction width incl. the augmented columns*/, int n_col_tiles, int nkb,
+               float* __restrict__ best_out, float* __restrict__ second_out, int32_t* __restrict__ idx_out, int ablate,
+               TcGate gate) {
+  using Cfg = TsCfg<BN>;
+  static_assert(BN % 64 == 0 && Cfg::kMaxK8 >= 1 && Cfg::kStages <= 16, "tile plan");
+  constexpr int S = Cfg::kStages;
+  constexpr int NK8H = (Cfg::kMaxK8 + 1) / 2;           // K = 8 steps of a row held by one thread (the other half: its twin warp)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bars());
+  uint64_t* a_full = bars;                              // [1] the A operand of the row tile is in TMEM
+  uint64_t* c_full = bars + 1;                          // [16]
+  uint64_t* c_empty = c_full + 16;                      // [16]
+  uint64_t* t_full = c_empty + 16;                      // [2]
+  uint64_t* t_empty = t_full + 2;                       // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t N = n_rows_dev ? (int64_t)n_rows_dev[0] : N_host;
+  const int n_row_tiles = (int)((N + TC_BM - 1) / TC_BM);
+  const int k8_total = (D + 7) >> 3;                    // K = 8 steps that hold real columns
+  // experiments (gdr_debug_set("tc_ablate", mask)): 1 no epilogue arithmetic, 2 no tcgen05.ld either, 4 no MMAs, 8 no centre stream
+  const int ab = ablate > 0 ? ablate : 0;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(a_full, TC_EPI_THREADS);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], TC_EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer: nothing but the centre stream =================
+    int s = 0;
+    uint32_t ph = 0;
+    const bool probe = (ab & 16) && blockIdx.x == 0;
+    long long p_tot = probe ? clock64() : 0, p_wait = 0;
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      for (int ct = 0; ct < n_col_tiles; ++ct) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          long long t0 = probe ? clock64() : 0;
+          mbar_wait(&c_empty[s], ph ^ 1);
+          if (probe) p_wait += clock64() - t0;
+          if (elect_one()) {
+            if (ab & 8) {
+              mbar_arrive(&c_full[s]);
+            } else {
+              mbar_expect_tx(&c_full[s], Cfg::kStageBytes);
+              tma_load_2d(smem + Cfg::c_stage(s), &map_c, kb * TC_BK, ct * BN, &c_full[s]);
+            }
+          }
+          __syncwarp();
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    if (probe && lane == 0) {
+      g_ts_probe[5] = clock64() - p_tot;
+      g_ts_probe[6] = p_wait;
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (uniform control flow, one elected lane issues) =================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+    uint32_t tile_it = 0, g = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const uint64_t dc0 = umma_desc_sw128(smem_u32(smem));
+    constexpr uint64_t kStage = Cfg::kStageBytes >> 4;
+    const uint32_t tmem_a = tmem_base + Cfg::kACol;
+    const bool probe = (ab & 16) && blockIdx.x == 0;
+    long long m_tot = probe ? clock64() : 0, m_wc = 0, m_wt = 0, m_wa = 0, m_is = 0, t0 = 0, t1 = 0;
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x, ++tile_it) {
+      if (probe) t0 = clock64();
+      mbar_wait(a_full, tile_it & 1);
+      tc_fence_after();
+      if (probe) m_wa += clock64() - t0;
+      for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+        const uint32_t a = g & 1, aph = (g >> 1) & 1;
+        if (probe) t0 = clock64();
+        mbar_wait(&t_empty[a], aph ^ 1);
+        tc_fence_after();
+        if (probe) m_wt += clock64() - t0;
+        const uint32_t tmem_d = tmem_base + a * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (probe) t0 = clock64();
+          mbar_wait(&c_full[s], ph);
+          tc_fence_after();
+          if (probe) {
+            t1 = clock64();
+            m_wc += t1 - t0;
+          }
+          const uint64_t d_c = dc0 + (uint64_t)s * kStage;
+          const int ksteps = min(TC_BK / 8, k8_total - kb * (TC_BK / 8));
+          if (elect_one()) {
+            const uint32_t ta = tmem_a + kb * TC_BK;
+            if (!(ab & 4) && ksteps == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_tf32_ts(tmem_d, ta + k * 8, d_c + (uint64_t)((k * 8 * 4) >> 4), idesc, (kb | k) != 0);
+            } else {
+              for (int k = 0; k < ((ab & 4) ? 0 : ksteps); ++k)
+                tc_mma_tf32_ts(tmem_d, ta + k * 8, d_c + (uint64_t)((k * 8 * 4) >> 4), idesc, (kb | k) != 0);
+            }
+            tc_commit(&c_empty[s]);
+            if (kb == nkb - 1) tc_commit(&t_full[a]);
+          }
+          __syncwarp();
+          if (probe) m_is += clock64() - t1;
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    if (probe && lane == 0) {
+      g_ts_probe[0] = clock64() - m_tot;
+      g_ts_probe[1] = m_wc;
+      g_ts_probe[2] = m_wt;
+      g_ts_probe[3] = m_wa;
+      g_ts_probe[4] = m_is;
+    }
+  } else {
+    // ================= epilogue (8 warps; warp w owns TMEM lanes [32 (w % 4), +32) and one column half) =================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = BN / 2;
+    float* s_merge = reinterpret_cast<float*>(tmem_base_smem + 4);
+    const int rl = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool chunk_skip = n_col_tiles * BN >= 4096;
+    // The row tile travels global -> registers -> TMEM: thread (quarter, lane) owns row rl and, of its K = 8 steps, those
+    // of its warp's parity (the twin warp of the lane quarter takes the others).  The loads of the NEXT row tile are
+    // issued at the start of the current one and rest in registers until its last accumulator is complete.
+    uint32_t xa[NK8H][8];
+    auto load_a = [&](int rt) {
+      const int64_t row = (int64_t)rt * TC_BM + rl;
+      const uint4* src = reinterpret_cast<const uint4*>(x1 + row * ldx1);
+#pragma unroll
+      for (int i = 0; i < NK8H; ++i) {
+        const int k8 = 2 * i + half;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (k8 < k8_total && row < N) {
+          lo = __ldg(src + 2 * k8);
+          hi = __ldg(src + 2 * k8 + 1);
+        }
+        xa[i][0] = lo.x, xa[i][1] = lo.y, xa[i][2] = lo.z, xa[i][3] = lo.w;
+        xa[i][4] = hi.x, xa[i][5] = hi.y, xa[i][6] = hi.z, xa[i][7] = hi.w;
+      }
+    };
+    auto store_a = [&]() {
+#pragma unroll
+      for (int i = 0; i < NK8H; ++i) {
+        const int k8 = 2 * i + half;
+        if (k8 < k8_total) tc_st_32x8(lane_addr + Cfg::kACol + k8 * 8, xa[i]);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(a_full);
+    };
+    uint32_t g = 0;
+    const bool probe = (ab & 16) && blockIdx.x == 0 && warp == 2;
+    long long e_tot = probe ? clock64() : 0, e_wt = 0, e_ld = 0, e_ar = 0, e_st = 0, t0 = 0, t1 = 0;
+    if ((int)blockIdx.x < n_row_tiles) {
+      load_a(blockIdx.x);
+      store_a();
+    }
+    for (int rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
+      const int64_t row = (int64_t)rt * TC_BM + rl;
+      const bool has_next = rt + (int)gridDim.x < n_row_tiles;
+      if (has_next) load_a(rt + gridDim.x);
+      float best = INFINITY, second = INFINITY;
+      int bidx = 0;
+      float tolmax = 0.f, limt = INFINITY;
+      const bool gated = chunk_skip && gate.xnorm != nullptr;
+      if (gated) {
+        const float xn = row < N ? gate.xnorm[row] : 0.f, xd = row < N ? gate.xdnorm[row] : 0.f;
+        const float cm = gate.cscal[0], cdm = gate.cscal[1];
+        tolmax = 1.001f * (2.02f * (xd * cm + xn * (cdm + 3.0517578125e-05f * cm) + 1.52587890625e-05f * cm * cm) +
+                           gate.band * xn * cm + 9.5367431640625e-07f * (xn * cm + cm * cm));
+        if (gate.seed != nullptr && row < N) limt = gate.seed[row] + tolmax;
+      }
+      for (int ct = 0; ct < n_col_tiles; ++ct, ++g) {
+        const uint32_t a = g & 1, aph = (g >> 1) & 1;
+        if (probe) t0 = clock64();
+        mbar_wait(&t_full[a], aph);
+        tc_fence_after();
+        if (probe) {
+          t1 = clock64();
+          e_wt += t1 - t0;
+        }
+        // every MMA of this row tile is complete: the next one takes its place in TMEM before this accumulator is read
+        if (ct == n_col_tiles - 1 && has_next) store_a();
+        if (probe) {
+          t0 = clock64();
+          e_st += t0 - t1;
+        }
+        const uint32_t tacc = lane_addr + a * BN + half * COLS;
+        const int j0 = ct * BN + half * COLS;
+        if (!(ab & 2)) {
+#pragma unroll 1
+          for (int h2 = 0; h2 < COLS / 64; ++h2) {
+            uint32_t v[2][32];
+            tc_ld_32x32(tacc + h2 * 64, v[0]);
+            tc_ld_32x32(tacc + h2 * 64 + 32, v[1]);
+            tc_wait_ld();
+            if (ab & 1) {
+              if (v[0][0] == 0x7fc12345u && v[1][31] == 0x7fc54321u) bidx = 1;
+              continue;
+            }
+            epi_chunk32(v[0], j0 + h2 * 64, chunk_skip, gated, tolmax, limt, best, second, bidx);
+            epi_chunk32(v[1], j0 + h2 * 64 + 32, chunk_skip, gated, tolmax, limt, best, second, bidx);
+          }
+          if (COLS % 64) {
+            uint32_t v[32];
+            tc_ld_32x32(tacc + (COLS / 64) * 64, v);
+            tc_wait_ld();
+            if (ab & 1) {
+              if (v[0] == 0x7fc12345u) bidx = 1;
+            } else {
+              epi_chunk32(v, j0 + (COLS / 64) * 64, chunk_skip, gated, tolmax, limt, best, second, bidx);
+            }
+          }
+        }
+        if (probe) {
+          t1 = clock64();
+          e_ld += t1 - t0;
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[a]);
+        if (probe) e_ar += clock64() - t1;
+      }
+      // merge the two column halves of each row: lower columns win ties
+      if (half == 1) {
+        s_merge[rl] = best;
+        s_merge[128 + rl] = second;
+        reinterpret_cast<int*>(s_merge)[256 + rl] = bidx;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      if (half == 0) {
+        const float b1 = s_merge[rl], s1 = s_merge[128 + rl];
+        const int i1 = reinterpret_cast<int*>(s_merge)[256 + rl];
+        const float nb = fminf(best, b1);
+        const float ns = fminf(fminf(second, s1), fmaxf(best, b1));
+        const int ni = b1 < best ? i1 : bidx;
+        if (row < N) {
+          best_out[row] = nb;
+          second_out[row] = ns;
+          idx_out[row] = ni;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+    }
+    if (probe && lane == 0) {
+      g_ts_probe[7] = clock64() - e_tot;
+      g_ts_probe[8] = e_wt;
+      g_ts_probe[9] = e_ld;
+      g_ts_probe[10] = e_ar;
+      g_ts_probe[11] = e_st;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1332,6 +1682,7 @@ static inline int dpad(int64_t D) { return (int)align_up(D, TC_BK); }
 constexpr int TC_AUG = 4;   // augmented columns of the first-level operands
 static inline int dpad1(int64_t D) { return (int)align_up(D + TC_AUG, TC_BK); }
 constexpr int TC_KPAD = 256;   // centres padded to the widest accumulator tile
+constexpr int TC_TS_BN = 192;  // accumulator width of the A-in-TMEM first level (its last tile may reach past Kp)
 
 int64_t kmeans_tc_xsplit_bytes(int64_t N, int64_t D) {
   return 2 * ws_need(N * dpad(D), 4) + 2 * ws_need(N, 4) + ws_need(N * dpad1(D), 4) + 256;
@@ -1372,7 +1723,7 @@ static bool tc_two_level(int64_t N, bool want_best) {
 int64_t kmeans_assign_tc_ws_bytes(int64_t N, int64_t K, int64_t D) {
   int Dp = dpad(D);
   int64_t Kp = align_up(K, TC_KPAD);
-  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need(Kp * dpad1(D), 4) /*augmented centres*/ +
+  return 3 * ws_need(Kp * Dp, 4) /*c_hi, c_lo, c^T*/ + ws_need((Kp + TC_TS_BN) * dpad1(D), 4) /*augmented centres*/ +
          3 * ws_need(Kp, 4) /*|c|^2, |c|, |c - tf32(c)|*/ + 256 /*cmax*/ +
          3 * ws_need(N, 4) /*best, second, idx*/ + ws_need(N, 4) /*amb list*/ + ws_need(N, 8) /*amb packed*/ +
          256 /*amb count*/ + ws_need(N, 4) /*second-level list*/ + 256 /*its count*/ +
@@ -1405,6 +1756,37 @@ static int launch_assign_tc(const CUtensorMap& m_xhi, const CUtensorMap& m_xlo, 
                                                                   (int)(Kp / BN), nkb, cnorm, best, second, idx, g_tc_ablate, gate);
   GDR_LAUNCHED();
   return GDR_OK;
+}
+
+template <int BN>
+static int launch_assign_tc_ts(const float* x1, int ldx1, const CUtensorMap& m_c, int64_t N_max, const int32_t* n_rows_dev,
+                               int D_eff, int n_col_tiles, int nkb, float* best, float* second, int32_t* idx, cudaStream_t s,
+                               TcGate gate) {
+  using Cfg = TsCfg<BN>;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.get();
+  if (!attr_set) {
+    GDR_CUDA(cudaFuncSetAttribute(k_assign_tc_ts<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr_set = true;
+  }
+  int sms = kSMs;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t tiles = cdiv(N_max, TC_BM);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  k_assign_tc_ts<BN><<<grid, TC_THREADS, Cfg::total(), s>>>(x1, ldx1, m_c, N_max, n_rows_dev, D_eff, n_col_tiles, nkb, best,
+                                                          second, idx, g_tc_ablate, gate);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// rows [r0, r1) of the augmented centre matrix as padding centres (score -1e30 for every row of X)
+__global__ void k_pad_aug(float* __restrict__ aug, int64_t r0, int64_t r1, int Dp1, int D) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n = (r1 - r0) * Dp1;
+  if (i < n) aug[r0 * Dp1 + i] = (int)(i % Dp1) == D + 2 ? to_tf32(-1e30f) : 0.f;
 }
 
 static int launch_assign_tc_pair(const CUtensorMap& m_x, const CUtensorMap& m_c, int64_t N_max, const int32_t* n_rows_dev,
@@ -1463,7 +1845,7 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
   float* c_hi = W.take<float>(Kp * Dp);
   float* c_lo = W.take<float>(Kp * Dp);
   float* c_t = W.take<float>(Kp * Dp);   // fp32 centres transposed [Dp][Kp] for the re-score kernel
-  float* c1 = W.take<float>(Kp * Dp1);   // augmented first-level centres
+  float* c1 = W.take<float>((Kp + TC_TS_BN) * Dp1);   // augmented first-level centres (+ padding rows of the last 192-tile)
   float* cnorm = W.take<float>(Kp);
   float* cnorm_sqrt = W.take<float>(Kp);
   float* cdnorm = W.take<float>(Kp);
@@ -1526,7 +1908,18 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
                                       g_tc_screen == 5 ? 1 : 0, s)))
         return rc;
     } else {
-      if ((rc = make_map(&m_c1, c1, Kp, Dp1, 256))) return rc;
+      // default: both operands from shared memory (k_assign_tc<1, 256, 1>).  tc_screen 6 (D + 4 <= 128): the row tile in
+      // tensor memory (k_assign_tc_ts, 192-centre tiles, all of shared memory is the centre ring) — measured at config E:
+      // 8.2 vs 7.6 ms (D = 100), 6.1 vs 5.4 ms (D = 47): the TF32 MMA runs at ~0.65 cycles per accumulator column
+      // whether A comes from shared or tensor memory, and 192-centre tiles pay the per-tile hand-shakes 53 times instead of 40
+      const int ka = (int)align_up(D + TC_AUG, 8);
+      const int ts_bn = (g_tc_screen == 6 && ka <= 512 - 2 * TC_TS_BN) ? TC_TS_BN : 0;
+      const int64_t k_rows = ts_bn == TC_TS_BN ? align_up(K, TC_TS_BN) : Kp;
+      if (k_rows > Kp) {
+        k_pad_aug<<<(unsigned)cdiv((k_rows - Kp) * Dp1, 256), 256, 0, s>>>(c1, Kp, k_rows, Dp1, (int)D);
+        GDR_LAUNCHED();
+      }
+      if ((rc = make_map(&m_c1, c1, std::max(Kp, k_rows), Dp1, ts_bn ? ts_bn : 256))) return rc;
       TcGate gate{nullptr, nullptr, nullptr, nullptr, TC_BAND};
       if (g_tc_gate) {
         gate.xnorm = xs.norm;
@@ -1540,9 +1933,13 @@ int kmeans_assign_tc_run(int64_t N, int64_t K, int64_t D, const float* X, int64_
           gate.seed = seed;
         }
       }
-      if ((rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
-                                         idx, s, gate)))
-        return rc;
+      if (ts_bn == TC_TS_BN)
+        rc = launch_assign_tc_ts<TC_TS_BN>(xs.x1, Dp1, m_c1, N, nullptr, (int)D + TC_AUG, (int)(k_rows / TC_TS_BN), nkb1, best,
+                                           second, idx, s, gate);
+      else
+        rc = launch_assign_tc<1, 256, 1>(m_x1, m_x1, m_c1, m_c1, N, nullptr, (int)D + TC_AUG, Kp, nkb1, cnorm, best, second,
+                                         idx, s, gate);
+      if (rc) return rc;
     }
     if (g_tc_ablate) return GDR_OK;   // timing experiment: first-level kernel only
     g_last_count1 = count1;
@@ -1593,6 +1990,14 @@ extern "C" {
 // debug read-back (synchronises the device): "tc_level2_rows" = rows the last two-level screen sent to level 2
 int gdr_debug_get(const char* key, int64_t* value_host) {
   GDR_CHECK_ARG(key && value_host, "debug_get: bad arguments");
+  if (!strncmp(key, "ts_probe_", 9)) {
+    long long h[16];
+    GDR_CUDA(cudaMemcpyFromSymbol(h, gdr::g_ts_probe, sizeof(h)));
+    const int i = atoi(key + 9);
+    GDR_CHECK_ARG(i >= 0 && i < 16, "debug_get: ts_probe index");
+    *value_host = h[i];
+    return GDR_OK;
+  }
   if (!strcmp(key, "tc_probe_cycles") || !strcmp(key, "tc_probe_ns") || !strcmp(key, "tc_probe_mmas")) {
     long long h[4] = {0, 0, 0, 0};
     GDR_CUDA(cudaMemcpyFromSymbol(h, gdr::g_tc_probe, sizeof(h)));

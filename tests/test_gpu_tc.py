@@ -58,7 +58,7 @@ def screen_mode():
     _lib.call("gdr_debug_set", b"tc_screen", 0)
 
 
-@pytest.mark.parametrize("mode", [2, 3, 4, 5])   # two-level screen: 256x128 / 128x256 CTA tiles, CTA pairs (cta_group::2; 2-SM TMA / forwarded 1-SM TMA)
+@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6])   # two-level screen: 256x128 / 128x256 CTA tiles, CTA pairs (cta_group::2; 2-SM TMA / forwarded 1-SM TMA), row tile in TMEM (128x192)
 @pytest.mark.parametrize("N,K,D,kind", [(300, 7, 3, "clustered"), (4099, 129, 100, "clustered"), (20000, 1000, 40, "clustered"),
                                         (20000, 333, 128, "zscore"), (50000, 1000, 128, "zscore"), (30011, 700, 100, "zscore"),
                                         (1, 1, 1, "clustered")])
