@@ -177,10 +177,11 @@ class Comm:
             so.append(0 if gather else tot_s)
             tot_s += int(cnt_mat[me][p])
         sc = arr(*[int(cnt_mat[me][p]) for p in range(w)])
+        so_arr = arr(*so)
         _lib.call("gdr_symm_barrier", h, st)              # every rank is done with what lay in the buffer
         for a, eb, reg in zip(srcs, rowb, regions):
             do = arr(*[reg + recv_off[p] * eb for p in range(w)])
-            _lib.call("gdr_symm_scatterv", h, a.data_ptr() if a.numel() else 0, ctypes.addressof(arr(*so)), ctypes.addressof(sc),
+            _lib.call("gdr_symm_scatterv", h, a.data_ptr() if a.numel() else 0, ctypes.addressof(so_arr), ctypes.addressof(sc),
                       ctypes.addressof(do), eb, st)
         _lib.call("gdr_symm_barrier", h, st)
         out = []
