@@ -787,6 +787,270 @@ __global__ void k_csr_to_coo(int64_t n_rows, const int32_t* __restrict__ rowptr,
   }
 }
 
+// ---------------- coarsening: one CTA per coarse row, cells accumulated in shared memory ----------------
+// P^T A P for a CSR A (clustgdd_agent_transduct.py:234-250) without sorting the edges.  The nodes are grouped by their
+// cluster (a counting sort of n_rows ids); the CTA that owns cluster a walks the adjacency rows of its nodes once and
+// accumulates cell (a, b = label[col]) into a dense shared-memory row of n_dst counters:
+//   count[b] += 1 (u32),  sum[b] += round(w / q_a) (i64 fixed point)
+// Integer accumulation is associative, so the result does not depend on the order in which the shared-memory atomics
+// land: bit-reproducible, and the weight sum is rounded to fp32 ONCE (closer to the exact sum than any fp32 summation
+// order).  q_a = pow2(max |w| of the cluster) * pow2(edges of the cluster) * 2^-62 — no overflow, ~2^-48 of the
+// largest weight.  The row is then compacted in column order into a scratch slice (at the cluster's edge offset),
+// and a second small kernel packs the slices into the final CSR.  HBM traffic: the edges once (8 B each), the
+// column labels through L2, the cells twice — against four (key, value) radix passes over all edges before.
+constexpr int CD_THREADS = 1024;
+constexpr int CD_HUB = 4096;          // rows at least this long are walked by the whole CTA
+
+__global__ void __launch_bounds__(256) k_cd_stats(int64_t n_rows, const int32_t* __restrict__ rowptr, const float* __restrict__ w,
+                                                  const int32_t* __restrict__ labels, int64_t n_src,
+                                                  int32_t* __restrict__ node_cnt, int32_t* __restrict__ edge_cnt,
+                                                  uint32_t* __restrict__ wmax_bits, int32_t* __restrict__ status) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int32_t a = labels[i];
+  if (a < 0 || a >= n_src) {
+    if (lane == 0) atomicOr(status, 1);
+    return;
+  }
+  const int32_t b = rowptr[i], e = rowptr[i + 1];
+  float m = 0.f;
+  if (w)
+    for (int32_t k = b + lane; k < e; k += 32) m = fmaxf(m, fabsf(w[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) {
+    atomicAdd(&node_cnt[a], 1);
+    atomicAdd(&edge_cnt[a], e - b);
+    if (w) atomicMax(&wmax_bits[a], __float_as_uint(m));     // non-negative floats order like their bit patterns
+  }
+}
+
+__global__ void k_cd_group(int64_t n_rows, const int32_t* __restrict__ labels, const int32_t* __restrict__ starts,
+                           int32_t* __restrict__ cursor, int32_t* __restrict__ nodes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t a = labels[i];
+    nodes[starts[a] + atomicAdd(&cursor[a], 1)] = (int32_t)i;
+  }
+}
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(CD_THREADS, 1)
+k_cd_accumulate(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                const float* __restrict__ w, const int32_t* __restrict__ labels_dst, const int32_t* __restrict__ starts,
+                const int32_t* __restrict__ nodes, const int32_t* __restrict__ edge_prefix, const uint32_t* __restrict__ wmax_bits,
+                int drop_diag, int32_t* __restrict__ next_cluster, int32_t* __restrict__ t_col, int32_t* __restrict__ t_cnt,
+                float* __restrict__ t_sum, int32_t* __restrict__ nnz_row, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char cd_smem[];
+  // 64-bit fixed-point sums as two 32-bit words with a carry (a 64-bit shared-memory add is a CAS spin loop)
+  uint32_t* s_lo = reinterpret_cast<uint32_t*>(cd_smem);                                            // [HAS_W ? n_dst : 0]
+  uint32_t* s_hi = s_lo + (HAS_W ? n_dst : 0);                                                      // [HAS_W ? n_dst : 0]
+  uint32_t* s_cnt = s_hi + (HAS_W ? n_dst : 0);                                                     // [n_dst]
+  __shared__ int s_a, s_hub_n, s_warp_tot[CD_THREADS / 32], s_hub[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t b = tid; b < n_dst; b += CD_THREADS) {
+    s_cnt[b] = 0;
+    if (HAS_W) s_lo[b] = s_hi[b] = 0u;
+  }
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_a = atomicAdd(next_cluster, 1);
+      s_hub_n = 0;
+    }
+    __syncthreads();
+    const int a = s_a;
+    if (a >= n_src) break;
+    const int32_t nb = starts[a], ne = starts[a + 1];
+    const int32_t n_edges = edge_prefix[a + 1] - edge_prefix[a];
+    // fixed-point step of this cluster: |sum of any cell| <= wmax * n_edges < 2^(ew + ee)
+    double inv_q = 0.0, q = 0.0;
+    if (HAS_W) {
+      int ew = 0, ee = 0;
+      frexpf(__uint_as_float(wmax_bits[a]), &ew);
+      frexp((double)(n_edges > 0 ? n_edges : 1), &ee);
+      q = ldexp(1.0, ew + ee - 62);
+      inv_q = ldexp(1.0, 62 - ew - ee);
+    }
+    auto add_cell = [&](int32_t b, float wk) {
+      if ((uint32_t)b >= (uint64_t)n_dst) {       // a label outside [0, n_dst) has no cell (the Python face never passes one)
+        atomicOr(status, 1);
+        return;
+      }
+      if (drop_diag && b == a) return;
+      atomicAdd(&s_cnt[b], 1u);
+      if (HAS_W) {
+        const unsigned long long v = (unsigned long long)__double2ll_rn((double)wk * inv_q);
+        const uint32_t lo = (uint32_t)v, old = atomicAdd(&s_lo[b], lo);
+        atomicAdd(&s_hi[b], (uint32_t)(v >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u));
+      }
+    };
+    // edges k, k + stride of one row together: both label gathers are in flight before the first atomic
+    auto add_edges = [&](int32_t k0, int32_t re, int32_t stride) {
+      for (int32_t k = k0; k < re; k += 2 * stride) {
+        const bool two = k + stride < re;
+        const int32_t j0 = colidx[k], j1 = two ? colidx[k + stride] : 0;
+        const float w0 = HAS_W ? w[k] : 0.f, w1 = (HAS_W && two) ? w[k + stride] : 0.f;
+        const int32_t c0 = __ldg(labels_dst + j0), c1 = two ? __ldg(labels_dst + j1) : 0;
+        add_cell(c0, w0);
+        if (two) add_cell(c1, w1);
+      }
+    };
+    // one warp per adjacency row; very long rows are left to the whole CTA
+    for (int32_t t = nb + warp; t < ne; t += CD_THREADS / 32) {
+      const int32_t i = nodes[t];
+      const int32_t rb = rowptr[i], re = rowptr[i + 1];
+      if (re - rb >= CD_HUB) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_hub_n, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < 64) {                 // (a 65th hub row of one cluster is walked by its warp like any other row)
+          if (lane == 0) s_hub[slot] = i;
+          continue;
+        }
+      }
+      add_edges(rb + lane, re, 32);
+    }
+    __syncthreads();
+    const int hubs = s_hub_n < 64 ? s_hub_n : 64;
+    for (int h = 0; h < hubs; ++h) {
+      const int32_t i = s_hub[h];
+      add_edges(rowptr[i] + tid, rowptr[i + 1], CD_THREADS);
+    }
+    __syncthreads();
+    // compact the row in column order: contiguous chunk per thread, block-wide exclusive scan of the chunk counts
+    const int64_t per = (n_dst + CD_THREADS - 1) / CD_THREADS;
+    const int64_t b0 = (int64_t)tid * per, b1 = b0 + per < n_dst ? b0 + per : n_dst;
+    int mine = 0;
+    for (int64_t b = b0; b < b1; ++b) mine += s_cnt[b] != 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int ww = 0; ww < CD_THREADS / 32; ++ww) {
+      if (ww < warp) base += s_warp_tot[ww];
+      total += s_warp_tot[ww];
+    }
+    int64_t out = (int64_t)edge_prefix[a] + base + incl - mine;
+    for (int64_t b = b0; b < b1; ++b) {
+      const uint32_t c = s_cnt[b];
+      if (c) {
+        t_col[out] = (int32_t)b;
+        t_cnt[out] = (int32_t)c;
+        if (HAS_W) {
+          t_sum[out] = (float)((double)(long long)(((unsigned long long)s_hi[b] << 32) | s_lo[b]) * q);
+          s_lo[b] = s_hi[b] = 0u;
+        }
+        s_cnt[b] = 0;
+        ++out;
+      }
+    }
+    if (tid == 0) nnz_row[a] = total;
+  }
+}
+
+// scratch slices -> final CSR arrays (one CTA per coarse row)
+__global__ void __launch_bounds__(256) k_cd_pack(int64_t n_src, const int32_t* __restrict__ edge_prefix, const int32_t* __restrict__ rowptr,
+                                                 const int32_t* __restrict__ t_col, const int32_t* __restrict__ t_cnt,
+                                                 const float* __restrict__ t_sum, int32_t* __restrict__ colidx,
+                                                 int32_t* __restrict__ counts, float* __restrict__ wsum, int64_t* __restrict__ nnz_out) {
+  for (int64_t a = blockIdx.x; a < n_src; a += gridDim.x) {
+    const int64_t src = edge_prefix[a], dst = rowptr[a];
+    const int n = rowptr[a + 1] - rowptr[a];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      colidx[dst + k] = t_col[src + k];
+      counts[dst + k] = t_cnt[src + k];
+      if (wsum) wsum[dst + k] = t_sum[src + k];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) nnz_out[0] = rowptr[n_src];
+}
+
+int g_coarsen_dense = 1;   // gdr_debug_set("coarsen_dense", 0): always the sort path
+
+static int64_t cd_small_bytes(int64_t n_rows, int64_t n_src) {
+  return ws_need(n_rows, 4) + 6 * ws_need(n_src + 1, 4) + scan_ws_bytes(n_src + 1) + 512;
+}
+
+// true when the dense path applies: CSR input, the coarse row fits in shared memory, the scratch fits in the workspace
+static bool cd_applicable(int64_t E, int64_t n_rows, int64_t n_src, int64_t n_dst, bool has_w, int64_t ws_bytes) {
+  if (!g_coarsen_dense || n_rows <= 0) return false;
+  const int64_t smem = n_dst * (has_w ? 12 : 4);
+  if (smem > 200 * 1024) return false;
+  if (E < 4 * n_src) return false;                    // hardly any edges per coarse row: the sort is the cheaper way
+  return 3 * ws_need(E, 4) + cd_small_bytes(n_rows, n_src) <= ws_bytes;
+}
+
+static int coarsen_dense(int64_t E, int64_t n_rows, const int32_t* csr_rowptr, const int32_t* csr_colidx, const float* w,
+                         const int32_t* labels_src, const int32_t* labels_dst, int64_t n_src, int64_t n_dst,
+                         int drop_diag, int32_t* rowptr, int32_t* colidx, int32_t* counts, float* wsum, int64_t* nnz_out_dev,
+                         void* ws, int64_t ws_bytes, cudaStream_t s) {
+  Workspace W(ws, ws_bytes);
+  int32_t* t_col = W.take<int32_t>(E);
+  int32_t* t_cnt = W.take<int32_t>(E);
+  float* t_sum = W.take<float>(E);
+  int32_t* nodes = W.take<int32_t>(n_rows);
+  int32_t* node_cnt = W.take<int32_t>(n_src + 1);     // the next five blocks are cleared together
+  int32_t* edge_cnt = W.take<int32_t>(n_src + 1);
+  uint32_t* wmax = W.take<uint32_t>(n_src + 1);
+  int32_t* cursor = W.take<int32_t>(n_src + 1);
+  int32_t* starts = W.take<int32_t>(n_src + 1);
+  int32_t* edge_prefix = W.take<int32_t>(n_src + 1);
+  int32_t* misc = W.take<int32_t>(64);                 // [0] next cluster, [1] status
+  const int64_t sws_b = scan_ws_bytes(n_src + 1);
+  void* sws = W.take<char>(sws_b);
+  if (!W.ok()) {
+    set_error("coarsen: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  GDR_CUDA(cudaMemsetAsync(node_cnt, 0, (char*)starts - (char*)node_cnt, s));
+  GDR_CUDA(cudaMemsetAsync(misc, 0, 256, s));
+  k_cd_stats<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, s>>>(n_rows, csr_rowptr, wsum ? w : nullptr, labels_src, n_src, node_cnt,
+                                                            edge_cnt, wmax, misc + 1);
+  GDR_LAUNCHED();
+  int rc;
+  if ((rc = exclusive_scan_i32(node_cnt, starts, n_src, sws, sws_b, s))) return rc;
+  if ((rc = exclusive_scan_i32(edge_cnt, edge_prefix, n_src, sws, sws_b, s))) return rc;
+  k_cd_group<<<grid_for(n_rows), 256, 0, s>>>(n_rows, labels_src, starts, cursor, nodes);
+  GDR_LAUNCHED();
+  int dev = 0, sms = kSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = (size_t)n_dst * (wsum ? 12 : 4);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_src, sms);
+  int32_t* nnz_row = node_cnt;                         // free again after the scan
+  if (wsum) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr.get() = true;
+    }
+    k_cd_accumulate<true><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, w, labels_dst, starts, nodes,
+                                                        edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, t_sum, nnz_row, misc + 1);
+  } else {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr.get() = true;
+    }
+    k_cd_accumulate<false><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, nullptr, labels_dst, starts,
+                                                         nodes, edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, nullptr, nnz_row,
+                                                         misc + 1);
+  }
+  GDR_LAUNCHED();
+  if ((rc = exclusive_scan_i32(nnz_row, rowptr, n_src, sws, sws_b, s))) return rc;
+  k_cd_pack<<<(unsigned)std::min<int64_t>(n_src, 8 * sms), 256, 0, s>>>(n_src, edge_prefix, rowptr, t_col, t_cnt, t_sum, colidx, counts,
+                                                                       wsum, nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
 }  // namespace gdr
 
 using namespace gdr;
@@ -1118,6 +1382,9 @@ int gdr_coarsen(int64_t E, const int64_t* src, const int64_t* dst, int64_t n_row
     set_error("coarsen: workspace too small");
     return GDR_EWORKSPACE;
   }
+  if (!src && cd_applicable(E, n_rows, n_src, n_dst, wsum != nullptr, ws_bytes))
+    return coarsen_dense(E, n_rows, csr_rowptr, csr_colidx, w, labels_src, labels_dst, n_src, n_dst, drop_diag,
+                         rowptr, colidx, counts, wsum, nnz_out_dev, ws, ws_bytes, s);
   Workspace W(ws, ws_bytes);
   uint64_t* keys = W.take<uint64_t>(E);
   uint32_t* payload = W.take<uint32_t>(E);

@@ -43,6 +43,7 @@ static int g_spmm_split = 0;      // number of column windows (1, 2, 4)
 extern int g_lloyd_graph;         // lloyd.cu
 extern int g_tc_screen;           // kmeans_tc.cu
 extern int g_tc_gate;             // kmeans_tc.cu
+extern int g_coarsen_dense;       // graph.cu
 extern int g_rs_match;            // primitives.cu
 extern int g_rs_max_bits;         // primitives.cu
 extern int g_tc_ablate;
@@ -441,6 +442,7 @@ int gdr_debug_set(const char* key, int value) {
   else if (!strcmp(key, "spmm_split")) gdr::g_spmm_split = value;
   else if (!strcmp(key, "lloyd_graph")) gdr::g_lloyd_graph = value;
   else if (!strcmp(key, "tc_screen")) gdr::g_tc_screen = value;
+  else if (!strcmp(key, "coarsen_dense")) gdr::g_coarsen_dense = value;
   else if (!strcmp(key, "tc_ablate")) gdr::g_tc_ablate = value;
   else if (!strcmp(key, "tc_gate")) gdr::g_tc_gate = value;
   else if (!strcmp(key, "rs_match")) gdr::g_rs_match = value;

@@ -1,0 +1,81 @@
+"""Stage 4 without a sort: one CTA per coarse row, cells accumulated in shared memory (integer counts, fixed-point weight
+sums) against the sort-based path and an fp64 scipy P^T A P (clustgdd_agent_transduct.py:234-250)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
+
+
+@pytest.fixture(scope="module")
+def gdr():
+    import gdr
+    return gdr
+
+
+def _graph(n, avg_deg, hubs, seed):
+    rng = np.random.RandomState(seed)
+    m = n * avg_deg // 2
+    u, v = rng.randint(0, n, m), rng.randint(0, n, m)
+    for h in range(hubs):                    # a few very long rows (walked by the whole CTA)
+        u = np.concatenate([u, np.full(6000, h)])
+        v = np.concatenate([v, rng.randint(0, n, 6000)])
+    return u.astype(np.int64), v.astype(np.int64)
+
+
+def _coarsen(gdr, A, labels, k, dense, weights=True, drop_diag=True):
+    from gdr import _lib
+    _lib.call("gdr_debug_set", b"coarsen_dense", int(dense))
+    try:
+        out = gdr.coarsen_edges(labels, labels, k, k, csr=A, weights=A.vals if weights else None, drop_diag=drop_diag)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("gdr_debug_set", b"coarsen_dense", 1)
+    return out
+
+
+@pytest.mark.parametrize("n,k,avg_deg,hubs,drop", [(5000, 50, 20, 0, True), (30000, 700, 30, 3, True), (30000, 700, 30, 3, False),
+                                                   (2000, 1500, 16, 1, True), (60000, 9000, 24, 2, True)])
+def test_dense_coarsen_equals_sort_path_and_fp64(gdr, n, k, avg_deg, hubs, drop):
+    u, v = _graph(n, avg_deg, hubs, seed=n + k)
+    A = gdr.sym_normalize(gdr.coo_to_csr(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV), None, (n, n), symmetrize=True,
+                                         binarize=True), 2)
+    rng = np.random.RandomState(7)
+    lab = rng.randint(0, k, n).astype(np.int32)
+    lab[lab == 3] = 4                        # an empty cluster
+    labels = torch.from_numpy(lab).to(DEV)
+    rp_s, ci_s, cnt_s, ws_s = _coarsen(gdr, A, labels, k, dense=False, drop_diag=drop)
+    rp_d, ci_d, cnt_d, ws_d = _coarsen(gdr, A, labels, k, dense=True, drop_diag=drop)
+    assert torch.equal(rp_s, rp_d) and torch.equal(ci_s, ci_d) and torch.equal(cnt_s, cnt_d)
+    torch.testing.assert_close(ws_d, ws_s, rtol=2e-6, atol=0)
+    # fp64 reference: the fixed-point sums are the exact sums rounded once
+    As = sp.csr_matrix((A.vals.cpu().numpy().astype(np.float64), A.colidx.cpu().numpy(), A.rowptr.cpu().numpy()), shape=(n, n))
+    P = sp.csr_matrix((np.ones(n), (np.arange(n), lab)), shape=(n, k))
+    S = (P.T @ As @ P).tocsr()
+    if drop:
+        S.setdiag(0)
+        S.eliminate_zeros()
+    S.sort_indices()
+    assert np.array_equal(S.indptr, rp_d.cpu().numpy()) and np.array_equal(S.indices, ci_d.cpu().numpy())
+    ref = S.data.astype(np.float32)
+    got = ws_d.cpu().numpy()
+    assert np.all(np.abs(got - ref) <= np.spacing(np.abs(ref)))      # within one fp32 ulp of the exact sum
+    # bit-reproducible although the shared-memory atomics land in any order
+    _, _, _, ws_d2 = _coarsen(gdr, A, labels, k, dense=True, drop_diag=drop)
+    assert torch.equal(ws_d, ws_d2)
+    # counts only
+    rp_c, ci_c, cnt_c, none = _coarsen(gdr, A, labels, k, dense=True, weights=False, drop_diag=drop)
+    assert none is None and torch.equal(rp_c, rp_d) and torch.equal(ci_c, ci_d) and torch.equal(cnt_c, cnt_d)
+
+
+def test_wide_coarse_rows_fall_back_to_the_sort(gdr):
+    n, k = 40000, 30000                      # 30000 x 12 B does not fit in shared memory
+    u, v = _graph(n, 12, 0, seed=5)
+    A = gdr.sym_normalize(gdr.coo_to_csr(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV), None, (n, n), symmetrize=True,
+                                         binarize=True), 2)
+    labels = torch.from_numpy(np.random.RandomState(1).randint(0, k, n).astype(np.int32)).to(DEV)
+    a = _coarsen(gdr, A, labels, k, dense=True)
+    b = _coarsen(gdr, A, labels, k, dense=False)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
