@@ -156,38 +156,22 @@ class Comm:
         import ctypes
         from . import _lib
         w, me = self.world, self.rank
-        tot = [sum(int(cnt_mat[s][d]) for s in range(w)) for d in range(w)]
-        recv_off = [sum(int(cnt_mat[s][p]) for s in range(me)) for p in range(w)]       # my rows' place on rank p
-        srcs, rowb, regions, need = [], [], [], 0
-        for a in arrays:
-            a = a.contiguous()
-            eb = a.element_size() * int(np.prod(a.shape[1:], dtype=np.int64))
-            if eb % 4:
-                raise ValueError("symm_exchange: rows must be multiples of 4 bytes")
-            srcs.append(a)
-            rowb.append(eb)
-            regions.append(need)
-            need += (max(tot) * eb + 255) // 256 * 256
+        srcs = [a.contiguous() for a in arrays]
+        rowb = [a.element_size() * int(np.prod(a.shape[1:], dtype=np.int64)) for a in srcs]
+        plan = exchange_plan(cnt_mat, me, rowb, gather)
+        tot, regions, need = plan["rows_here"], plan["regions"], plan["bytes"]
         cur = getattr(self, "_symm", None)
-        h, base = self.symm(max(need, 256, cur[2] if cur is not None else 0))
+        h, base = self.symm(max(need, cur[2] if cur is not None else 0))
         st = torch.cuda.current_stream().cuda_stream
         arr = ctypes.c_int64 * w
-        so, tot_s = [], 0
-        for p in range(w):
-            so.append(0 if gather else tot_s)
-            tot_s += int(cnt_mat[me][p])
-        sc = arr(*[int(cnt_mat[me][p]) for p in range(w)])
-        so_arr = arr(*so)
+        sc, so_arr = arr(*plan["send_cnt"]), arr(*plan["send_off"])      # named: ctypes.addressof of a temporary dangles
         _lib.call("gdr_symm_barrier", h, st)              # every rank is done with what lay in the buffer
-        for a, eb, reg in zip(srcs, rowb, regions):
-            do = arr(*[reg + recv_off[p] * eb for p in range(w)])
+        for a, eb, dst in zip(srcs, rowb, plan["dst_off_bytes"]):
+            do = arr(*dst)
             _lib.call("gdr_symm_scatterv", h, a.data_ptr() if a.numel() else 0, ctypes.addressof(so_arr), ctypes.addressof(sc),
                       ctypes.addressof(do), eb, st)
         _lib.call("gdr_symm_barrier", h, st)
-        out = []
-        for a, eb, reg in zip(srcs, rowb, regions):
-            out.append(_device_view(base + reg, (tot[me],) + tuple(a.shape[1:]), a.dtype, a.device))
-        return out
+        return [_device_view(base + reg, (tot,) + tuple(a.shape[1:]), a.dtype, a.device) for a, reg in zip(srcs, regions)]
 
     def close(self):
         """Destroys the library communicator (call before torch.distributed.destroy_process_group)."""
@@ -290,6 +274,29 @@ class Comm:
         out = torch.empty(m * self.world, dtype=local.dtype, device=local.device)
         self.all_gather_rows(block, out)
         return torch.cat([out[r * m: r * m + int(counts[r])] for r in range(self.world)])
+
+
+def exchange_plan(cnt_mat, me: int, row_bytes, gather: bool = False) -> dict:
+    """Where rank ``me`` reads and writes in a symmetric-buffer exchange (pure host arithmetic; tests/test_parallel_gloo.py
+    replays it for every rank of a world against a byte-level simulation).  ``cnt_mat[src][dst]`` rows go from src to dst;
+    array a (``row_bytes[a]`` per row) occupies the SAME region of every rank's buffer, rows in source-rank order.
+    ``gather``: every destination receives the sender's whole block (send offset 0)."""
+    w = len(cnt_mat)
+    tot = [sum(int(cnt_mat[s][d]) for s in range(w)) for d in range(w)]
+    place = [sum(int(cnt_mat[s][p]) for s in range(me)) for p in range(w)]         # my rows' first row on rank p
+    regions, need = [], 0
+    for eb in row_bytes:
+        if eb <= 0 or eb % 4:
+            raise ValueError("symm_exchange: rows must be multiples of 4 bytes")
+        regions.append(need)
+        need += (max(tot) * eb + 255) // 256 * 256
+    send_cnt = [int(cnt_mat[me][p]) for p in range(w)]
+    send_off, acc = [], 0
+    for p in range(w):
+        send_off.append(0 if gather else acc)
+        acc += send_cnt[p]
+    return {"rows_here": tot[me], "regions": regions, "bytes": max(need, 256), "send_cnt": send_cnt, "send_off": send_off,
+            "dst_off_bytes": [[reg + place[p] * eb for p in range(w)] for reg, eb in zip(regions, row_bytes)]}
 
 
 class _DevWindow:

@@ -529,3 +529,50 @@ def test_world1_drivers_without_process_group(oracle, slabs, row_chunks):
         np.testing.assert_allclose(adj_syn.to_dense().numpy()[fin], S[fin], rtol=1e-5, atol=1e-8)
         rows = np.repeat(np.arange(n), np.diff(rpo))
         assert np.array_equal(cnt.numpy(), o.coarsen_counts(rows, cio, labels, labels, 17, 17, drop_diag=True)[2])
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("gather", [False, True])
+def test_symmetric_buffer_exchange_plan(world, gather):
+    """exchange_plan (the host arithmetic of Comm.symm_exchange / all_gather_symm) replayed for every rank of a world on
+    byte buffers: every row lands once, in source-rank order, regions do not overlap, nothing is written out of bounds."""
+    import gdr
+    from gdr.parallel import exchange_plan
+    rng = np.random.RandomState(world + 10 * gather)
+    if gather:
+        block = rng.randint(0, 50, world)
+        block[rng.randint(world)] = 0                       # an empty block
+        cnt = [[int(block[s])] * world for s in range(world)]
+    else:
+        cnt = rng.randint(0, 40, (world, world))
+        cnt[rng.randint(world), :] = 0                      # a rank that sends nothing
+        cnt[:, rng.randint(world)] = 0                      # a rank that receives nothing
+        cnt = cnt.tolist()
+    row_bytes = [8, 4, 12]
+    plans = [exchange_plan(cnt, me, row_bytes, gather) for me in range(world)]
+    size = plans[0]["bytes"]
+    assert all(p["bytes"] == size and p["regions"] == plans[0]["regions"] for p in plans)      # same layout on every rank
+    bufs = [np.full(size, 0xEE, np.uint8) for _ in range(world)]
+    written = [np.zeros(size, np.int32) for _ in range(world)]
+    sends = []
+    for me in range(world):
+        n_send = max(cnt[me]) if gather else sum(cnt[me])
+        sends.append([rng.randint(0, 255, n_send * eb).astype(np.uint8) for eb in row_bytes])
+    for me, p in enumerate(plans):
+        for a, eb in enumerate(row_bytes):
+            for dst in range(world):
+                n = p["send_cnt"][dst] * eb
+                src = sends[me][a][p["send_off"][dst] * eb: p["send_off"][dst] * eb + n]
+                off = p["dst_off_bytes"][a][dst]
+                assert off % 4 == 0 and off + n <= size
+                bufs[dst][off: off + n] = src
+                written[dst][off: off + n] += 1
+    for d in range(world):
+        assert written[d].max() <= 1                                         # no byte written twice
+        for a, eb in enumerate(row_bytes):
+            reg = plans[d]["regions"][a]
+            rows = plans[d]["rows_here"]
+            want = np.concatenate([sends[s][a][(0 if gather else sum(cnt[s][:d])) * eb: ((0 if gather else sum(cnt[s][:d])) + cnt[s][d]) * eb]
+                                   for s in range(world)] + [np.zeros(0, np.uint8)])
+            assert np.array_equal(bufs[d][reg: reg + rows * eb], want)
+            assert written[d][reg: reg + rows * eb].min(initial=1) == 1
