@@ -128,6 +128,10 @@ _SIGNATURES = {
     "gdr_coarsen_route": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp]),
     "gdr_coarse_merge_edges_ws_bytes": (i64, [i64]),
     "gdr_coarse_merge_edges": (i32, [i64, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "gdr_cluster_stats": (i32, [i64, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+    "gdr_coarse_merge_edges_dense_ok": (i32, [i64, i64, i32]),
+    "gdr_coarse_merge_edges_dense_ws_bytes": (i64, [i64, i64]),
+    "gdr_coarse_merge_edges_dense": (i32, [i64, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_ws_bytes": (i64, [i64, i64, i64]),
     "gdr_coarsen": (i32, [i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "gdr_coarsen_scale": (i32, [i64, vp, vp, vp, vp, vp, vp, vp]),

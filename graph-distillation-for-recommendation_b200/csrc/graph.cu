@@ -834,13 +834,25 @@ __global__ void k_cd_group(int64_t n_rows, const int32_t* __restrict__ labels, c
   }
 }
 
-template <bool HAS_W>
+// PAIRS: the edges of coarse row a are the (key, weight) pairs [starts[a], starts[a + 1]) of a list grouped by coarse row
+// (key = column << la | local row: the owner side of the multi-GPU exchange); the fixed-point step comes from the
+// GLOBAL per-cluster (edges, max |w|), so that every rank count and the single-GPU form round every term identically.
+struct CdPairs {
+  const uint64_t* keys;
+  const float* w;
+  int la;
+  int64_t a_lo;
+  const int32_t* g_edges;
+  const uint32_t* g_wmax;
+};
+
+template <bool HAS_W, bool PAIRS>
 __global__ void __launch_bounds__(CD_THREADS, 1)
 k_cd_accumulate(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const float* __restrict__ w, const int32_t* __restrict__ labels_dst, const int32_t* __restrict__ starts,
                 const int32_t* __restrict__ nodes, const int32_t* __restrict__ edge_prefix, const uint32_t* __restrict__ wmax_bits,
                 int drop_diag, int32_t* __restrict__ next_cluster, int32_t* __restrict__ t_col, int32_t* __restrict__ t_cnt,
-                float* __restrict__ t_sum, int32_t* __restrict__ nnz_row, int32_t* __restrict__ status) {
+                float* __restrict__ t_sum, int32_t* __restrict__ nnz_row, int32_t* __restrict__ status, CdPairs pr) {
   extern __shared__ __align__(16) unsigned char cd_smem[];
   // 64-bit fixed-point sums as two 32-bit words with a carry (a 64-bit shared-memory add is a CAS spin loop)
   uint32_t* s_lo = reinterpret_cast<uint32_t*>(cd_smem);                                            // [HAS_W ? n_dst : 0]
@@ -862,12 +874,12 @@ k_cd_accumulate(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr
     const int a = s_a;
     if (a >= n_src) break;
     const int32_t nb = starts[a], ne = starts[a + 1];
-    const int32_t n_edges = edge_prefix[a + 1] - edge_prefix[a];
+    const int32_t n_edges = !HAS_W ? 0 : (PAIRS ? pr.g_edges[pr.a_lo + a] : edge_prefix[a + 1] - edge_prefix[a]);
     // fixed-point step of this cluster: |sum of any cell| <= wmax * n_edges < 2^(ew + ee)
     double inv_q = 0.0, q = 0.0;
     if (HAS_W) {
       int ew = 0, ee = 0;
-      frexpf(__uint_as_float(wmax_bits[a]), &ew);
+      frexpf(__uint_as_float(PAIRS ? pr.g_wmax[pr.a_lo + a] : wmax_bits[a]), &ew);
       frexp((double)(n_edges > 0 ? n_edges : 1), &ee);
       q = ldexp(1.0, ew + ee - 62);
       inv_q = ldexp(1.0, 62 - ew - ee);
@@ -896,8 +908,17 @@ k_cd_accumulate(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr
         if (two) add_cell(c1, w1);
       }
     };
+    if (PAIRS) {
+      for (int32_t k = nb + tid; k < ne; k += 2 * CD_THREADS) {
+        const bool two = k + CD_THREADS < ne;
+        const uint64_t k0 = pr.keys[k], k1 = two ? pr.keys[k + CD_THREADS] : 0ull;
+        const float w0 = HAS_W ? pr.w[k] : 0.f, w1 = (HAS_W && two) ? pr.w[k + CD_THREADS] : 0.f;
+        add_cell((int32_t)(k0 >> pr.la), w0);
+        if (two) add_cell((int32_t)(k1 >> pr.la), w1);
+      }
+    }
     // one warp per adjacency row; very long rows are left to the whole CTA
-    for (int32_t t = nb + warp; t < ne; t += CD_THREADS / 32) {
+    for (int32_t t = nb + warp; !PAIRS && t < ne; t += CD_THREADS / 32) {
       const int32_t i = nodes[t];
       const int32_t rb = rowptr[i], re = rowptr[i + 1];
       if (re - rb >= CD_HUB) {
@@ -912,7 +933,7 @@ k_cd_accumulate(int64_t n_src, int64_t n_dst, const int32_t* __restrict__ rowptr
       add_edges(rb + lane, re, 32);
     }
     __syncthreads();
-    const int hubs = s_hub_n < 64 ? s_hub_n : 64;
+    const int hubs = PAIRS ? 0 : (s_hub_n < 64 ? s_hub_n : 64);
     for (int h = 0; h < hubs; ++h) {
       const int32_t i = s_hub[h];
       add_edges(rowptr[i] + tid, rowptr[i + 1], CD_THREADS);
@@ -1028,20 +1049,21 @@ static int coarsen_dense(int64_t E, int64_t n_rows, const int32_t* csr_rowptr, c
   if (wsum) {
     static PerDevice<bool> attr;
     if (!attr.get()) {
-      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr.get() = true;
     }
-    k_cd_accumulate<true><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, w, labels_dst, starts, nodes,
-                                                        edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, t_sum, nnz_row, misc + 1);
+    k_cd_accumulate<true, false><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, w, labels_dst, starts, nodes,
+                                                               edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, t_sum, nnz_row,
+                                                               misc + 1, CdPairs{});
   } else {
     static PerDevice<bool> attr;
     if (!attr.get()) {
-      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr.get() = true;
     }
-    k_cd_accumulate<false><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, nullptr, labels_dst, starts,
-                                                         nodes, edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, nullptr, nnz_row,
-                                                         misc + 1);
+    k_cd_accumulate<false, false><<<grid, CD_THREADS, smem, s>>>(n_src, n_dst, csr_rowptr, csr_colidx, nullptr, labels_dst, starts,
+                                                                nodes, edge_prefix, wmax, drop_diag, misc, t_col, t_cnt, nullptr,
+                                                                nnz_row, misc + 1, CdPairs{});
   }
   GDR_LAUNCHED();
   if ((rc = exclusive_scan_i32(nnz_row, rowptr, n_src, sws, sws_b, s))) return rc;
@@ -1049,6 +1071,28 @@ static int coarsen_dense(int64_t E, int64_t n_rows, const int32_t* csr_rowptr, c
                                                                        wsum, nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
+}
+
+// key (owner tag | row << bbits | col) -> (col << la) | (row - a_lo): a stable sort on the low la bits groups by coarse row
+__global__ void k_cd_swap_keys(int64_t m, const uint64_t* __restrict__ in, int bbits, int la, int64_t a_lo, uint64_t* __restrict__ out) {
+  const uint64_t cell_mask = (1ull << ROUTE_SHIFT) - 1ull, bmask = (1ull << bbits) - 1ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t cell = in[i] & cell_mask;
+    out[i] = ((cell & bmask) << la) | (uint64_t)((int64_t)(cell >> bbits) - a_lo);
+  }
+}
+// starts[a] = first pair of local coarse row a in the grouped list (binary search), starts[n_rows] = m
+__global__ void k_cd_pair_starts(int64_t m, const uint64_t* __restrict__ keys, int la, int64_t n_rows, int32_t* __restrict__ starts) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a > n_rows) return;
+  const uint64_t amask = (1ull << la) - 1ull;
+  int64_t lo = 0, hi = m;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)(keys[mid] & amask) < a) lo = mid + 1;
+    else hi = mid;
+  }
+  starts[a] = (int32_t)lo;
 }
 
 }  // namespace gdr
@@ -1613,6 +1657,114 @@ int gdr_coarse_merge_edges(int64_t m, const uint64_t* keys_in, const float* w_in
                                             colidx, counts, wsum);
   GDR_LAUNCHED();
   k_rowptr_from_ukeys_range<<<grid_for(m + 1), 256, 0, s>>>(R.pos + m, a_lo, n_rows, bbits, R.ukeys, rowptr, nnz_out_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+// ---------------- owner-side merge of routed edges in shared memory (multi-GPU stage 4) ----------------
+// per-cluster (edges, max |w|, nodes) of this rank's rows: summed / maxed over the ranks they fix the fixed-point step
+int gdr_cluster_stats(int64_t n_rows, const int32_t* rowptr, const float* w, const int32_t* labels, int64_t n_src,
+                      int32_t* nodes_out, int32_t* edges_out, uint32_t* wmax_bits_out, int32_t* status_dev, gdr_stream_t stream) {
+  GDR_CHECK_ARG(n_rows >= 0 && n_src > 0 && nodes_out && edges_out && wmax_bits_out && status_dev, "cluster_stats: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  GDR_CUDA(cudaMemsetAsync(nodes_out, 0, n_src * 4, s));
+  GDR_CUDA(cudaMemsetAsync(edges_out, 0, n_src * 4, s));
+  GDR_CUDA(cudaMemsetAsync(wmax_bits_out, 0, n_src * 4, s));
+  GDR_CUDA(cudaMemsetAsync(status_dev, 0, 4, s));
+  if (n_rows == 0) return GDR_OK;
+  GDR_CHECK_ARG(rowptr && labels, "cluster_stats: null pointer");
+  k_cd_stats<<<(unsigned)cdiv(n_rows * 32, 256), 256, 0, s>>>(n_rows, rowptr, w, labels, n_src, nodes_out, edges_out, wmax_bits_out,
+                                                            status_dev);
+  GDR_LAUNCHED();
+  return GDR_OK;
+}
+
+int64_t gdr_coarse_merge_edges_dense_ws_bytes(int64_t m, int64_t n_rows) {
+  m = m > 0 ? m : 1;
+  return ws_need(m, 8) + ws_need(m, 4) + sort_pairs_ws_bytes(m) + 3 * ws_need(m, 4) + 3 * ws_need(n_rows + 1, 4) +
+         scan_ws_bytes(n_rows + 1) + 1024;
+}
+
+// 1 when gdr_coarse_merge_edges_dense applies to this shape (the coarse row fits in shared memory), else 0
+int gdr_coarse_merge_edges_dense_ok(int64_t n_rows, int64_t n_dst, int has_weights) {
+  return (g_coarsen_dense && n_rows > 0 && n_rows < (1ll << 24) && n_dst * (has_weights ? 12 : 4) <= 200 * 1024) ? 1 : 0;
+}
+
+int gdr_coarse_merge_edges_dense(int64_t m, const uint64_t* keys_in, const float* w_in, int64_t a_lo, int64_t n_rows, int64_t n_src,
+                                 int64_t n_dst, const int32_t* cluster_edges, const uint32_t* cluster_wmax_bits, int32_t* rowptr,
+                                 int32_t* colidx, int32_t* counts, float* wsum, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes,
+                                 gdr_stream_t stream) {
+  GDR_CHECK_ARG(m >= 0 && n_rows >= 0 && n_src > 0 && n_dst > 0 && a_lo >= 0 && a_lo + n_rows <= n_src && rowptr && nnz_out_dev,
+                "coarse_merge_edges_dense: bad arguments");
+  GDR_CHECK_ARG(m < (1ll << 31), "coarse_merge_edges_dense: size exceeds int32");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0 || n_rows == 0) {
+    GDR_CUDA(cudaMemsetAsync(rowptr, 0, (n_rows + 1) * 4, s));
+    GDR_CUDA(cudaMemsetAsync(nnz_out_dev, 0, 8, s));
+    return GDR_OK;
+  }
+  GDR_CHECK_ARG(keys_in && colidx && counts && (!wsum || (w_in && cluster_edges && cluster_wmax_bits)),
+                "coarse_merge_edges_dense: null pointer");
+  if (!gdr_coarse_merge_edges_dense_ok(n_rows, n_dst, wsum != nullptr)) {
+    set_error("coarse_merge_edges_dense: a coarse row of %lld cells does not fit in shared memory", (long long)n_dst);
+    return GDR_EUNSUPPORTED;
+  }
+  if (ws_bytes < gdr_coarse_merge_edges_dense_ws_bytes(m, n_rows)) {
+    set_error("coarse_merge_edges_dense: workspace too small");
+    return GDR_EWORKSPACE;
+  }
+  Workspace W(ws, ws_bytes);
+  uint64_t* keys = W.take<uint64_t>(m);
+  uint32_t* payload = W.take<uint32_t>(m);
+  const int64_t sws_b = sort_pairs_ws_bytes(m);
+  void* sws = W.take<char>(sws_b);
+  int32_t* t_col = W.take<int32_t>(m);
+  int32_t* t_cnt = W.take<int32_t>(m);
+  float* t_sum = W.take<float>(m);
+  int32_t* starts = W.take<int32_t>(n_rows + 1);
+  int32_t* nnz_row = W.take<int32_t>(n_rows + 1);
+  int32_t* misc = W.take<int32_t>(64);
+  const int64_t scan_b = scan_ws_bytes(n_rows + 1);
+  void* scan_ws = W.take<char>(scan_b);
+  const int bbits = bits_for(n_dst), la = std::max(7, bits_for(n_rows));      // >= 7: the sort leaves the bits above alone
+  k_cd_swap_keys<<<grid_for(m), 256, 0, s>>>(m, keys_in, bbits, la, a_lo, keys);
+  GDR_LAUNCHED();
+  uint32_t* pl = wsum ? payload : nullptr;
+  if (pl) GDR_CUDA(cudaMemcpyAsync(payload, w_in, m * 4, cudaMemcpyDeviceToDevice, s));
+  uint64_t* skeys = keys;
+  uint32_t* spay = pl;
+  int rc = sort_pairs_ex(m, la, keys, pl, sws, sws_b, &skeys, pl ? &spay : nullptr, s);      // stable: groups by coarse row
+  if (rc) return rc;
+  k_cd_pair_starts<<<(unsigned)cdiv(n_rows + 1, 256), 256, 0, s>>>(m, skeys, la, n_rows, starts);
+  GDR_LAUNCHED();
+  GDR_CUDA(cudaMemsetAsync(misc, 0, 256, s));
+  int dev = 0, sms = kSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = (size_t)n_dst * (wsum ? 12 : 4);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_rows, sms);
+  CdPairs pr{skeys, reinterpret_cast<const float*>(spay), la, a_lo, cluster_edges, cluster_wmax_bits};
+  if (wsum) {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr.get() = true;
+    }
+    k_cd_accumulate<true, true><<<grid, CD_THREADS, smem, s>>>(n_rows, n_dst, nullptr, nullptr, nullptr, nullptr, starts, nullptr, starts,
+                                                              nullptr, 0, misc, t_col, t_cnt, t_sum, nnz_row, misc + 1, pr);
+  } else {
+    static PerDevice<bool> attr;
+    if (!attr.get()) {
+      GDR_CUDA(cudaFuncSetAttribute(k_cd_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr.get() = true;
+    }
+    k_cd_accumulate<false, true><<<grid, CD_THREADS, smem, s>>>(n_rows, n_dst, nullptr, nullptr, nullptr, nullptr, starts, nullptr,
+                                                               starts, nullptr, 0, misc, t_col, t_cnt, nullptr, nnz_row, misc + 1, pr);
+  }
+  GDR_LAUNCHED();
+  if ((rc = exclusive_scan_i32(nnz_row, rowptr, n_rows, scan_ws, scan_b, s))) return rc;
+  k_cd_pack<<<(unsigned)std::min<int64_t>(n_rows, 8 * sms), 256, 0, s>>>(n_rows, starts, rowptr, t_col, t_cnt, t_sum, colidx, counts, wsum,
+                                                                        nnz_out_dev);
   GDR_LAUNCHED();
   return GDR_OK;
 }

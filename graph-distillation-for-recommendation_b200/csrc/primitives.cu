@@ -445,7 +445,9 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
   int64_t nb = cdiv(n, RS_THREADS * rounds);
   const int passes = rs_passes(key_bits, rs_max_bits(n));
   // the scatter kernel is built for digit widths 7..11; a narrower plan runs as 7 bits (its digits then overlap the
-  // next pass's, which sorts those bits again: still a stable LSD sort; keys are < 2^key_bits, the bits above are zero)
+  // next pass's, which sorts those bits again: still a stable LSD sort).  A digit never reaches above bit key_bits - 1 as
+  // long as key_bits >= 7 (the last pass is shifted DOWN onto already sorted bits instead), so callers may keep unrelated
+  // bits above the sorted field; below 7 bits the bits above the field must be zero.
   const int bits = std::max(7, rs_digit_bits(key_bits, rs_max_bits(n)));
   const int step = rs_digit_bits(key_bits, rs_max_bits(n));
   const int bins = 1 << bits;
@@ -461,7 +463,7 @@ int sort_pairs_ex(int64_t n, int key_bits, uint64_t* keys, uint32_t* vals, void*
   uint32_t* vout = vals ? valt : nullptr;
   const size_t hist_smem = (size_t)bins * 4;
   for (int p = 0; p < passes; ++p) {
-    int shift = step * p;
+    int shift = std::max(0, std::min(step * p, key_bits - bits));
     if (rounds == 16) k_rs_hist<16><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
     else k_rs_hist<4><<<(unsigned)nb, RS_THREADS, hist_smem, s>>>(kin, n, shift, bits, table, (int)nb);
     GDR_LAUNCHED();

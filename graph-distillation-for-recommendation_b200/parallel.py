@@ -654,9 +654,25 @@ class CudaOps:
         st = starts.cpu().tolist()
         return keys, w_out, [int(st[r + 1] - st[r]) for r in range(world)]
 
-    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None):
+    def cluster_stats(self, A_local, labels_local, n):
+        """Per coarse row, over THIS rank's rows: (edges int32 [n], bit pattern of the largest |weight| int32 [n])
+        (gdr_cluster_stats).  Summed / maxed over the ranks they fix the fixed-point step of coarse_merge_edges."""
+        dev = labels_local.device
+        nodes = torch.empty(n, dtype=torch.int32, device=dev)
+        edges = torch.empty(n, dtype=torch.int32, device=dev)
+        wmax = torch.empty(n, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._lib.call("gdr_cluster_stats", int(A_local.shape[0]), self.ptr(A_local.rowptr), self.ptr(A_local.vals),
+                       self.ptr(labels_local), int(n), self.ptr(nodes), self.ptr(edges), self.ptr(wmax), self.ptr(status),
+                       self.stream())
+        return edges, wmax
+
+    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None, stats=None):
         """Pairs received from every rank (source-rank order = global CSR order) -> CSR (rowptr, colidx, counts, wsum) of
-        the coarse rows [a_lo, a_lo + n_rows): stable sort by cell, run lengths, fp32 sums in that order."""
+        the coarse rows [a_lo, a_lo + n_rows).  With ``stats`` = the global (edges, max |w| bits) per coarse row and a
+        coarse row that fits in shared memory: grouped by row, cells accumulated in shared memory — the sums are those of the
+        single-GPU gdr_coarsen, bit for bit (gdr_coarse_merge_edges_dense).  Otherwise: stable sort by cell, run lengths,
+        fp32 sums in CSR order (gdr_coarse_merge_edges)."""
         n_dst = n if n_dst is None else n_dst
         m = int(keys.shape[0])
         dev = keys.device
@@ -665,10 +681,20 @@ class CudaOps:
         counts = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
         wsum = torch.empty(max(m, 1), dtype=torch.float32, device=dev) if w is not None else None
         nnz = torch.zeros(1, dtype=torch.int64, device=dev)
-        ws = self.workspace(self._lib.query("gdr_coarse_merge_edges_ws_bytes", m), dev)
-        self._lib.call("gdr_coarse_merge_edges", m, self.ptr(keys) if m else 0, self.ptr(w) if (m and w is not None) else 0,
-                       int(a_lo), int(n_rows), int(n), int(n_dst), self.ptr(rowptr), self.ptr(colidx), self.ptr(counts),
-                       self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
+        dense = (stats is not None or w is None) and n_rows > 0 and \
+            self._lib.query("gdr_coarse_merge_edges_dense_ok", int(n_rows), int(n_dst), int(w is not None))
+        if dense:
+            ws = self.workspace(self._lib.query("gdr_coarse_merge_edges_dense_ws_bytes", m, int(n_rows)), dev)
+            self._lib.call("gdr_coarse_merge_edges_dense", m, self.ptr(keys) if m else 0,
+                           self.ptr(w) if (m and w is not None) else 0, int(a_lo), int(n_rows), int(n), int(n_dst),
+                           self.ptr(stats[0]) if stats is not None else 0, self.ptr(stats[1]) if stats is not None else 0,
+                           self.ptr(rowptr), self.ptr(colidx), self.ptr(counts), self.ptr(wsum), self.ptr(nnz), self.ptr(ws),
+                           ws.numel(), self.stream())
+        else:
+            ws = self.workspace(self._lib.query("gdr_coarse_merge_edges_ws_bytes", m), dev)
+            self._lib.call("gdr_coarse_merge_edges", m, self.ptr(keys) if m else 0, self.ptr(w) if (m and w is not None) else 0,
+                           int(a_lo), int(n_rows), int(n), int(n_dst), self.ptr(rowptr), self.ptr(colidx), self.ptr(counts),
+                           self.ptr(wsum), self.ptr(nnz), self.ptr(ws), ws.numel(), self.stream())
         k = int(nnz.item())
         return rowptr, colidx[:k], counts[:k], (None if wsum is None else wsum[:k])
 
@@ -1142,6 +1168,11 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
     if merge == "route" and hasattr(ops, "coarsen_route"):
         # every edge goes to the owner of its coarse row once; the owner sorts + reduces (one sort per edge, sums in CSR order)
         keys, w, send_counts = ops.coarsen_route(A_local, lab_l, labels_all, n, world)
+        stats = None
+        if hasattr(ops, "cluster_stats"):
+            # per-cluster (edges, max |w|) of the whole graph: the owner's shared-memory merge then rounds like one GPU does
+            edges, wmax = ops.cluster_stats(A_local, lab_l, n)
+            stats = (comm.all_reduce(edges, "sum"), comm.all_reduce(wmax, "max"))
         mark("route")
         if comm.symm_ok() and keys.is_cuda:
             recv_k, recv_w = comm.symm_exchange([keys, w], comm.count_matrix(send_counts, keys.device))
@@ -1149,7 +1180,10 @@ def dist_graph_compress(comm: Comm, part: RowPartition, labels_local: torch.Tens
             recv_k, rc = comm.all_to_all_rows(keys, send_counts)
             recv_w, _ = comm.all_to_all_rows(w, send_counts, recv_counts=rc)
         mark("all_to_all")
-        rowptr, colidx, counts, wsum = ops.coarse_merge_edges(recv_k, recv_w, a_lo, n_rows, n)
+        if stats is not None:
+            rowptr, colidx, counts, wsum = ops.coarse_merge_edges(recv_k, recv_w, a_lo, n_rows, n, stats=stats)
+        else:
+            rowptr, colidx, counts, wsum = ops.coarse_merge_edges(recv_k, recv_w, a_lo, n_rows, n)
         mark("merge_edges")
     else:
         # local coarsening first, then (cell, count, sum) records by key range: less traffic when cells repeat a lot locally

@@ -539,6 +539,21 @@ int64_t gdr_coarse_merge_edges_ws_bytes(int64_t m);
 int     gdr_coarse_merge_edges(int64_t m, const uint64_t* keys_in, const float* w_in, int64_t a_lo, int64_t n_rows,
                                int64_t n_src, int64_t n_dst, int32_t* rowptr, int32_t* colidx, int32_t* counts,
                                float* wsum, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
+/* The same merge without sorting the cells: the routed pairs are grouped by coarse row (a stable sort on the row bits
+ * only) and one CTA per coarse row accumulates its cells in shared memory — integer counts and 64-bit fixed-point weight
+ * sums, as gdr_coarsen does on one GPU.  cluster_edges / cluster_wmax_bits: per coarse row of the WHOLE graph, the number
+ * of edges leaving it and the bit pattern of their largest |weight| (gdr_cluster_stats on every rank's rows, summed /
+ * maxed over the ranks): they fix the fixed-point step, so every term is rounded as on one GPU and the sums are
+ * bit-identical to gdr_coarsen's for any number of ranks.  _ok: 1 when a coarse row of n_dst cells fits in shared memory. */
+int     gdr_cluster_stats(int64_t n_rows, const int32_t* rowptr, const float* w, const int32_t* labels, int64_t n_src,
+                          int32_t* nodes_out, int32_t* edges_out, uint32_t* wmax_bits_out, int32_t* status_dev,
+                          gdr_stream_t stream);
+int     gdr_coarse_merge_edges_dense_ok(int64_t n_rows, int64_t n_dst, int has_weights);
+int64_t gdr_coarse_merge_edges_dense_ws_bytes(int64_t m, int64_t n_rows);
+int     gdr_coarse_merge_edges_dense(int64_t m, const uint64_t* keys_in, const float* w_in, int64_t a_lo, int64_t n_rows,
+                                     int64_t n_src, int64_t n_dst, const int32_t* cluster_edges,
+                                     const uint32_t* cluster_wmax_bits, int32_t* rowptr, int32_t* colidx, int32_t* counts,
+                                     float* wsum, int64_t* nnz_out_dev, void* ws, int64_t ws_bytes, gdr_stream_t stream);
 /* gdr_kmeans_lloyd on a row partition: Xc_local = this rank's N_local rows (may be 0) of the mean-centred matrix of
  * N_total rows, centres replicated.  Each iteration all-reduces [K x ld sums | K counts | n_changed] inside the replayed
  * CUDA graph; the replicated centres stay bit-identical across ranks; empty clusters are relocated from the globally

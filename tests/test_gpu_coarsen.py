@@ -79,3 +79,41 @@ def test_wide_coarse_rows_fall_back_to_the_sort(gdr):
     a = _coarsen(gdr, A, labels, k, dense=True)
     b = _coarsen(gdr, A, labels, k, dense=False)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("n,k,world", [(60000, 9000, 2), (30000, 700, 3), (20000, 100, 2)])
+def test_owner_side_merge_in_shared_memory(gdr, n, k, world):
+    """The multi-GPU stage 4 at the owner of a key range, replayed on one GPU: the pairs gdr_coarsen_route addresses to
+    each owner, merged by the sort and in shared memory (gdr_coarse_merge_edges_dense with the global per-cluster
+    fixed-point step) — structure and counts equal, sums bit-identical to the single-GPU gdr_coarsen rows."""
+    from gdr import parallel as par
+    u, v = _graph(n, 24, 2, seed=n + k)
+    A = gdr.sym_normalize(gdr.coo_to_csr(torch.from_numpy(u).to(DEV), torch.from_numpy(v).to(DEV), None, (n, n), symmetrize=True,
+                                         binarize=True), 2)
+    lab = np.random.RandomState(3).randint(0, k, n).astype(np.int32)
+    labels = torch.from_numpy(lab).to(DEV)
+    ops = par.CudaOps()
+    rp1, ci1, cnt1, ws1 = _coarsen(gdr, A, labels, k, dense=True)
+    keys, w, counts = ops.coarsen_route(A, labels, labels, k, world)
+    stats = ops.cluster_stats(A, labels, k)
+    cr = (k + world - 1) // world
+    off = 0
+    for r in range(world):
+        a_lo = min(k, r * cr)
+        n_rows = min(k, a_lo + cr) - a_lo
+        seg_k, seg_w = keys[off: off + counts[r]], w[off: off + counts[r]]
+        off += counts[r]
+        d = ops.coarse_merge_edges(seg_k, seg_w, a_lo, n_rows, k, stats=stats)
+        from gdr import _lib
+        _lib.call("gdr_debug_set", b"coarsen_dense", 0)
+        try:
+            s = ops.coarse_merge_edges(seg_k, seg_w, a_lo, n_rows, k, stats=stats)
+        finally:
+            _lib.call("gdr_debug_set", b"coarsen_dense", 1)
+        assert torch.equal(d[0], s[0]) and torch.equal(d[1], s[1]) and torch.equal(d[2], s[2])
+        torch.testing.assert_close(d[3], s[3], rtol=2e-6, atol=0)
+        b, e = int(rp1[a_lo]), int(rp1[a_lo + n_rows])
+        assert torch.equal(d[0] + b, rp1[a_lo: a_lo + n_rows + 1]) and torch.equal(d[1], ci1[b:e]) and torch.equal(d[2], cnt1[b:e])
+        assert torch.equal(d[3], ws1[b:e])                                  # the same fixed-point step: bit-identical sums
+        c = ops.coarse_merge_edges(seg_k, None, a_lo, n_rows, k)             # counts only
+        assert c[3] is None and torch.equal(c[0], d[0]) and torch.equal(c[1], d[1]) and torch.equal(c[2], d[2])

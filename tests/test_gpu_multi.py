@@ -118,22 +118,23 @@ def _worker(rank, world, port):
         _, syn1 = gdr.graph_compress(labels, A_full, [])
         kk = int(labels.max()) + 1
         _, _, cnt1, _ = gdr.coarsen_edges(labels, labels, kk, kk, csr=A_full, drop_diag=True)
-        # transports: NCCL send/recv (symm False) and posted stores through the symmetric buffer (gdr_symm_scatterv)
-        for merge, symm in (("records", True), ("route", False), ("route", True)):
-            comm.use_symm_exchange = symm
-            adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
-                                                      merge=merge)
-            assert torch.equal(adj_syn._indices(), syn1._indices())
-            assert torch.equal(counts, cnt1)
-            torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
-            if merge == "route":    # CSR-order fp32 sums here, once-rounded exact sums on one GPU (shared-memory form)
-                torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=2e-6, atol=0)
-        # routing form: the exchange order is the global CSR order -> the weight sums are those of the single-GPU SORT path, bit for bit
-        _lib_dbg = __import__("gdr")._lib
-        _lib_dbg.call("gdr_debug_set", b"coarsen_dense", 0)
-        _, syn_sort = gdr.graph_compress(labels, A_full, [])
+        # transports: NCCL send/recv (symm False) and posted stores through the symmetric buffer (gdr_symm_scatterv);
+        # forms: cells accumulated in shared memory (dense 1: exact sums rounded once, with the GLOBAL per-cluster fixed-point
+        # step) and the sort (dense 0: fp32 sums in global CSR order) — the routed result equals one GPU's bit for bit in both
+        from gdr import _lib as _lib_dbg
+        for dense in (1, 0):
+            _lib_dbg.call("gdr_debug_set", b"coarsen_dense", dense)
+            _, syn_d = gdr.graph_compress(labels, A_full, [])
+            for merge, symm in (("records", True), ("route", False), ("route", True)):
+                comm.use_symm_exchange = symm
+                adj_syn, counts = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
+                                                          merge=merge)
+                assert torch.equal(adj_syn._indices(), syn1._indices())
+                assert torch.equal(counts, cnt1)
+                torch.testing.assert_close(adj_syn._values(), syn1._values(), rtol=1e-5, atol=1e-9)
+                if merge == "route":
+                    assert torch.equal(adj_syn._values(), syn_d._values())
         _lib_dbg.call("gdr_debug_set", b"coarsen_dense", 1)
-        assert torch.equal(adj_syn._values(), syn_sort._values())
         # not replicated: this rank's key range of the coarse rows
         a_lo, rp_p, ci_p, v_p, c_p = par.dist_graph_compress(comm, part, labels[part.lo:part.hi].contiguous(), A_local, ops=ops,
                                                              replicate=False)
