@@ -135,9 +135,21 @@ class Comm:
         return mat.view(self.world, self.world).tolist()
 
     def symm_ok(self) -> bool:
-        """True when exchanges can go through peer memory (NCCL process group on CUDA, peer access not found broken)."""
-        return self.dist is not None and self.world > 1 and self.backend == "nccl" and not _P2P_BROKEN \
-            and getattr(self, "use_symm_exchange", True)
+        """True when exchanges can go through peer memory (NCCL process group on CUDA, peer access available).  The first
+        call creates a small symmetric buffer to find out — collective, like every call that follows it."""
+        global _P2P_BROKEN
+        if self.dist is None or self.world <= 1 or self.backend != "nccl" or _P2P_BROKEN \
+                or not getattr(self, "use_symm_exchange", True):
+            return False
+        if getattr(self, "_symm", None) is None:
+            try:
+                self.symm(1 << 20)
+            except Exception as e:       # GdrError from gdr_symm_create: no peer access between these GPUs
+                import warnings
+                warnings.warn(f"peer memory unavailable ({e}); exchanges go through NCCL")
+                _P2P_BROKEN = True
+                return False
+        return True
 
     def symm_exchange(self, arrays, cnt_mat):
         """Variable all-to-all of several arrays with the SAME row split, through the symmetric buffer (gdr_symm_scatterv:
@@ -860,9 +872,11 @@ def describe(world: int, row_chunks: Optional[int] = None, hop: str = "auto") ->
     s2 = (f"stage 2: NCCL all-gather of the propagated rows per hop, pipelined over {rc} row chunk(s); " if hop == "nccl" or _P2P_BROKEN
           else "stage 2: hop fused with its all-gather (SpMM epilogue stores every row into all peers' gathered operand over "
                "NVLink, one stream-ordered barrier per hop; first distribution of X started under stage 1); ")
-    return ("stage 1: pair slices, all-to-all by owner, all-gather of degrees; " + s2 +
-            "stage 3: one packed all-reduce [sums | counts | n_changed] per Lloyd iteration; "
-            "stage 4: key-range all-to-all of the local (cell, count, sum) runs")
+    xch = "all-to-all over NCCL" if _P2P_BROKEN else "posted NVLink stores into the owners' symmetric buffers"
+    return (f"stage 1: pair slices routed to the owner of the row ({xch}), all-gather of degrees; " + s2 +
+            "stage 3: one grouped all-reduce [sums | counts | n_changed] per Lloyd iteration inside the replayed CUDA graph; "
+            f"stage 4: (cell, weight) pairs routed to the owner of the coarse row ({xch}), merged there in shared memory, result "
+            "replicated on every rank")
 
 
 _P2P_BROKEN = False      # set when peer memory turned out to be unavailable: the NCCL hop is used from then on
