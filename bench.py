@@ -985,6 +985,8 @@ def multi_parity(gdr, par, comm, part, ops, dev, w, A_ref, tgt_ref, C0, u_sl, v_
                                and torch.equal(adj_syn._indices(), syn1._indices()))
     vdiff = (adj_syn._values() - syn1._values()).abs().max() / syn1._values().abs().max() if out["counts_equal"] else torch.tensor(1.0)
     out["coarse_values_close"] = bool(vdiff.item() <= 1e-5)
+    # informative, not part of `status`: the owner-side shared-memory merge uses the single-GPU fixed-point step
+    out["coarse_values_bit_equal"] = bool(out["counts_equal"] and torch.equal(adj_syn._values(), syn1._values()))
     flags = [k for k, v in out.items() if isinstance(v, bool)]
     t = torch.tensor([1 if out[k] else 0 for k in flags], dtype=torch.int32, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
