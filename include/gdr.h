@@ -368,7 +368,10 @@ int gdr_add_row_vector(int64_t rows, int64_t D, float* X, int64_t ldx, const flo
 /* Segmented edge counting:  for every input edge e (src,dst[,w]) form the key
  * (labels_src[src], labels_dst[dst]); output the CSR (n_src x n_dst) of
  *   counts[a,b] = #edges with that key   (int32, exact)
- *   wsum[a,b]   = sum of w over them     (fp32, summed in input order; nullable)
+ *   wsum[a,b]   = sum of w over them     (fp32; nullable).  CSR input whose coarse row fits in shared memory (n_dst
+ *                 <= ~17 K with weights): one CTA per coarse row accumulates the cells there, the weights as 64-bit
+ *                 fixed-point integers -> the exact sum rounded to fp32 once, bit-reproducible.  Otherwise (COO input,
+ *                 wider rows, gdr_debug_set("coarsen_dense", 0)): radix sort by cell, fp32 sums in input order.
  *   replaces  build_condensed_bipartite           distill_recsys.py:184-201
  *             graph_compress (P^T A P)            clustgdd_agent_transduct.py:234-250
  *                                                 clustgdd_agent_induct.py:258-274
@@ -528,8 +531,10 @@ int     gdr_csr_from_keys(int64_t m, const uint64_t* keys_in, int64_t row_lo, in
  * pair tagged with the owner rank of its coarse row (top byte of the key; dropped diagonal pairs: bucket 127) and groups
  * the pairs by owner with ONE stable partition pass — keys_out / w_out sorted by owner, owner_starts_dev[0..128] the
  * first pair of every owner.  After the all-to-all the owner runs gdr_coarse_merge_edges: sort + integer run lengths +
- * fp32 sums in the exchange order, which is the global CSR order — counts AND sums are bit-identical to the
- * single-device gdr_coarsen.  Output: CSR of the coarse rows [a_lo, a_lo + n_rows). */
+ * fp32 sums in the exchange order, which is the global CSR order — counts AND sums are bit-identical to the SORT form of
+ * the single-device gdr_coarsen (COO input, or a coarse row too wide for shared memory; its default for a CSR is the
+ * shared-memory form, whose owner-side counterpart is gdr_coarse_merge_edges_dense below).  Output: CSR of the coarse
+ * rows [a_lo, a_lo + n_rows).  (clustgdd_agent_transduct.py:234-250, distill_recsys.py:184-201) */
 int64_t gdr_coarsen_route_ws_bytes(int64_t E);
 int     gdr_coarsen_route(int64_t E, const int64_t* src, const int64_t* dst, int64_t n_rows, const int32_t* csr_rowptr,
                           const int32_t* csr_colidx, const float* w, const int32_t* labels_src, const int32_t* labels_dst,
