@@ -245,8 +245,21 @@ class OracleOps:
         counts = [int((owner == r).sum()) for r in range(world)]
         return (torch.from_numpy(key[order]), None if w is None else torch.from_numpy(w[order].astype(np.float32)), counts)
 
-    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None):
+    def cluster_stats(self, A, labels_local, n):
+        """per coarse row over this rank's rows: (edges, bit pattern of max |w|) — what gdr_cluster_stats returns"""
+        lab = labels_local.numpy().astype(np.int64)
+        deg = np.diff(A.rowptr.numpy()).astype(np.int64)
+        edges = np.zeros(n, np.int64)
+        np.add.at(edges, lab, deg)
+        rows = np.repeat(np.arange(A.shape[0]), deg)
+        wmax = np.zeros(n, np.float32)
+        np.maximum.at(wmax, lab[rows], np.abs(A.vals.numpy()))
+        return torch.from_numpy(edges.astype(np.int32)), torch.from_numpy(wmax.view(np.int32).copy())
+
+    def coarse_merge_edges(self, keys, w, a_lo, n_rows, n, n_dst=None, stats=None):
         n_dst = n if n_dst is None else n_dst
+        if stats is not None:      # the driver hands over the GLOBAL per-cluster stats: every rank must hold the same
+            self.last_stats = (stats[0].numpy().copy(), stats[1].numpy().copy())
         bb = self._bits(n_dst)
         key = keys.numpy() & ((1 << 56) - 1)
         order = np.argsort(key, kind="stable")
@@ -464,6 +477,14 @@ def _worker(rank, world, port, case):
             assert np.array_equal(counts.numpy(), cnt_ref)          # integer cell counts, CSR order, independent of the rank count
             ad = adj_syn.coalesce()
             assert ad._nnz() == cnt_ref.shape[0]
+            # the routing form hands the owner the per-cluster (edges, max |w|) of the WHOLE graph, identical on every rank
+            edges_g, wmax_g = ops.last_stats
+            deg_all = np.diff(rpo).astype(np.int64)
+            edges_ref = np.zeros(17, np.int64)
+            np.add.at(edges_ref, labels, deg_all)
+            wmax_ref = np.zeros(17, np.float32)
+            np.maximum.at(wmax_ref, labels[rows], np.abs(vo))
+            assert np.array_equal(edges_g, edges_ref.astype(np.int32)) and np.array_equal(wmax_g.view(np.float32), wmax_ref)
             # this rank's own key range, not replicated
             a_lo, rp_p, ci_p, v_p, c_p = par.dist_graph_compress(comm, part, torch.from_numpy(labels[lo:hi].copy()), A_local,
                                                                  ops=ops, replicate=False)
