@@ -44,7 +44,7 @@ for name in (sys.argv[1:] or ["B", "E"]):
         truth = torch.empty(n, dtype=torch.int32, device=dev)
         assign_labels(X, C, truth)
         out = torch.empty(n, dtype=torch.int32, device=dev)
-        for screen, sname in ((3, "SS 128x256"), (0, "TS 128x192")):
+        for screen, sname in ((3, "SS 128x256"), (6, "TS 128x192")):
             _lib.call("gdr_debug_set", b"tc_screen", screen)
             out.fill_(-1)
             t = timed(lambda: assign_labels(X, C, out, tc_operand=op, ws=ws))
