@@ -16,7 +16,7 @@ build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/comm.cuh include/gdr.h
 
 $(OUT): $(OBJS)
 	@mkdir -p $(PKG)/lib
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -lcuda -ldl
+	$(NVCC) -shared -o $@ $(OBJS) -lcuda -ldl
 
 clean:
 	rm -rf build $(OUT)
